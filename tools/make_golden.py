@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""Build tests/golden/*.npz from the reference (run in the build container only).
+
+  python tools/make_golden.py [/root/reference]
+
+Two kinds of fixtures are produced:
+  A. golden_*.npz  -- the reference's OWN artefacts under data/subset (wavs, IBM/VAD label files,
+     *_upsampled.h5, *.mat), reduced to what the parity tests need;
+  B. ref_*.npz     -- outputs of the reference's own Python modules imported from
+     <reference>/packages and run here on seeded inputs / seeded weights
+     (avvad.synth.seeded_tensor), so the GPU box -- which never sees /root/reference -- can
+     check the oracle and the CUDA path against the real implementation.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(REPO, "audio-visual-vad_b200"))
+sys.path.insert(0, REPO)
+
+from h5min import H5File, read_wav_int16  # noqa: E402
+from avvad import synth  # noqa: E402
+
+REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+OUT = os.path.join(REPO, "tests", "golden")
+SUB = os.path.join(REF, "data", "subset")
+os.makedirs(OUT, exist_ok=True)
+warnings.filterwarnings("ignore")
+
+
+def golden_frontend():
+    """clean wavs + IBM/VAD label files of test/34M (the only split generated at 62.5 fps)."""
+    d = {}
+    base = os.path.join(SUB, "processed/ntcd_timit/Clean/test/34M")
+    for utt in ("sa1", "sa2", "si494"):
+        wav, fs = read_wav_int16(os.path.join(base, utt + ".wav"))
+        assert fs == 16000
+        ibm = H5File(os.path.join(base, utt + "_ibm_labels.h5"))["Y"]
+        vad = H5File(os.path.join(base, utt + "_vad_labels.h5"))["Y"]
+        assert set(np.unique(ibm)) <= {0.0, 1.0} and set(np.unique(vad)) <= {0.0, 1.0}
+        d[utt + "_wav"] = wav
+        d[utt + "_ibm_shape"] = np.asarray(ibm.shape)
+        d[utt + "_ibm_bits"] = np.packbits(ibm.astype(np.uint8).ravel())
+        d[utt + "_vad"] = vad.astype(np.uint8)
+    # noisy file of the same utterance: what the AV model actually consumes
+    noisy = os.path.join(SUB, "processed/ntcd_timit/Noisy/Babble/-5/test/34M/sa1.wav")
+    if os.path.exists(noisy):
+        d["sa1_noisy_wav"] = read_wav_int16(noisy)[0]
+    st = H5File(os.path.join(SUB, "processed/ntcd_timit/Noisy/ntcd_timit_power_spec_statistics.h5"))
+    d["audio_mean"] = st["X_train_mean"].astype(np.float32)
+    d["audio_std"] = st["X_train_std"].astype(np.float32)
+    sv = H5File(os.path.join(SUB, "processed/ntcd_timit/matlab_raw/ntcd_timit_statistics.h5"))
+    d["video_mean"] = sv["X_train_mean"].astype(np.float32)
+    d["video_std"] = sv["X_train_std"].astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "golden_frontend_34M.npz"), **d)
+    print("golden_frontend_34M.npz", {k: v.shape for k, v in d.items()})
+
+
+def golden_upsample():
+    """Recover src(k) for every frame of every shipped *_upsampled.h5 by matching it to the
+    inverse-DCT frames of the .mat it was made from (argmax correlation); keep a small pixel
+    excerpt of test/34M/sa1 to pin the DCT->ROI decode."""
+    from oracle.video import dct_to_roi, roi_to_u8_per_frame
+
+    d = {}
+    names = []
+    for split, spk, utt in (("test", "34M", "sa1"), ("test", "34M", "sa2"), ("test", "34M", "si494"),
+                            ("dev", "08F", "sa1"), ("train", "01M", "sa1")):
+        up = os.path.join(SUB, f"processed/ntcd_timit/matlab_raw/{split}/{spk}/{utt}_upsampled.h5")
+        mat = os.path.join(SUB, f"raw/ntcd_timit/matlab_raw/{split}/{spk}/{utt}.mat")
+        if not (os.path.exists(up) and os.path.exists(mat)):
+            continue
+        X = H5File(up)["X"]  # (67,67,T)
+        D = H5File(mat)["data"]  # (F,4489)
+        src = np.stack([roi_to_u8_per_frame(dct_to_roi(row)) for row in D]).astype(np.float64)  # (F,67,67)
+        Xf = np.moveaxis(X, -1, 0).astype(np.float64)  # (T,67,67)
+        a = src.reshape(len(src), -1)
+        b = Xf.reshape(len(Xf), -1)
+        a0 = a - a.mean(1, keepdims=True)
+        b0 = b - b.mean(1, keepdims=True)
+        # frames are near-duplicates of neighbours: use mean |diff| (exact match ~0.3) not correlation
+        idx = np.empty(len(b), dtype=np.int64)
+        err = np.empty(len(b))
+        for k in range(len(b)):
+            lo = max(0, int(k * 12 / 25) - 3)
+            hi = min(len(a), lo + 8)
+            e = np.abs(a[lo:hi] - b[k][None]).mean(1)
+            idx[k] = lo + int(np.argmin(e))
+            err[k] = e.min()
+        tag = f"{split}_{spk}_{utt}"
+        names.append(tag)
+        d[tag + "_F"] = np.asarray(D.shape[0])
+        d[tag + "_T"] = np.asarray(X.shape[-1])
+        d[tag + "_src"] = idx.astype(np.int32)
+        d[tag + "_maxerr"] = np.asarray(err.max())
+        print(tag, "F", D.shape[0], "T", X.shape[-1], "match err max", err.max(), "first", idx[:14])
+        if tag == "test_34M_sa1":
+            d["sa1_mat_rows"] = D[:12].astype(np.float32)  # DCT rows of source frames 0..11
+            d["sa1_X_first24"] = np.moveaxis(X[:, :, :24], -1, 0).astype(np.uint8)  # integer-valued f32
+            assert np.all(X[:, :, :24] == np.rint(X[:, :, :24]))
+    d["names"] = np.asarray(names)
+    np.savez_compressed(os.path.join(OUT, "golden_upsample.npz"), **d)
+
+
+def ref_models():
+    """Reference modules on seeded weights/inputs."""
+    sys.path.insert(0, REF)
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models.Video_Net import DeepVAD_video
+    from packages.models.AV_Net import DeepVAD_AV
+    from packages.models.compact_bilinear_pooling import CountSketchFn_forward
+    from packages.models.utils import binary_cross_entropy, f1_loss, method3
+    from packages.models.wavenet_autoencoder import wavenet_autoencoder
+    from packages.utils import collate_many2many_AV, collate_many2many_audio, collate_many2many_video
+
+    d = {}
+    g = torch.Generator().manual_seed(1234)
+    mean_a, std_a = synth.synth_audio_stats(0)
+
+    # ---- audio-only ----
+    m = synth.fill_module_(DeepVAD_audio(2, 1024, 1), seed=11).eval()
+    xa = torch.randn(3, 20, 513, generator=g)
+    la = [20, 13, 7]
+    with torch.no_grad():
+        d["audio_x"], d["audio_len"], d["audio_out"] = xa.numpy(), np.asarray(la), m(xa, la).numpy()
+
+    # ---- video-only ----
+    m = synth.fill_module_(DeepVAD_video(2, 1024, 1), seed=12).eval()
+    xv = torch.randn(2, 6, 67, 67, generator=g)
+    lv = [6, 4]
+    with torch.no_grad():
+        d["video_x"], d["video_len"], d["video_out"] = xv.numpy(), np.asarray(lv), m(xv, lv).numpy()
+        d["video_out_last"] = m(xv, torch.tensor(lv), return_last=True).numpy()
+        # trunk features for a handful of frames (pins the ResNet restatement layer by layer)
+        f = m.features(xv.view(12, 1, 67, 67).repeat(1, 3, 1, 1)).squeeze()
+        d["video_feat"] = f.numpy()
+
+    # ---- AV, concat fusion (the only AV variant the reference can execute on torch 2.x) ----
+    m = synth.fill_module_(DeepVAD_AV(2, 1024, 1, use_mcb=False, eps=1e-8), seed=13).eval()
+    xa2 = torch.randn(2, 6, 513, generator=g)
+    with torch.no_grad():
+        d["av_audio"], d["av_video"], d["av_len"] = xa2.numpy(), xv.numpy(), np.asarray(lv)
+        d["av_out"] = m(xa2, xv, lv).numpy()
+    # y_dim = 513 (IBM variant, train_AV_net.py:65-66)
+    m = synth.fill_module_(DeepVAD_AV(2, 1024, 513, use_mcb=False, eps=1e-8), seed=14).eval()
+    with torch.no_grad():
+        d["av513_out"] = m(xa2, xv, lv).numpy()
+
+    # ---- count sketch (the part of MCB that still runs) ----
+    h1 = synth.seeded_tensor("mcb.sketch1.h", (513,), torch.int64, 15)
+    s1 = synth.seeded_tensor("mcb.sketch1.s", (513,), torch.float32, 15)
+    xs = torch.randn(2, 5, 513, generator=g)
+    d["sketch_x"], d["sketch_out"] = xs.numpy(), CountSketchFn_forward(h1, s1, 1024, xs).numpy()
+
+    # ---- loss / metrics ----
+    r = torch.randn(37, 1, generator=g) * 3
+    t = (torch.rand(37, 1, generator=g) > 0.4).float()
+    d["bce_r"], d["bce_t"] = r.numpy(), t.numpy()
+    d["bce_out"] = binary_cross_entropy(r, t, 1e-8).numpy()
+    yh = (torch.sigmoid(r[:, 0]) > 0.5).int()
+    d["f1_out"] = np.asarray([v.item() for v in f1_loss(yh, t[:, 0].long(), 1e-8)], dtype=np.float32)
+
+    # ---- collate ----
+    batch = [(torch.randn(513, L, generator=g), torch.randn(67, 67, L, generator=g),
+              (torch.rand(1, L, generator=g) > 0.5).float(), L) for L in (5, 3, 4)]
+    lens, pa, pv, pt = collate_many2many_AV(batch)
+    d["collate_in_a"] = np.concatenate([b[0].numpy().ravel() for b in batch])
+    d["collate_in_v"] = np.concatenate([b[1].numpy().ravel() for b in batch])
+    d["collate_in_t"] = np.concatenate([b[2].numpy().ravel() for b in batch])
+    d["collate_lens"], d["collate_a"], d["collate_v"], d["collate_t"] = lens.numpy(), pa.numpy(), pv.numpy(), pt.numpy()
+
+    # ---- WaveNet encoder (dead code, but named by north_star) ----
+    wn = wavenet_autoencoder(filter_width=2, quantization_channel=16, dilations=[1, 2, 4, 8, 1, 2, 4, 8],
+                             en_residual_channel=32, en_dilation_channel=32, en_bottleneck_width=16,
+                             en_pool_kernel_size=10, use_bias=True)
+    synth.fill_module_(wn, seed=16).eval()
+    xw = torch.randn(2, 16, 400, generator=g)
+    with torch.no_grad():
+        d["wavenet_x"], d["wavenet_out"] = xw.numpy(), wn(xw).numpy()
+
+    # ---- reference front-end library call (torch.stft is what stft_pytorch wraps) ----
+    np.savez_compressed(os.path.join(OUT, "ref_models.npz"), **d)
+    print("ref_models.npz", {k: v.shape for k, v in d.items()})
+
+
+if __name__ == "__main__":
+    golden_frontend()
+    golden_upsample()
+    ref_models()
