@@ -1,0 +1,310 @@
+"""Host-side drivers of the libavvad C ABI.
+
+PyTorch is used only as plumbing here: device memory (tensors as buffers), the current CUDA stream and
+parameter storage.  All arithmetic of the hot path happens inside libavvad.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+
+FPS_NUM, FPS_DEN = 25, 12  # 62.5 / 30 (scripts/create_video_train_files_upsampled.py:58-59)
+
+# conv layer index (include/avvad.h) -> (conv key, bn key) under the `features.` prefix
+RESNET_LAYER_KEYS = [("0", "1")]
+for _stage in (4, 5, 6, 7):
+    RESNET_LAYER_KEYS += [(f"{_stage}.0.conv1", f"{_stage}.0.bn1"), (f"{_stage}.0.conv2", f"{_stage}.0.bn2")]
+    if _stage != 4:
+        RESNET_LAYER_KEYS += [(f"{_stage}.0.downsample.0", f"{_stage}.0.downsample.1")]
+    RESNET_LAYER_KEYS += [(f"{_stage}.1.conv1", f"{_stage}.1.bn1"), (f"{_stage}.1.conv2", f"{_stage}.1.bn2")]
+assert len(RESNET_LAYER_KEYS) == 20
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _i32(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    return torch.tensor(list(x), dtype=torch.int32, device=device)
+
+
+class _Workspace:
+    """Grow-only byte buffer reused across calls (caller-owned scratch of the C ABI)."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+# ---------------------------------------------------------------------------------------------
+# front end / upsampling
+# ---------------------------------------------------------------------------------------------
+def stft_num_frames(n_samples: int, fs=16000, wlen_sec=64e-3, hop_percent=0.25, pad_at_end=True) -> int:
+    return int(L.lib().avvad_stft_num_frames(int(n_samples), float(fs), float(wlen_sec), float(hop_percent),
+                                             1 if pad_at_end else 0))
+
+
+def upsampled_length(n_src: int, num=FPS_NUM, den=FPS_DEN) -> int:
+    return int(L.lib().avvad_upsampled_length(int(n_src), num, den))
+
+
+def frontend_logpower(wave: torch.Tensor, n_samples, n_frames, t_max: int, mean: Optional[torch.Tensor],
+                      std: Optional[torch.Tensor], eps=1e-8, normalise=True, out: Optional[torch.Tensor] = None):
+    """(B,N) fp32 waveforms -> (B,t_max,513) standardised log-power features."""
+    L.require_cuda(wave)
+    assert wave.dim() == 2 and wave.dtype == torch.float32
+    wave = wave.contiguous()
+    B = wave.shape[0]
+    dev = wave.device
+    ns, nf = _i32(n_samples, dev), _i32(n_frames, dev)
+    if out is None:
+        out = torch.empty(B, t_max, 513, dtype=torch.float32, device=dev)
+    peak = torch.empty(B, dtype=torch.float32, device=dev)
+    m = _f32(mean.reshape(-1), dev) if mean is not None else None
+    s = _f32(std.reshape(-1), dev) if std is not None else None
+    L.check(L.lib().avvad_frontend_logpower(L.ptr(wave), wave.stride(0), L.ptr(ns), L.ptr(nf), B, t_max,
+                                            1 if normalise else 0, L.ptr(m), L.ptr(s), eps, L.ptr(out), L.ptr(peak),
+                                            L.stream_ptr()))
+    return out
+
+
+def stft(wave: torch.Tensor, n_samples, n_frames, t_max: int) -> torch.Tensor:
+    """(B,N) -> (B,513,t_max,2) real view, as the legacy torch.stft the reference calls."""
+    L.require_cuda(wave)
+    wave = wave.contiguous()
+    B, dev = wave.shape[0], wave.device
+    ns, nf = _i32(n_samples, dev), _i32(n_frames, dev)
+    out = torch.empty(B, 513, t_max, 2, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_stft(L.ptr(wave), wave.stride(0), L.ptr(ns), L.ptr(nf), B, t_max, L.ptr(out),
+                               L.stream_ptr()))
+    return out
+
+
+def upsample_gather(src: torch.Tensor, n_src, n_out, t_max: int, mean=0.0, std=1.0, eps=1e-8, standardise=False,
+                    num=FPS_NUM, den=FPS_DEN, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,F,H,W) u8/f32 frames at 30 fps -> (B,t_max,H,W) fp32 at 62.5 fps (SURVEY U + A4)."""
+    L.require_cuda(src)
+    assert src.dim() == 4 and src.dtype in (torch.uint8, torch.float32)
+    src = src.contiguous()
+    B, F, H, W = src.shape
+    dev = src.device
+    a, b = _i32(n_src, dev), _i32(n_out, dev)
+    if out is None:
+        out = torch.empty(B, t_max, H, W, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_upsample_gather(L.ptr(src), 1 if src.dtype == torch.float32 else 0, L.ptr(a), L.ptr(b), B,
+                                          F, t_max, H * W, num, den, float(mean), float(std), float(eps),
+                                          1 if standardise else 0, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def upsample_index(n_src: int, n_out: int, device="cuda", num=FPS_NUM, den=FPS_DEN) -> torch.Tensor:
+    out = torch.empty(n_out, dtype=torch.int32, device=device)
+    L.check(L.lib().avvad_upsample_index(n_src, n_out, num, den, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# generic tensor-core ops (exposed for tests)
+# ---------------------------------------------------------------------------------------------
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out_bf16=False, relu=False):
+    """C = A @ W^T (+bias); A (M,K) bf16, W (N,K) bf16."""
+    L.require_cuda(a, w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    c = torch.empty(M, N, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=a.device)
+    b = _f32(bias, a.device) if bias is not None else None
+    L.check(L.lib().avvad_gemm_bf16(L.ptr(a), K, L.ptr(w), K, L.ptr(b), L.ptr(c), N, 1 if out_bf16 else 0,
+                                    1 if relu else 0, M, N, K, L.stream_ptr()))
+    return c
+
+
+def conv2d_nhwc_bf16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], stride: int, pad: int,
+                     residual: Optional[torch.Tensor] = None, relu=False) -> torch.Tensor:
+    """x (n,H,W,Cin) bf16, w (Cout,R,S,Cin) bf16 -> (n,OH,OW,Cout) bf16."""
+    L.require_cuda(x, w)
+    x, w = x.contiguous(), w.contiguous()
+    n, H, W, Cin = x.shape
+    Cout, R, S, _ = w.shape
+    OH = (H + 2 * pad - R) // stride + 1
+    OW = (W + 2 * pad - S) // stride + 1
+    out = torch.empty(n, OH, OW, Cout, dtype=torch.bfloat16, device=x.device)
+    b = _f32(bias, x.device) if bias is not None else None
+    r = residual.contiguous() if residual is not None else None
+    L.check(L.lib().avvad_conv2d_nhwc_bf16(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(r), L.ptr(out), n, H, W, Cin, Cout, R,
+                                           S, stride, pad, 1 if relu else 0, L.stream_ptr()))
+    return out
+
+
+def pack_rows_bf16(src: torch.Tensor, dst: torch.Tensor, col_off: int, zero_tail: bool):
+    """dst[m, col_off:col_off+cols] = bf16(src[m, :]) (dst is a (rows, ld) bf16 operand buffer)."""
+    rows, cols = src.shape
+    L.check(L.lib().avvad_pack_rows_bf16(L.ptr(src), src.stride(0), L.ptr(dst), dst.stride(0), col_off, rows, cols,
+                                         1 if zero_tail else 0, L.stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------
+# model blocks
+# ---------------------------------------------------------------------------------------------
+class ResNet18Trunk:
+    """Eval-mode ResNet-18 trunk (children[:-1]) on (M,67,67) fp32 ROIs -> (M,512)."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        L.check(L.lib().avvad_resnet18_create(C.byref(h)))
+        self.h = h
+        self.ws = _Workspace()
+        self.chunk = 2048
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                L.lib().avvad_resnet18_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def load(self, sd: Dict[str, torch.Tensor], device, prefix="features.", bn_eps=1e-5):
+        keep = []
+        for i, (ck, bk) in enumerate(RESNET_LAYER_KEYS):
+            w = _f32(sd[prefix + ck + ".weight"], device)
+            g = _f32(sd[prefix + bk + ".weight"], device)
+            b = _f32(sd[prefix + bk + ".bias"], device)
+            m = _f32(sd[prefix + bk + ".running_mean"], device)
+            v = _f32(sd[prefix + bk + ".running_var"], device)
+            keep += [w, g, b, m, v]
+            L.check(L.lib().avvad_resnet18_set_conv(self.h, i, L.ptr(w), L.ptr(g), L.ptr(b), L.ptr(m), L.ptr(v),
+                                                    bn_eps, L.stream_ptr()))
+        torch.cuda.current_stream().synchronize()  # sources may be temporaries
+        del keep
+
+    def forward(self, frames: torch.Tensor, feat: Optional[torch.Tensor] = None,
+                feat_bf16: Optional[torch.Tensor] = None, col_off=0, want_f32=True):
+        L.require_cuda(frames)
+        assert frames.dtype == torch.float32 and frames.shape[-2:] == (67, 67)
+        frames = frames.contiguous()
+        n = frames.numel() // (67 * 67)
+        nbytes = L.lib().avvad_resnet18_workspace_bytes(n, self.chunk)
+        ws = self.ws.get(nbytes, frames.device)
+        if feat is None and want_f32:
+            feat = torch.empty(n, 512, dtype=torch.float32, device=frames.device)
+        ld = feat_bf16.stride(-2) if feat_bf16 is not None else 0
+        L.check(L.lib().avvad_resnet18_forward(self.h, L.ptr(frames), n, self.chunk, L.ptr(ws), ws.numel(),
+                                               L.ptr(feat), L.ptr(feat_bf16), ld, col_off, L.stream_ptr()))
+        return feat
+
+    def forward_upto(self, frames: torch.Tensor, upto: int, shape: Tuple[int, int, int]) -> torch.Tensor:
+        """Test hook: NHWC bf16 activation after conv layer `upto` (shape = (h, w, c))."""
+        frames = frames.contiguous()
+        n = frames.numel() // (67 * 67)
+        nbytes = L.lib().avvad_resnet18_workspace_bytes(n, n)
+        ws = self.ws.get(nbytes, frames.device)
+        out = torch.empty((n,) + tuple(shape), dtype=torch.bfloat16, device=frames.device)
+        L.check(L.lib().avvad_resnet18_forward_upto(self.h, L.ptr(frames), n, upto, L.ptr(ws), ws.numel(), L.ptr(out),
+                                                    L.stream_ptr()))
+        return out
+
+
+class Mcb:
+    """MCB + signed sqrt + whole-tensor L2 + BatchNorm1d(eval)."""
+
+    def __init__(self):
+        h = C.c_void_p()
+        L.check(L.lib().avvad_mcb_create(C.byref(h)))
+        self.h = h
+        self.ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                L.lib().avvad_mcb_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def load(self, sd: Dict[str, torch.Tensor], device, eps=1e-8):
+        h1 = sd["mcb.sketch1.h"].to(device=device, dtype=torch.int64).contiguous()
+        h2 = sd["mcb.sketch2.h"].to(device=device, dtype=torch.int64).contiguous()
+        s1, s2 = _f32(sd["mcb.sketch1.s"], device), _f32(sd["mcb.sketch2.s"], device)
+        g, b = _f32(sd["mcb_bn.weight"], device), _f32(sd["mcb_bn.bias"], device)
+        m, v = _f32(sd["mcb_bn.running_mean"], device), _f32(sd["mcb_bn.running_var"], device)
+        L.check(L.lib().avvad_mcb_load(self.h, L.ptr(h1), L.ptr(s1), L.ptr(h2), L.ptr(s2), L.ptr(g), L.ptr(b),
+                                       L.ptr(m), L.ptr(v), eps, L.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def forward(self, audio: torch.Tensor, video: torch.Tensor, out_bf16: Optional[torch.Tensor] = None,
+                out_f32: Optional[torch.Tensor] = None):
+        L.require_cuda(audio, video)
+        audio = audio.reshape(-1, 513).contiguous()
+        video = video.reshape(-1, 512).contiguous()
+        rows = audio.shape[0]
+        nbytes = L.lib().avvad_mcb_workspace_bytes(rows)
+        ws = self.ws.get(nbytes, audio.device)
+        ld = out_bf16.stride(-2) if out_bf16 is not None else 0
+        L.check(L.lib().avvad_mcb_forward(self.h, L.ptr(audio), L.ptr(video), rows, L.ptr(ws), ws.numel(),
+                                          L.ptr(out_bf16), ld, L.ptr(out_f32), L.stream_ptr()))
+
+
+class Lstm:
+    """L-layer LSTM + Linear head over padded batches."""
+
+    def __init__(self, layers: int, input_size: int, hidden: int, y_dim: int):
+        h = C.c_void_p()
+        L.check(L.lib().avvad_lstm_create(C.byref(h), layers, input_size, hidden, y_dim))
+        self.h = h
+        self.layers, self.input_size, self.hidden, self.y_dim = layers, input_size, hidden, y_dim
+        self.ld = int(L.lib().avvad_lstm_input_ld(self.h))
+        self.ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                L.lib().avvad_lstm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def load(self, sd: Dict[str, torch.Tensor], device, lstm_prefix: str, head_prefix: str):
+        keep = []
+        for l in range(self.layers):
+            t = [_f32(sd[f"{lstm_prefix}.{k}_l{l}"], device) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+            keep += t
+            L.check(L.lib().avvad_lstm_set_layer(self.h, l, *[L.ptr(x) for x in t], L.stream_ptr()))
+        w, b = _f32(sd[head_prefix + ".weight"], device), _f32(sd[head_prefix + ".bias"], device)
+        L.check(L.lib().avvad_lstm_set_head(self.h, L.ptr(w), L.ptr(b), L.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def new_input(self, B: int, T: int, device) -> torch.Tensor:
+        """bf16 operand buffer (B,T,ld); columns >= input_size must stay zero."""
+        return torch.zeros(B, T, self.ld, dtype=torch.bfloat16, device=device)
+
+    def forward(self, x_bf16: torch.Tensor, lengths, want_post=False, want_dec=False, want_last=False):
+        L.require_cuda(x_bf16)
+        B, T, ld = x_bf16.shape
+        assert ld == self.ld and x_bf16.is_contiguous() and x_bf16.dtype == torch.bfloat16
+        dev = x_bf16.device
+        lens = _i32(lengths, dev)
+        nbytes = L.lib().avvad_lstm_workspace_bytes(self.h, B, T)
+        ws = self.ws.get(nbytes, dev)
+        logits = torch.empty(B, T, self.y_dim, dtype=torch.float32, device=dev)
+        post = torch.empty_like(logits) if want_post else None
+        dec = torch.empty(B, T, self.y_dim, dtype=torch.int32, device=dev) if want_dec else None
+        last = torch.empty(B, self.y_dim, dtype=torch.float32, device=dev) if want_last else None
+        L.check(L.lib().avvad_lstm_forward(self.h, L.ptr(x_bf16), L.ptr(lens), B, T, L.ptr(ws), ws.numel(),
+                                           L.ptr(logits), L.ptr(post), L.ptr(dec), L.ptr(last), L.stream_ptr()))
+        return logits, post, dec, last
+
+
+def launch_count() -> int:
+    return int(L.lib().avvad_launch_count())

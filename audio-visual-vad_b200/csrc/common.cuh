@@ -1,0 +1,69 @@
+// Shared host/device helpers for libavvad (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/avvad.h"
+
+namespace avvad {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define AVVAD_CHECK_ARG(cond, msg)                                         \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      ::avvad::set_error(std::string("bad argument: ") + (msg));           \
+      return AVVAD_ERR_ARG;                                                \
+    }                                                                      \
+  } while (0)
+
+#define AVVAD_CUDA(call)                                                                      \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      ::avvad::set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                \
+      return AVVAD_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define AVVAD_LAUNCHED()                                                                      \
+  do {                                                                                        \
+    ::avvad::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) {                                                                 \
+      ::avvad::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(e__) +    \
+                         " at " + __FILE__ + ":" + std::to_string(__LINE__));                 \
+      return AVVAD_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ---- small device helpers ---------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_fast(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_fast(float x) {
+  // 2*sigmoid(2x)-1, clamped so __expf never overflows to inf/inf
+  float e = __expf(-2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+  return (1.0f - e) / (1.0f + e);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+}  // namespace avvad

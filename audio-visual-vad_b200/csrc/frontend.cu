@@ -1,0 +1,219 @@
+// Audio front end: peak normalise -> frame/Hann -> 1024-pt rFFT -> |.|^2 -> log(.+eps) -> standardise,
+// fused in one kernel (plus a small abs-max reduction).  Two consecutive frames of one utterance are
+// packed into the real/imaginary parts of a single complex FFT held in shared memory.
+//
+// Reference semantics: packages/processing/stft.py:123-151, packages/data_handling.py:441,454-457,
+// scripts/evaluate_AV_net.py:225-230, packages/utils.py:157-166 (zero padding happens BEFORE the
+// standardisation, so padded frames hold (0-mean)/(std+eps)).
+#include <math.h>
+
+#include <mutex>
+
+#include "fft.cuh"
+
+namespace avvad {
+
+static float2* g_tw_dev = nullptr;
+static std::mutex g_tw_mu;
+
+const float2* fft_twiddles_device() {
+  std::lock_guard<std::mutex> lk(g_tw_mu);
+  if (g_tw_dev) return g_tw_dev;
+  float2 host[512];
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < 512; ++k) {
+    double a = -two_pi * (double)k / 1024.0;
+    host[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  float2* d = nullptr;
+  if (cudaMalloc(&d, sizeof(host)) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return nullptr;
+  }
+  g_tw_dev = d;
+  return g_tw_dev;
+}
+
+// ---- per-utterance max|x| ----------------------------------------------------------------------
+__global__ void absmax_kernel(const float* __restrict__ wave, int64_t wave_stride,
+                              const int32_t* __restrict__ n_samples, float* __restrict__ peak) {
+  const int b = blockIdx.y;
+  const int n = n_samples[b];
+  const float* x = wave + (int64_t)b * wave_stride;
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    // non-negative floats order like their bit patterns
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
+  }
+}
+
+// ---- fused STFT / log-power kernel ---------------------------------------------------------------
+// MODE 0: standardised log-power (B, t_max, 513);  MODE 1: raw complex STFT (B, 513, t_max, 2).
+template <int MODE>
+__global__ void __launch_bounds__(kFftThreads)
+frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32_t* __restrict__ n_samples,
+                const int32_t* __restrict__ n_frames, int t_max, const float* __restrict__ peak,
+                const float* __restrict__ mean, const float* __restrict__ stdv, float eps,
+                const float2* __restrict__ tw_g, float* __restrict__ out) {
+  __shared__ float2 sa[kFftN];
+  __shared__ float2 sb[kFftN];
+  __shared__ float2 stw[512];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 2;
+  const int t1 = t0 + 1;
+  const int T = min(n_frames[b], t_max);
+  const bool has1 = t1 < t_max;
+
+  if (t0 >= T) {
+    if (MODE == 0) {
+      // both rows are collate padding: (0 - mean) / (std + eps)
+      for (int k = tid; k < 513; k += kFftThreads) {
+        float v = mean ? (0.f - mean[k]) / (stdv[k] + eps) : 0.f;
+        out[((int64_t)b * t_max + t0) * 513 + k] = v;
+        if (has1) out[((int64_t)b * t_max + t1) * 513 + k] = v;
+      }
+    } else {
+      for (int k = tid; k < 513; k += kFftThreads) {
+        float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * 513 + k) * t_max;
+        o[t0] = make_float2(0.f, 0.f);
+        if (has1) o[t1] = make_float2(0.f, 0.f);
+      }
+    }
+    return;
+  }
+
+  stw[tid] = tw_g[tid];
+  stw[tid + 256] = tw_g[tid + 256];
+
+  const int n = n_samples[b];
+  const float* x = wave + (int64_t)b * wave_stride;
+  const bool live1 = t1 < T;
+  const float pk = peak ? peak[b] : 1.0f;
+  const bool norm = peak != nullptr;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = tid + q * kFftThreads;
+    // periodic Hann: 0.5 - 0.5*cos(2*pi*i/1024); cos from the twiddle table
+    const float c = (i < 512) ? stw[i].x : -stw[i - 512].x;
+    const float w = 0.5f - 0.5f * c;
+    const int i0 = t0 * 256 + i;
+    const int i1 = i0 + 256;
+    float v0 = (i0 < n) ? x[i0] : 0.f;  // samples past the end are the pad-at-end zeros
+    float v1 = (live1 && i1 < n) ? x[i1] : 0.f;
+    if (norm) {
+      v0 = __fdiv_rn(v0, pk);
+      v1 = __fdiv_rn(v1, pk);
+    }
+    sa[i] = make_float2(v0 * w, v1 * w);
+  }
+  __syncthreads();
+  fft1024_smem(sa, sb, stw, tid);
+
+  for (int k = tid; k < 513; k += kFftThreads) {
+    const float2 zk = sa[k];
+    const float2 zn = sa[(kFftN - k) & (kFftN - 1)];
+    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+    const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+    if (MODE == 0) {
+      float m = 0.f, inv = 1.f;
+      if (mean) {
+        m = mean[k];
+        inv = stdv[k] + eps;
+      }
+      const float la = logf(ar * ar + ai * ai + eps);
+      out[((int64_t)b * t_max + t0) * 513 + k] = mean ? (la - m) / inv : la;
+      if (has1) {
+        float lb;
+        if (live1) {
+          lb = logf(br * br + bi * bi + eps);
+          lb = mean ? (lb - m) / inv : lb;
+        } else {
+          lb = mean ? (0.f - m) / inv : 0.f;
+        }
+        out[((int64_t)b * t_max + t1) * 513 + k] = lb;
+      }
+    } else {
+      float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * 513 + k) * t_max;
+      o[t0] = make_float2(ar, ai);
+      if (has1) o[t1] = live1 ? make_float2(br, bi) : make_float2(0.f, 0.f);
+    }
+  }
+}
+
+}  // namespace avvad
+
+using namespace avvad;
+
+extern "C" int64_t avvad_stft_num_frames(int64_t n_samples, double fs, double wlen_sec, double hop_percent,
+                                         int pad_at_end) {
+  // stft.py:123-139, same double-precision expressions in the same order
+  if (wlen_sec * fs != (double)(int64_t)(wlen_sec * fs)) return -1;
+  const int64_t nfft = (int64_t)(wlen_sec * fs);
+  const int64_t hop = (int64_t)(hop_percent * (double)nfft);
+  int64_t n = n_samples;
+  if (pad_at_end) {
+    const double utt_len = (double)n_samples / fs;
+    const double q = utt_len / wlen_sec / hop_percent;
+    if (ceil(q) != (double)(int64_t)q) n += hop;
+  }
+  if (n < nfft || hop <= 0) return 0;
+  return 1 + (n - nfft) / hop;
+}
+
+static int launch_frontend(int mode, const float* wave, int64_t wave_stride, const int32_t* n_samples,
+                           const int32_t* n_frames, int32_t B, int32_t t_max, int normalise,
+                           const float* mean, const float* stdv, float eps, float* out,
+                           float* peak_scratch, cudaStream_t st) {
+  AVVAD_CHECK_ARG(wave && n_samples && n_frames && out, "null pointer");
+  AVVAD_CHECK_ARG(B > 0 && t_max > 0 && wave_stride > 0, "B, t_max, wave_stride must be positive");
+  AVVAD_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "mean and std must both be given or both NULL");
+  AVVAD_CHECK_ARG(!normalise || peak_scratch, "peak_scratch required when normalise != 0");
+  const float2* tw = fft_twiddles_device();
+  if (!tw) {
+    set_error("twiddle table allocation failed (no CUDA device?)");
+    return AVVAD_ERR_CUDA;
+  }
+  if (normalise) {
+    AVVAD_CUDA(cudaMemsetAsync(peak_scratch, 0, sizeof(float) * B, st));
+    int chunks = (int)std::min<int64_t>(64, ceil_div(wave_stride, 256 * 16));
+    absmax_kernel<<<dim3(chunks, B), 256, 0, st>>>(wave, wave_stride, n_samples, peak_scratch);
+    AVVAD_LAUNCHED();
+  }
+  dim3 grid((t_max + 1) / 2, B);
+  if (mode == 0)
+    frontend_kernel<0><<<grid, kFftThreads, 0, st>>>(wave, wave_stride, n_samples, n_frames, t_max,
+                                                     normalise ? peak_scratch : nullptr, mean, stdv, eps, tw, out);
+  else
+    frontend_kernel<1><<<grid, kFftThreads, 0, st>>>(wave, wave_stride, n_samples, n_frames, t_max, nullptr,
+                                                     nullptr, nullptr, 0.f, tw, out);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_frontend_logpower(const float* wave, int64_t wave_stride, const int32_t* n_samples,
+                                       const int32_t* n_frames, int32_t B, int32_t t_max, int normalise,
+                                       const float* mean, const float* stdv, float eps, float* out,
+                                       float* peak_scratch, void* stream) {
+  return launch_frontend(0, wave, wave_stride, n_samples, n_frames, B, t_max, normalise, mean, stdv, eps, out,
+                         peak_scratch, (cudaStream_t)stream);
+}
+
+extern "C" int avvad_stft(const float* wave, int64_t wave_stride, const int32_t* n_samples,
+                          const int32_t* n_frames, int32_t B, int32_t t_max, float* out_ft2, void* stream) {
+  return launch_frontend(1, wave, wave_stride, n_samples, n_frames, B, t_max, 0, nullptr, nullptr, 0.f, out_ft2,
+                         nullptr, (cudaStream_t)stream);
+}

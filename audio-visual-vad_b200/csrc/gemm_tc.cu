@@ -1,0 +1,132 @@
+// Host launchers for the tcgen05 engine + the exported GEMM / NHWC-conv / row-pack entry points.
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "gemm_tc.cuh"
+
+namespace avvad {
+namespace tc {
+
+template <int BN, int AMODE>
+static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int KB,
+                    const EpiParams& ep, int epi_mode, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));
+    return AVVAD_ERR_CUDA;
+  }
+  const int n_tiles = (int)ceil_div(N, BN);
+  const int64_t m_tiles = ceil_div(M, BM);
+  const int64_t tiles = m_tiles * n_tiles;
+  if (tiles <= 0) return AVVAD_OK;
+  AVVAD_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
+  tc_gemm_kernel<BN, AMODE><<<(unsigned)tiles, kThreads, C::kSmemBytes, st>>>(ap, Wt, ldw, M, N, KB, n_tiles, ep,
+                                                                               epi_mode);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
+           const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
+  AVVAD_CHECK_ARG(K > 0 && K % BK == 0, "K must be a positive multiple of 64");
+  AVVAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ap.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0,
+                  "operands must be 16-byte aligned");
+  AVVAD_CHECK_ARG(ldw % 8 == 0 && (amode != A_PLAIN || ap.lda % 8 == 0), "leading dimensions must be multiples of 8");
+  const int KB = K / BK;
+  int bn = bn_hint;
+  if (bn != 64 && bn != 128 && bn != 256) bn = (N <= 64) ? 64 : 128;
+  if (epi_mode == EPI_LSTM) AVVAD_CHECK_ARG(N % 32 == 0, "LSTM epilogue needs N % 32 == 0");
+#define AVVAD_TC_CASE(BNV)                                                                           \
+  case BNV:                                                                                          \
+    return amode == A_PLAIN ? launch_t<BNV, A_PLAIN>(ap, Wt, ldw, M, N, KB, ep, epi_mode, st)        \
+                            : launch_t<BNV, A_CONV>(ap, Wt, ldw, M, N, KB, ep, epi_mode, st);
+  switch (bn) {
+    AVVAD_TC_CASE(64)
+    AVVAD_TC_CASE(128)
+    AVVAD_TC_CASE(256)
+  }
+#undef AVVAD_TC_CASE
+  return AVVAD_ERR_ARG;
+}
+
+__global__ void pack_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
+                                 int64_t ld_dst, int64_t col_off, int64_t rows, int64_t cols, int64_t width) {
+  // one thread per destination element in [col_off, col_off + width)
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * width) return;
+  const int64_t r = idx / width, j = idx - r * width;
+  const float v = (j < cols) ? src[r * ld_src + j] : 0.f;
+  dst[r * ld_dst + col_off + j] = __float2bfloat16_rn(v);
+}
+
+}  // namespace tc
+}  // namespace avvad
+
+using namespace avvad;
+
+static int bn_override() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_BN");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+extern "C" int avvad_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* Cp,
+                               int64_t ldc, int c_is_bf16, int relu, int64_t M, int64_t N, int64_t K, void* stream) {
+  AVVAD_CHECK_ARG(A && W && Cp, "null pointer");
+  AVVAD_CHECK_ARG(M > 0 && N > 0 && N < (1 << 30), "bad M/N");
+  tc::AParams ap{};
+  ap.A = (const __nv_bfloat16*)A;
+  ap.lda = lda;
+  tc::EpiParams ep{};
+  ep.bias = bias;
+  ep.C = Cp;
+  ep.ldc = ldc;
+  ep.relu = relu;
+  return tc::launch(tc::A_PLAIN, ap, (const __nv_bfloat16*)W, ldw, M, (int)N, (int)K, ep,
+                    c_is_bf16 ? tc::EPI_BF16 : tc::EPI_F32, bn_override(), (cudaStream_t)stream);
+}
+
+extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float* bias, const void* residual,
+                                      void* out, int64_t n, int H, int W, int Cin, int Cout, int R, int S, int stride,
+                                      int pad, int relu, void* stream) {
+  AVVAD_CHECK_ARG(in && w && out, "null pointer");
+  AVVAD_CHECK_ARG(n > 0 && H > 0 && W > 0 && R > 0 && S > 0 && stride > 0 && pad >= 0, "bad conv shape");
+  AVVAD_CHECK_ARG(Cin % 64 == 0 && Cout % 32 == 0, "Cin must be a multiple of 64 and Cout of 32");
+  const int OH = (H + 2 * pad - R) / stride + 1;
+  const int OW = (W + 2 * pad - S) / stride + 1;
+  AVVAD_CHECK_ARG(OH > 0 && OW > 0, "empty output");
+  tc::AParams ap{};
+  ap.A = (const __nv_bfloat16*)in;
+  ap.H = H; ap.W = W; ap.Cin = Cin; ap.OH = OH; ap.OW = OW; ap.R = R; ap.S = S; ap.stride = stride; ap.pad = pad;
+  ap.cpb = Cin / 64;
+  tc::EpiParams ep{};
+  ep.bias = bias;
+  ep.residual = (const __nv_bfloat16*)residual;
+  ep.C = out;
+  ep.ldc = Cout;
+  ep.relu = relu;
+  const int64_t M = n * OH * OW;
+  const int K = R * S * Cin;
+  return tc::launch(tc::A_CONV, ap, (const __nv_bfloat16*)w, K, M, Cout, K, ep, tc::EPI_BF16, bn_override(),
+                    (cudaStream_t)stream);
+}
+
+extern "C" int avvad_pack_rows_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t col_off,
+                                    int64_t rows, int64_t cols, int zero_tail, void* stream) {
+  AVVAD_CHECK_ARG(src && dst && rows > 0 && cols > 0 && col_off >= 0 && col_off + cols <= ld_dst, "bad argument");
+  const int64_t width = zero_tail ? (ld_dst - col_off) : cols;
+  const int64_t total = rows * width;
+  tc::pack_rows_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, (__nv_bfloat16*)dst, ld_dst, col_off, rows, cols, width);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}

@@ -1,0 +1,301 @@
+// Multi-layer unidirectional LSTM over padded (B,T,I) batches with per-sequence lengths, plus the Linear head,
+// sigmoid and 0.5 threshold.
+//
+// Reference semantics: packages/models/AV_Net.py:127-140 (pack_padded_sequence -> nn.LSTM -> pad_packed_sequence
+// -> nn.Linear), scripts/evaluate_AV_net.py:239-240.  nn.LSTM: gates i,f,g,o; c' = s(f)c + s(i)tanh(g);
+// h' = s(o)tanh(c'); zero initial state; outputs for t >= len_b are exactly zero so the head emits its bias there.
+//
+// B200 mapping: the input projection X*W_ih^T (+b_ih+b_hh) of ALL time steps is one tcgen05 GEMM; every time
+// step is one tcgen05 GEMM h_{t-1}*W_hh^T whose epilogue fuses the gate non-linearities, the cell update, the
+// length mask and the bf16 store of h_t (both as next-step operand and as layer output).  Weight rows are
+// re-ordered gate-interleaved (row 4u+g) so that one epilogue thread owns all four gates of a hidden unit.
+#include "gemm_tc.cuh"
+
+namespace avvad {
+
+// W [4H][I] f32 (PyTorch gate-major: row g*H+u) -> bf16 [4H][ld] with row 4u+g, zero padded to ld
+__global__ void pack_lstm_w_kernel(const float* __restrict__ w, int H, int I, int ld, __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)4 * H * ld;
+  if (idx >= total) return;
+  const int np = (int)(idx / ld), j = (int)(idx - (int64_t)np * ld);
+  const int u = np >> 2, g = np & 3;
+  out[idx] = __float2bfloat16_rn(j < I ? w[(int64_t)(g * H + u) * I + j] : 0.f);
+}
+__global__ void pack_lstm_b_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
+                                   float* __restrict__ out) {
+  const int np = blockIdx.x * blockDim.x + threadIdx.x;
+  if (np >= 4 * H) return;
+  const int u = np >> 2, g = np & 3;
+  out[np] = b_ih[g * H + u] + b_hh[g * H + u];
+}
+__global__ void pack_head_kernel(const float* __restrict__ w, int64_t n, float* __restrict__ w32,
+                                 __nv_bfloat16* __restrict__ w16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  w32[i] = w[i];
+  w16[i] = __float2bfloat16_rn(w[i]);
+}
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// y_dim == 1 head: one warp per (b,t) row of the last layer's output
+__global__ void head1_kernel(const __nv_bfloat16* __restrict__ hseq, int64_t rows, int H, const float* __restrict__ w,
+                             const float* __restrict__ b, float* __restrict__ logits, float* __restrict__ post,
+                             int32_t* __restrict__ dec) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* hr = hseq + row * H;
+  float acc = 0.f;
+  for (int j = lane * 8; j < H; j += 256) {
+    const uint4 v = *reinterpret_cast<const uint4*>(hr + j);
+    const float4 w0 = *reinterpret_cast<const float4*>(w + j);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + j + 4);
+    const float2 a = unpack_bf16x2(v.x), c = unpack_bf16x2(v.y), d = unpack_bf16x2(v.z), e = unpack_bf16x2(v.w);
+    acc += a.x * w0.x + a.y * w0.y + c.x * w0.z + c.y * w0.w + d.x * w1.x + d.y * w1.y + e.x * w1.z + e.y * w1.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const float l = acc + b[0];
+    if (logits) logits[row] = l;
+    const float p = sigmoid_acc(l);
+    if (post) post[row] = p;
+    if (dec) dec[row] = p > 0.5f ? 1 : 0;
+  }
+}
+
+__global__ void post_dec_kernel(const float* __restrict__ logits, int64_t n, float* __restrict__ post,
+                                int32_t* __restrict__ dec) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p = sigmoid_acc(logits[i]);
+  if (post) post[i] = p;
+  if (dec) dec[i] = p > 0.5f ? 1 : 0;
+}
+
+// hlast[b][:] = hseq[b][len_b - 1][:]
+__global__ void gather_last_kernel(const __nv_bfloat16* __restrict__ hseq, const int32_t* __restrict__ lengths, int T,
+                                   int H, __nv_bfloat16* __restrict__ hlast) {
+  const int b = blockIdx.x;
+  int t = lengths[b] - 1;
+  t = t < 0 ? 0 : (t >= T ? T - 1 : t);
+  const uint4* src = reinterpret_cast<const uint4*>(hseq + ((int64_t)b * T + t) * H);
+  uint4* dst = reinterpret_cast<uint4*>(hlast + (int64_t)b * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace avvad
+
+using namespace avvad;
+
+struct avvad_lstm {
+  int layers, input_size, H, y_dim;
+  int64_t ld0;               // padded layer-0 input width
+  __nv_bfloat16* w_ih[8];    // [4H][ld_l]
+  __nv_bfloat16* w_hh[8];    // [4H][H]
+  float* bias[8];            // [4H] gate-interleaved, b_ih + b_hh
+  float* head_w32;           // [y_dim][H]
+  __nv_bfloat16* head_w16;   // [y_dim][H]
+  float* head_b;             // [y_dim]
+  bool set[8];
+  bool head_set;
+};
+
+extern "C" int avvad_lstm_create(avvad_lstm** out, int layers, int input_size, int hidden, int y_dim) {
+  AVVAD_CHECK_ARG(out, "null out");
+  AVVAD_CHECK_ARG(layers >= 1 && layers <= 8, "1..8 layers supported");
+  AVVAD_CHECK_ARG(hidden > 0 && hidden % 64 == 0, "hidden size must be a multiple of 64");
+  AVVAD_CHECK_ARG(input_size > 0 && y_dim > 0, "bad sizes");
+  avvad_lstm* h = new avvad_lstm();
+  h->layers = layers;
+  h->input_size = input_size;
+  h->H = hidden;
+  h->y_dim = y_dim;
+  h->ld0 = (input_size + 63) / 64 * 64;
+  h->head_set = false;
+  for (int l = 0; l < 8; ++l) {
+    h->w_ih[l] = h->w_hh[l] = nullptr;
+    h->bias[l] = nullptr;
+    h->set[l] = false;
+  }
+  for (int l = 0; l < layers; ++l) {
+    const int64_t ld = l == 0 ? h->ld0 : hidden;
+    AVVAD_CUDA(cudaMalloc(&h->w_ih[l], sizeof(__nv_bfloat16) * 4 * hidden * ld));
+    AVVAD_CUDA(cudaMalloc(&h->w_hh[l], sizeof(__nv_bfloat16) * 4 * hidden * (int64_t)hidden));
+    AVVAD_CUDA(cudaMalloc(&h->bias[l], sizeof(float) * 4 * hidden));
+  }
+  AVVAD_CUDA(cudaMalloc(&h->head_w32, sizeof(float) * (int64_t)y_dim * hidden));
+  AVVAD_CUDA(cudaMalloc(&h->head_w16, sizeof(__nv_bfloat16) * (int64_t)y_dim * hidden));
+  AVVAD_CUDA(cudaMalloc(&h->head_b, sizeof(float) * y_dim));
+  *out = h;
+  return AVVAD_OK;
+}
+
+extern "C" void avvad_lstm_destroy(avvad_lstm* h) {
+  if (!h) return;
+  for (int l = 0; l < 8; ++l) {
+    cudaFree(h->w_ih[l]);
+    cudaFree(h->w_hh[l]);
+    cudaFree(h->bias[l]);
+  }
+  cudaFree(h->head_w32);
+  cudaFree(h->head_w16);
+  cudaFree(h->head_b);
+  delete h;
+}
+
+extern "C" int avvad_lstm_set_layer(avvad_lstm* h, int layer, const float* w_ih, const float* w_hh, const float* b_ih,
+                                    const float* b_hh, void* stream) {
+  AVVAD_CHECK_ARG(h && layer >= 0 && layer < h->layers, "bad handle/layer");
+  AVVAD_CHECK_ARG(w_ih && w_hh && b_ih && b_hh, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->H;
+  const int I = layer == 0 ? h->input_size : H;
+  const int ld = layer == 0 ? (int)h->ld0 : H;
+  pack_lstm_w_kernel<<<(unsigned)ceil_div((int64_t)4 * H * ld, 256), 256, 0, st>>>(w_ih, H, I, ld, h->w_ih[layer]);
+  AVVAD_LAUNCHED();
+  pack_lstm_w_kernel<<<(unsigned)ceil_div((int64_t)4 * H * H, 256), 256, 0, st>>>(w_hh, H, H, H, h->w_hh[layer]);
+  AVVAD_LAUNCHED();
+  pack_lstm_b_kernel<<<(unsigned)ceil_div(4 * H, 256), 256, 0, st>>>(b_ih, b_hh, H, h->bias[layer]);
+  AVVAD_LAUNCHED();
+  h->set[layer] = true;
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_lstm_set_head(avvad_lstm* h, const float* w, const float* b, void* stream) {
+  AVVAD_CHECK_ARG(h && w && b, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)h->y_dim * h->H;
+  pack_head_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(w, n, h->head_w32, h->head_w16);
+  AVVAD_LAUNCHED();
+  AVVAD_CUDA(cudaMemcpyAsync(h->head_b, b, sizeof(float) * h->y_dim, cudaMemcpyDeviceToDevice, st));
+  h->head_set = true;
+  return AVVAD_OK;
+}
+
+extern "C" int64_t avvad_lstm_input_ld(const avvad_lstm* h) { return h ? h->ld0 : 0; }
+
+namespace {
+struct LstmWs {
+  float* xproj;
+  __nv_bfloat16* hseq[2];
+  __nv_bfloat16* hbuf[2];
+  float* c;
+  __nv_bfloat16* hlast;
+  size_t total;
+};
+LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
+  LstmWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (uint8_t*)base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t H = h->H;
+  w.xproj = (float*)take((size_t)B * T * 4 * H * sizeof(float));
+  w.hseq[0] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
+  w.hseq[1] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
+  w.hbuf[0] = (__nv_bfloat16*)take((size_t)B * H * 2);
+  w.hbuf[1] = (__nv_bfloat16*)take((size_t)B * H * 2);
+  w.c = (float*)take((size_t)B * H * sizeof(float));
+  w.hlast = (__nv_bfloat16*)take((size_t)B * H * 2);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" size_t avvad_lstm_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return carve(h, B, T, nullptr).total;
+}
+
+static int run_head(avvad_lstm* h, const __nv_bfloat16* hs, int64_t rows, float* logits, float* post, int32_t* dec,
+                    cudaStream_t st) {
+  const int H = h->H;
+  if (h->y_dim == 1) {
+    head1_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(hs, rows, H, h->head_w32, h->head_b, logits, post,
+                                                                     dec);
+    AVVAD_LAUNCHED();
+    return AVVAD_OK;
+  }
+  AVVAD_CHECK_ARG(logits, "logits buffer required when y_dim > 1");
+  int rc = avvad_gemm_bf16(hs, H, h->head_w16, H, h->head_b, logits, h->y_dim, 0, 0, rows, h->y_dim, H, st);
+  if (rc) return rc;
+  if (post || dec) {
+    const int64_t n = rows * h->y_dim;
+    post_dec_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(logits, n, post, dec);
+    AVVAD_LAUNCHED();
+  }
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                                  void* workspace, size_t workspace_bytes, float* logits, float* post, int32_t* dec,
+                                  float* last_logits, void* stream) {
+  AVVAD_CHECK_ARG(h && x_bf16 && lengths && workspace && B > 0 && T > 0, "bad argument");
+  AVVAD_CHECK_ARG(logits || post || dec || last_logits, "no output requested");
+  for (int l = 0; l < h->layers; ++l)
+    if (!h->set[l]) {
+      set_error("lstm: layer " + std::to_string(l) + " not loaded");
+      return AVVAD_ERR_STATE;
+    }
+  if (!h->head_set) {
+    set_error("lstm: head not loaded");
+    return AVVAD_ERR_STATE;
+  }
+  if (workspace_bytes < avvad_lstm_workspace_bytes(h, B, T)) {
+    set_error("lstm: workspace too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = h->H;
+  const int H4 = 4 * H;
+  LstmWs ws = carve(h, B, T, workspace);
+  const int64_t rows = B * T;
+
+  const __nv_bfloat16* layer_in = (const __nv_bfloat16*)x_bf16;
+  int64_t ld_in = h->ld0;
+  __nv_bfloat16* layer_out = nullptr;
+  for (int l = 0; l < h->layers; ++l) {
+    layer_out = ws.hseq[l & 1];
+    // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'
+    int rc = avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4, ld_in, st);
+    if (rc) return rc;
+    // (2) recurrence
+    AVVAD_CUDA(cudaMemsetAsync(ws.hbuf[0], 0, (size_t)B * H * 2, st));
+    AVVAD_CUDA(cudaMemsetAsync(ws.c, 0, (size_t)B * H * sizeof(float), st));
+    for (int t = 0; t < (int)T; ++t) {
+      tc::AParams ap{};
+      ap.A = ws.hbuf[t & 1];
+      ap.lda = H;
+      tc::EpiParams ep{};
+      ep.xproj = ws.xproj;
+      ep.c_state = ws.c;
+      ep.h_next = ws.hbuf[(t + 1) & 1];
+      ep.hseq = layer_out;
+      ep.lengths = lengths;
+      ep.t = t;
+      ep.T = (int)T;
+      ep.H4 = H4;
+      rc = tc::launch(tc::A_PLAIN, ap, h->w_hh[l], H, B, H4, H, ep, tc::EPI_LSTM, 64, st);
+      if (rc) return rc;
+    }
+    layer_in = layer_out;
+    ld_in = H;
+  }
+  if (logits || post || dec) {
+    float* lg = logits;
+    int rc = run_head(h, layer_out, rows, lg, post, dec, st);
+    if (rc) return rc;
+  }
+  if (last_logits) {
+    gather_last_kernel<<<(unsigned)B, 128, 0, st>>>(layer_out, lengths, (int)T, H, ws.hlast);
+    AVVAD_LAUNCHED();
+    int rc = run_head(h, ws.hlast, B, last_logits, nullptr, nullptr, st);
+    if (rc) return rc;
+  }
+  return AVVAD_OK;
+}

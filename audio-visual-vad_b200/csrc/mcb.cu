@@ -1,0 +1,259 @@
+// Multimodal Compact Bilinear fusion: count sketches -> circular convolution (in-SMEM FFT) -> signed sqrt
+// -> whole-tensor L2 normalisation -> BatchNorm1d (eval) -> bf16 LSTM operand.
+//
+// Reference semantics: packages/models/compact_bilinear_pooling.py:7-27,140-173 and
+// packages/models/AV_Net.py:111-121.  The two real sketches are packed into one complex 1024-point FFT
+// (Z = px + i*py); X and Y are separated by Hermitian symmetry, multiplied, and transformed back with a second
+// forward FFT of the conjugate.  The scatter-add of the reference is replaced by a deterministic inverse
+// (CSR) gather that sums colliding inputs in index order, which is the order the reference's CPU
+// scatter_add_ visits them.
+#include <vector>
+
+#include "fft.cuh"
+
+namespace avvad {
+
+constexpr int kMcbOut = 1024;
+constexpr int kNA = 513, kNV = 512;
+
+struct McbTables {
+  const int32_t* off1;  // [1025]
+  const int32_t* idx1;  // [513]
+  const float* s1;      // [513]
+  const int32_t* off2;  // [1025]
+  const int32_t* idx2;  // [512]
+  const float* s2;      // [512]
+};
+
+__global__ void __launch_bounds__(kFftThreads)
+mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video, McbTables tb,
+               const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq) {
+  __shared__ float2 sa[kFftN];
+  __shared__ float2 sb[kFftN];
+  __shared__ float2 stw[512];
+  __shared__ float xa[kNA];
+  __shared__ float xv[kNV];
+  __shared__ float red[8];
+
+  const int tid = threadIdx.x;
+  const int64_t row = blockIdx.x;
+  stw[tid] = tw_g[tid];
+  stw[tid + 256] = tw_g[tid + 256];
+  for (int i = tid; i < kNA; i += kFftThreads) xa[i] = audio[row * kNA + i];
+  for (int i = tid; i < kNV; i += kFftThreads) xv[i] = video[row * kNV + i];
+  __syncthreads();
+
+  // count sketches: out[j] = sum_{i : h_i = j} s_i * x_i
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = tid + q * kFftThreads;
+    float px = 0.f, py = 0.f;
+    for (int e = tb.off1[j]; e < tb.off1[j + 1]; ++e) {
+      const int i = tb.idx1[e];
+      px += xa[i] * tb.s1[i];
+    }
+    for (int e = tb.off2[j]; e < tb.off2[j + 1]; ++e) {
+      const int i = tb.idx2[e];
+      py += xv[i] * tb.s2[i];
+    }
+    sa[j] = make_float2(px, py);
+  }
+  __syncthreads();
+  fft1024_smem(sa, sb, stw, tid);
+
+  // P[k] = X[k]*Y[k]; store conj(P) so that a second forward FFT yields N * ifft(P)
+  for (int k = tid; k <= 512; k += kFftThreads) {
+    if (k == 0 || k == 512) {
+      const float2 z = sa[k];
+      sa[k] = make_float2(z.x * z.y, 0.f);
+    } else {
+      const float2 zk = sa[k];
+      const float2 zn = sa[kFftN - k];
+      const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 Y = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      const float2 P = cmul(X, Y);
+      sa[k] = make_float2(P.x, -P.y);        // conj(P[k])
+      sa[kFftN - k] = make_float2(P.x, P.y);  // conj(P[N-k]) = P[k]
+    }
+  }
+  __syncthreads();
+  fft1024_smem(sa, sb, stw, tid);
+
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = tid + q * kFftThreads;
+    const float p = sa[j].x * (1.0f / kFftN);
+    // torch.sign(p) * sqrt(|p| + eps)   (sign(0) = 0)
+    const float r = sqrtf(fabsf(p) + eps);
+    const float y = (p > 0.f) ? r : ((p < 0.f) ? -r : 0.f);
+    y_out[row * kMcbOut + j] = y;
+    ss += y * y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    rowsq[row] = t;
+  }
+}
+
+// whole-tensor L2 norm: deterministic two-level reduction in double
+__global__ void __launch_bounds__(1024) mcb_norm_kernel(const float* __restrict__ rowsq, int64_t rows,
+                                                        float* __restrict__ norm_out) {
+  __shared__ double sm[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < rows; i += 1024) acc += (double)rowsq[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm_out[0] = (float)sqrt(sm[0]);
+}
+
+__global__ void mcb_apply_kernel(const float* __restrict__ y, const float* __restrict__ norm,
+                                 const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                                 const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta, int64_t rows,
+                                 __nv_bfloat16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kMcbOut) return;
+  const int64_t r = idx / kMcbOut;
+  const int j = (int)(idx - r * kMcbOut);
+  const float v = y[idx] / norm[0];
+  const float o = (v - bn_mean[j]) * bn_invstd[j] * bn_gamma[j] + bn_beta[j];
+  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
+  if (out_f32) out_f32[idx] = o;
+}
+
+__global__ void bn_invstd_kernel(const float* __restrict__ var, float eps, float* __restrict__ invstd, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) invstd[i] = 1.0f / sqrtf(var[i] + eps);
+}
+
+}  // namespace avvad
+
+using namespace avvad;
+
+struct avvad_mcb {
+  int32_t *off1, *idx1, *off2, *idx2;
+  float *s1, *s2;
+  float *bn_gamma, *bn_beta, *bn_mean, *bn_invstd;
+  float eps;
+  bool loaded;
+};
+
+extern "C" int avvad_mcb_create(avvad_mcb** out) {
+  AVVAD_CHECK_ARG(out, "null out");
+  avvad_mcb* h = new avvad_mcb();
+  h->loaded = false;
+  AVVAD_CUDA(cudaMalloc(&h->off1, sizeof(int32_t) * 1025));
+  AVVAD_CUDA(cudaMalloc(&h->off2, sizeof(int32_t) * 1025));
+  AVVAD_CUDA(cudaMalloc(&h->idx1, sizeof(int32_t) * kNA));
+  AVVAD_CUDA(cudaMalloc(&h->idx2, sizeof(int32_t) * kNV));
+  AVVAD_CUDA(cudaMalloc(&h->s1, sizeof(float) * kNA));
+  AVVAD_CUDA(cudaMalloc(&h->s2, sizeof(float) * kNV));
+  AVVAD_CUDA(cudaMalloc(&h->bn_gamma, sizeof(float) * kMcbOut));
+  AVVAD_CUDA(cudaMalloc(&h->bn_beta, sizeof(float) * kMcbOut));
+  AVVAD_CUDA(cudaMalloc(&h->bn_mean, sizeof(float) * kMcbOut));
+  AVVAD_CUDA(cudaMalloc(&h->bn_invstd, sizeof(float) * kMcbOut));
+  *out = h;
+  return AVVAD_OK;
+}
+
+extern "C" void avvad_mcb_destroy(avvad_mcb* h) {
+  if (!h) return;
+  cudaFree(h->off1); cudaFree(h->off2); cudaFree(h->idx1); cudaFree(h->idx2);
+  cudaFree(h->s1); cudaFree(h->s2);
+  cudaFree(h->bn_gamma); cudaFree(h->bn_beta); cudaFree(h->bn_mean); cudaFree(h->bn_invstd);
+  delete h;
+}
+
+static int build_csr(const int64_t* h_dev, int n, int32_t* off_dev, int32_t* idx_dev, cudaStream_t st) {
+  std::vector<int64_t> hh(n);
+  AVVAD_CUDA(cudaMemcpyAsync(hh.data(), h_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
+  AVVAD_CUDA(cudaStreamSynchronize(st));
+  std::vector<int32_t> off(kMcbOut + 1, 0), idx(n);
+  for (int i = 0; i < n; ++i) {
+    if (hh[i] < 0 || hh[i] >= kMcbOut) {
+      set_error("mcb: sketch index out of range [0,1024)");
+      return AVVAD_ERR_ARG;
+    }
+    off[hh[i] + 1]++;
+  }
+  for (int j = 0; j < kMcbOut; ++j) off[j + 1] += off[j];
+  std::vector<int32_t> cur(off.begin(), off.end() - 1);
+  for (int i = 0; i < n; ++i) idx[cur[hh[i]]++] = i;  // ascending i inside each bucket
+  AVVAD_CUDA(cudaMemcpyAsync(off_dev, off.data(), sizeof(int32_t) * (kMcbOut + 1), cudaMemcpyHostToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(idx_dev, idx.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  AVVAD_CUDA(cudaStreamSynchronize(st));
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_mcb_load(avvad_mcb* h, const int64_t* h1, const float* s1, const int64_t* h2, const float* s2,
+                              const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                              float eps, void* stream) {
+  AVVAD_CHECK_ARG(h && h1 && s1 && h2 && s2 && bn_gamma && bn_beta && bn_mean && bn_var, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = build_csr(h1, kNA, h->off1, h->idx1, st);
+  if (rc) return rc;
+  rc = build_csr(h2, kNV, h->off2, h->idx2, st);
+  if (rc) return rc;
+  AVVAD_CUDA(cudaMemcpyAsync(h->s1, s1, sizeof(float) * kNA, cudaMemcpyDeviceToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(h->s2, s2, sizeof(float) * kNV, cudaMemcpyDeviceToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(h->bn_gamma, bn_gamma, sizeof(float) * kMcbOut, cudaMemcpyDeviceToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(h->bn_beta, bn_beta, sizeof(float) * kMcbOut, cudaMemcpyDeviceToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(h->bn_mean, bn_mean, sizeof(float) * kMcbOut, cudaMemcpyDeviceToDevice, st));
+  bn_invstd_kernel<<<4, 256, 0, st>>>(bn_var, eps, h->bn_invstd, kMcbOut);
+  AVVAD_LAUNCHED();
+  h->eps = eps;
+  h->loaded = true;
+  return AVVAD_OK;
+}
+
+extern "C" size_t avvad_mcb_workspace_bytes(int64_t rows) {
+  if (rows <= 0) return 0;
+  return align_up((size_t)rows * kMcbOut * sizeof(float), 256) + align_up((size_t)rows * sizeof(float), 256) + 256;
+}
+
+extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* video, int64_t rows, void* workspace,
+                                 size_t workspace_bytes, void* out_bf16, int64_t ld_out, float* out_f32,
+                                 void* stream) {
+  AVVAD_CHECK_ARG(h && audio && video && workspace && rows > 0, "bad argument");
+  AVVAD_CHECK_ARG(out_bf16 || out_f32, "at least one output required");
+  AVVAD_CHECK_ARG(!out_bf16 || ld_out >= kMcbOut, "ld_out must be >= 1024");
+  if (!h->loaded) {
+    set_error("mcb: not loaded");
+    return AVVAD_ERR_STATE;
+  }
+  if (workspace_bytes < avvad_mcb_workspace_bytes(rows)) {
+    set_error("mcb: workspace too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  AVVAD_CHECK_ARG(rows < (1ll << 31), "too many rows");
+  const float2* tw = fft_twiddles_device();
+  if (!tw) {
+    set_error("twiddle table allocation failed");
+    return AVVAD_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* y = reinterpret_cast<float*>(workspace);
+  float* rowsq = reinterpret_cast<float*>((uint8_t*)workspace + align_up((size_t)rows * kMcbOut * sizeof(float), 256));
+  float* norm = reinterpret_cast<float*>((uint8_t*)rowsq + align_up((size_t)rows * sizeof(float), 256));
+  McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
+  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq);
+  AVVAD_LAUNCHED();
+  mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
+  AVVAD_LAUNCHED();
+  const int64_t total = rows * kMcbOut;
+  mcb_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, h->bn_mean, h->bn_invstd, h->bn_gamma,
+                                                                   h->bn_beta, rows, (__nv_bfloat16*)out_bf16, ld_out,
+                                                                   out_f32);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}

@@ -1,0 +1,380 @@
+// ResNet-18 trunk on single-channel 67x67 mouth ROIs (eval-mode BatchNorm folded into the convolutions).
+//
+// Reference semantics: packages/models/AV_Net.py:78-94 (channel triple + torchvision resnet18 children[:-1]).
+// Data layout: activations NHWC bf16 [frame][h][w][c]; weights bf16 [Cout][R][S][Cin] (K order = tap-major,
+// channel-minor, the order the implicit-GEMM producer walks); folded bias fp32.
+//   conv1 7x7/2 + BN + ReLU + maxpool 3x3/2 : one fused kernel per frame (fp32 direct conv; the three identical
+//                                             input channels are folded into one by summing the weights)
+//   layer1..4 (19 convs)                     : tcgen05 implicit GEMM (gemm_tc.cuh) with fused bias/residual/ReLU
+//   global average pool                      : small bandwidth kernel, emits fp32 features and/or the bf16
+//                                              LSTM operand columns
+#include "gemm_tc.cuh"
+
+namespace avvad {
+
+struct ConvSpec {
+  int cin, cout, k, stride, pad, hin, hout;
+};
+// index order documented in include/avvad.h
+static const ConvSpec kSpecs[20] = {
+    {3, 64, 7, 2, 3, 67, 34},                                                            // 0 conv1 (+pool -> 17)
+    {64, 64, 3, 1, 1, 17, 17},   {64, 64, 3, 1, 1, 17, 17},                              // 1,2  l1.0
+    {64, 64, 3, 1, 1, 17, 17},   {64, 64, 3, 1, 1, 17, 17},                              // 3,4  l1.1
+    {64, 128, 3, 2, 1, 17, 9},   {128, 128, 3, 1, 1, 9, 9},  {64, 128, 1, 2, 0, 17, 9},  // 5,6,7  l2.0 (+ds)
+    {128, 128, 3, 1, 1, 9, 9},   {128, 128, 3, 1, 1, 9, 9},                              // 8,9  l2.1
+    {128, 256, 3, 2, 1, 9, 5},   {256, 256, 3, 1, 1, 5, 5},  {128, 256, 1, 2, 0, 9, 5},  // 10,11,12 l3.0
+    {256, 256, 3, 1, 1, 5, 5},   {256, 256, 3, 1, 1, 5, 5},                              // 13,14 l3.1
+    {256, 512, 3, 2, 1, 5, 3},   {512, 512, 3, 1, 1, 3, 3},  {256, 512, 1, 2, 0, 5, 3},  // 15,16,17 l4.0
+    {512, 512, 3, 1, 1, 3, 3},   {512, 512, 3, 1, 1, 3, 3},                              // 18,19 l4.1
+};
+constexpr int64_t kFrameHW = 67 * 67;
+constexpr int64_t kActBytesPerFrame = 17 * 17 * 64 * 2;  // largest NHWC bf16 activation (after the pool)
+
+// ---- weight folding / packing ----------------------------------------------------------------------
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, const float* __restrict__ mean,
+                                 const float* __restrict__ var, float eps, int cout, int cin, int k,
+                                 __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = cout * cin * k * k;
+  if (idx < cout) {
+    const float sc = gamma[idx] / sqrtf(var[idx] + eps);
+    bias[idx] = beta[idx] - mean[idx] * sc;
+  }
+  if (idx >= total) return;
+  // destination order [o][r][s][i]
+  const int i = idx % cin;
+  const int s = (idx / cin) % k;
+  const int r = (idx / (cin * k)) % k;
+  const int o = idx / (cin * k * k);
+  const float sc = gamma[o] / sqrtf(var[o] + eps);
+  wp[idx] = __float2bfloat16_rn(w[((o * cin + i) * k + r) * k + s] * sc);
+}
+
+// conv1: fold 3 identical input channels and the BN scale -> fp32 [49][64] (tap-major, channel-minor)
+__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, const float* __restrict__ mean,
+                                  const float* __restrict__ var, float eps, float* __restrict__ w1,
+                                  float* __restrict__ bias) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 64) {
+    const float sc = gamma[idx] / sqrtf(var[idx] + eps);
+    bias[idx] = beta[idx] - mean[idx] * sc;
+  }
+  if (idx >= 49 * 64) return;
+  const int o = idx % 64, tap = idx / 64;
+  const float sc = gamma[o] / sqrtf(var[o] + eps);
+  const float sum = w[(o * 3 + 0) * 49 + tap] + w[(o * 3 + 1) * 49 + tap] + w[(o * 3 + 2) * 49 + tap];
+  w1[idx] = sum * sc;
+}
+
+// ---- conv1 + BN + ReLU + maxpool, one CTA per frame ---------------------------------------------------
+constexpr int kC1Threads = 256;
+constexpr int kImgPitch = 76;
+constexpr size_t kC1Smem = (73 * kImgPitch + 49 * 64 + 64) * sizeof(float) + 1156 * 64 * sizeof(__nv_bfloat16);
+
+__global__ void __launch_bounds__(kC1Threads)
+conv1_pool_kernel(const float* __restrict__ frames, const float* __restrict__ w1, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t c1_smem[];
+  float* img = reinterpret_cast<float*>(c1_smem);  // [73][76], 3-pixel zero border
+  float* wsm = img + 73 * kImgPitch;               // [49][64]
+  float* bsm = wsm + 49 * 64;                      // [64]
+  __nv_bfloat16* cv = reinterpret_cast<__nv_bfloat16*>(bsm + 64);  // conv+ReLU output [34*34][64]
+
+  const int tid = threadIdx.x;
+  const float* f = frames + (int64_t)blockIdx.x * kFrameHW;
+  for (int i = tid; i < 73 * kImgPitch; i += kC1Threads) {
+    const int r = i / kImgPitch - 3, c = i % kImgPitch - 3;
+    img[i] = (r >= 0 && r < 67 && c >= 0 && c < 67) ? f[r * 67 + c] : 0.f;
+  }
+  for (int i = tid; i < 49 * 64; i += kC1Threads) wsm[i] = w1[i];
+  if (tid < 64) bsm[tid] = bias[tid];
+  __syncthreads();
+
+#pragma unroll 1
+  for (int cg = 0; cg < 4; ++cg) {
+    for (int p = tid; p < 1156; p += kC1Threads) {
+      const int oh = p / 34, ow = p - oh * 34;
+      float acc[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc[q] = bsm[cg * 16 + q];
+      const float* ip = img + (2 * oh) * kImgPitch + 2 * ow;
+#pragma unroll
+      for (int r = 0; r < 7; ++r) {
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const float x = ip[r * kImgPitch + s];
+          const float4* w4 = reinterpret_cast<const float4*>(wsm + (r * 7 + s) * 64 + cg * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w = w4[q];
+            acc[4 * q + 0] = fmaf(x, w.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      uint4 o0, o1;
+      o0.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+      o0.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+      o0.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+      o0.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+      o1.x = pack_bf16x2(fmaxf(acc[8], 0.f), fmaxf(acc[9], 0.f));
+      o1.y = pack_bf16x2(fmaxf(acc[10], 0.f), fmaxf(acc[11], 0.f));
+      o1.z = pack_bf16x2(fmaxf(acc[12], 0.f), fmaxf(acc[13], 0.f));
+      o1.w = pack_bf16x2(fmaxf(acc[14], 0.f), fmaxf(acc[15], 0.f));
+      uint4* dst = reinterpret_cast<uint4*>(cv + p * 64 + cg * 16);
+      dst[0] = o0;
+      dst[1] = o1;
+    }
+  }
+  __syncthreads();
+
+  // 3x3 / stride 2 / pad 1 max pool; inputs are >= 0 so clipping the window equals -inf padding
+  __nv_bfloat16* o = out + (int64_t)blockIdx.x * 289 * 64;
+  for (int item = tid; item < 289 * 8; item += kC1Threads) {
+    const int pp = item >> 3, ch = item & 7;
+    const int ph = pp / 17, pw = pp - ph * 17;
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * ph + dy;
+      if (y < 0 || y >= 34) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * pw + dx;
+        if (x < 0 || x >= 34) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(cv + (y * 34 + x) * 64 + ch * 8);
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
+        m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
+      }
+    }
+    uint4 r;
+    r.x = pack_bf16x2(m[0], m[1]);
+    r.y = pack_bf16x2(m[2], m[3]);
+    r.z = pack_bf16x2(m[4], m[5]);
+    r.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(o + pp * 64 + ch * 8) = r;
+  }
+}
+
+// ---- global average pool over the 3x3x512 map -----------------------------------------------------------
+__global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ act, int64_t n_frames, int hw, int C,
+                               float* __restrict__ feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16,
+                               int64_t col_off) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = C / 8;
+  if (idx >= n_frames * chunks) return;
+  const int64_t f = idx / chunks;
+  const int ch = (int)(idx - f * chunks);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __nv_bfloat16* p = act + f * hw * C + ch * 8;
+  for (int i = 0; i < hw; ++i) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p + (int64_t)i * C);
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+  }
+  const float inv = 1.0f / (float)hw;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s[q] *= inv;
+  if (feat) {
+    float4* o = reinterpret_cast<float4*>(feat + f * C + ch * 8);
+    o[0] = make_float4(s[0], s[1], s[2], s[3]);
+    o[1] = make_float4(s[4], s[5], s[6], s[7]);
+  }
+  if (feat_bf16) {
+    __nv_bfloat16* o = feat_bf16 + f * ld_bf16 + col_off + ch * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = __float2bfloat16_rn(s[q]);  // col_off may be odd (513): scalar stores
+  }
+}
+
+}  // namespace avvad
+
+using namespace avvad;
+
+struct avvad_resnet18 {
+  __nv_bfloat16* w[20];
+  float* bias[20];
+  float* w1;  // conv1 folded fp32 [49][64]
+  bool set[20];
+  bool smem_attr;
+};
+
+extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
+  AVVAD_CHECK_ARG(out, "null out");
+  avvad_resnet18* h = new avvad_resnet18();
+  for (int i = 0; i < 20; ++i) {
+    h->w[i] = nullptr;
+    h->bias[i] = nullptr;
+    h->set[i] = false;
+  }
+  h->w1 = nullptr;
+  h->smem_attr = false;
+  for (int i = 0; i < 20; ++i) {
+    const ConvSpec& s = kSpecs[i];
+    AVVAD_CUDA(cudaMalloc(&h->bias[i], sizeof(float) * s.cout));
+    if (i == 0) {
+      AVVAD_CUDA(cudaMalloc(&h->w1, sizeof(float) * 49 * 64));
+    } else {
+      AVVAD_CUDA(cudaMalloc(&h->w[i], sizeof(__nv_bfloat16) * (size_t)s.cout * s.cin * s.k * s.k));
+    }
+  }
+  *out = h;
+  return AVVAD_OK;
+}
+
+extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
+  if (!h) return;
+  for (int i = 0; i < 20; ++i) {
+    cudaFree(h->w[i]);
+    cudaFree(h->bias[i]);
+  }
+  cudaFree(h->w1);
+  delete h;
+}
+
+extern "C" int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float* w, const float* gamma,
+                                       const float* beta, const float* mean, const float* var, float bn_eps,
+                                       void* stream) {
+  AVVAD_CHECK_ARG(h && layer >= 0 && layer < 20, "bad handle/layer");
+  AVVAD_CHECK_ARG(w && gamma && beta && mean && var, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvSpec& s = kSpecs[layer];
+  if (layer == 0) {
+    pack_conv1_kernel<<<(49 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, h->w1, h->bias[0]);
+  } else {
+    const int total = s.cout * s.cin * s.k * s.k;
+    pack_conv_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, s.cout, s.cin, s.k,
+                                                          h->w[layer], h->bias[layer]);
+  }
+  AVVAD_LAUNCHED();
+  h->set[layer] = true;
+  return AVVAD_OK;
+}
+
+static int64_t chunk_of(int64_t n_frames, int64_t chunk) {
+  if (chunk <= 0) chunk = 2048;
+  return n_frames < chunk ? n_frames : chunk;
+}
+
+extern "C" size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk_frames) {
+  if (n_frames <= 0) return 0;
+  return (size_t)(4 * align_up((size_t)chunk_of(n_frames, chunk_frames) * kActBytesPerFrame, 1024));
+}
+
+static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const __nv_bfloat16* residual,
+                    __nv_bfloat16* out, int64_t n, int relu, cudaStream_t st) {
+  const ConvSpec& s = kSpecs[layer];
+  return avvad_conv2d_nhwc_bf16(in, h->w[layer], h->bias[layer], residual, out, n, s.hin, s.hin, s.cin, s.cout, s.k,
+                                s.k, s.stride, s.pad, relu, st);
+}
+
+// Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
+// Returns the buffer index holding the last produced activation in *last.
+static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4], int upto,
+                           int* last, cudaStream_t st) {
+  if (!h->smem_attr) {
+    AVVAD_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1Smem));
+    h->smem_attr = true;
+  }
+  conv1_pool_kernel<<<(unsigned)n, kC1Threads, kC1Smem, st>>>(frames, h->w1, h->bias[0], buf[0]);
+  AVVAD_LAUNCHED();
+  int cur = 0;
+  *last = cur;
+  if (upto == 0) return AVVAD_OK;
+  int layer = 1;
+  for (int stage = 0; stage < 4; ++stage) {
+    for (int blk = 0; blk < 2; ++blk) {
+      int o[3], k = 0;
+      for (int i = 0; i < 4; ++i)
+        if (i != cur) o[k++] = i;
+      const bool ds = (stage > 0 && blk == 0);
+      const int la = layer, lb = layer + 1, lds = layer + 2;
+      int rc = run_conv(h, la, buf[cur], nullptr, buf[o[0]], n, 1, st);
+      if (rc) return rc;
+      if (upto == la) { *last = o[0]; return AVVAD_OK; }
+      const __nv_bfloat16* res = buf[cur];
+      if (ds) {
+        rc = run_conv(h, lds, buf[cur], nullptr, buf[o[1]], n, 0, st);
+        if (rc) return rc;
+        if (upto == lds) { *last = o[1]; return AVVAD_OK; }
+        res = buf[o[1]];
+      }
+      rc = run_conv(h, lb, buf[o[0]], res, buf[o[2]], n, 1, st);
+      if (rc) return rc;
+      cur = o[2];
+      *last = cur;
+      if (upto == lb) return AVVAD_OK;
+      layer += ds ? 3 : 2;
+    }
+  }
+  return AVVAD_OK;
+}
+
+static int check_loaded(avvad_resnet18* h) {
+  for (int i = 0; i < 20; ++i)
+    if (!h->set[i]) {
+      set_error("resnet18: conv layer " + std::to_string(i) + " not loaded");
+      return AVVAD_ERR_STATE;
+    }
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_frames, int64_t chunk_frames,
+                                      void* workspace, size_t workspace_bytes, float* feat, void* feat_bf16,
+                                      int64_t ld_bf16, int64_t col_off, void* stream) {
+  AVVAD_CHECK_ARG(h && frames && workspace && n_frames > 0, "bad argument");
+  AVVAD_CHECK_ARG(feat || feat_bf16, "at least one output required");
+  int rc = check_loaded(h);
+  if (rc) return rc;
+  if (workspace_bytes < avvad_resnet18_workspace_bytes(n_frames, chunk_frames)) {
+    set_error("resnet18: workspace too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t mc = chunk_of(n_frames, chunk_frames);
+  const size_t bsz = align_up((size_t)mc * kActBytesPerFrame, 1024);
+  __nv_bfloat16* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
+  for (int64_t f0 = 0; f0 < n_frames; f0 += mc) {
+    const int64_t n = (n_frames - f0 < mc) ? (n_frames - f0) : mc;
+    int last = 0;
+    rc = run_trunk_chunk(h, frames + f0 * kFrameHW, n, buf, 20, &last, st);
+    if (rc) return rc;
+    const int64_t total = n * (512 / 8);
+    avgpool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+        buf[last], n, 9, 512, feat ? feat + f0 * 512 : nullptr,
+        feat_bf16 ? (__nv_bfloat16*)feat_bf16 + f0 * ld_bf16 : nullptr, ld_bf16, col_off);
+    AVVAD_LAUNCHED();
+  }
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frames, int64_t n_frames, int upto,
+                                           void* workspace, size_t workspace_bytes, void* out_act, void* stream) {
+  AVVAD_CHECK_ARG(h && frames && workspace && out_act && n_frames > 0 && upto >= 0 && upto < 20, "bad argument");
+  int rc = check_loaded(h);
+  if (rc) return rc;
+  if (workspace_bytes < avvad_resnet18_workspace_bytes(n_frames, n_frames)) {
+    set_error("resnet18: workspace too small (forward_upto runs a single chunk)");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bsz = align_up((size_t)n_frames * kActBytesPerFrame, 1024);
+  __nv_bfloat16* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
+  int last = 0;
+  rc = run_trunk_chunk(h, frames, n_frames, buf, upto, &last, st);
+  if (rc) return rc;
+  const ConvSpec& s = kSpecs[upto];
+  const int ho = (upto == 0) ? 17 : s.hout;
+  const size_t bytes = (size_t)n_frames * ho * ho * s.cout * sizeof(__nv_bfloat16);
+  AVVAD_CUDA(cudaMemcpyAsync(out_act, buf[last], bytes, cudaMemcpyDeviceToDevice, st));
+  return AVVAD_OK;
+}

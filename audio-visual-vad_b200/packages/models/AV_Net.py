@@ -1,0 +1,87 @@
+"""Audio-visual VAD network -- same class, constructor, parameters and state_dict as the reference
+(packages/models/AV_Net.py:12-141); ``forward`` runs on libavvad (sm_100a) instead of cuDNN/ATen."""
+import torch
+import torch.nn as nn
+import torchvision.models as models
+
+from .compact_bilinear_pooling import CompactBilinearPooling
+from .utils import weights_init_normal
+from ._engine import E, EngineCache, check_inference_only, device_of
+
+
+class DeepVAD_AV(nn.Module):
+    def __init__(self, lstm_layers, lstm_hidden_size, y_dim, use_mcb=False, eps=1e-8):
+        super().__init__()
+        self.lstm_layers = lstm_layers
+        self.lstm_hidden_size = lstm_hidden_size
+        self.y_dim = y_dim
+        self.dropout = nn.Dropout(p=0.05)
+        self.use_mcb = use_mcb
+        self.eps = eps
+
+        # parameter containers only: the child named 'features' must exist (train_AV_net.py:242-245)
+        resnet = models.resnet18(weights=None)
+        self.num_video_ftrs = 512
+        self.features = nn.Sequential(*list(resnet.children())[:-1])
+        self.bn = nn.BatchNorm1d(self.num_video_ftrs, eps=self.eps, momentum=0.1, affine=True)  # unused, kept for keys
+        self.num_audio_ftrs = 513
+        if self.use_mcb:
+            self.mcb_output_size = 1024
+            self.lstm_input_size = self.mcb_output_size
+            self.mcb = CompactBilinearPooling(self.num_audio_ftrs, self.num_video_ftrs, self.mcb_output_size)
+            self.mcb_bn = nn.BatchNorm1d(self.mcb_output_size, eps=self.eps, momentum=0.1, affine=True)
+        else:
+            self.lstm_input_size = self.num_audio_ftrs + self.num_video_ftrs
+        self.lstm_merged = nn.LSTM(input_size=self.lstm_input_size, hidden_size=self.lstm_hidden_size,
+                                   num_layers=self.lstm_layers, bidirectional=False)
+        self.vad_merged = nn.Linear(self.lstm_hidden_size, y_dim)
+        object.__setattr__(self, "_engines", EngineCache())
+
+    def __getstate__(self):  # ctypes handles are per-process: drop them when pickled (mp spawn)
+        d = self.__dict__.copy()
+        d.pop("_engines", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        object.__setattr__(self, "_engines", EngineCache())
+
+    def weight_init(self, mean=0.0, std=0.02):
+        for m in self.named_parameters():
+            weights_init_normal(m, mean=mean, std=std)
+
+    def _build(self, device):
+        def builder(old):
+            eng = old or {"trunk": E.ResNet18Trunk(),
+                          "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim),
+                          "mcb": E.Mcb() if self.use_mcb else None}
+            sd = self.state_dict()
+            eng["trunk"].load(sd, device)
+            eng["lstm"].load(sd, device, "lstm_merged", "vad_merged")
+            if self.use_mcb:
+                eng["mcb"].load(sd, device, self.eps)
+            return eng
+        return self._engines.get(self, device, builder)
+
+    def forward(self, audio, video, lengths, return_posteriors=False):
+        """audio (B,T,513), video (B,T,67,67), lengths list / CPU / CUDA tensor -> logits (B,T,y_dim)."""
+        device = device_of(audio, video)
+        check_inference_only(self)
+        eng = self._build(device)
+        batch, frames, height, width = video.size()
+        M = batch * frames
+        x = eng["lstm"].new_input(batch, frames, device)
+        xv = x.view(M, x.shape[-1])
+        vid = video.detach().to(torch.float32).reshape(M, height, width)
+        aud = audio.detach().to(torch.float32).reshape(M, self.num_audio_ftrs).contiguous()
+        if self.use_mcb:
+            feat = eng["trunk"].forward(vid)
+            eng["mcb"].forward(aud, feat, out_bf16=xv)
+        else:
+            E.pack_rows_bf16(aud, xv, 0, False)
+            eng["trunk"].forward(vid, feat_bf16=xv, col_off=self.num_audio_ftrs, want_f32=False)
+        logits, post, dec, _ = eng["lstm"].forward(x, lengths, want_post=return_posteriors,
+                                                   want_dec=return_posteriors)
+        if return_posteriors:
+            return logits, post, dec
+        return logits

@@ -1,0 +1,61 @@
+"""Video-only VAD network (reference: packages/models/Video_Net.py:12-125); forward on libavvad."""
+import torch
+import torch.nn as nn
+import torchvision.models as models
+
+from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
+from ._engine import E, EngineCache, check_inference_only, device_of
+
+
+class DeepVAD_video(nn.Module):
+    def __init__(self, lstm_layers, lstm_hidden_size, y_dim):
+        super().__init__()
+        resnet = models.resnet18(weights=None)
+        self.lstm_input_size = 512
+        self.lstm_layers = lstm_layers
+        self.lstm_hidden_size = lstm_hidden_size
+        self.y_dim = y_dim
+        self.features = nn.Sequential(*list(resnet.children())[:-1])
+        self.mean = torch.as_tensor([0.485, 0.456, 0.406])
+        self.std = torch.as_tensor([0.229, 0.224, 0.225])
+        self.lstm_video = nn.LSTM(input_size=self.lstm_input_size, hidden_size=self.lstm_hidden_size,
+                                  num_layers=self.lstm_layers, bidirectional=False)
+        self.vad_video = nn.Linear(self.lstm_hidden_size, y_dim)
+        self.dropout = nn.Dropout(p=0.5)
+        object.__setattr__(self, "_engines", EngineCache())
+
+    def __getstate__(self):
+        d = self.__dict__.copy()
+        d.pop("_engines", None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        object.__setattr__(self, "_engines", EngineCache())
+
+    def weight_init(self, mean=0.0, std=0.02):
+        for m in self.named_parameters():
+            weights_init_normal(m, mean=mean, std=std)
+
+    def _build(self, device):
+        def builder(old):
+            eng = old or {"trunk": E.ResNet18Trunk(),
+                          "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
+            sd = self.state_dict()
+            eng["trunk"].load(sd, device)
+            eng["lstm"].load(sd, device, "lstm_video", "vad_video")
+            return eng
+        return self._engines.get(self, device, builder)
+
+    def forward(self, x, lengths, return_last=False):
+        """x (B,T,67,67), lengths -> logits (B,T,y_dim), or (B,y_dim) at the last valid step."""
+        device = device_of(x)
+        check_inference_only(self)
+        eng = self._build(device)
+        batch, frames, height, width = x.size()
+        M = batch * frames
+        xb = eng["lstm"].new_input(batch, frames, device)
+        eng["trunk"].forward(x.detach().to(torch.float32).reshape(M, height, width), feat_bf16=xb.view(M, -1),
+                             col_off=0, want_f32=False)
+        logits, _, _, last = eng["lstm"].forward(xb, lengths, want_last=return_last)
+        return last if return_last else logits

@@ -1,0 +1,70 @@
+"""Collate functions and helpers with the reference's names and return conventions
+(packages/utils.py:5-6,42-185): zero-pad every item of a batch to the longest sequence, move time
+to axis 1, return ``(lengths LongTensor, padded..., target)``."""
+import torch
+
+
+def count_parameters(model):
+    return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def _pad_time_last(items, seq_length):
+    """Stack tensors (..., T_i) into (B, T, ...) with zero padding on the right."""
+    out = items[0].new_zeros((len(items), seq_length) + tuple(items[0].shape[:-1]))
+    for i, t in enumerate(items):
+        L = t.shape[-1]
+        out[i, :L] = t.movedim(-1, 0)
+    return out.contiguous()
+
+
+def collate_many2many_video(batch):
+    lengths = [item[-1] for item in batch]
+    T = max(lengths)
+    data = _pad_time_last([item[0].float() for item in batch], T)      # (B,T,H,W)
+    target = _pad_time_last([item[1].float() for item in batch], T)    # (B,T,y_dim)
+    return torch.LongTensor(lengths), data, target
+
+
+def collate_many2many_audio(batch):
+    lengths = [item[-1] for item in batch]
+    T = max(lengths)
+    data = _pad_time_last([item[0].float() for item in batch], T)      # (B,T,x_dim)
+    target = _pad_time_last([item[1].float() for item in batch], T)
+    return torch.LongTensor(lengths), data, target
+
+
+def collate_many2many_AV(batch):
+    lengths = [item[-1] for item in batch]
+    T = max(lengths)
+    audio = _pad_time_last([item[0].float() for item in batch], T)     # (B,T,x_dim)
+    video = _pad_time_last([item[1].float() for item in batch], T)     # (B,T,H,W)
+    target = _pad_time_last([item[2].float() for item in batch], T)    # (B,T,y_dim)
+    return torch.LongTensor(lengths), audio, video, target
+
+
+def _pad_wave(waves, n):
+    out = waves[0].new_zeros((len(waves), n))
+    for i, w in enumerate(waves):
+        out[i, :w.shape[-1]] = w
+    return out
+
+
+def collate_many2many_audio_waveform(batch):
+    """Items (wave (N,), label (y_dim,T), time_length, length): waveform batches for the on-device
+    front end (packages/utils.py:110-146)."""
+    lengths = [item[-1] for item in batch]
+    time_lengths = [item[-2] for item in batch]
+    data = _pad_wave([item[0].float() for item in batch], max(time_lengths))
+    target = _pad_time_last([item[1].float() for item in batch], max(lengths))
+    return torch.LongTensor(lengths), data, target
+
+
+def collate_many2many_AV_waveform(batch):
+    """Items (wave, video (H,W,T), label, time_length, length) (packages/utils.py:187-227)."""
+    lengths = [item[-1] for item in batch]
+    time_lengths = [item[-2] for item in batch]
+    T = max(lengths)
+    audio = _pad_wave([item[0].float() for item in batch], max(time_lengths))
+    video = _pad_time_last([item[1].float() for item in batch], T)
+    target = _pad_time_last([item[2].float() for item in batch], T)
+    return torch.LongTensor(lengths), audio, video, target

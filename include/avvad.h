@@ -1,0 +1,193 @@
+/*
+ * libavvad -- B200-native (sm_100a) hot path of sp-uhh/audio-visual-vad, C ABI.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (as void*); nothing
+ * allocates across the ABI except the opaque per-model handles, and all scratch memory is passed
+ * in by the caller after a *_workspace_bytes() query.  All functions return 0 on success or a
+ * negative avvad_status; avvad_last_error() returns a thread-local description.  There is no CPU
+ * fallback: a call without a CUDA device fails with AVVAD_ERR_CUDA.
+ *
+ * The reference (pure Python) has no FFI of its own; each entry point below names the reference
+ * code it replaces (paths relative to the reference repo root).  INTEGRATION.md shows the
+ * ctypes stubs a maintainer would add to packages/ to bind them.
+ */
+#ifndef AVVAD_H_
+#define AVVAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  AVVAD_OK = 0,
+  AVVAD_ERR_ARG = -1,     /* bad shape / null pointer / unsupported parameter        */
+  AVVAD_ERR_CUDA = -2,    /* CUDA runtime error (see avvad_last_error)               */
+  AVVAD_ERR_STATE = -3,   /* handle not fully loaded                                 */
+  AVVAD_ERR_WORKSPACE = -4 /* workspace too small                                    */
+} avvad_status;
+
+const char* avvad_last_error(void);
+int avvad_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+uint64_t avvad_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Audio front end
+ * replaces: packages/processing/stft.py:102-152 (stft_pytorch: pad-at-end rule, periodic Hann,
+ *           1024-pt rFFT, hop 256, center=False), packages/data_handling.py:441 (x / max|x|),
+ *           :454-457 (re^2+im^2, log(.+eps)), scripts/evaluate_AV_net.py:225-230 ((x-mu)/(sigma+eps)),
+ *           and the zero-pad-to-max-T of packages/utils.py:157-166 (collate).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Frame count of stft_pytorch(center=False) for an n_samples-long signal, including the
+ * pad-at-end rule evaluated in the reference's double arithmetic (stft.py:134-139). */
+int64_t avvad_stft_num_frames(int64_t n_samples, double fs, double wlen_sec, double hop_percent,
+                              int pad_at_end);
+
+/* wave      : f32 [B][wave_stride] device, utterance b uses the first n_samples[b] samples
+ * n_samples : i32 [B] device
+ * n_frames  : i32 [B] device -- frames to emit per utterance (<= avvad_stft_num_frames; the
+ *             reference trims to the label/video length, data_handling.py:483-486)
+ * mean,std  : f32 [513] device or NULL (no standardisation)
+ * out       : f32 [B][t_max][513] device.  Rows t >= n_frames[b] get the collate value
+ *             (0-mean)/(std+eps) (or 0 when mean==NULL).
+ * peak_scratch : f32 [B] device scratch (per-utterance max|x|), only used when normalise!=0
+ * nfft must be 1024 and hop 256 (the reference's 64 ms / 25 % at 16 kHz). */
+int avvad_frontend_logpower(const float* wave, int64_t wave_stride, const int32_t* n_samples,
+                            const int32_t* n_frames, int32_t B, int32_t t_max, int normalise,
+                            const float* mean, const float* std, float eps, float* out,
+                            float* peak_scratch, void* stream);
+
+/* Raw STFT, (B, 513, t_max, 2) real view like the legacy torch.stft the reference calls
+ * (stft.py:145-151).  No normalisation / log. */
+int avvad_stft(const float* wave, int64_t wave_stride, const int32_t* n_samples,
+               const int32_t* n_frames, int32_t B, int32_t t_max, float* out_ft2, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Video frame-rate conversion (SURVEY §8a U + A4)
+ * replaces: scripts/create_video_train_files_upsampled.py:116-173 (ffmpeg fps=62.5 + x264 + decode)
+ *           and scripts/evaluate_AV_net.py:176-182 ((H,W,T)->(T,H,W), standardise).
+ * src(k) = (den*(2k+1)-1) / (2*num) with num/den = fps_out/fps_in (25/12 for 30 -> 62.5).
+ * ---------------------------------------------------------------------------------------- */
+int64_t avvad_upsampled_length(int64_t n_src, int32_t num, int32_t den);
+
+/* src      : u8 or f32 [B][f_max][hw] device (src_is_f32 selects)
+ * n_src    : i32 [B] source frames per utterance; n_out: i32 [B] frames to emit
+ * out      : f32 [B][t_max][hw]; rows k >= n_out[b] get (0-mean)/(std+eps). */
+int avvad_upsample_gather(const void* src, int src_is_f32, const int32_t* n_src, const int32_t* n_out,
+                          int32_t B, int32_t f_max, int32_t t_max, int32_t hw, int32_t num, int32_t den,
+                          float mean, float std, float eps, int standardise, float* out, void* stream);
+
+/* Just the index map (i32 [n_out]) -- exposed so callers/tests can check it bit-exactly. */
+int avvad_upsample_index(int32_t n_src, int32_t n_out, int32_t num, int32_t den, int32_t* out_idx,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ResNet-18 trunk on single-channel 67x67 ROIs (eval-mode BN folded)
+ * replaces: packages/models/AV_Net.py:78-94 / Video_Net.py:60-75 (repeat to 3 channels +
+ *           torchvision resnet18 children[:-1]).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct avvad_resnet18 avvad_resnet18;
+
+int avvad_resnet18_create(avvad_resnet18** out);
+void avvad_resnet18_destroy(avvad_resnet18* h);
+
+/* Conv layer order (index): 0 conv1(7x7/2,3->64); 1..4 layer1.{0,1}.conv{1,2};
+ * 5 l2.0.conv1, 6 l2.0.conv2, 7 l2.0.downsample, 8 l2.1.conv1, 9 l2.1.conv2; 10..14 layer3 likewise;
+ * 15..19 layer4 likewise.  w is the f32 OIHW torch weight; gamma/beta/mean/var the following
+ * BatchNorm2d's weight/bias/running_mean/running_var (eps 1e-5).  The layer is folded
+ * (w*gamma/sqrt(var+eps), beta-mean*gamma/sqrt(var+eps)) and repacked to bf16 [O][R][S][I]
+ * (conv1: 3 input channels summed to 1, K padded 49->64) on the device. */
+int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float* w, const float* gamma,
+                            const float* beta, const float* mean, const float* var, float bn_eps,
+                            void* stream);
+
+size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk_frames);
+
+/* frames : f32 [n_frames][67][67] device (already standardised, as the reference's forward gets)
+ * feat   : f32 [n_frames][512] device (may be NULL)
+ * feat_bf16 : optional bf16 [n_frames][ld_bf16] destination written at column col_off (the LSTM
+ *          operand buffer of the concat fusion), may be NULL
+ * debug_act : optional; when non-NULL must hold n_frames*17*17*64 bf16 and receives the
+ *          activations after layer `debug_layer` (tests only), for the FIRST chunk. */
+int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_frames,
+                           int64_t chunk_frames, void* workspace, size_t workspace_bytes,
+                           float* feat, void* feat_bf16, int64_t ld_bf16, int64_t col_off,
+                           void* stream);
+
+/* Test hook: run the trunk up to and including conv layer `upto` (see order above; 0 = conv1 +
+ * maxpool) and copy that activation (bf16 NHWC) to out_act. */
+int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frames, int64_t n_frames, int upto,
+                                void* workspace, size_t workspace_bytes, void* out_act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * bf16 tensor-core GEMM  C[M][N] = A[M][K] * W[N][K]^T (+bias)   (tcgen05 / TMEM)
+ * Exposed for tests and for the LSTM / head projections.  A, W bf16 row-major with K % 64 == 0
+ * and 16-byte aligned rows; C f32 or bf16.
+ * ---------------------------------------------------------------------------------------- */
+int avvad_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias,
+                    void* C, int64_t ldc, int c_is_bf16, int relu, int64_t M, int64_t N, int64_t K,
+                    void* stream);
+
+/* Generic NHWC bf16 convolution through the same engine (tests; ResNet uses it internally).
+ * in [n][H][W][Cin], w [Cout][R][S][Cin], out [n][OH][OW][Cout], residual optional (same as out). */
+int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float* bias, const void* residual,
+                           void* out, int64_t n, int H, int W, int Cin, int Cout, int R, int S,
+                           int stride, int pad, int relu, void* stream);
+
+/* f32 -> bf16 row repack: dst[m][col_off + j] = bf16(src[m][j]) for j < cols; optional zero fill of
+ * [col_off+cols, ld_dst) when zero_tail != 0. */
+int avvad_pack_rows_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t col_off,
+                         int64_t rows, int64_t cols, int zero_tail, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MCB fusion
+ * replaces: packages/models/compact_bilinear_pooling.py:140-173 and AV_Net.py:111-121
+ *           (count sketches -> circular convolution -> signed sqrt -> whole-tensor L2 -> BN1d eval).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct avvad_mcb avvad_mcb;
+int avvad_mcb_create(avvad_mcb** out);
+void avvad_mcb_destroy(avvad_mcb* h);
+/* h1,h2: i64 [513]/[512] device; s1,s2 f32; BN1d(1024) eval parameters. */
+int avvad_mcb_load(avvad_mcb* h, const int64_t* h1, const float* s1, const int64_t* h2, const float* s2,
+                   const float* bn_gamma, const float* bn_beta, const float* bn_mean,
+                   const float* bn_var, float eps, void* stream);
+size_t avvad_mcb_workspace_bytes(int64_t rows);
+/* audio f32 [rows][513], video f32 [rows][512] -> out_bf16 [rows][ld_out] (first 1024 columns),
+ * optional out_f32 [rows][1024] (post-BN, for tests). */
+int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* video, int64_t rows,
+                      void* workspace, size_t workspace_bytes, void* out_bf16, int64_t ld_out,
+                      float* out_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 2-layer (generic L) unidirectional LSTM over padded batches + Linear head (SURVEY R1,R2,H1,H2)
+ * replaces: AV_Net.py:127-140, Audio_Net.py:50-59, Video_Net.py:101-116
+ *           (pack_padded_sequence -> nn.LSTM -> pad_packed_sequence -> nn.Linear) and the
+ *           sigmoid / >0.5 of scripts/evaluate_AV_net.py:239-240.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct avvad_lstm avvad_lstm;
+int avvad_lstm_create(avvad_lstm** out, int layers, int input_size, int hidden, int y_dim);
+void avvad_lstm_destroy(avvad_lstm* h);
+/* PyTorch layout: w_ih [4H][I_l], w_hh [4H][H], b_ih/b_hh [4H]; gate order i,f,g,o. */
+int avvad_lstm_set_layer(avvad_lstm* h, int layer, const float* w_ih, const float* w_hh,
+                         const float* b_ih, const float* b_hh, void* stream);
+int avvad_lstm_set_head(avvad_lstm* h, const float* w, const float* b, void* stream);
+/* Padded input width (bf16 elements) the caller must lay the layer-0 operand out with. */
+int64_t avvad_lstm_input_ld(const avvad_lstm* h);
+size_t avvad_lstm_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T);
+/* x_bf16  : bf16 [B][T][ld_x] device, ld_x == avvad_lstm_input_ld(h), columns >= input_size zero
+ * lengths : i32 [B] device
+ * logits  : f32 [B][T][y_dim]; rows t >= len_b receive the head bias (zeros through the Linear)
+ * post, dec : optional f32 / i32 [B][T][y_dim]: sigmoid(logit) and (sigmoid > 0.5)
+ * last_logits: optional f32 [B][y_dim]: head applied to the last valid step (return_last=True) */
+int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                       void* workspace, size_t workspace_bytes, float* logits, float* post,
+                       int32_t* dec, float* last_logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVVAD_H_ */
