@@ -308,3 +308,18 @@ class Lstm:
 
 def launch_count() -> int:
     return int(L.lib().avvad_launch_count())
+
+
+def profile_enable(on: bool):
+    L.check(L.lib().avvad_profile_enable(1 if on else 0))
+
+
+def profile_read(cat: int):
+    """(ms, flops, launches) of the recorded tensor-core launches of one category."""
+    ms, fl, n = C.c_double(), C.c_double(), C.c_uint64()
+    L.check(L.lib().avvad_profile_read(cat, C.byref(ms), C.byref(fl), C.byref(n)))
+    return ms.value, fl.value, n.value
+
+
+def profile_clear():
+    L.check(L.lib().avvad_profile_clear())

@@ -2,11 +2,34 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <vector>
 
 #include "gemm_tc.cuh"
 
 namespace avvad {
 namespace tc {
+
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----------------
+struct ProfRec {
+  cudaEvent_t beg, end;
+  int cat;
+  double flops;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
 
 template <int BN, int AMODE>
 static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int KB,
@@ -27,9 +50,27 @@ static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int
   const int64_t tiles = m_tiles * n_tiles;
   if (tiles <= 0) return AVVAD_OK;
   AVVAD_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
+  ProfRec rec{};
+  bool prof = false;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof = g_prof_on;
+    if (prof) {
+      rec.beg = prof_event();
+      rec.end = prof_event();
+    }
+  }
+  if (prof) cudaEventRecord(rec.beg, st);
   tc_gemm_kernel<BN, AMODE><<<(unsigned)tiles, kThreads, C::kSmemBytes, st>>>(ap, Wt, ldw, M, N, KB, n_tiles, ep,
                                                                                epi_mode);
   AVVAD_LAUNCHED();
+  if (prof) {
+    cudaEventRecord(rec.end, st);
+    rec.cat = (AMODE == A_CONV) ? 0 : (epi_mode == EPI_LSTM ? 2 : 1);
+    rec.flops = 2.0 * (double)M * (double)N * (double)KB * BK;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   return AVVAD_OK;
 }
 
@@ -70,6 +111,46 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int64_t ld_src, 
 }  // namespace avvad
 
 using namespace avvad;
+
+extern "C" int avvad_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(tc::g_prof_mu);
+  tc::g_prof_on = on != 0;
+  return AVVAD_OK;
+}
+
+// Sums the recorded tensor-core launches of category `cat` (0 = implicit-GEMM conv, 1 = plain GEMM,
+// 2 = LSTM step) since the last call, then clears ALL records.  Synchronises the device.
+extern "C" int avvad_profile_read(int cat, double* ms, double* flops, uint64_t* launches) {
+  AVVAD_CHECK_ARG(ms && flops && launches, "null pointer");
+  AVVAD_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(tc::g_prof_mu);
+  double t = 0, f = 0;
+  uint64_t n = 0;
+  for (auto& r : tc::g_prof) {
+    if (r.cat == cat) {
+      float e = 0.f;
+      if (cudaEventElapsedTime(&e, r.beg, r.end) == cudaSuccess) {
+        t += e;
+        f += r.flops;
+        ++n;
+      }
+    }
+  }
+  *ms = t;
+  *flops = f;
+  *launches = n;
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_profile_clear(void) {
+  std::lock_guard<std::mutex> lk(tc::g_prof_mu);
+  for (auto& r : tc::g_prof) {
+    tc::g_prof_pool.push_back(r.beg);
+    tc::g_prof_pool.push_back(r.end);
+  }
+  tc::g_prof.clear();
+  return AVVAD_OK;
+}
 
 static int bn_override() {
   static int v = [] {

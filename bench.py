@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""AV-VAD inference benchmark (BASELINE.json metric: AV-VAD frames/sec, device-timed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[2]): full audio-visual net (DeepVAD_AV, use_mcb=True as in
+scripts/train_AV_net.py:70) inference on a batch of 256 synthetic utterances per GPU: 81,920
+samples of 16 kHz audio (317 STFT frames) + 152 mouth-ROI frames (67x67, 30 fps) each.  One "step" =
+one pass of the whole hot path over one batch: peak-normalise -> STFT/log-power/standardise ->
+30->62.5 fps gather/standardise -> ResNet-18 -> MCB fusion -> 2-layer LSTM -> head -> sigmoid/threshold.
+
+  value : frames/s with the raw inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through AVVADPipeline.infer_host with pinned HOST buffers (H2D of the raw inputs and
+          D2H of posteriors+decisions inside the timed region)
+  roofline : the tcgen05 implicit-GEMM convolution kernel (ResNet trunk), algorithmic FLOPs / device
+          time of those launches measured with CUDA events inside the timed region
+  cpu_baseline : the reference forward as a CPU port (oracle/reference_port.py) on a bounded sample
+
+`--impl reference` times that CPU port alone (the reference's own CPU implementation of the path:
+the reference cannot be pip-installed -- it has no setup.py -- and its MCB branch does not run on
+torch >= 1.8).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "audio-visual-vad_b200")
+for _p in (REPO, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_SAMPLES = 81920   # 5.12 s @ 16 kHz  -> 317 STFT frames
+N_SRC = 152         # 30 fps ROI frames -> 317 frames at 62.5 fps
+T_FRAMES = 317
+METRIC = "AV-VAD frames/sec (device-timed)"
+# tensor-core work per frame of the 19 implicit-GEMM convolutions (layer1-4; conv1 runs as a direct conv)
+CONV_MAC_PER_FRAME = 216_633_600 - 1156 * 64 * 49
+
+
+def synth_batch(B: int, seed: int):
+    """Synthetic raw inputs of the reference's shapes."""
+    from avvad import synth
+
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(N_SAMPLES, dtype=torch.float32) / 16000.0
+    f_env = 0.5 + 3.5 * torch.rand(B, 1, generator=g)
+    ph = 6.2831853 * torch.rand(B, 1, generator=g)
+    env = 0.55 + 0.45 * torch.sin(6.2831853 * f_env * t[None, :] + ph)
+    wave = (0.1 * torch.randn(B, N_SAMPLES, generator=g) * env).clamp_(-1, 1)
+    vid = torch.rand(B * N_SRC, 1, 71, 71, generator=g) * 255.0
+    vid = torch.nn.functional.avg_pool2d(vid, 5, stride=1)  # low-pass -> (.,1,67,67)
+    lo, hi = vid.amin(), vid.amax()
+    vid = ((vid - lo) / (hi - lo) * 255.0).round_().clamp_(0, 255).to(torch.uint8).view(B, N_SRC, 67, 67)
+    mean, std = synth.synth_audio_stats(0)
+    return wave.contiguous(), vid.contiguous(), mean, std
+
+
+def synth_weights(B: int, seed=0):
+    from avvad import synth
+
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), seed)
+    # running statistics of mcb_bn at the scale the whole-tensor L2 norm produces for this batch size
+    sd["mcb_bn.running_mean"] = torch.zeros(1024)
+    sd["mcb_bn.running_var"] = torch.full((1024,), 1.0 / (B * T_FRAMES * 1024.0))
+    return sd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", 1383.8)), float(d.get("hbm_gbs", 6453.7)), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(sd, wave, vid, mean, std, n_utt: int, reps: int):
+    """CPU port of the reference forward on `n_utt` utterances of the same workload."""
+    from avvad import synth
+    from oracle.reference_port import RefDeepVADAV, cpu_av_step
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = RefDeepVADAV(2, 1024, 1, use_mcb=True).load_reference_state_dict(sd).eval()
+    waves = [wave[i].numpy() for i in range(n_utt)]
+    vids = [vid[i].numpy() for i in range(n_utt)]
+    best = None
+    frames = 0
+    for r in range(reps + 1):  # first pass is the warm-up
+        t0 = time.perf_counter()
+        post, dec, lens = cpu_av_step(model, waves, vids, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD)
+        dt = time.perf_counter() - t0
+        frames = int(sum(lens))
+        if r > 0:
+            best = dt if best is None else min(best, dt)
+    return frames / best, cores, frames, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    B_s = args.ref_batch
+    wave, vid, mean, std = synth_batch(B_s, seed=1234)
+    sd = synth_weights(B_s)
+    from avvad import synth
+    from oracle.reference_port import RefDeepVADAV, cpu_av_step
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = RefDeepVADAV(2, 1024, 1, use_mcb=True).load_reference_state_dict(sd).eval()
+    waves = [wave[i].numpy() for i in range(B_s)]
+    vids = [vid[i].numpy() for i in range(B_s)]
+    for _ in range(args.warmup):
+        cpu_av_step(model, waves, vids, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD)
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        _, _, lens = cpu_av_step(model, waves, vids, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD)
+        frames += int(sum(lens))
+    dt = time.perf_counter() - t0
+    val = frames / dt
+    sample = f"{B_s} utterances x {T_FRAMES} frames per step (bounded sample of the batch-256 workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "AV-VAD (DeepVAD_AV, MCB fusion) inference, synthetic utterances 81,920 samples + "
+                               "152 ROI frames -> 317 frames each; CPU port of the reference forward "
+                               "(torchvision resnet18 + nn.LSTM + torch.fft MCB, torch.stft front end)",
+                   "batch_per_step": B_s, "frames_per_utterance": T_FRAMES},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: a CUDA device is required (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from avvad import engine as E
+    from avvad import synth
+    from avvad.pipeline import AVVADPipeline
+
+    B = args.batch
+    wave_h, vid_h, mean, std = synth_batch(B, seed=1234 + rank)
+    sd = synth_weights(B)
+    pipe = AVVADPipeline(sd, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD, use_mcb=True, device=dev)
+    wave_p, vid_p = wave_h.pin_memory(), vid_h.pin_memory()
+    wave_d, vid_d = wave_p.to(dev), vid_p.to(dev)
+    ns = torch.full((B,), N_SAMPLES, dtype=torch.int32, device=dev)
+    nsrc = torch.full((B,), N_SRC, dtype=torch.int32, device=dev)
+    lens = torch.full((B,), T_FRAMES, dtype=torch.int32, device=dev)
+    assert AVVADPipeline.frame_counts([N_SAMPLES], [N_SRC]) == [T_FRAMES]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return pipe.infer_device(wave_d, ns, vid_d, nsrc, lengths=lens, t_max=T_FRAMES)
+
+    def step_host():
+        w = pipe._buf("wave_dev", tuple(wave_p.shape), wave_p.dtype)
+        v = pipe._buf("video_dev", tuple(vid_p.shape), vid_p.dtype)
+        w.copy_(wave_p, non_blocking=True)
+        v.copy_(vid_p, non_blocking=True)
+        _, post, dec = pipe.infer_device(w, ns, v, nsrc, lengths=lens, t_max=T_FRAMES)
+        hp.copy_(post, non_blocking=True)
+        hd.copy_(dec, non_blocking=True)
+
+    hp = torch.empty(B, T_FRAMES, 1, dtype=torch.float32, pin_memory=True)
+    hd = torch.empty(B, T_FRAMES, 1, dtype=torch.int32, pin_memory=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    # ---- timed region: device-resident inputs ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    E.profile_clear()
+    E.profile_enable(True)
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    E.profile_enable(False)
+    ms = e0.elapsed_time(e1)
+    launches = E.launch_count() - l0
+    clocks = sampler.stop()
+    conv_ms, conv_flops, conv_n = E.profile_read(0)
+    gemm_ms, gemm_flops, gemm_n = E.profile_read(1)
+    lstm_ms, lstm_flops, lstm_n = E.profile_read(2)
+    E.profile_clear()
+
+    # ---- end to end: pinned host buffers in, host posteriors out ----
+    for _ in range(2):
+        step_host()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    g0.record()
+    for _ in range(args.steps):
+        step_host()
+    g1.record()
+    barrier()
+    # host clock around a synchronised region (covers enqueue + copies + kernels); never below the device time
+    e2e_ms = max(1e3 * (time.perf_counter() - t0), g0.elapsed_time(g1))
+
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    frames_per_step = B * T_FRAMES * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+    e2e_val = frames_per_step * args.steps / (e2e_ms / 1e3)
+    peak_tf, peak_hbm, peak_src = measured_peaks()
+    achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "AV-VAD (DeepVAD_AV, MCB fusion, 2x LSTM-1024) inference, batch 256 synthetic "
+                               "utterances per GPU: 81,920 samples + 152 ROI frames (67x67) -> 317 frames each; "
+                               "raw audio/video in, posteriors + decisions out",
+                   "batch_per_gpu": B, "frames_per_utterance": T_FRAMES, "frames_per_step": frames_per_step,
+                   "parallelism": f"utterance-sharded x{world}, no collective",
+                   "l2": "inputs (259 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(wave_p.numel() * 4 + vid_p.numel()) * world,
+                "d2h_bytes_per_step": int(hp.numel() * 4 + hd.numel() * 4) * world},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<BN,A_CONV> (tcgen05 implicit-GEMM conv, 19 layers)",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
+                     "share_of_step": conv_ms / ms if ms > 0 else None,
+                     "flops_per_launch_avg": conv_flops / conv_n if conv_n else None},
+        "breakdown_ms_per_step": {"conv_tc": conv_ms / args.steps, "gemm_tc": gemm_ms / args.steps,
+                                  "lstm_step_tc": lstm_ms / args.steps, "lstm_step_launches": int(lstm_n / args.steps),
+                                  "lstm_step_tflops": (lstm_flops / (lstm_ms / 1e3) / 1e12) if lstm_ms > 0 else None,
+                                  "gemm_tflops": (gemm_flops / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                v, cores, fr, thr = cpu_baseline(sd, wave_h, vid_h, mean, std, args.ref_batch, 1)
+                line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                                        "sample": f"{args.ref_batch} utterances ({fr} frames) of the same synthetic "
+                                                  f"batch, best of 1 after a warm-up, {thr} torch threads"}
+            except Exception as ex:  # the CPU leg must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": f"failed: {type(ex).__name__}: {ex}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=8, help="utterances per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

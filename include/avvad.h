@@ -34,6 +34,14 @@ int avvad_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 uint64_t avvad_launch_count(void);
 
+/* Per-launch device timing of the tensor-core kernels (CUDA events on the launching stream), used by
+ * bench.py for the roofline figure.  cat: 0 = implicit-GEMM convolution, 1 = plain GEMM, 2 = LSTM step.
+ * avvad_profile_read sums the launches of one category recorded since the last avvad_profile_clear
+ * (it synchronises the device); flops = 2*M*N*K per launch. */
+int avvad_profile_enable(int on);
+int avvad_profile_read(int cat, double* ms, double* flops, uint64_t* launches);
+int avvad_profile_clear(void);
+
 /* ------------------------------------------------------------------------------------------
  * Audio front end
  * replaces: packages/processing/stft.py:102-152 (stft_pytorch: pad-at-end rule, periodic Hann,
