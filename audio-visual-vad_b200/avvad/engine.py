@@ -323,3 +323,13 @@ def profile_read(cat: int):
 
 def profile_clear():
     L.check(L.lib().avvad_profile_clear())
+
+
+def profile_dump(cat: int, max_n=200000):
+    """Per-launch (ms, flops) arrays of one category, in launch order."""
+    import numpy as np
+
+    ms = (C.c_double * max_n)()
+    fl = (C.c_double * max_n)()
+    n = int(L.lib().avvad_profile_dump(cat, ms, fl, max_n))
+    return np.frombuffer(ms, dtype=np.float64, count=n).copy(), np.frombuffer(fl, dtype=np.float64, count=n).copy()

@@ -1,6 +1,5 @@
 // Audio front end: peak normalise -> frame/Hann -> 1024-pt rFFT -> |.|^2 -> log(.+eps) -> standardise,
-// fused in one kernel (plus a small abs-max reduction).  Two consecutive frames of one utterance are
-// packed into the real/imaginary parts of a single complex FFT held in shared memory.
+// fused in one kernel (plus a small abs-max reduction); the FFT of each frame runs in shared memory.
 //
 // Reference semantics: packages/processing/stft.py:123-151, packages/data_handling.py:441,454-457,
 // scripts/evaluate_AV_net.py:225-230, packages/utils.py:157-166 (zero padding happens BEFORE the
@@ -59,6 +58,9 @@ __global__ void absmax_kernel(const float* __restrict__ wave, int64_t wave_strid
 }
 
 // ---- fused STFT / log-power kernel ---------------------------------------------------------------
+// One CTA per (frame, utterance): the windowed frame is the real part of a 1024-point complex FFT held in
+// shared memory (imaginary part zero), so a frame's features never depend on which other frames share the
+// launch (trim / batch invariance is bit-exact).
 // MODE 0: standardised log-power (B, t_max, 513);  MODE 1: raw complex STFT (B, 513, t_max, 2).
 template <int MODE>
 __global__ void __launch_bounds__(kFftThreads)
@@ -72,25 +74,17 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 2;
-  const int t1 = t0 + 1;
+  const int t = blockIdx.x;
   const int T = min(n_frames[b], t_max);
-  const bool has1 = t1 < t_max;
 
-  if (t0 >= T) {
+  if (t >= T) {
     if (MODE == 0) {
-      // both rows are collate padding: (0 - mean) / (std + eps)
-      for (int k = tid; k < 513; k += kFftThreads) {
-        float v = mean ? (0.f - mean[k]) / (stdv[k] + eps) : 0.f;
-        out[((int64_t)b * t_max + t0) * 513 + k] = v;
-        if (has1) out[((int64_t)b * t_max + t1) * 513 + k] = v;
-      }
+      // collate padding: zeros are padded BEFORE standardisation -> (0 - mean) / (std + eps)
+      for (int k = tid; k < 513; k += kFftThreads)
+        out[((int64_t)b * t_max + t) * 513 + k] = mean ? (0.f - mean[k]) / (stdv[k] + eps) : 0.f;
     } else {
-      for (int k = tid; k < 513; k += kFftThreads) {
-        float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * 513 + k) * t_max;
-        o[t0] = make_float2(0.f, 0.f);
-        if (has1) o[t1] = make_float2(0.f, 0.f);
-      }
+      for (int k = tid; k < 513; k += kFftThreads)
+        reinterpret_cast<float2*>(out)[((int64_t)b * 513 + k) * t_max + t] = make_float2(0.f, 0.f);
     }
     return;
   }
@@ -100,7 +94,6 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
 
   const int n = n_samples[b];
   const float* x = wave + (int64_t)b * wave_stride;
-  const bool live1 = t1 < T;
   const float pk = peak ? peak[b] : 1.0f;
   const bool norm = peak != nullptr;
   __syncthreads();
@@ -110,46 +103,21 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
     // periodic Hann: 0.5 - 0.5*cos(2*pi*i/1024); cos from the twiddle table
     const float c = (i < 512) ? stw[i].x : -stw[i - 512].x;
     const float w = 0.5f - 0.5f * c;
-    const int i0 = t0 * 256 + i;
-    const int i1 = i0 + 256;
+    const int i0 = t * 256 + i;
     float v0 = (i0 < n) ? x[i0] : 0.f;  // samples past the end are the pad-at-end zeros
-    float v1 = (live1 && i1 < n) ? x[i1] : 0.f;
-    if (norm) {
-      v0 = __fdiv_rn(v0, pk);
-      v1 = __fdiv_rn(v1, pk);
-    }
-    sa[i] = make_float2(v0 * w, v1 * w);
+    if (norm) v0 = __fdiv_rn(v0, pk);
+    sa[i] = make_float2(v0 * w, 0.f);
   }
   __syncthreads();
   fft1024_smem(sa, sb, stw, tid);
 
   for (int k = tid; k < 513; k += kFftThreads) {
-    const float2 zk = sa[k];
-    const float2 zn = sa[(kFftN - k) & (kFftN - 1)];
-    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
-    const float br = 0.5f * (zk.y + zn.y), bi = 0.5f * (zn.x - zk.x);
+    const float2 z = sa[k];
     if (MODE == 0) {
-      float m = 0.f, inv = 1.f;
-      if (mean) {
-        m = mean[k];
-        inv = stdv[k] + eps;
-      }
-      const float la = logf(ar * ar + ai * ai + eps);
-      out[((int64_t)b * t_max + t0) * 513 + k] = mean ? (la - m) / inv : la;
-      if (has1) {
-        float lb;
-        if (live1) {
-          lb = logf(br * br + bi * bi + eps);
-          lb = mean ? (lb - m) / inv : lb;
-        } else {
-          lb = mean ? (0.f - m) / inv : 0.f;
-        }
-        out[((int64_t)b * t_max + t1) * 513 + k] = lb;
-      }
+      const float la = logf(z.x * z.x + z.y * z.y + eps);
+      out[((int64_t)b * t_max + t) * 513 + k] = mean ? (la - mean[k]) / (stdv[k] + eps) : la;
     } else {
-      float2* o = reinterpret_cast<float2*>(out) + ((int64_t)b * 513 + k) * t_max;
-      o[t0] = make_float2(ar, ai);
-      if (has1) o[t1] = live1 ? make_float2(br, bi) : make_float2(0.f, 0.f);
+      reinterpret_cast<float2*>(out)[((int64_t)b * 513 + k) * t_max + t] = z;
     }
   }
 }
@@ -193,7 +161,7 @@ static int launch_frontend(int mode, const float* wave, int64_t wave_stride, con
     absmax_kernel<<<dim3(chunks, B), 256, 0, st>>>(wave, wave_stride, n_samples, peak_scratch);
     AVVAD_LAUNCHED();
   }
-  dim3 grid((t_max + 1) / 2, B);
+  dim3 grid(t_max, B);
   if (mode == 0)
     frontend_kernel<0><<<grid, kFftThreads, 0, st>>>(wave, wave_stride, n_samples, n_frames, t_max,
                                                      normalise ? peak_scratch : nullptr, mean, stdv, eps, tw, out);

@@ -34,7 +34,7 @@ static cudaEvent_t prof_event() {
 template <int BN, int AMODE>
 static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int KB,
                     const EpiParams& ep, int epi_mode, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, AMODE>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -61,12 +61,19 @@ static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int
     }
   }
   if (prof) cudaEventRecord(rec.beg, st);
-  tc_gemm_kernel<BN, AMODE><<<(unsigned)tiles, kThreads, C::kSmemBytes, st>>>(ap, Wt, ldw, M, N, KB, n_tiles, ep,
-                                                                               epi_mode);
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
+  const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
+  tc_gemm_kernel<BN, AMODE><<<grid, kThreads, C::kSmemBytes, st>>>(ap, Wt, ldw, M, N, KB, n_tiles, tiles, ep,
+                                                                    epi_mode);
   AVVAD_LAUNCHED();
   if (prof) {
     cudaEventRecord(rec.end, st);
-    rec.cat = (AMODE == A_CONV) ? 0 : (epi_mode == EPI_LSTM ? 2 : 1);
+    rec.cat = (AMODE == A_CONV) ? 0 : (AMODE == A_CONV1 ? 3 : (epi_mode == EPI_LSTM ? 2 : 1));
     rec.flops = 2.0 * (double)M * (double)N * (double)KB * BK;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(rec);
@@ -79,6 +86,10 @@ int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, i
   AVVAD_CHECK_ARG(K > 0 && K % BK == 0, "K must be a positive multiple of 64");
   AVVAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ap.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0,
                   "operands must be 16-byte aligned");
+  if (amode == A_CONV1) {
+    AVVAD_CHECK_ARG(K == 64 && N == 64 && ap.A32, "stem conv expects K=64 (49 padded), N=64");
+    return launch_t<64, A_CONV1>(ap, Wt, ldw, M, N, 1, ep, epi_mode, st);
+  }
   AVVAD_CHECK_ARG(ldw % 8 == 0 && (amode != A_PLAIN || ap.lda % 8 == 0), "leading dimensions must be multiples of 8");
   const int KB = K / BK;
   int bn = bn_hint;
@@ -142,6 +153,23 @@ extern "C" int avvad_profile_read(int cat, double* ms, double* flops, uint64_t* 
   return AVVAD_OK;
 }
 
+// Per-launch records of one category, in launch order: ms[i], flops[i]; returns the count (<= max_n).
+extern "C" int64_t avvad_profile_dump(int cat, double* ms, double* flops, int64_t max_n) {
+  if (!ms || !flops || max_n <= 0) return 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return 0;
+  std::lock_guard<std::mutex> lk(tc::g_prof_mu);
+  int64_t n = 0;
+  for (auto& r : tc::g_prof) {
+    if (r.cat != cat || n >= max_n) continue;
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, r.beg, r.end) != cudaSuccess) continue;
+    ms[n] = e;
+    flops[n] = r.flops;
+    ++n;
+  }
+  return n;
+}
+
 extern "C" int avvad_profile_clear(void) {
   std::lock_guard<std::mutex> lk(tc::g_prof_mu);
   for (auto& r : tc::g_prof) {
@@ -189,6 +217,11 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
   ap.A = (const __nv_bfloat16*)in;
   ap.H = H; ap.W = W; ap.Cin = Cin; ap.OH = OH; ap.OW = OW; ap.R = R; ap.S = S; ap.stride = stride; ap.pad = pad;
   ap.cpb = Cin / 64;
+  static int use_ca = [] {
+    const char* e = getenv("AVVAD_CA");
+    return e ? atoi(e) : 0;
+  }();
+  ap.use_ca = use_ca;
   tc::EpiParams ep{};
   ep.bias = bias;
   ep.residual = (const __nv_bfloat16*)residual;

@@ -8,6 +8,8 @@
 //   layer1..4 (19 convs)                     : tcgen05 implicit GEMM (gemm_tc.cuh) with fused bias/residual/ReLU
 //   global average pool                      : small bandwidth kernel, emits fp32 features and/or the bf16
 //                                              LSTM operand columns
+#include <stdlib.h>
+
 #include "gemm_tc.cuh"
 
 namespace avvad {
@@ -29,6 +31,8 @@ static const ConvSpec kSpecs[20] = {
 };
 constexpr int64_t kFrameHW = 67 * 67;
 constexpr int64_t kActBytesPerFrame = 17 * 17 * 64 * 2;  // largest NHWC bf16 activation (after the pool)
+constexpr int64_t kStemBytesPerFrame = 34 * 34 * 64 * 2;  // conv1 output before the pool
+constexpr int64_t kStemSubChunk = 512;                    // 512 * 148 KB = 76 MB: conv1 -> pool stays L2-resident
 
 // ---- weight folding / packing ----------------------------------------------------------------------
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
@@ -49,6 +53,59 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   const int o = idx / (cin * k * k);
   const float sc = gamma[o] / sqrtf(var[o] + eps);
   wp[idx] = __float2bfloat16_rn(w[((o * cin + i) * k + r) * k + s] * sc);
+}
+
+// conv1 for the tensor-core stem: same folding, bf16 [64 out][64 k] with k = r*7+s (49..63 zero)
+__global__ void pack_conv1_tc_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                     const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ w1b) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int o = idx / 64, k = idx % 64;
+  float v = 0.f;
+  if (k < 49) {
+    const float sc = gamma[o] / sqrtf(var[o] + eps);
+    v = (w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k]) * sc;
+  }
+  w1b[idx] = __float2bfloat16_rn(v);
+}
+
+// NHWC bf16 3x3 / stride 2 / pad 1 max pool (inputs are post-ReLU, so clipping the window == -inf padding)
+__global__ void maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int64_t n_frames, int H, int OH, int C,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = C / 8;
+  const int64_t total = n_frames * OH * OH * chunks;
+  if (idx >= total) return;
+  const int ch = (int)(idx % chunks);
+  int64_t pp = idx / chunks;
+  const int pw = (int)(pp % OH);
+  pp /= OH;
+  const int ph = (int)(pp % OH);
+  const int64_t f = pp / OH;
+  float m[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) m[q] = 0.f;
+  const __nv_bfloat16* base = in + f * H * H * C + ch * 8;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy) {
+    const int y = 2 * ph + dy;
+    if (y < 0 || y >= H) continue;
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const int x = 2 * pw + dx;
+      if (x < 0 || x >= H) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(base + ((int64_t)y * H + x) * C);
+      const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
+      m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
+    }
+  }
+  uint4 r;
+  r.x = pack_bf16x2(m[0], m[1]);
+  r.y = pack_bf16x2(m[2], m[3]);
+  r.z = pack_bf16x2(m[4], m[5]);
+  r.w = pack_bf16x2(m[6], m[7]);
+  *reinterpret_cast<uint4*>(out + ((f * OH + ph) * OH + pw) * C + ch * 8) = r;
 }
 
 // conv1: fold 3 identical input channels and the BN scale -> fp32 [49][64] (tap-major, channel-minor)
@@ -201,7 +258,8 @@ using namespace avvad;
 struct avvad_resnet18 {
   __nv_bfloat16* w[20];
   float* bias[20];
-  float* w1;  // conv1 folded fp32 [49][64]
+  float* w1;  // conv1 folded fp32 [49][64] (direct-conv stem, AVVAD_STEM=simt)
+  __nv_bfloat16* w1b;  // conv1 folded bf16 [64][64] (tensor-core stem)
   bool set[20];
   bool smem_attr;
 };
@@ -215,12 +273,14 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     h->set[i] = false;
   }
   h->w1 = nullptr;
+  h->w1b = nullptr;
   h->smem_attr = false;
   for (int i = 0; i < 20; ++i) {
     const ConvSpec& s = kSpecs[i];
     AVVAD_CUDA(cudaMalloc(&h->bias[i], sizeof(float) * s.cout));
     if (i == 0) {
       AVVAD_CUDA(cudaMalloc(&h->w1, sizeof(float) * 49 * 64));
+      AVVAD_CUDA(cudaMalloc(&h->w1b, sizeof(__nv_bfloat16) * 64 * 64));
     } else {
       AVVAD_CUDA(cudaMalloc(&h->w[i], sizeof(__nv_bfloat16) * (size_t)s.cout * s.cin * s.k * s.k));
     }
@@ -236,6 +296,7 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
     cudaFree(h->bias[i]);
   }
   cudaFree(h->w1);
+  cudaFree(h->w1b);
   delete h;
 }
 
@@ -248,6 +309,8 @@ extern "C" int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float
   const ConvSpec& s = kSpecs[layer];
   if (layer == 0) {
     pack_conv1_kernel<<<(49 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, h->w1, h->bias[0]);
+    AVVAD_LAUNCHED();
+    pack_conv1_tc_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, var, bn_eps, h->w1b);
   } else {
     const int total = s.cout * s.cin * s.k * s.k;
     pack_conv_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, s.cout, s.cin, s.k,
@@ -265,7 +328,9 @@ static int64_t chunk_of(int64_t n_frames, int64_t chunk) {
 
 extern "C" size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk_frames) {
   if (n_frames <= 0) return 0;
-  return (size_t)(4 * align_up((size_t)chunk_of(n_frames, chunk_frames) * kActBytesPerFrame, 1024));
+  const int64_t mc = chunk_of(n_frames, chunk_frames);
+  const int64_t sub = mc < kStemSubChunk ? mc : kStemSubChunk;
+  return (size_t)(4 * align_up((size_t)mc * kActBytesPerFrame, 1024)) + align_up((size_t)sub * kStemBytesPerFrame, 1024);
 }
 
 static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const __nv_bfloat16* residual,
@@ -277,14 +342,45 @@ static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const
 
 // Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
 // Returns the buffer index holding the last produced activation in *last.
-static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4], int upto,
-                           int* last, cudaStream_t st) {
-  if (!h->smem_attr) {
-    AVVAD_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1Smem));
-    h->smem_attr = true;
+static bool stem_simt() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_STEM");
+    return (e && std::string(e) == "simt") ? 1 : 0;
+  }();
+  return v != 0;
+}
+
+static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4],
+                           __nv_bfloat16* stem, int upto, int* last, cudaStream_t st) {
+  if (stem_simt()) {
+    if (!h->smem_attr) {
+      AVVAD_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1Smem));
+      h->smem_attr = true;
+    }
+    conv1_pool_kernel<<<(unsigned)n, kC1Threads, kC1Smem, st>>>(frames, h->w1, h->bias[0], buf[0]);
+    AVVAD_LAUNCHED();
+  } else {
+    // stem on the tensor cores: im2col(7x7/2) producer -> tcgen05 GEMM (K 49->64) -> bias+ReLU -> bf16, then a
+    // bandwidth max-pool; sub-chunked so the 34x34x64 intermediate stays in L2
+    for (int64_t f0 = 0; f0 < n; f0 += kStemSubChunk) {
+      const int64_t nn = (n - f0 < kStemSubChunk) ? (n - f0) : kStemSubChunk;
+      tc::AParams ap{};
+      ap.A = reinterpret_cast<const __nv_bfloat16*>(h->w1b);  // unused by the stem producer (alignment check only)
+      ap.A32 = frames + f0 * kFrameHW;
+      ap.H = 67; ap.W = 67; ap.OH = 34; ap.OW = 34;
+      tc::EpiParams ep{};
+      ep.bias = h->bias[0];
+      ep.C = stem;
+      ep.ldc = 64;
+      ep.relu = 1;
+      int rc = tc::launch(tc::A_CONV1, ap, h->w1b, 64, nn * 34 * 34, 64, 64, ep, tc::EPI_BF16, 64, st);
+      if (rc) return rc;
+      const int64_t total = nn * 17 * 17 * 8;
+      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
+                                                                          buf[0] + f0 * 17 * 17 * 64);
+      AVVAD_LAUNCHED();
+    }
   }
-  conv1_pool_kernel<<<(unsigned)n, kC1Threads, kC1Smem, st>>>(frames, h->w1, h->bias[0], buf[0]);
-  AVVAD_LAUNCHED();
   int cur = 0;
   *last = cur;
   if (upto == 0) return AVVAD_OK;
@@ -342,10 +438,11 @@ extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, in
   const size_t bsz = align_up((size_t)mc * kActBytesPerFrame, 1024);
   __nv_bfloat16* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
+  __nv_bfloat16* stem = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + 4 * bsz);
   for (int64_t f0 = 0; f0 < n_frames; f0 += mc) {
     const int64_t n = (n_frames - f0 < mc) ? (n_frames - f0) : mc;
     int last = 0;
-    rc = run_trunk_chunk(h, frames + f0 * kFrameHW, n, buf, 20, &last, st);
+    rc = run_trunk_chunk(h, frames + f0 * kFrameHW, n, buf, stem, 20, &last, st);
     if (rc) return rc;
     const int64_t total = n * (512 / 8);
     avgpool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
@@ -369,8 +466,9 @@ extern "C" int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frame
   const size_t bsz = align_up((size_t)n_frames * kActBytesPerFrame, 1024);
   __nv_bfloat16* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
+  __nv_bfloat16* stem = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + 4 * bsz);
   int last = 0;
-  rc = run_trunk_chunk(h, frames, n_frames, buf, upto, &last, st);
+  rc = run_trunk_chunk(h, frames, n_frames, buf, stem, upto, &last, st);
   if (rc) return rc;
   const ConvSpec& s = kSpecs[upto];
   const int ho = (upto == 0) ? 17 : s.hout;

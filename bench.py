@@ -245,9 +245,14 @@ def run_ours(args, rank, world, local_rank):
     hp = torch.empty(B, T_FRAMES, 1, dtype=torch.float32, pin_memory=True)
     hd = torch.empty(B, T_FRAMES, 1, dtype=torch.int32, pin_memory=True)
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.ncu else max(args.warmup, 3)
+    for _ in range(n_warm):
         step_device()
     barrier()
+    if args.ncu:  # launch-list / ncu capture mode: one more pass, no timing claims, no JSON line
+        step_device()
+        barrier()
+        return
 
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local_rank)
@@ -266,9 +271,22 @@ def run_ours(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     launches = E.launch_count() - l0
     clocks = sampler.stop()
+    if os.environ.get("AVVAD_LAYER_DUMP") and rank == 0:
+        # per-layer table of the implicit-GEMM convolutions (grouped by algorithmic FLOPs per launch)
+        lms, lfl = E.profile_dump(0)
+        rows = {}
+        for m_, f_ in zip(lms, lfl):
+            r = rows.setdefault(f_, [0, 0.0])
+            r[0] += 1
+            r[1] += m_
+        table = [{"flops_per_launch": k, "launches": v[0], "ms_total": v[1], "tflops": k * v[0] / (v[1] / 1e3) / 1e12}
+                 for k, v in sorted(rows.items())]
+        with open(os.environ["AVVAD_LAYER_DUMP"], "w") as fh:
+            json.dump({"steps": args.steps, "layers": table}, fh, indent=1)
     conv_ms, conv_flops, conv_n = E.profile_read(0)
     gemm_ms, gemm_flops, gemm_n = E.profile_read(1)
     lstm_ms, lstm_flops, lstm_n = E.profile_read(2)
+    stem_ms, stem_flops, stem_n = E.profile_read(3)
     E.profile_clear()
 
     # ---- end to end: pinned host buffers in, host posteriors out ----
@@ -320,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
                      "share_of_step": conv_ms / ms if ms > 0 else None,
                      "flops_per_launch_avg": conv_flops / conv_n if conv_n else None},
         "breakdown_ms_per_step": {"conv_tc": conv_ms / args.steps, "gemm_tc": gemm_ms / args.steps,
-                                  "lstm_step_tc": lstm_ms / args.steps, "lstm_step_launches": int(lstm_n / args.steps),
+                                  "lstm_step_tc": lstm_ms / args.steps, "stem_tc": stem_ms / args.steps, "lstm_step_launches": int(lstm_n / args.steps),
                                   "lstm_step_tflops": (lstm_flops / (lstm_ms / 1e3) / 1e12) if lstm_ms > 0 else None,
                                   "gemm_tflops": (gemm_flops / (gemm_ms / 1e3) / 1e12) if gemm_ms > 0 else None},
     }
@@ -350,6 +368,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8, help="utterances per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling mode: warm-up + one pass, prints nothing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

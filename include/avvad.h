@@ -41,6 +41,8 @@ uint64_t avvad_launch_count(void);
 int avvad_profile_enable(int on);
 int avvad_profile_read(int cat, double* ms, double* flops, uint64_t* launches);
 int avvad_profile_clear(void);
+/* Per-launch records (launch order) of one category; returns how many were written (<= max_n). */
+int64_t avvad_profile_dump(int cat, double* ms, double* flops, int64_t max_n);
 
 /* ------------------------------------------------------------------------------------------
  * Audio front end
