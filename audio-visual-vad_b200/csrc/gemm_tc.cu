@@ -4,7 +4,7 @@
 #include <mutex>
 #include <vector>
 
-#include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace avvad {
 namespace tc {
@@ -29,6 +29,48 @@ static cudaEvent_t prof_event() {
   cudaEvent_t e = nullptr;
   cudaEventCreate(&e);
   return e;
+}
+
+// generic begin/end used by both engines
+int prof_begin(cudaStream_t st, void** tok) {
+  *tok = nullptr;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return 0;
+  ProfRec* r = new ProfRec();
+  r->beg = prof_event();
+  r->end = prof_event();
+  cudaEventRecord(r->beg, st);
+  *tok = r;
+  return 1;
+}
+void prof_end(cudaStream_t st, void* tok, int cat, double flops) {
+  if (!tok) return;
+  ProfRec* r = static_cast<ProfRec*>(tok);
+  cudaEventRecord(r->end, st);
+  r->cat = cat;
+  r->flops = flops;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
+
+static bool use_tma() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_TMA");
+    if (e && atoi(e) == 0) return 0;
+    return tma_available() ? 1 : 0;
+  }();
+  return v != 0;
+}
+
+// Plain GEMM through whichever operand-staging engine is active (TMA by default, cp.async with AVVAD_TMA=0).
+int gemm_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
+                  const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
+  if (use_tma()) return launch_tma_gemm(A, lda, Wt, ldw, M, N, K, ep, epi_mode, bn_hint, st);
+  AParams ap{};
+  ap.A = A;
+  ap.lda = lda;
+  return launch(A_PLAIN, ap, Wt, ldw, M, N, K, ep, epi_mode, bn_hint, st);
 }
 
 template <int BN, int AMODE>
@@ -200,8 +242,8 @@ extern "C" int avvad_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
   ep.C = Cp;
   ep.ldc = ldc;
   ep.relu = relu;
-  return tc::launch(tc::A_PLAIN, ap, (const __nv_bfloat16*)W, ldw, M, (int)N, (int)K, ep,
-                    c_is_bf16 ? tc::EPI_BF16 : tc::EPI_F32, bn_override(), (cudaStream_t)stream);
+  return tc::gemm_dispatch((const __nv_bfloat16*)A, lda, (const __nv_bfloat16*)W, ldw, M, (int)N, (int)K, ep,
+                           c_is_bf16 ? tc::EPI_BF16 : tc::EPI_F32, bn_override(), (cudaStream_t)stream);
 }
 
 extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float* bias, const void* residual,
@@ -228,6 +270,9 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
   ep.C = out;
   ep.ldc = Cout;
   ep.relu = relu;
+  if (tc::use_tma() && OW <= 128)
+    return tc::launch_tma_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, W, Cin, Cout, R, S,
+                               stride, pad, bn_override(), (cudaStream_t)stream);
   const int64_t M = n * OH * OW;
   const int K = R * S * Cin;
   return tc::launch(tc::A_CONV, ap, (const __nv_bfloat16*)w, K, M, Cout, K, ep, tc::EPI_BF16, bn_override(),

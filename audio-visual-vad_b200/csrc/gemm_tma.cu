@@ -1,0 +1,225 @@
+// Host side of the TMA-fed tcgen05 engine: tensor-map encoding (driver entry point fetched at run time, libcuda
+// is not linked), tile-phase selection and launch.
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "gemm_tma.cuh"
+
+namespace avvad {
+namespace tc {
+
+int prof_begin(cudaStream_t st, void** tok);
+void prof_end(cudaStream_t st, void* tok, int cat, double flops);
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+bool tma_available() { return encode_fn() != nullptr; }
+
+// rank-4 bf16 tensor, dims innermost first
+static int encode4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                   const uint32_t box[4], const uint32_t estr[4]) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return AVVAD_ERR_CUDA;
+  }
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {estr[0], estr[1], estr[2], estr[3]};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank 4) failed with CUresult " + std::to_string((int)r) + " dims=" +
+              std::to_string(dims[0]) + "," + std::to_string(dims[1]) + "," + std::to_string(dims[2]) + "," +
+              std::to_string(dims[3]) + " box=" + std::to_string(box[0]) + "," + std::to_string(box[1]) + "," +
+              std::to_string(box[2]) + "," + std::to_string(box[3]));
+    return AVVAD_ERR_CUDA;
+  }
+  return AVVAD_OK;
+}
+
+static int encode2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes,
+                   uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return AVVAD_ERR_CUDA;
+  }
+  cuuint64_t gd[2] = {inner, outer};
+  cuuint64_t gs[1] = {stride_bytes};
+  cuuint32_t bx[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank 2) failed with CUresult " + std::to_string((int)r));
+    return AVVAD_ERR_CUDA;
+  }
+  return AVVAD_OK;
+}
+
+template <int BN>
+static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep, int epi_mode, int cat, double flops,
+                     cudaStream_t st) {
+  using C = TmaCfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+  });
+  if (attr_err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));
+    return AVVAD_ERR_CUDA;
+  }
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  if (g.total_tiles <= 0) return AVVAD_OK;
+  const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
+  const unsigned grid = (unsigned)(g.total_tiles < resident ? g.total_tiles : resident);
+  void* tok = nullptr;
+  prof_begin(st, &tok);
+  tc_tma_kernel<BN><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, ep, epi_mode);
+  AVVAD_LAUNCHED();
+  prof_end(st, tok, cat, flops);
+  return AVVAD_OK;
+}
+
+static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep, int epi_mode, int cat,
+                    double flops, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_bn<64>(maps, g, ep, epi_mode, cat, flops, st);
+    case 128: return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
+    case 256: return launch_bn<256>(maps, g, ep, epi_mode, cat, flops, st);
+  }
+  set_error("bad BN");
+  return AVVAD_ERR_ARG;
+}
+
+static int pick_bn(int N, int hint) {
+  if (hint == 64 || hint == 128 || hint == 256) {
+    if (N % hint == 0 || hint == 64) return hint;
+  }
+  if (N <= 64) return 64;
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  return 64;
+}
+
+int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
+                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st) {
+  const int OH = (H + 2 * pad - R) / stride + 1;
+  const int OW = (W + 2 * pad - S) / stride + 1;
+  AVVAD_CHECK_ARG(OW <= 128 && Cin % 64 == 0, "TMA conv: OW <= 128 and Cin % 64 == 0 required");
+  TmaGeom g{};
+  g.mode = 1;
+  g.OH = OH; g.OW = OW; g.stride = stride; g.pad = pad; g.S = S; g.cpb = Cin / 64; g.KB = R * S * (Cin / 64);
+  g.n_frames = n;
+  g.N = Cout;
+  const int bn = pick_bn(Cout, bn_hint);
+  g.n_tiles = (Cout + bn - 1) / bn;
+  // choose up to two (band height, frames per tile) phases maximising the fill of the 128 accumulator rows
+  double best = -1;
+  int bh0 = 1, bF0 = 1, bnb0 = OH, brem = 0, bF1 = 1;
+  for (int hb0 = 1; hb0 <= OH; ++hb0) {
+    if (hb0 * OW > 128) break;
+    const int nb0 = OH / hb0;
+    const int rem = OH - nb0 * hb0;
+    int F0 = (nb0 == 1 && rem == 0) ? 128 / (hb0 * OW) : 128 / (hb0 * OW);
+    if (F0 < 1) continue;
+    if (nb0 > 1) F0 = 1;  // several bands per frame: one frame per tile keeps the tile enumeration simple
+    if (F0 > 256) F0 = 256;
+    double tiles_per_frame = (double)nb0 / F0;
+    int F1 = 1;
+    if (rem > 0) {
+      F1 = 128 / (rem * OW);
+      if (F1 < 1) continue;
+      if (F1 > 256) F1 = 256;
+      tiles_per_frame += 1.0 / F1;
+    }
+    const double eff = (double)OH * OW / (128.0 * tiles_per_frame);
+    if (eff > best + 1e-9) {
+      best = eff; bh0 = hb0; bF0 = F0; bnb0 = nb0; brem = rem; bF1 = F1;
+    }
+  }
+  AVVAD_CHECK_ARG(best > 0, "TMA conv: no valid tiling");
+  g.h0[0] = 0; g.hb[0] = bh0; g.nb[0] = bnb0; g.F[0] = bF0;
+  g.tiles0 = ((n + bF0 - 1) / bF0) * bnb0;
+  int64_t tiles1 = 0;
+  g.h0[1] = bnb0 * bh0; g.hb[1] = brem > 0 ? brem : 1; g.nb[1] = 1; g.F[1] = bF1;
+  if (brem > 0) tiles1 = (n + bF1 - 1) / bF1;
+  g.total_tiles = (g.tiles0 + tiles1) * g.n_tiles;
+
+  TmaMaps maps;
+  const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  for (int p = 0; p < 2; ++p) {
+    const int hb = g.hb[p], F = g.F[p];
+    const uint32_t box[4] = {64, (uint32_t)((OW - 1) * stride + 1), (uint32_t)((hb - 1) * stride + 1), (uint32_t)F};
+    int rc = encode4(&maps.a[p], in, dims, strides, box, estr);
+    if (rc) return rc;
+    g.bytesA[p] = (uint32_t)F * hb * OW * 128u;
+  }
+  const int K = R * S * Cin;
+  int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, 64, (uint32_t)bn);
+  if (rc) return rc;
+  g.bytesB = (uint32_t)bn * 128u;
+  const double flops = 2.0 * (double)n * OH * OW * Cout * K;
+  return dispatch(bn, maps, g, ep, EPI_BF16, 0, flops, st);
+}
+
+int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
+                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
+  AVVAD_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0, "TMA gemm: K % 64, lda % 8, ldw % 8 required");
+  TmaGeom g{};
+  g.mode = 0;
+  g.KB = K / 64;
+  g.cpb = g.KB;  // never wraps
+  g.S = 1;
+  g.n_frames = M;
+  g.N = N;
+  int bn = pick_bn(N, bn_hint);
+  g.n_tiles = (N + bn - 1) / bn;
+  g.total_tiles = ((M + BM - 1) / BM) * g.n_tiles;
+  g.tiles0 = g.total_tiles;
+  g.hb[0] = g.hb[1] = 1; g.nb[0] = g.nb[1] = 1; g.F[0] = g.F[1] = 1; g.OW = 128; g.OH = 1;
+  TmaMaps maps;
+  const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+  const uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)M, (uint64_t)lda * 2 * (uint64_t)M};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  int rc = encode4(&maps.a[0], A, dims, strides, box, estr);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0];
+  g.bytesA[0] = g.bytesA[1] = 128u * 128u;
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)bn);
+  if (rc) return rc;
+  g.bytesB = (uint32_t)bn * 128u;
+  const double flops = 2.0 * (double)M * N * K;
+  return dispatch(bn, maps, g, ep, epi_mode, epi_mode == EPI_LSTM ? 2 : 1, flops, st);
+}
+
+}  // namespace tc
+}  // namespace avvad

@@ -1,0 +1,253 @@
+// TMA-fed variant of the tcgen05 engine (sm_100a): operands are staged by the Tensor Memory Accelerator instead of
+// per-thread cp.async gathers, so operand delivery costs one instruction per box instead of ~2000 per K block.
+//
+//   warp 0 (lane 0) : TMA producer.  Per K block it arms full[s] with the expected byte count and issues
+//                     cp.async.bulk.tensor: a 4-D box {64 ch, OW, hb, F} of the NHWC activation for the A
+//                     operand (the box IS the im2col tile of one filter tap: the tap only shifts the box
+//                     coordinates, out-of-image pixels are zero-filled by the hardware, stride-2 convolutions use
+//                     the map's traversal strides) and a 2-D box {64, BN} of the packed weights for B.  Both land
+//                     in the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect.
+//   warp 1          : TMEM allocation; lane 0 issues tcgen05.mma / tcgen05.commit (as in gemm_tc.cuh).
+//   warps 2-5       : epilogue (TMEM -> registers -> bias / residual / ReLU / LSTM cell -> global).
+//
+// An output tile is F whole frames x a band of hb output rows (F*hb*OW <= 128 accumulator rows).  Up to two
+// "phases" with different (hb, F) cover a frame (e.g. 17x17: two 7-row bands per frame + one 3-row band over
+// two frames = 90 % of the 128 MMA rows; 9x9: 7 rows x 2 frames + 2 rows x 7 frames = 98 %).  A plain GEMM is the
+// degenerate case C=K, W=M, H=1.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_tc.cuh"
+
+namespace avvad {
+namespace tc {
+
+constexpr int kTmaThreads = 192;
+
+struct TmaGeom {
+  int mode;             // 0 = plain GEMM rows, 1 = convolution boxes
+  int n_tiles;          // tiles along N
+  int64_t total_tiles;  // all (m, n) tiles
+  int64_t tiles0;       // m-tiles of phase 0 (conv)
+  int h0[2], hb[2], nb[2], F[2];  // per phase: first output row, band height, bands per frame, frames per tile
+  int OH, OW, stride, pad, S, cpb, KB;
+  int64_t n_frames;     // conv: frames in this launch; gemm: M
+  int N;
+  uint32_t bytesA[2];   // TMA box bytes per phase
+  uint32_t bytesB;
+};
+
+struct TmaMaps {
+  CUtensorMap a[2];
+  CUtensorMap b;
+};
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+template <int BN>
+struct TmaCfg {
+  static constexpr uint32_t kABytes = BM * 128;
+  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
+  // ring depth: fill ~200 KB per SM
+  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 3 : 4);
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct TileCoord {
+  int phase, n_base;
+  int64_t n0;   // conv: first frame; gemm: first row
+  int hstart;   // conv: first output row of the band
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const TmaGeom& g, int64_t tile, int BN) {
+  TileCoord t;
+  t.n_base = (int)(tile % g.n_tiles) * BN;
+  int64_t mt = tile / g.n_tiles;
+  if (g.mode == 0) {
+    t.phase = 0;
+    t.n0 = mt * BM;
+    t.hstart = 0;
+    return t;
+  }
+  t.phase = (mt < g.tiles0) ? 0 : 1;
+  if (t.phase) mt -= g.tiles0;
+  const int nb = g.nb[t.phase];
+  const int band = (int)(mt % nb);
+  t.n0 = (mt / nb) * g.F[t.phase];
+  t.hstart = g.h0[t.phase] + band * g.hb[t.phase];
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTmaThreads)
+tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiParams ep, const int epi_mode) {
+  using C = TmaCfg<BN>;
+  constexpr int S = C::kStages;
+  constexpr uint32_t kTmemCols = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + S * C::kStageBytes;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S * C::kStageBytes + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar0 + 8 * s, 1);        // full: the producer's arrive.expect_tx (+ TMA transaction bytes)
+      mbar_init(bar0 + 8 * (S + s), 1);  // empty: tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar0 + 8 * (2 * S + a), 1);      // tmem full
+      mbar_init(bar0 + 8 * (2 * S + 2 + a), 4);  // tmem empty: one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.a[1]);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(g, tile, BN);
+        const uint32_t bytes = g.bytesA[t.phase] + g.bytesB;
+        int tap = 0, cb = 0, fr = 0, fs = 0;
+        for (int kb = 0; kb < g.KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+          const uint32_t full = bar0 + 8 * s;
+          const uint32_t sa = base + s * C::kStageBytes;
+          mbar_arrive_expect_tx(full, bytes);
+          if (g.mode == 0) {
+            tma_load_4d(sa, &maps.a[0], kb * BK, (int)t.n0, 0, 0, full);
+          } else {
+            tma_load_4d(sa, &maps.a[t.phase], cb * BK, fs - g.pad, t.hstart * g.stride + fr - g.pad, (int)t.n0, full);
+          }
+          tma_load_2d(sa + C::kABytes, &maps.b, kb * BK, t.n_base, full);
+          if (++cb == g.cpb) {
+            cb = 0;
+            ++tap;
+            if (++fs == g.S) {
+              fs = 0;
+              ++fr;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t it = 0, tl = 0;
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_acc + acc * BN;
+        for (int kb = 0; kb < g.KB; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(bar0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(d_tmem, make_sw128_desc(sa + k * 32), make_sw128_desc(sb + k * 32), idesc, (kb | k) != 0);
+          umma_commit(bar0 + 8 * (S + s));
+        }
+        umma_commit(bar0 + 8 * (2 * S + acc));
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      const TileCoord t = decode_tile(g, tile, BN);
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      // output row of accumulator row r = q*32 + lane
+      const int r = q * 32 + lane;
+      int64_t m = -1;
+      if (g.mode == 0) {
+        if (t.n0 + r < g.n_frames) m = t.n0 + r;
+      } else {
+        const int hb = g.hb[t.phase];
+        const int per_frame = hb * g.OW;
+        const int f = r / per_frame;
+        const int rem = r - f * per_frame;
+        const int hh = rem / g.OW;
+        const int ww = rem - hh * g.OW;
+        const int oh = t.hstart + hh;
+        if (f < g.F[t.phase] && t.n0 + f < g.n_frames && oh < g.OH)
+          m = ((t.n0 + f) * g.OH + oh) * g.OW + ww;
+      }
+      mbar_wait(bar0 + 8 * (2 * S + acc), aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_acc + acc * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(t_row + j * 32, v);
+        tmem_ld_wait();
+        const int n0 = t.n_base + j * 32;
+        if (m >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m, n0, g.N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar0 + 8 * (2 * S + 2 + acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_acc, kTmemCols);
+  }
+}
+
+// host side (gemm_tma.cu)
+bool tma_available();
+int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
+                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st);
+int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
+                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
+
+}  // namespace tc
+}  // namespace avvad

@@ -268,9 +268,6 @@ extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32
     AVVAD_CUDA(cudaMemsetAsync(ws.hbuf[0], 0, (size_t)B * H * 2, st));
     AVVAD_CUDA(cudaMemsetAsync(ws.c, 0, (size_t)B * H * sizeof(float), st));
     for (int t = 0; t < (int)T; ++t) {
-      tc::AParams ap{};
-      ap.A = ws.hbuf[t & 1];
-      ap.lda = H;
       tc::EpiParams ep{};
       ep.xproj = ws.xproj;
       ep.c_state = ws.c;
@@ -280,7 +277,7 @@ extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32
       ep.t = t;
       ep.T = (int)T;
       ep.H4 = H4;
-      rc = tc::launch(tc::A_PLAIN, ap, h->w_hh[l], H, B, H4, H, ep, tc::EPI_LSTM, 64, st);
+      rc = tc::gemm_dispatch(ws.hbuf[t & 1], H, h->w_hh[l], H, B, H4, H, ep, tc::EPI_LSTM, 64, st);
       if (rc) return rc;
     }
     layer_in = layer_out;
