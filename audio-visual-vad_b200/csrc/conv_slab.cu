@@ -1,0 +1,143 @@
+// Host side of the slab convolution: geometry search, tensor maps, launch.
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "conv_slab.cuh"
+
+namespace avvad {
+namespace tc {
+
+int prof_begin(cudaStream_t st, void** tok);
+void prof_end(cudaStream_t st, void* tok, int cat, double flops);
+int encode_act_map(CUtensorMap* m, const void* ptr, int Cin, int W, int H, int64_t n, const uint32_t box[4],
+                   const uint32_t estr[4]);
+int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t bn);
+
+static int slab_mode() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_SLAB");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
+static int slab_bo() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_SLAB_BO");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+bool slab_supported(int H, int W, int Cin, int Cout, int R, int S, int stride, int pad) {
+  if (!tma_available() || slab_mode() == 0) return false;
+  if (!(R == 3 && S == 3 && stride == 1 && pad == 1 && H == W && Cin % 64 == 0 && Cout % 64 == 0)) return false;
+  if (slab_mode() == 1) return Cin == 64 && Cout == 64;  // layer1-type: weights fit in shared memory
+  return true;
+}
+
+struct SlabPlan {
+  int F, hb, mb, bn, b_stages;
+  bool resident;
+  size_t smem;
+  double eff;
+};
+
+static bool plan(int H, int Cin, int Cout, SlabPlan* out) {
+  const int OW = H, OH = H, Wp = OW + 2;
+  const int cpb = Cin / 64;
+  SlabPlan best{};
+  best.eff = -1;
+  const int bn = 64;
+  const bool resident = (Cout == 64) && ((size_t)9 * cpb * bn * 128 <= 80 * 1024);
+  for (int hb = 1; hb <= OH; ++hb) {
+    const int Hs = hb + 2;
+    if (Hs > 256 || Wp > 256) continue;
+    const int fmax = (hb == OH) ? 64 : 1;  // several frames per slab only for whole-frame bands
+    for (int F = 1; F <= fmax; ++F) {
+      const int rows = F * Hs * Wp;
+      const int P = rows - 2 * Wp - 2;
+      const int mb = (P + 127) / 128;
+      if (2 * mb * bn > 512) break;
+      const int slab_rows = mb * 128 + 2 * Wp + 2;
+      if (slab_rows < rows) continue;
+      const size_t slab_bytes = ((size_t)slab_rows * 128 + 1023) / 1024 * 1024;
+      const int b_stages = resident ? 0 : 6;
+      const size_t wbytes = resident ? (size_t)9 * cpb * bn * 128 : (size_t)b_stages * bn * 128;
+      const size_t smem = 2 * slab_bytes + wbytes + 256 + 1024 + (size_t)Cout * 4;
+      if (smem > 225 * 1024) continue;
+      const int nb = (OH + hb - 1) / hb;
+      // valid outputs per frame / MMA rows per frame
+      const double eff = (double)OH * OW / ((double)nb * mb * 128.0 / F);
+      // prefer higher efficiency, then more accumulator blocks per weight load
+      if (eff > best.eff + 1e-9 || (eff > best.eff - 1e-9 && mb > best.mb)) {
+        best.F = F; best.hb = hb; best.mb = mb; best.bn = bn; best.b_stages = b_stages; best.resident = resident;
+        best.smem = smem; best.eff = eff;
+      }
+    }
+  }
+  if (best.eff <= 0) return false;
+  *out = best;
+  return true;
+}
+
+template <int BN, bool RES>
+static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep, size_t smem, double flops,
+                    cudaStream_t st) {
+  static std::mutex mu;
+  static size_t attr_set = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (smem > attr_set) {
+      AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = smem;
+    }
+  }
+  static int num_sms = [] {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  const unsigned grid = (unsigned)(g.total_tiles < num_sms ? g.total_tiles : num_sms);
+  void* tok = nullptr;
+  prof_begin(st, &tok);
+  tc_slab_kernel<BN, RES><<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
+  AVVAD_LAUNCHED();
+  prof_end(st, tok, 0, flops);
+  return AVVAD_OK;
+}
+
+int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int Cin,
+                     int Cout, cudaStream_t st) {
+  SlabPlan p;
+  if (!plan(H, Cin, Cout, &p)) {
+    set_error("slab conv: no feasible plan");
+    return AVVAD_ERR_ARG;
+  }
+  SlabGeom g{};
+  g.n_frames = n;
+  g.OH = H; g.OW = H; g.Wp = H + 2; g.hb = p.hb; g.Hs = p.hb + 2; g.F = p.F; g.mb = p.mb;
+  g.nb = (H + p.hb - 1) / p.hb;
+  g.cpb = Cin / 64;
+  g.N = Cout;
+  g.n_tiles = Cout / p.bn;
+  g.total_tiles = ((n + p.F - 1) / p.F) * g.nb * g.n_tiles;
+  g.slab_rows = p.mb * 128 + 2 * g.Wp + 2;
+  g.slab_tx = (uint32_t)p.F * g.Hs * g.Wp * 128u;
+  g.use_base_offset = slab_bo();
+  g.b_stages = p.b_stages;
+  SlabMaps maps;
+  const uint32_t box[4] = {64, (uint32_t)g.Wp, (uint32_t)g.Hs, (uint32_t)p.F};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  int rc = encode_act_map(&maps.a, in, Cin, H, H, n, box, estr);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps.b, w, (uint64_t)9 * Cin, (uint64_t)Cout, (uint32_t)p.bn);
+  if (rc) return rc;
+  const double flops = 2.0 * (double)n * H * H * Cout * 9.0 * Cin;
+  if (p.resident) return launch_k<64, true>(maps, g, ep, p.smem, flops, st);
+  return launch_k<64, false>(maps, g, ep, p.smem, flops, st);
+}
+
+}  // namespace tc
+}  // namespace avvad

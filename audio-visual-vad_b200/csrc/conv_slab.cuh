@@ -1,0 +1,278 @@
+// "Slab" convolution for 3x3 / stride 1 / pad 1 layers on sm_100a: the input of a tile is loaded ONCE, with its
+// halo, as one TMA box per 64-channel block ({64, OW+2, hb+2, F}; the zero border comes from TMA out-of-bounds
+// fill), and the nine filter taps are nine row-shifted views of that resident slab: the UMMA A descriptor of tap
+// (r,s) simply starts (r*(OW+2)+s) rows further down.  GEMM rows are positions of the padded grid, so a few rows
+// per image row (the two border columns) and per band (the two border rows) are computed and dropped -- in exchange
+// the A operand crosses L2 once instead of nine times and one weight K-block feeds `mb` accumulator blocks.
+// Weights are either fully resident in shared memory (layer1: 9 x [64][64] bf16 = 72 KB, loaded once per CTA) or
+// streamed through a ring (wider layers).
+//
+//   warp 0  : TMA producer (slabs; weight ring or the one-off resident weight load)
+//   warp 1  : TMEM alloc + tcgen05.mma issue (mb accumulator blocks x 9 taps x cpb channel blocks x 4 K16 steps)
+//   warps 2-9: two epilogue groups (TMEM -> bias / residual / ReLU -> NHWC bf16), accumulators double-buffered
+#pragma once
+#include "gemm_tma.cuh"
+
+namespace avvad {
+namespace tc {
+
+constexpr int kSlabThreads = 320;
+constexpr int kSlabEpiWarps = 8;
+
+struct SlabGeom {
+  int64_t n_frames, total_tiles;
+  int OH, OW, Wp, Hs, hb, F, nb, mb, cpb, n_tiles, N;
+  int slab_rows;        // rows allocated per slab buffer (>= mb*128 + 2*Wp + 2)
+  uint32_t slab_tx;     // bytes one slab TMA box delivers
+  int use_base_offset;  // descriptor base_offset = (start >> 7) & 7 for row-shifted starts
+  int b_stages;         // weight ring depth (streamed mode)
+};
+
+struct SlabMaps {
+  CUtensorMap a;
+  CUtensorMap b;
+};
+
+__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t saddr, int use_bo) {
+  uint64_t d = make_sw128_desc(saddr);
+  if (use_bo) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+// dynamic smem: [slab 0][slab 1][weights: resident KB tiles or ring][barriers]
+template <int BN, bool RESIDENT_B>
+__global__ void __launch_bounds__(kSlabThreads)
+tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t slab_bytes = ((uint32_t)g.slab_rows * 128u + 1023u) & ~1023u;
+  const uint32_t b_tile = BN * 128u;
+  const int KB = 9 * g.cpb;
+  const int nB = RESIDENT_B ? KB : g.b_stages;
+  const uint32_t w_base = base + 2 * slab_bytes;
+  const uint32_t bar0 = w_base + (uint32_t)nB * b_tile;
+  // barriers: slab_full[2] | slab_empty[2] | tfull[2] | tempty[2] | b_full[nB'] | b_empty[nB']  (nB' <= 8 when streamed)
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int kBarBFull = 8, kBarBEmpty = 16;  // streamed ring: up to 8 stages; resident: b_full = BAR(8)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - base) + 8 * 24);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t acc_cols = (uint32_t)g.mb * BN;  // columns of one accumulator stage
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(0 + i), 1);              // slab full (expect_tx)
+      mbar_init(BAR(2 + i), 1);              // slab empty (tcgen05.commit)
+      mbar_init(BAR(4 + i), 1);              // tmem full
+      mbar_init(BAR(6 + i), kSlabEpiWarps);  // tmem empty
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(BAR(kBarBFull + i), 1);
+      mbar_init(BAR(kBarBEmpty + i), 1);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&maps.a);
+    tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
+    tmem_relinquish();
+  }
+  {  // folded-BN bias -> shared memory (zero when absent); the region sits behind the barriers
+    float* bs = reinterpret_cast<float*>(smem + (bar0 - base) + 8 * 24 + 16);
+    for (int i = threadIdx.x; i < g.N; i += kSlabThreads) bs[i] = ep.bias ? ep.bias[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      if (RESIDENT_B) {
+        // all weight K blocks, once (n_tiles == 1 in this mode)
+        mbar_arrive_expect_tx(BAR(kBarBFull), (uint32_t)KB * b_tile);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_base + kb * b_tile, &maps.b, kb * BK, 0, BAR(kBarBFull));
+      }
+      uint32_t si = 0, bi = 0;  // slab / weight-ring counters
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+        const int n_base = (int)(tile % g.n_tiles) * BN;
+        const int64_t mt = tile / g.n_tiles;
+        const int band = (int)(mt % g.nb);
+        const int n0 = (int)((mt / g.nb) * g.F);
+        const int hstart = band * g.hb;
+        for (int cb = 0; cb < g.cpb; ++cb, ++si) {
+          const int sb = si & 1;
+          mbar_wait(BAR(2 + sb), ((si >> 1) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(BAR(0 + sb), g.slab_tx);
+          tma_load_4d(base + sb * slab_bytes, &maps.a, cb * BK, -1, hstart - 1, n0, BAR(0 + sb));
+          if (!RESIDENT_B) {
+            for (int tap = 0; tap < 9; ++tap, ++bi) {
+              const int bs = bi % g.b_stages;
+              mbar_wait(BAR(kBarBEmpty + bs), ((bi / g.b_stages) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(BAR(kBarBFull + bs), b_tile);
+              tma_load_2d(w_base + bs * b_tile, &maps.b, (tap * g.cpb + cb) * BK, n_base, BAR(kBarBFull + bs));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      uint32_t si = 0, bi = 0, tl = 0;
+      if (RESIDENT_B) {
+        mbar_wait(BAR(kBarBFull), 0);
+        tc_fence_after();
+      }
+      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+        mbar_wait(BAR(6 + acc), aph ^ 1u);
+        tc_fence_after();
+        for (int cb = 0; cb < g.cpb; ++cb, ++si) {
+          const int sb = si & 1;
+          mbar_wait(BAR(0 + sb), (si >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t slab_lo = desc_lo(base + sb * slab_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t w_lo;
+            int bs = 0;
+            if (RESIDENT_B) {
+              w_lo = desc_lo(w_base + (uint32_t)(tap * g.cpb + cb) * b_tile);
+            } else {
+              bs = bi % g.b_stages;
+              mbar_wait(BAR(kBarBFull + bs), (bi / g.b_stages) & 1u);
+              tc_fence_after();
+              w_lo = desc_lo(w_base + bs * b_tile);
+            }
+            const int fr = tap / 3, fs = tap - fr * 3;
+            // descriptor low words count 16-byte units: one slab row = 8, one accumulator block (128 rows) = 1024
+            uint32_t a_lo = slab_lo + (uint32_t)(fr * g.Wp + fs) * 8u;
+            uint32_t d_tmem = tmem_acc + acc * acc_cols;
+            const uint32_t first = (cb | tap) != 0;
+            for (int m = 0; m < g.mb; ++m, a_lo += 1024u, d_tmem += BN) {
+              umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
+              umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
+              umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
+              umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+            }
+            if (!RESIDENT_B) {
+              umma_commit(BAR(kBarBEmpty + bs));
+              ++bi;
+            }
+          }
+          umma_commit(BAR(2 + sb));
+        }
+        umma_commit(BAR(4 + acc));
+      }
+    }
+  } else {
+    // ================= epilogue: warps 2..9 =================
+    // A tile has mb * (BN/32) units of 128 rows x 32 columns; unit u = (m, j) is handled by the four warps of
+    // group (u & 1) (one TMEM lane quarter each).  The residual of every unit a thread owns is requested BEFORE
+    // the wait on the accumulator, so its latency hides behind the tile's MMAs; the folded-BN bias sits in smem.
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;  // 0 or 1
+    uint32_t tl = 0;
+    const int per_frame = g.Hs * g.Wp;
+    constexpr int kJ = BN / 32;
+    constexpr int kMaxUnits = 4;  // per warp and tile (mb * kJ <= 8)
+    const float* bias_s = reinterpret_cast<const float*>(smem + (bar0 - base) + 8 * 24 + 16);
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      const int n_base = (int)(tile % g.n_tiles) * BN;
+      const int64_t mt = tile / g.n_tiles;
+      const int band = (int)(mt % g.nb);
+      const int64_t n0 = (mt / g.nb) * g.F;
+      const int hstart = band * g.hb;
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      const int units = g.mb * kJ;
+      int64_t mo[kMaxUnits];
+      uint4 rb[kMaxUnits][4];
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = grp + 2 * i;
+        mo[i] = -1;
+        if (u < units) {
+          const int m = u / kJ, j = u - m * kJ;
+          const int p = m * 128 + q * 32 + lane;  // position in the padded grid of the slab
+          const int f = p / per_frame;
+          const int rem = p - f * per_frame;
+          const int y = rem / g.Wp;
+          const int x = rem - y * g.Wp;
+          if (f < g.F && y < g.hb && x < g.OW && n0 + f < g.n_frames && hstart + y < g.OH)
+            mo[i] = ((n0 + f) * g.OH + hstart + y) * g.OW + x;
+          if (mo[i] >= 0 && ep.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + mo[i] * ep.ldc + n_base + j * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
+          }
+        }
+      }
+      mbar_wait(BAR(4 + acc), aph);
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i) {
+        const int u = grp + 2 * i;
+        if (u < units) {  // warp-uniform
+          const int m = u / kJ, j = u - m * kJ;
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + acc * acc_cols + (uint32_t)m * BN + (uint32_t)j * 32 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (mo[i] >= 0) {
+            const int nc = n_base + j * 32;
+            float f32[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) f32[c] = __uint_as_float(v[c]) + bias_s[nc + c];
+            if (ep.residual) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float2 a = unpack_bf16x2(rb[i][c].x), b2 = unpack_bf16x2(rb[i][c].y);
+                const float2 c2 = unpack_bf16x2(rb[i][c].z), d2 = unpack_bf16x2(rb[i][c].w);
+                f32[8 * c + 0] += a.x;  f32[8 * c + 1] += a.y;  f32[8 * c + 2] += b2.x; f32[8 * c + 3] += b2.y;
+                f32[8 * c + 4] += c2.x; f32[8 * c + 5] += c2.y; f32[8 * c + 6] += d2.x; f32[8 * c + 7] += d2.y;
+              }
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) f32[c] = fmaxf(f32[c], 0.f);
+            }
+            uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + mo[i] * ep.ldc + nc);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 o;
+              o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
+              o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
+              o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
+              o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
+              cp[c] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(6 + acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_acc, tmem_cols);
+  }
+}
+
+int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int Cin,
+                     int Cout, cudaStream_t st);
+bool slab_supported(int H, int W, int Cin, int Cout, int R, int S, int stride, int pad);
+
+}  // namespace tc
+}  // namespace avvad

@@ -4,7 +4,7 @@
 #include <mutex>
 #include <vector>
 
-#include "gemm_tma.cuh"
+#include "conv_slab.cuh"
 
 namespace avvad {
 namespace tc {
@@ -270,6 +270,9 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
   ep.C = out;
   ep.ldc = Cout;
   ep.relu = relu;
+  if (tc::use_tma() && tc::slab_supported(H, W, Cin, Cout, R, S, stride, pad))
+    return tc::launch_slab_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, Cin, Cout,
+                                (cudaStream_t)stream);
   if (tc::use_tma() && OW <= 128)
     return tc::launch_tma_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, W, Cin, Cout, R, S,
                                stride, pad, bn_override(), (cudaStream_t)stream);

@@ -129,6 +129,22 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
       : "memory");
 }
+// Same instruction with the two descriptors given as (low word, shared high word): the high word of a K-major
+// SWIZZLE_128B descriptor (SBO, version, layout) is constant, so stepping a descriptor is one 32-bit add on the
+// low word ((address >> 4) | LBO << 16) -- keeps the single issuing thread ahead of 48-cycle MMAs.
+constexpr uint32_t kDescHi = (64u) | (1u << 14) | (2u << 29);  // SBO=1024>>4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(kDescHi)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

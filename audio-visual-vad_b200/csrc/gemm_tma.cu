@@ -77,6 +77,16 @@ static int encode2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t out
   return AVVAD_OK;
 }
 
+int encode_act_map(CUtensorMap* m, const void* ptr, int Cin, int W, int H, int64_t n, const uint32_t box[4],
+                   const uint32_t estr[4]) {
+  const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+  const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+  return encode4(m, ptr, dims, strides, box, estr);
+}
+int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t bn) {
+  return encode2(m, ptr, K, N, K * 2, 64, bn);
+}
+
 template <int BN>
 static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {

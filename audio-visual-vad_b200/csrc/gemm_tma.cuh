@@ -184,11 +184,12 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiPa
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(bar0 + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sa = base + s * C::kStageBytes;
-          const uint32_t sb = sa + C::kABytes;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d_tmem, make_sw128_desc(sa + k * 32), make_sw128_desc(sb + k * 32), idesc, (kb | k) != 0);
+          const uint32_t a_lo = desc_lo(base + s * C::kStageBytes);
+          const uint32_t b_lo = a_lo + (C::kABytes >> 4);
+          umma_f16_lo(d_tmem, a_lo, b_lo, idesc, kb != 0);
+          umma_f16_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1);
+          umma_f16_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1);
+          umma_f16_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1);
           umma_commit(bar0 + 8 * (S + s));
         }
         umma_commit(bar0 + 8 * (2 * S + acc));
