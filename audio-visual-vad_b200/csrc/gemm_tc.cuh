@@ -212,14 +212,25 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, co
     *reinterpret_cast<uint4*>(ep.hseq + ((int64_t)b * ep.T + ep.t) * H + u0) = hp;
     return;
   }
+  // NOTE: every access to f[] below uses a compile-time index (fully unrolled loops with predicates); a runtime
+  // index would push the array to local memory and turn the whole epilogue into L1 traffic.
   float f[32];
 #pragma unroll
   for (int q = 0; q < 32; ++q) f[q] = __uint_as_float(v[q]);
   const bool full = (n0 + 32 <= N);
   if (ep.bias) {
+    if (full) {
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);  // n0 % 32 == 0 -> 16-byte aligned
 #pragma unroll
-    for (int q = 0; q < 32; ++q)
-      if (full || n0 + q < N) f[q] += ep.bias[n0 + q];
+      for (int q = 0; q < 8; ++q) {
+        const float4 b4 = __ldg(bp + q);
+        f[4 * q + 0] += b4.x; f[4 * q + 1] += b4.y; f[4 * q + 2] += b4.z; f[4 * q + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (n0 + q < N) f[q] += __ldg(ep.bias + n0 + q);
+    }
   }
   if (mode == EPI_BF16) {
     __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.C) + m * ep.ldc + n0;
@@ -249,11 +260,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, co
         cp[q] = o;
       }
     } else {
-      for (int q = 0; q < 32 && n0 + q < N; ++q) {
-        float x = f[q];
-        if (ep.residual) x += __bfloat162float(ep.residual[m * ep.ldc + n0 + q]);
-        if (ep.relu) x = fmaxf(x, 0.f);
-        crow[q] = __float2bfloat16_rn(x);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        if (n0 + q < N) {
+          float x = f[q];
+          if (ep.residual) x += __bfloat162float(ep.residual[m * ep.ldc + n0 + q]);
+          if (ep.relu) x = fmaxf(x, 0.f);
+          crow[q] = __float2bfloat16_rn(x);
+        }
       }
     }
   } else {  // EPI_F32
@@ -267,7 +281,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, co
 #pragma unroll
       for (int q = 0; q < 8; ++q) cp[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
     } else {
-      for (int q = 0; q < 32 && n0 + q < N; ++q) crow[q] = f[q];
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        if (n0 + q < N) crow[q] = f[q];
     }
   }
 }

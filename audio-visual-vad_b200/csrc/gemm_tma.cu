@@ -33,7 +33,7 @@ bool tma_available() { return encode_fn() != nullptr; }
 
 // rank-4 bf16 tensor, dims innermost first
 static int encode4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
-                   const uint32_t box[4], const uint32_t estr[4]) {
+                   const uint32_t box[4], const uint32_t estr[4], bool sw32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -44,8 +44,8 @@ static int encode4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], cons
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {estr[0], estr[1], estr[2], estr[3]};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(rank 4) failed with CUresult " + std::to_string((int)r) + " dims=" +
               std::to_string(dims[0]) + "," + std::to_string(dims[1]) + "," + std::to_string(dims[2]) + "," +
@@ -57,7 +57,7 @@ static int encode4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], cons
 }
 
 static int encode2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes,
-                   uint32_t box_inner, uint32_t box_outer) {
+                   uint32_t box_inner, uint32_t box_outer, bool sw32 = false) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -68,8 +68,8 @@ static int encode2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t out
   cuuint32_t bx[2] = {box_inner, box_outer};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gd, gs, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(rank 2) failed with CUresult " + std::to_string((int)r));
     return AVVAD_ERR_CUDA;
@@ -87,14 +87,14 @@ int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, u
   return encode2(m, ptr, K, N, K * 2, 64, bn);
 }
 
-template <int BN>
+template <int BN, int KE = 64>
 static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {
-  using C = TmaCfg<BN>;
+  using C = TmaCfg<BN, KE>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
   });
   if (attr_err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));
@@ -110,7 +110,7 @@ static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep,
   const unsigned grid = (unsigned)(g.total_tiles < resident ? g.total_tiles : resident);
   void* tok = nullptr;
   prof_begin(st, &tok);
-  tc_tma_kernel<BN><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, ep, epi_mode);
+  tc_tma_kernel<BN, KE><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, ep, epi_mode);
   AVVAD_LAUNCHED();
   prof_end(st, tok, cat, flops);
   return AVVAD_OK;
@@ -138,13 +138,16 @@ static int pick_bn(int N, int hint) {
 }
 
 int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
-                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st) {
+                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st, int cat,
+                    double flops_override) {
   const int OH = (H + 2 * pad - R) / stride + 1;
   const int OW = (W + 2 * pad - S) / stride + 1;
-  AVVAD_CHECK_ARG(OW <= 128 && Cin % 64 == 0, "TMA conv: OW <= 128 and Cin % 64 == 0 required");
+  const int KE = (Cin % 64 == 0) ? 64 : 16;  // 16-channel inputs (packed stem) use 32-byte K blocks
+  AVVAD_CHECK_ARG(OW <= 128 && Cin % KE == 0, "TMA conv: OW <= 128 and Cin % 64 == 0 (or Cin == 16) required");
+  AVVAD_CHECK_ARG(KE == 64 || Cout == 64, "16-channel TMA conv supports Cout == 64 only");
   TmaGeom g{};
   g.mode = 1;
-  g.OH = OH; g.OW = OW; g.stride = stride; g.pad = pad; g.S = S; g.cpb = Cin / 64; g.KB = R * S * (Cin / 64);
+  g.OH = OH; g.OW = OW; g.stride = stride; g.pad = pad; g.S = S; g.cpb = Cin / KE; g.KB = R * S * (Cin / KE);
   g.n_frames = n;
   g.N = Cout;
   const int bn = pick_bn(Cout, bn_hint);
@@ -187,17 +190,19 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
   const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   for (int p = 0; p < 2; ++p) {
     const int hb = g.hb[p], F = g.F[p];
-    const uint32_t box[4] = {64, (uint32_t)((OW - 1) * stride + 1), (uint32_t)((hb - 1) * stride + 1), (uint32_t)F};
-    int rc = encode4(&maps.a[p], in, dims, strides, box, estr);
+    const uint32_t box[4] = {(uint32_t)KE, (uint32_t)((OW - 1) * stride + 1), (uint32_t)((hb - 1) * stride + 1),
+                             (uint32_t)F};
+    int rc = encode4(&maps.a[p], in, dims, strides, box, estr, KE == 16);
     if (rc) return rc;
-    g.bytesA[p] = (uint32_t)F * hb * OW * 128u;
+    g.bytesA[p] = (uint32_t)F * hb * OW * (uint32_t)(KE * 2);
   }
   const int K = R * S * Cin;
-  int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, 64, (uint32_t)bn);
+  int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)KE, (uint32_t)bn, KE == 16);
   if (rc) return rc;
-  g.bytesB = (uint32_t)bn * 128u;
-  const double flops = 2.0 * (double)n * OH * OW * Cout * K;
-  return dispatch(bn, maps, g, ep, EPI_BF16, 0, flops, st);
+  g.bytesB = (uint32_t)bn * (uint32_t)(KE * 2);
+  const double flops = flops_override > 0 ? flops_override : 2.0 * (double)n * OH * OW * Cout * K;
+  if (KE == 16) return launch_bn<64, 16>(maps, g, ep, EPI_BF16, cat, flops, st);
+  return dispatch(bn, maps, g, ep, EPI_BF16, cat, flops, st);
 }
 
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,

@@ -58,19 +58,35 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accum, uint32_t hi) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(hi)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
-template <int BN>
+// KE = bf16 elements per K block: 64 (128-byte rows, SWIZZLE_128B, four K16 UMMAs per block) or 16 (32-byte rows,
+// SWIZZLE_32B, one UMMA per block -- used by the stem convolution whose packed input has 16 "channels").
+template <int BN, int KE = 64>
 struct TmaCfg {
-  static constexpr uint32_t kABytes = BM * 128;
-  static constexpr uint32_t kBBytes = BN * 128;
+  static constexpr uint32_t kRowBytes = KE * 2;
+  static constexpr uint32_t kABytes = BM * kRowBytes;
+  static constexpr uint32_t kBBytes = BN * kRowBytes;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
-  static constexpr int kStages = (BN == 256) ? 4 : ((BN == 128) ? 3 : 4);
+  static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? 3 : 4));
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
+  static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
 };
 
 struct TileCoord {
@@ -98,10 +114,11 @@ __device__ __forceinline__ TileCoord decode_tile(const TmaGeom& g, int64_t tile,
   return t;
 }
 
-template <int BN>
+template <int BN, int KE>
 __global__ void __launch_bounds__(kTmaThreads)
-tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiParams ep, const int epi_mode) {
-  using C = TmaCfg<BN>;
+tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaGeom g, const EpiParams ep,
+              const int epi_mode) {
+  using C = TmaCfg<BN, KE>;
   constexpr int S = C::kStages;
   constexpr uint32_t kTmemCols = 2 * BN;
   extern __shared__ uint8_t smem_raw[];
@@ -153,11 +170,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiPa
           const uint32_t sa = base + s * C::kStageBytes;
           mbar_arrive_expect_tx(full, bytes);
           if (g.mode == 0) {
-            tma_load_4d(sa, &maps.a[0], kb * BK, (int)t.n0, 0, 0, full);
+            tma_load_4d(sa, &maps.a[0], kb * KE, (int)t.n0, 0, 0, full);
           } else {
-            tma_load_4d(sa, &maps.a[t.phase], cb * BK, fs - g.pad, t.hstart * g.stride + fr - g.pad, (int)t.n0, full);
+            tma_load_4d(sa, &maps.a[t.phase], cb * KE, fs - g.pad, t.hstart * g.stride + fr - g.pad, (int)t.n0, full);
           }
-          tma_load_2d(sa + C::kABytes, &maps.b, kb * BK, t.n_base, full);
+          tma_load_2d(sa + C::kABytes, &maps.b, kb * KE, t.n_base, full);
           if (++cb == g.cpb) {
             cb = 0;
             ++tap;
@@ -186,10 +203,12 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiPa
           tc_fence_after();
           const uint32_t a_lo = desc_lo(base + s * C::kStageBytes);
           const uint32_t b_lo = a_lo + (C::kABytes >> 4);
-          umma_f16_lo(d_tmem, a_lo, b_lo, idesc, kb != 0);
-          umma_f16_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1);
-          umma_f16_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1);
-          umma_f16_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1);
+          umma_f16_lo2(d_tmem, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
+          if (KE == 64) {
+            umma_f16_lo2(d_tmem, a_lo + 2, b_lo + 2, idesc, 1, C::kDescHiWord);
+            umma_f16_lo2(d_tmem, a_lo + 4, b_lo + 4, idesc, 1, C::kDescHiWord);
+            umma_f16_lo2(d_tmem, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
+          }
           umma_commit(bar0 + 8 * (S + s));
         }
         umma_commit(bar0 + 8 * (2 * S + acc));
@@ -246,7 +265,8 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const TmaGeom g, const EpiPa
 // host side (gemm_tma.cu)
 bool tma_available();
 int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
-                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st);
+                    int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st, int cat = 0,
+                    double flops_override = 0.0);
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                     const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 

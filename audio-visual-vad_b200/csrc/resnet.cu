@@ -10,7 +10,7 @@
 //                                              LSTM operand columns
 #include <stdlib.h>
 
-#include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace avvad {
 
@@ -32,6 +32,7 @@ static const ConvSpec kSpecs[20] = {
 constexpr int64_t kFrameHW = 67 * 67;
 constexpr int64_t kActBytesPerFrame = 17 * 17 * 64 * 2;  // largest NHWC bf16 activation (after the pool)
 constexpr int64_t kStemBytesPerFrame = 34 * 34 * 64 * 2;  // conv1 output before the pool
+constexpr int64_t kPackBytesPerFrame = 37 * 34 * 16 * 2;  // packed stem input T[37][34][16] bf16
 constexpr int64_t kStemSubChunk = 512;                    // 512 * 148 KB = 76 MB: conv1 -> pool stays L2-resident
 
 // ---- weight folding / packing ----------------------------------------------------------------------
@@ -67,6 +68,89 @@ __global__ void pack_conv1_tc_kernel(const float* __restrict__ w, const float* _
     v = (w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k]) * sc;
   }
   w1b[idx] = __float2bfloat16_rn(v);
+}
+
+// Stem input packing (space-to-depth with the horizontal window baked in):
+//   T[n][y][x][j*4 + b*2 + d] = P[2y+b][2(x+j)+d],  P = frame zero-padded by 3,  y in [0,37), x in [0,34), j in [0,4)
+// so the 7x7/stride-2 convolution becomes a 4x1 / stride-1 convolution over 16 "channels":
+//   out[oh][ow][o] = sum_{a<4} sum_{k<16} W'[o][a*16+k] * T[oh+a][ow][k],  W'[o][a*16 + j*4+b*2+d] = w[o][2a+b][2j+d]
+// and each filter row `a` is one 32-byte K16 slice that a TMA box can fetch.
+__global__ void stem_pack_kernel(const float* __restrict__ frames, int64_t n_frames, __nv_bfloat16* __restrict__ T) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = n_frames * 37 * 34;
+  if (idx >= total) return;
+  const int x = (int)(idx % 34);
+  const int y = (int)((idx / 34) % 37);
+  const int64_t n = idx / (34 * 37);
+  const float* f = frames + n * (67 * 67);
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int r = 2 * y + b - 3;
+      const int c0 = 2 * (x + j) - 3;
+      const bool rok = (unsigned)r < 67u;
+      const float v0 = (rok && (unsigned)c0 < 67u) ? __ldg(f + r * 67 + c0) : 0.f;
+      const float v1 = (rok && (unsigned)(c0 + 1) < 67u) ? __ldg(f + r * 67 + c0 + 1) : 0.f;
+      pk[j * 2 + b] = pack_bf16x2(v0, v1);
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(T + idx * 16);
+  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// Stem im2col rows: A[m][r*7+s] = frame[2oh-3+r][2ow-3+s] (zero outside), m = (n*34+oh)*34+ow, bf16 [M][64]
+// (columns 49..63 zero).  128-byte rows make the following K=64 GEMM a stream of 16 KB contiguous TMA boxes.
+__global__ void stem_im2col_kernel(const float* __restrict__ frames, int64_t n_frames, __nv_bfloat16* __restrict__ A) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_frames * 1156) return;
+  const int64_t n = m / 1156;
+  const int rem = (int)(m - n * 1156);
+  const int oh = rem / 34, ow = rem - oh * 34;
+  const float* f = frames + n * (67 * 67);
+  const int ih0 = 2 * oh - 3, iw0 = 2 * ow - 3;
+  float v[50];
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const int ih = ih0 + r;
+    const bool rok = (unsigned)ih < 67u;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+      const int iw = iw0 + c;
+      v[r * 7 + c] = (rok && (unsigned)iw < 67u) ? __ldg(f + ih * 67 + iw) : 0.f;
+    }
+  }
+  v[49] = 0.f;
+  uint4* o = reinterpret_cast<uint4*>(A + m * 64);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = c * 8 + q * 2;
+      w[q] = (k < 50) ? pack_bf16x2(v[k], k + 1 < 50 ? v[k + 1] : 0.f) : 0u;
+    }
+    o[c] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// conv1 weights for the packed stem: bf16 [64 out][64 k], k = a*16 + j*4 + b*2 + d  <->  tap (r=2a+b, s=2j+d)
+__global__ void pack_conv1_s2d_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ w1s) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int o = idx / 64, k = idx % 64;
+  const int a = k / 16, j = (k % 16) / 4, b = (k % 4) / 2, d = k % 2;
+  const int r = 2 * a + b, s = 2 * j + d;
+  float v = 0.f;
+  if (r < 7 && s < 7) {
+    const float sc = gamma[o] / sqrtf(var[o] + eps);
+    const int tap = r * 7 + s;
+    v = (w[(o * 3 + 0) * 49 + tap] + w[(o * 3 + 1) * 49 + tap] + w[(o * 3 + 2) * 49 + tap]) * sc;
+  }
+  w1s[idx] = __float2bfloat16_rn(v);
 }
 
 // NHWC bf16 3x3 / stride 2 / pad 1 max pool (inputs are post-ReLU, so clipping the window == -inf padding)
@@ -259,7 +343,8 @@ struct avvad_resnet18 {
   __nv_bfloat16* w[20];
   float* bias[20];
   float* w1;  // conv1 folded fp32 [49][64] (direct-conv stem, AVVAD_STEM=simt)
-  __nv_bfloat16* w1b;  // conv1 folded bf16 [64][64] (tensor-core stem)
+  __nv_bfloat16* w1b;  // conv1 folded bf16 [64][64], k = r*7+s (cp.async stem, AVVAD_STEM=cpasync)
+  __nv_bfloat16* w1s;  // conv1 folded bf16 [64][64] in packed-stem K order (TMA stem, default)
   bool set[20];
   bool smem_attr;
 };
@@ -274,6 +359,7 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
   }
   h->w1 = nullptr;
   h->w1b = nullptr;
+  h->w1s = nullptr;
   h->smem_attr = false;
   for (int i = 0; i < 20; ++i) {
     const ConvSpec& s = kSpecs[i];
@@ -281,6 +367,7 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     if (i == 0) {
       AVVAD_CUDA(cudaMalloc(&h->w1, sizeof(float) * 49 * 64));
       AVVAD_CUDA(cudaMalloc(&h->w1b, sizeof(__nv_bfloat16) * 64 * 64));
+      AVVAD_CUDA(cudaMalloc(&h->w1s, sizeof(__nv_bfloat16) * 64 * 64));
     } else {
       AVVAD_CUDA(cudaMalloc(&h->w[i], sizeof(__nv_bfloat16) * (size_t)s.cout * s.cin * s.k * s.k));
     }
@@ -297,6 +384,7 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
   }
   cudaFree(h->w1);
   cudaFree(h->w1b);
+  cudaFree(h->w1s);
   delete h;
 }
 
@@ -311,6 +399,8 @@ extern "C" int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float
     pack_conv1_kernel<<<(49 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, h->w1, h->bias[0]);
     AVVAD_LAUNCHED();
     pack_conv1_tc_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, var, bn_eps, h->w1b);
+    AVVAD_LAUNCHED();
+    pack_conv1_s2d_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, var, bn_eps, h->w1s);
   } else {
     const int total = s.cout * s.cin * s.k * s.k;
     pack_conv_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, s.cout, s.cin, s.k,
@@ -330,7 +420,9 @@ extern "C" size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk
   if (n_frames <= 0) return 0;
   const int64_t mc = chunk_of(n_frames, chunk_frames);
   const int64_t sub = mc < kStemSubChunk ? mc : kStemSubChunk;
-  return (size_t)(4 * align_up((size_t)mc * kActBytesPerFrame, 1024)) + align_up((size_t)sub * kStemBytesPerFrame, 1024);
+  (void)sub;
+  return (size_t)(4 * align_up((size_t)mc * kActBytesPerFrame, 1024)) +
+         align_up((size_t)kStemSubChunk * 2 * kStemBytesPerFrame, 1024);  // stem output + im2col rows, <= 512 frames each
 }
 
 static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const __nv_bfloat16* residual,
@@ -342,17 +434,69 @@ static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const
 
 // Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
 // Returns the buffer index holding the last produced activation in *last.
-static bool stem_simt() {
+// 0 = im2col pack + TMA GEMM (default), 1 = direct fp32 conv, 2 = cp.async im2col producer, 3 = K16/SWIZZLE_32B boxes
+static int stem_mode() {
   static int v = [] {
     const char* e = getenv("AVVAD_STEM");
-    return (e && std::string(e) == "simt") ? 1 : 0;
+    if (e && std::string(e) == "simt") return 1;
+    if (e && std::string(e) == "cpasync") return 2;
+    if (e && std::string(e) == "k16") return tc::tma_available() ? 3 : 2;
+    return tc::tma_available() ? 0 : 2;
   }();
-  return v != 0;
+  return v;
 }
 
 static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4],
                            __nv_bfloat16* stem, int upto, int* last, cudaStream_t st) {
-  if (stem_simt()) {
+  if (stem_mode() == 0) {
+    // stem = im2col pack (bandwidth kernel) -> plain K=64 tcgen05 GEMM fed by 16 KB contiguous TMA boxes with fused
+    // bias+ReLU -> max-pool; 256-frame sub-chunks keep both 38 MB intermediates L2-resident.
+    static const int64_t kSub = [] {
+      const char* e = getenv("AVVAD_STEM_SUB");
+      int64_t v = e ? atoll(e) : 256;
+      return (v >= 64 && v <= 512) ? v : 256;  // workspace holds 512 frames of stem output + 512 of im2col rows
+    }();
+    __nv_bfloat16* cols = stem + kSub * (kStemBytesPerFrame / 2);
+    for (int64_t f0 = 0; f0 < n; f0 += kSub) {
+      const int64_t nn = (n - f0 < kSub) ? (n - f0) : kSub;
+      const int64_t M = nn * 1156;
+      stem_im2col_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(frames + f0 * kFrameHW, nn, cols);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.bias = h->bias[0];
+      ep.C = stem;
+      ep.ldc = 64;
+      ep.relu = 1;
+      int rc = tc::gemm_dispatch(cols, 64, h->w1b, 64, M, 64, 64, ep, tc::EPI_BF16, 64, st);
+      if (rc) return rc;
+      const int64_t total = nn * 17 * 17 * 8;
+      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
+                                                                          buf[0] + f0 * 17 * 17 * 64);
+      AVVAD_LAUNCHED();
+    }
+  } else if (stem_mode() == 3) {
+    // stem on TMA boxes: pack -> 4x1 conv over 16 packed channels (K16 / SWIZZLE_32B) -> bias+ReLU -> max-pool,
+    // sub-chunked so the 34x34x64 intermediate stays in L2.  The pack buffer lives behind the stem scratch.
+    __nv_bfloat16* packed = stem + kStemSubChunk * (kStemBytesPerFrame / 2);
+    for (int64_t f0 = 0; f0 < n; f0 += kStemSubChunk) {
+      const int64_t nn = (n - f0 < kStemSubChunk) ? (n - f0) : kStemSubChunk;
+      const int64_t tot = nn * 37 * 34;
+      stem_pack_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(frames + f0 * kFrameHW, nn, packed);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.bias = h->bias[0];
+      ep.C = stem;
+      ep.ldc = 64;
+      ep.relu = 1;
+      int rc = tc::launch_tma_conv(packed, h->w1s, ep, nn, 37, 34, 16, 64, 4, 1, 1, 0, 64, st, 3,
+                                   2.0 * (double)nn * 1156 * 64 * 49);
+      if (rc) return rc;
+      const int64_t total = nn * 17 * 17 * 8;
+      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
+                                                                          buf[0] + f0 * 17 * 17 * 64);
+      AVVAD_LAUNCHED();
+    }
+  } else if (stem_mode() == 1) {
     if (!h->smem_attr) {
       AVVAD_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1Smem));
       h->smem_attr = true;
