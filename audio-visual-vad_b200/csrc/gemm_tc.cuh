@@ -540,6 +540,8 @@ tc_gemm_kernel(AParams ap, const __nv_bfloat16* __restrict__ Wt, int64_t ldw, in
 // ---- host-side launcher -----------------------------------------------------------------------------
 int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
            const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
+int prof_begin(cudaStream_t st, void** tok);
+void prof_end(cudaStream_t st, void* tok, int cat, double flops);
 int gemm_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                   const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 

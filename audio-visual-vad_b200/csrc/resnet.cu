@@ -10,7 +10,10 @@
 //                                              LSTM operand columns
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "gemm_tma.cuh"
+#include "stem_fused.cuh"
 
 namespace avvad {
 
@@ -434,14 +437,17 @@ static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const
 
 // Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
 // Returns the buffer index holding the last produced activation in *last.
-// 0 = im2col pack + TMA GEMM (default), 1 = direct fp32 conv, 2 = cp.async im2col producer, 3 = K16/SWIZZLE_32B boxes
+// 0 = fused stem kernel (default), 1 = direct fp32 conv, 2 = cp.async im2col producer, 3 = K16/SWIZZLE_32B boxes,
+// 4 = im2col pack + TMA GEMM + separate pool
 static int stem_mode() {
   static int v = [] {
     const char* e = getenv("AVVAD_STEM");
     if (e && std::string(e) == "simt") return 1;
     if (e && std::string(e) == "cpasync") return 2;
     if (e && std::string(e) == "k16") return tc::tma_available() ? 3 : 2;
-    return tc::tma_available() ? 0 : 2;
+    if (e && std::string(e) == "gemm") return 4;
+    if (e && std::string(e) == "fused") return 0;
+    return 0;
   }();
   return v;
 }
@@ -449,6 +455,25 @@ static int stem_mode() {
 static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4],
                            __nv_bfloat16* stem, int upto, int* last, cudaStream_t st) {
   if (stem_mode() == 0) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+      attr_err = cudaFuncSetAttribute(tc::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::kStemSmem);
+    });
+    AVVAD_CUDA(attr_err);
+    static int num_sms = [] {
+      int dev = 0, v = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+      return v > 0 ? v : 148;
+    }();
+    const unsigned grid = (unsigned)(n < num_sms ? n : num_sms);
+    void* tok = nullptr;
+    tc::prof_begin(st, &tok);
+    tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(frames, n, h->w1b, h->bias[0], buf[0]);
+    AVVAD_LAUNCHED();
+    tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
+  } else if (stem_mode() == 4) {
     // stem = im2col pack (bandwidth kernel) -> plain K=64 tcgen05 GEMM fed by 16 KB contiguous TMA boxes with fused
     // bias+ReLU -> max-pool; 256-frame sub-chunks keep both 38 MB intermediates L2-resident.
     static const int64_t kSub = [] {
