@@ -77,6 +77,33 @@ static int encode2(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t out
   return AVVAD_OK;
 }
 
+// generic rank-N (<= 5) bf16 SWIZZLE_128B map, unit traversal strides
+int encode_tiled_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || rank < 1 || rank > 5) {
+    set_error("cuTensorMapEncodeTiled unavailable or bad rank");
+    return AVVAD_ERR_CUDA;
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i < rank - 1) gs[i] = strides_bytes[i];
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(rank " + std::to_string(rank) + ") failed with CUresult " +
+              std::to_string((int)r));
+    return AVVAD_ERR_CUDA;
+  }
+  return AVVAD_OK;
+}
+
 int encode_act_map(CUtensorMap* m, const void* ptr, int Cin, int W, int H, int64_t n, const uint32_t box[4],
                    const uint32_t estr[4]) {
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};

@@ -9,7 +9,12 @@
 // step is one tcgen05 GEMM h_{t-1}*W_hh^T whose epilogue fuses the gate non-linearities, the cell update, the
 // length mask and the bf16 store of h_t (both as next-step operand and as layer output).  Weight rows are
 // re-ordered gate-interleaved (row 4u+g) so that one epilogue thread owns all four gates of a hidden unit.
-#include "gemm_tc.cuh"
+#include <stdlib.h>
+
+#include <mutex>
+#include <string>
+
+#include "lstm_persist.cuh"
 
 namespace avvad {
 
@@ -177,6 +182,13 @@ extern "C" int avvad_lstm_set_head(avvad_lstm* h, const float* w, const float* b
 
 extern "C" int64_t avvad_lstm_input_ld(const avvad_lstm* h) { return h ? h->ld0 : 0; }
 
+namespace avvad {
+namespace tc {
+int encode_tiled_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
+}
+}  // namespace avvad
+
 namespace {
 struct LstmWs {
   float* xproj;
@@ -184,6 +196,7 @@ struct LstmWs {
   __nv_bfloat16* hbuf[2];
   float* c;
   __nv_bfloat16* hlast;
+  unsigned int* counters;
   size_t total;
 };
 LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
@@ -202,6 +215,7 @@ LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
   w.hbuf[1] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.c = (float*)take((size_t)B * H * sizeof(float));
   w.hlast = (__nv_bfloat16*)take((size_t)B * H * 2);
+  w.counters = (unsigned int*)take(256);
   w.total = off;
   return w;
 }
@@ -210,6 +224,77 @@ LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
 extern "C" size_t avvad_lstm_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T) {
   if (!h || B <= 0 || T <= 0) return 0;
   return carve(h, B, T, nullptr).total;
+}
+
+// ---- persistent recurrence (one cooperative launch per layer and batch group) ---------------------------------
+static int persist_mode() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_LSTM");
+    if (e && std::string(e) == "steps") return 0;
+    return tc::tma_available() ? 1 : 0;
+  }();
+  return v;
+}
+
+static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, __nv_bfloat16* hseq,
+                                     const int32_t* lengths, int64_t B, int64_t T, unsigned int* counters,
+                                     cudaStream_t st, bool* done) {
+  *done = false;
+  const int H = h->H;
+  if (!persist_mode() || H % 64 != 0 || H > 1024 || T < 1) return AVVAD_OK;
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  static int coop = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    return v;
+  }();
+  const int n_slices = 4 * H / 64;
+  const int max_ms = num_sms / n_slices;
+  if (!coop || max_ms < 1) return AVVAD_OK;
+  const size_t smem = (size_t)(H / 64) * 8192 + tc::kLstmStages * 16384 + 256 + 1024;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [smem] {
+    attr_err = cudaFuncSetAttribute(tc::lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  AVVAD_CUDA(attr_err);
+  const int64_t Bg = (int64_t)max_ms * 128;
+  for (int64_t g0 = 0; g0 < B; g0 += Bg) {
+    const int64_t Bc = (B - g0 < Bg) ? (B - g0) : Bg;
+    const int m_slices = (int)((Bc + 127) / 128);
+    tc::LstmMaps maps;
+    __nv_bfloat16* hs = hseq + g0 * T * H;
+    const uint64_t hd[3] = {(uint64_t)H, (uint64_t)T, (uint64_t)Bc};
+    const uint64_t hstr[2] = {(uint64_t)H * 2, (uint64_t)T * H * 2};
+    const uint32_t hbox[3] = {64, 1, 128};
+    int rc = tc::encode_tiled_bf16(&maps.h, hs, 3, hd, hstr, hbox);
+    if (rc) return rc;
+    const uint64_t wd[2] = {(uint64_t)H, (uint64_t)4 * H};
+    const uint64_t wstr[1] = {(uint64_t)H * 2};
+    const uint32_t wbox[2] = {64, 64};
+    rc = tc::encode_tiled_bf16(&maps.w, h->w_hh[l], 2, wd, wstr, wbox);
+    if (rc) return rc;
+    tc::LstmGeom g{};
+    g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64; g.n_slices = n_slices;
+    g.xproj = xproj + g0 * T * 4 * H;
+    g.hseq = hs;
+    g.lengths = lengths + g0;
+    g.counters = counters;
+    AVVAD_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+    void* args[2] = {(void*)&maps, (void*)&g};
+    void* tok = nullptr;
+    tc::prof_begin(st, &tok);
+    AVVAD_CUDA(cudaLaunchCooperativeKernel((const void*)tc::lstm_persist_kernel, dim3(n_slices * m_slices),
+                                           dim3(tc::kLstmThreads), args, smem, st));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    tc::prof_end(st, tok, 2, 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1));
+  }
+  *done = true;
+  return AVVAD_OK;
 }
 
 static int run_head(avvad_lstm* h, const __nv_bfloat16* hs, int64_t rows, float* logits, float* post, int32_t* dec,
@@ -264,7 +349,15 @@ extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32
     // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'
     int rc = avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4, ld_in, st);
     if (rc) return rc;
-    // (2) recurrence
+    // (2) recurrence: one persistent cooperative kernel per layer, or (fallback) one GEMM launch per time step
+    bool done = false;
+    rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done);
+    if (rc) return rc;
+    if (done) {
+      layer_in = layer_out;
+      ld_in = H;
+      continue;
+    }
     AVVAD_CUDA(cudaMemsetAsync(ws.hbuf[0], 0, (size_t)B * H * 2, st));
     AVVAD_CUDA(cudaMemsetAsync(ws.c, 0, (size_t)B * H * sizeof(float), st));
     for (int t = 0; t < (int)T; ++t) {
