@@ -542,6 +542,8 @@ int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, i
            const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 int prof_begin(cudaStream_t st, void** tok);
 void prof_end(cudaStream_t st, void* tok, int cat, double flops);
+int prof_group_begin(cudaStream_t st, void** tok);
+void prof_group_end(cudaStream_t st, void* tok, int cat, double flops);
 int gemm_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                   const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 

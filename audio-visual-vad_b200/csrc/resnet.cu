@@ -553,6 +553,13 @@ static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __
   int cur = 0;
   *last = cur;
   if (upto == 0) return AVVAD_OK;
+  // one profiling record for the chunk's 19 implicit-GEMM convolutions (216,633,600 - 3,625,216 MAC per frame)
+  void* gtok = nullptr;
+  if (upto >= 20) tc::prof_group_begin(st, &gtok);
+  struct GroupEnd {
+    cudaStream_t st; void* tok; double flops;
+    ~GroupEnd() { tc::prof_group_end(st, tok, 0, flops); }
+  } group_end{st, gtok, 2.0 * (double)n * (216633600.0 - 1156.0 * 64.0 * 49.0)};
   int layer = 1;
   for (int stage = 0; stage < 4; ++stage) {
     for (int blk = 0; blk < 2; ++blk) {

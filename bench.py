@@ -271,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     launches = E.launch_count() - l0
     clocks = sampler.stop()
-    if os.environ.get("AVVAD_LAYER_DUMP") and rank == 0:
+    if os.environ.get("AVVAD_LAYER_DUMP") and rank == 0:  # needs AVVAD_PROFILE_PER_LAUNCH=1 for per-layer rows
         # per-layer table of the implicit-GEMM convolutions (grouped by algorithmic FLOPs per launch)
         lms, lfl = E.profile_dump(0)
         rows = {}
@@ -331,9 +331,16 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(hp.numel() * 4 + hd.numel() * 4) * world},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "tc_gemm_kernel<BN,A_CONV> (tcgen05 implicit-GEMM conv, 19 layers)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "tcgen05 implicit-GEMM convolutions of the ResNet-18 trunk (19 layers: tc_tma_kernel "
+                               "<BN=128/256> TMA-box im2col, tc_slab_kernel<64> for layer1)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak_tf) if achieved else None,
+                     # dram__bytes_read+write per conv launch, averaged over the 19 launches of one 2048-frame chunk
+                     # (profiles/r01_final_trunk_ncu.md; ncu --set full, one capture)
+                     "traffic": 67.39e6, "traffic_unit": "bytes per launch (ncu dram bytes, avg of 19 launches)",
+                     "algorithmic_flops_per_frame": 2 * CONV_MAC_PER_FRAME,
+                     "peak_source": peak_src,
                      "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
                      "flops_per_launch_avg": conv_flops / conv_n if conv_n else None},
