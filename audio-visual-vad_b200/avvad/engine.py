@@ -333,3 +333,79 @@ def profile_dump(cat: int, max_n=200000):
     fl = (C.c_double * max_n)()
     n = int(L.lib().avvad_profile_dump(cat, ms, fl, max_n))
     return np.frombuffer(ms, dtype=np.float64, count=n).copy(), np.frombuffer(fl, dtype=np.float64, count=n).copy()
+
+
+def batch_bce(logits: torch.Tensor, target: torch.Tensor, lengths, eps=1e-8, want_grad=False):
+    """Sum over utterances of the per-utterance mean BCE (scripts/train_AV_net.py:298-301).
+    Returns (loss 0-dim, per_utterance (B,), dlogits or None)."""
+    L.require_cuda(logits, target)
+    B, T, Y = logits.shape
+    lg = logits.detach().to(torch.float32).contiguous()
+    tg = target.detach().to(torch.float32).contiguous()
+    lens = _i32(lengths, lg.device)
+    loss = torch.empty(1, dtype=torch.float32, device=lg.device)
+    per = torch.empty(B, dtype=torch.float32, device=lg.device)
+    grad = torch.empty_like(lg) if want_grad else None
+    L.check(L.lib().avvad_bce_loss(L.ptr(lg), L.ptr(tg), L.ptr(lens), B, T, Y, eps, L.ptr(loss), L.ptr(per),
+                                   L.ptr(grad), L.stream_ptr()))
+    return loss[0], per, grad
+
+
+def batch_f1(logits: torch.Tensor, target: torch.Tensor, lengths, epsilon=1e-8):
+    """Per-utterance (accuracy, precision, recall, f1) of sigmoid(logit) > 0.5 (packages/models/utils.py:164-203).
+    logits/target (B,T) or (B,T,1).  Returns (metrics (B,4), decisions (B,T) int32)."""
+    L.require_cuda(logits, target)
+    lg = logits.detach().to(torch.float32).reshape(logits.shape[0], -1).contiguous()
+    tg = target.detach().to(torch.float32).reshape(target.shape[0], -1).contiguous()
+    B, T = lg.shape
+    lens = _i32(lengths, lg.device)
+    met = torch.empty(B, 4, dtype=torch.float32, device=lg.device)
+    dec = torch.empty(B, T, dtype=torch.int32, device=lg.device)
+    L.check(L.lib().avvad_f1_metrics(L.ptr(lg), L.ptr(tg), L.ptr(lens), B, T, epsilon, L.ptr(met), L.ptr(dec),
+                                     L.stream_ptr()))
+    return met, dec
+
+
+class WaveNetEncoder:
+    """Dilated valid Conv1d encoder on the tcgen05 GEMM engine."""
+
+    def __init__(self, filter_width, quantization_channel, dilations, residual_channel, dilation_channel,
+                 bottleneck_width, pool_size):
+        dil = (C.c_int32 * len(dilations))(*[int(d) for d in dilations])
+        h = C.c_void_p()
+        L.check(L.lib().avvad_wavenet_create(C.byref(h), filter_width, quantization_channel, dil, len(dilations),
+                                             residual_channel, dilation_channel, bottleneck_width, pool_size))
+        self.h = h
+        self.n_dil = len(dilations)
+        self.bottleneck, self.pool = bottleneck_width, pool_size
+        self.ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                L.lib().avvad_wavenet_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def load(self, sd: Dict[str, torch.Tensor], device):
+        def put(kind, index, name):
+            w = _f32(sd[name + ".weight"], device)
+            b = _f32(sd[name + ".bias"], device) if (name + ".bias") in sd else None
+            L.check(L.lib().avvad_wavenet_set_layer(self.h, kind, index, L.ptr(w), L.ptr(b), L.stream_ptr()))
+            return w, b
+        keep = [put(0, 0, "en_causal_layer"), put(3, 0, "bottleneck_layer")]
+        for i in range(self.n_dil):
+            keep.append(put(1, i, f"en_dilation_layer_stack.{i}"))
+            keep.append(put(2, i, f"en_dense_layer_stack.{i}"))
+        torch.cuda.current_stream().synchronize()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L.require_cuda(x)
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, N = x.shape
+        nbytes = L.lib().avvad_wavenet_workspace_bytes(self.h, B, N)
+        ws = self.ws.get(nbytes, x.device)
+        out = torch.empty(B, self.bottleneck, self.pool, dtype=torch.float32, device=x.device)
+        L.check(L.lib().avvad_wavenet_encode(self.h, L.ptr(x), B, N, L.ptr(ws), ws.numel(), L.ptr(out), L.stream_ptr()))
+        return out

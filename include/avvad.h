@@ -197,6 +197,37 @@ int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths
                        void* workspace, size_t workspace_bytes, float* logits, float* post,
                        int32_t* dec, float* last_logits, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-loop loss and metrics over padded batches
+ * replaces: the per-utterance Python loops of scripts/train_AV_net.py:298-301 (sum over utterances of
+ *           packages/models/utils.py:113 binary_cross_entropy) and :311-329 (packages/models/utils.py:164-203 f1_loss).
+ * ---------------------------------------------------------------------------------------- */
+/* logits,target: f32 [B][T][y_dim]; lengths i32 [B]; loss f32[1]; per_utt f32[B] (per-utterance mean BCE);
+ * dlogits: optional f32 [B][T][y_dim] = d loss / d logits (zero on padded steps). */
+int avvad_bce_loss(const float* logits, const float* target, const int32_t* lengths, int32_t B, int32_t T,
+                   int32_t y_dim, float eps, float* loss, float* per_utt, float* dlogits, void* stream);
+/* y_dim == 1.  metrics f32 [B][4] = (accuracy, precision, recall, f1) per utterance; dec optional i32 [B][T]. */
+int avvad_f1_metrics(const float* logits, const float* target, const int32_t* lengths, int32_t B, int32_t T,
+                     float epsilon, float* metrics, int32_t* dec, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * WaveNet-style encoder (unused by the reference's scripts but on the path by north_star decree)
+ * replaces: packages/models/wavenet_autoencoder.py:74-93 (_encode).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct avvad_wavenet avvad_wavenet;
+int avvad_wavenet_create(avvad_wavenet** out, int filter_width, int quantization_channel, const int32_t* dilations,
+                         int n_dilations, int residual_channel, int dilation_channel, int bottleneck_width,
+                         int pool_size);
+void avvad_wavenet_destroy(avvad_wavenet* h);
+/* kind: 0 en_causal_layer, 1 en_dilation_layer_stack[index], 2 en_dense_layer_stack[index], 3 bottleneck_layer.
+ * w: torch Conv1d weight f32 [O][I][k]; bias f32 [O] or NULL. */
+int avvad_wavenet_set_layer(avvad_wavenet* h, int kind, int index, const float* w, const float* bias, void* stream);
+int64_t avvad_wavenet_encoded_length(const avvad_wavenet* h, int64_t n_samples);
+size_t avvad_wavenet_workspace_bytes(const avvad_wavenet* h, int64_t B, int64_t N);
+/* x f32 (B, quantization_channel, N) -> out f32 (B, bottleneck_width, pool_size) */
+int avvad_wavenet_encode(avvad_wavenet* h, const float* x, int64_t B, int64_t N, void* workspace,
+                         size_t workspace_bytes, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
