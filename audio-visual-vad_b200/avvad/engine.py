@@ -306,6 +306,59 @@ class Lstm:
         return logits, post, dec, last
 
 
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def lstm_train_forward(lstm: "Lstm", x_bf16: torch.Tensor, lengths):
+    """Forward that keeps the activations BPTT needs.  Returns (logits (B,T,1), tape)."""
+    L.require_cuda(x_bf16)
+    B, T, ld = x_bf16.shape
+    assert ld == lstm.ld and x_bf16.is_contiguous()
+    dev = x_bf16.device
+    lens = _i32(lengths, dev)
+    nbytes = L.lib().avvad_lstm_workspace_bytes(lstm.h, B, T)
+    ws = lstm.ws.get(nbytes, dev)
+    tb = L.lib().avvad_lstm_tape_bytes(lstm.layers, lstm.hidden, B, T)
+    tape = torch.empty(tb, dtype=torch.uint8, device=dev)
+    logits = torch.empty(B, T, lstm.y_dim, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_lstm_forward_train(lstm.h, L.ptr(x_bf16), L.ptr(lens), B, T, L.ptr(ws), ws.numel(),
+                                             L.ptr(tape), tape.numel(), L.ptr(logits), L.stream_ptr()))
+    return logits, (tape, lens, x_bf16)
+
+
+def lstm_train_backward(lstm: "Lstm", tape_pack, dlogits: torch.Tensor, want_dx=False):
+    """BPTT.  Returns dict(weight_ih=[...], weight_hh=[...], bias=[...], head_w, head_b, dx)."""
+    tape, lens, x_bf16 = tape_pack
+    B, T, _ = x_bf16.shape
+    dev = x_bf16.device
+    H, Lyr = lstm.hidden, lstm.layers
+    dl = dlogits.detach().to(torch.float32).contiguous()
+    nbytes = L.lib().avvad_lstm_backward_workspace_bytes(lstm.h, B, T)
+    if not hasattr(lstm, "bws"):
+        lstm.bws = _Workspace()
+    ws = lstm.bws.get(nbytes, dev)
+    dwi = [torch.empty(4 * H, lstm.input_size if l == 0 else H, dtype=torch.float32, device=dev) for l in range(Lyr)]
+    dwh = [torch.empty(4 * H, H, dtype=torch.float32, device=dev) for _ in range(Lyr)]
+    dbs = [torch.empty(4 * H, dtype=torch.float32, device=dev) for _ in range(Lyr)]
+    dhw = torch.empty(lstm.y_dim, H, dtype=torch.float32, device=dev)
+    dhb = torch.empty(lstm.y_dim, dtype=torch.float32, device=dev)
+    dx = torch.empty(B, T, lstm.input_size, dtype=torch.float32, device=dev) if want_dx else None
+    L.check(L.lib().avvad_lstm_backward(lstm.h, L.ptr(x_bf16), L.ptr(lens), B, T, L.ptr(tape), L.ptr(dl), L.ptr(ws),
+                                        ws.numel(), _ptr_array(dwi), _ptr_array(dwh), _ptr_array(dbs), L.ptr(dhw),
+                                        L.ptr(dhb), L.ptr(dx), L.stream_ptr()))
+    return {"weight_ih": dwi, "weight_hh": dwh, "bias": dbs, "head_w": dhw, "head_b": dhb, "dx": dx}
+
+
+def adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+              lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    """In-place torch.optim.Adam update of one contiguous fp32 tensor."""
+    assert param.is_contiguous() and grad.is_contiguous() and param.dtype == torch.float32
+    L.check(L.lib().avvad_adam_step(L.ptr(param), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), param.numel(), lr,
+                                    betas[0], betas[1], eps, step, L.stream_ptr()))
+
+
 def launch_count() -> int:
     return int(L.lib().avvad_launch_count())
 

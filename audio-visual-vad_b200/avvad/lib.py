@@ -53,6 +53,12 @@ PROTOTYPES = {
     "avvad_mcb_load": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, VP, C.c_float, VP]),
     "avvad_mcb_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "avvad_mcb_forward": (C.c_int, [VP, VP, VP, C.c_int64, VP, C.c_size_t, VP, C.c_int64, VP, VP]),
+    "avvad_lstm_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64, C.c_int64]),
+    "avvad_lstm_forward_train": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int64, VP, C.c_size_t, VP, C.c_size_t, VP, VP]),
+    "avvad_lstm_backward_workspace_bytes": (C.c_size_t, [VP, C.c_int64, C.c_int64]),
+    "avvad_lstm_backward": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int64, VP, VP, VP, C.c_size_t, VP, VP, VP, VP, VP, VP,
+                                      VP]),
+    "avvad_adam_step": (C.c_int, [VP, VP, VP, VP, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, VP]),
     "avvad_bce_loss": (C.c_int, [VP, VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_float, VP, VP, VP, VP]),
     "avvad_f1_metrics": (C.c_int, [VP, VP, VP, C.c_int32, C.c_int32, C.c_float, VP, VP, VP]),
     "avvad_wavenet_create": (C.c_int, [C.POINTER(VP), C.c_int, C.c_int, VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),

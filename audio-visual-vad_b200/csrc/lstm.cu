@@ -189,6 +189,21 @@ int encode_tiled_bf16(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 }
 }  // namespace avvad
 
+namespace avvad {
+struct TapeView {
+  __nv_bfloat16* gates;
+  float* c;
+  __nv_bfloat16* hseq;
+};
+TapeView tape_layer(void* tape, int l, int H, int64_t B, int64_t T);
+int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
+                       float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
+                       float* dx, cudaStream_t st);
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T);
+}  // namespace avvad
+
 namespace {
 struct LstmWs {
   float* xproj;
@@ -238,7 +253,8 @@ static int persist_mode() {
 
 static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, __nv_bfloat16* hseq,
                                      const int32_t* lengths, int64_t B, int64_t T, unsigned int* counters,
-                                     cudaStream_t st, bool* done) {
+                                     cudaStream_t st, bool* done, __nv_bfloat16* gates_out = nullptr,
+                                     float* c_out = nullptr) {
   *done = false;
   const int H = h->H;
   if (!persist_mode() || H % 64 != 0 || H > 1024 || T < 1) return AVVAD_OK;
@@ -284,6 +300,8 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     g.hseq = hs;
     g.lengths = lengths + g0;
     g.counters = counters;
+    g.gates_out = gates_out ? gates_out + g0 * T * 4 * H : nullptr;
+    g.c_out = c_out ? c_out + g0 * T * H : nullptr;
     AVVAD_CUDA(cudaMemsetAsync(counters, 0, 256, st));
     void* args[2] = {(void*)&maps, (void*)&g};
     void* tok = nullptr;
@@ -317,9 +335,9 @@ static int run_head(avvad_lstm* h, const __nv_bfloat16* hs, int64_t rows, float*
   return AVVAD_OK;
 }
 
-extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
-                                  void* workspace, size_t workspace_bytes, float* logits, float* post, int32_t* dec,
-                                  float* last_logits, void* stream) {
+static int lstm_forward_impl(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                             void* workspace, size_t workspace_bytes, float* logits, float* post, int32_t* dec,
+                             float* last_logits, void* tape, void* stream) {
   AVVAD_CHECK_ARG(h && x_bf16 && lengths && workspace && B > 0 && T > 0, "bad argument");
   AVVAD_CHECK_ARG(logits || post || dec || last_logits, "no output requested");
   for (int l = 0; l < h->layers; ++l)
@@ -346,13 +364,22 @@ extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32
   __nv_bfloat16* layer_out = nullptr;
   for (int l = 0; l < h->layers; ++l) {
     layer_out = ws.hseq[l & 1];
+    TapeView tv{};
+    if (tape) {
+      tv = tape_layer(tape, l, H, B, T);
+      layer_out = tv.hseq;
+    }
     // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'
     int rc = avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4, ld_in, st);
     if (rc) return rc;
     // (2) recurrence: one persistent cooperative kernel per layer, or (fallback) one GEMM launch per time step
     bool done = false;
-    rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done);
+    rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done, tv.gates, tv.c);
     if (rc) return rc;
+    if (tape && !done) {
+      set_error("lstm: the training forward needs the persistent recurrence (TMA + cooperative launch, H <= 1024)");
+      return AVVAD_ERR_STATE;
+    }
     if (done) {
       layer_in = layer_out;
       ld_in = H;
@@ -388,4 +415,47 @@ extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32
     if (rc) return rc;
   }
   return AVVAD_OK;
+}
+
+
+extern "C" int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                                  void* workspace, size_t workspace_bytes, float* logits, float* post, int32_t* dec,
+                                  float* last_logits, void* stream) {
+  return lstm_forward_impl(h, x_bf16, lengths, B, T, workspace, workspace_bytes, logits, post, dec, last_logits, nullptr,
+                           stream);
+}
+
+extern "C" size_t avvad_lstm_tape_bytes(int layers, int hidden, int64_t B, int64_t T);
+
+// Training forward: identical arithmetic, but every layer's output sequence, post-activation gates and cell states
+// are kept in `tape` (avvad_lstm_tape_bytes) for avvad_lstm_backward.
+extern "C" int avvad_lstm_forward_train(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                                        void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes,
+                                        float* logits, void* stream) {
+  AVVAD_CHECK_ARG(h && tape && logits, "bad argument");
+  if (tape_bytes < avvad_lstm_tape_bytes(h->layers, h->H, B, T)) {
+    set_error("lstm: tape too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  return lstm_forward_impl(h, x_bf16, lengths, B, T, workspace, workspace_bytes, logits, nullptr, nullptr, nullptr, tape,
+                           stream);
+}
+
+extern "C" size_t avvad_lstm_backward_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return lstm_backward_workspace(h->layers, h->input_size, h->ld0, h->H, B, T);
+}
+
+// dlogits f32 [B][T][1] (e.g. from avvad_bce_loss).  Gradients in PyTorch layout, fp32: dW_ih[l] [4H][I_l],
+// dW_hh[l] [4H][H], db[l] [4H] (= grad of bias_ih_l and of bias_hh_l), dW_head [1][H], db_head [1];
+// dx optional f32 [B][T][input_size] (gradient w.r.t. the layer-0 input).
+extern "C" int avvad_lstm_backward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                                   void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
+                                   float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head,
+                                   float* db_head, float* dx, void* stream) {
+  AVVAD_CHECK_ARG(h && x_bf16 && lengths && tape && dlogits && workspace && dW_ih && dW_hh && db && dW_head && db_head,
+                  "null pointer");
+  return lstm_backward_impl(h->layers, h->input_size, h->ld0, h->H, h->y_dim, h->w_ih, h->w_hh, h->head_w32, x_bf16,
+                            lengths, B, T, tape, dlogits, workspace, workspace_bytes, dW_ih, dW_hh, db, dW_head, db_head,
+                            dx, (cudaStream_t)stream);
 }

@@ -28,6 +28,9 @@ struct LstmGeom {
   __nv_bfloat16* hseq;  // [B][T][H] bf16 layer output
   const int32_t* lengths;
   unsigned int* counters;  // [m_slices], zeroed before the launch
+  // training only (may be null): post-activation gates (i,f,g,o per unit, bf16 [B][T][4H]) and cell states (f32 [B][T][H])
+  __nv_bfloat16* gates_out;
+  float* c_out;
 };
 
 struct LstmMaps {
@@ -166,16 +169,28 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       }
       if (row_ok) {
         float hv[16];
+        __nv_bfloat16* gsave = g.gates_out ? g.gates_out + ((int64_t)b * g.T + t) * H4 + ns * 64 : nullptr;
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const uint32_t* vv = (u < 8) ? v0 : v1;
           const int o = (u & 7) * 4;
-          const float gi = __uint_as_float(vv[o + 0]) + x[u].x;
-          const float gf = __uint_as_float(vv[o + 1]) + x[u].y;
-          const float gg = __uint_as_float(vv[o + 2]) + x[u].z;
-          const float go = __uint_as_float(vv[o + 3]) + x[u].w;
-          c[u] = sigmoidf_fast(gf) * c[u] + sigmoidf_fast(gi) * tanhf_fast(gg);
-          hv[u] = sigmoidf_fast(go) * tanhf_fast(c[u]);
+          const float gi = sigmoidf_fast(__uint_as_float(vv[o + 0]) + x[u].x);
+          const float gf = sigmoidf_fast(__uint_as_float(vv[o + 1]) + x[u].y);
+          const float gg = tanhf_fast(__uint_as_float(vv[o + 2]) + x[u].z);
+          const float go = sigmoidf_fast(__uint_as_float(vv[o + 3]) + x[u].w);
+          c[u] = gf * c[u] + gi * gg;
+          hv[u] = go * tanhf_fast(c[u]);
+          if (gsave) {
+            uint2 pk;
+            pk.x = pack_bf16x2(gi, gf);
+            pk.y = pack_bf16x2(gg, go);
+            *reinterpret_cast<uint2*>(gsave + 4 * u) = pk;
+          }
+        }
+        if (g.c_out) {
+          float4* cp = reinterpret_cast<float4*>(g.c_out + ((int64_t)b * g.T + t) * g.H + ns * 16);
+#pragma unroll
+          for (int u4 = 0; u4 < 4; ++u4) cp[u4] = make_float4(c[4 * u4], c[4 * u4 + 1], c[4 * u4 + 2], c[4 * u4 + 3]);
         }
         const bool live = t < len;
         uint4 h0, h1;

@@ -1,0 +1,336 @@
+// Training step of the LSTM + Linear head: back-propagation through time, weight-gradient GEMMs
+// and a fused Adam update.  The forward that feeds it is avvad_lstm_forward with a non-null `tape` (the persistent
+// recurrence then also stores the post-activation gates and the cell states).
+//
+// Reference semantics: autograd of packages/models/AV_Net.py:127-140 / Audio_Net.py:50-59 (nn.LSTM + nn.Linear over
+// packed sequences) and torch.optim.Adam(lr, betas=(0.9,0.999)) (scripts/train_AV_net.py:238,305-307).
+//
+//   per layer, t = T-1 .. 0 : cell kernel  (dY_t + dh_rec, dc) -> dgates_t (bf16, gate-interleaved), dc
+//                             tcgen05 GEMM  dh_rec = dgates_t * W_hh          (B operand: W_hh^T, K = 4H)
+//   after the loop          : dX  = dG * W_ih                                  (GEMM, K = 4H)
+//                             dW_ih = dG^T * X, dW_hh = dG^T * H_prev          (GEMMs over K = B*T on transposed copies)
+//                             db = column sums of dG
+// Gradients are returned in PyTorch's layout (gate-major rows i,f,g,o), fp32.
+#include <vector>
+
+#include "gemm_tc.cuh"
+
+namespace avvad {
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// one thread per (b, u)
+__global__ void lstm_bwd_cell_kernel(const __nv_bfloat16* __restrict__ gates, const float* __restrict__ cst,
+                                     const float* __restrict__ dY, const float* __restrict__ dl,
+                                     const float* __restrict__ w_head, const float* __restrict__ dh_rec,
+                                     float* __restrict__ dc, const int32_t* __restrict__ lengths, int B, int T, int H,
+                                     int t, int has_rec, __nv_bfloat16* __restrict__ dG) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, u = idx - b * H;
+  const int64_t row = (int64_t)b * T + t;
+  uint2* out = reinterpret_cast<uint2*>(dG + row * 4 * H + 4 * u);
+  if (t >= lengths[b]) {  // padded step: no gradient flows (packed-sequence semantics)
+    *out = make_uint2(0u, 0u);
+    dc[idx] = 0.f;
+    return;
+  }
+  const uint2 gp = *reinterpret_cast<const uint2*>(gates + row * 4 * H + 4 * u);
+  const float gi = bf16lo(gp.x), gf = bf16hi(gp.x), gg = bf16lo(gp.y), go = bf16hi(gp.y);
+  const float c = cst[row * H + u];
+  const float cp = t > 0 ? cst[(row - 1) * H + u] : 0.f;
+  float dh = dY ? dY[row * H + u] : dl[row] * w_head[u];
+  if (has_rec) dh += dh_rec[idx];
+  const float tc = tanhf(c);
+  const float d_o = dh * tc * go * (1.f - go);
+  const float dcc = dh * go * (1.f - tc * tc) + dc[idx];
+  const float d_i = dcc * gg * gi * (1.f - gi);
+  const float d_g = dcc * gi * (1.f - gg * gg);
+  const float d_f = dcc * cp * gf * (1.f - gf);
+  dc[idx] = dcc * gf;
+  uint2 o;
+  o.x = pack_bf16x2(d_i, d_f);
+  o.y = pack_bf16x2(d_g, d_o);
+  *out = o;
+}
+
+// bf16 [R][ld] (first C columns) -> [C][Rp] with zero fill for r >= R; `shift` > 0 reads row r - shift*? (see below)
+// mode 0: plain transpose.  mode 1: H_prev transpose: out[c][b*T + t] = in[b*T + t - 1][c] for t > 0, else 0.
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t R, int C, int64_t ld, int64_t Rp,
+                                      int mode, int T, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (r < R && c < C) {
+      if (mode == 0) v = in[r * ld + c];
+      else if ((r % T) != 0) v = in[(r - 1) * ld + c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + threadIdx.x;
+    if (c < C && r < Rp) out[(int64_t)c * Rp + r] = tile[threadIdx.x][i];
+  }
+}
+
+// W' (gate-interleaved rows 4u+g) bf16 [4H][ld] -> W'^T bf16 [cols][4H]
+__global__ void transpose_w_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, int ld,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * cols) return;
+  const int c = (int)(idx / rows), r = (int)(idx - (int64_t)c * rows);
+  out[idx] = w[(int64_t)r * ld + c];
+}
+
+// dW' f32 [4H][ldw] (interleaved rows) -> torch layout f32 [4H][I] (row g*H+u), first I columns
+__global__ void deinterleave_w_kernel(const float* __restrict__ dwp, int H, int I, int ldw, float* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)4 * H * I) return;
+  const int i = (int)(idx % I);
+  const int rt = (int)(idx / I);  // torch row g*H+u
+  const int g = rt / H, u = rt - g * H;
+  out[idx] = dwp[(int64_t)(4 * u + g) * ldw + i];
+}
+
+// db[g*H+u] = sum_r dG[r][4u+g]   (one block per 64 interleaved columns; fixed-order reduction)
+__global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ dG, int64_t R, int H,
+                                                        float* __restrict__ db) {
+  __shared__ float sm[4][64];
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int part = threadIdx.x >> 6;
+  float acc = 0.f;
+  for (int64_t r = part; r < R; r += 4) acc += __bfloat162float(dG[r * 4 * H + col]);
+  sm[part][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float t = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
+    const int u = col >> 2, g = col & 3;
+    db[g * H + u] = t;
+  }
+}
+
+// y_dim == 1 head: dW[u] = sum_r dl[r] * h[r][u]; db = sum_r dl[r].  Two-stage deterministic reduction.
+__global__ void __launch_bounds__(256) head_grad_partial_kernel(const float* __restrict__ dl,
+                                                                const __nv_bfloat16* __restrict__ h, int64_t R, int H,
+                                                                int rows_per_block, float* __restrict__ partial) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < R) ? r0 + rows_per_block : R;
+  for (int u = threadIdx.x; u < H; u += 256) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += dl[r] * __bfloat162float(h[r * H + u]);
+    partial[(int64_t)blockIdx.x * (H + 1) + u] = acc;
+  }
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += dl[r];
+    partial[(int64_t)blockIdx.x * (H + 1) + H] = acc;
+  }
+}
+__global__ void head_grad_final_kernel(const float* __restrict__ partial, int nblocks, int H, float* __restrict__ dw,
+                                       float* __restrict__ db) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > H) return;
+  float acc = 0.f;
+  for (int i = 0; i < nblocks; ++i) acc += partial[(int64_t)i * (H + 1) + u];
+  if (u < H) dw[u] = acc; else db[0] = acc;
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2_sqrt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace avvad
+
+using namespace avvad;
+
+// ---- tape / workspace geometry (shared with lstm.cu through these helpers) --------------------------------------
+extern "C" size_t avvad_lstm_tape_bytes(int layers, int hidden, int64_t B, int64_t T) {
+  if (layers <= 0 || hidden <= 0 || B <= 0 || T <= 0) return 0;
+  const size_t per = align_up((size_t)B * T * 4 * hidden * 2, 256) + align_up((size_t)B * T * hidden * 4, 256) +
+                     align_up((size_t)B * T * hidden * 2, 256);
+  return per * layers + 256;
+}
+
+extern "C" int avvad_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, int64_t step, void* stream) {
+  AVVAD_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "bad argument");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                            beta2, eps, bc1, sqrtf(bc2));
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+namespace avvad {
+// exposed to lstm.cu
+int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
+                       float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
+                       float* dx, cudaStream_t st);
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T);
+
+struct TapeView {
+  __nv_bfloat16* gates;
+  float* c;
+  __nv_bfloat16* hseq;
+};
+TapeView tape_layer(void* tape, int l, int H, int64_t B, int64_t T) {
+  const size_t g = align_up((size_t)B * T * 4 * H * 2, 256), c = align_up((size_t)B * T * H * 4, 256),
+               h = align_up((size_t)B * T * H * 2, 256);
+  uint8_t* p = (uint8_t*)tape + (size_t)l * (g + c + h);
+  TapeView v;
+  v.gates = (__nv_bfloat16*)p;
+  v.c = (float*)(p + g);
+  v.hseq = (__nv_bfloat16*)(p + g + c);
+  return v;
+}
+
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T) {
+  (void)layers; (void)input_size;
+  const int64_t BT = B * T, BTp = (BT + 63) / 64 * 64;
+  const int64_t maxI = ld0 > H ? ld0 : H;
+  size_t s = 0;
+  s += align_up((size_t)BT * 4 * H * 2, 256);          // dG
+  s += align_up((size_t)4 * H * BTp * 2, 256);         // dG^T
+  s += align_up((size_t)maxI * BTp * 2, 256);          // X^T / H_prev^T
+  s += 2 * align_up((size_t)BT * maxI * 4, 256);       // dY ping-pong (f32)
+  s += 2 * align_up((size_t)B * H * 4, 256);           // dh_rec, dc
+  s += align_up((size_t)4 * H * maxI * 4, 256);        // dW' (interleaved)
+  s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
+  s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
+  return s + 1024;
+}
+
+int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
+                       float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
+                       float* dx, cudaStream_t st) {
+  AVVAD_CHECK_ARG(y_dim == 1, "LSTM backward currently supports y_dim == 1 (the VAD head)");
+  AVVAD_CHECK_ARG(workspace_bytes >= lstm_backward_workspace(layers, input_size, ld0, H, B, T), "workspace too small");
+  const int64_t BT = B * T, BTp = (BT + 63) / 64 * 64;
+  const int64_t maxI = ld0 > H ? ld0 : H;
+  const int H4 = 4 * H;
+  uint8_t* p = (uint8_t*)workspace;
+  auto take = [&](size_t bytes) { void* q = p; p += align_up(bytes, 256); return q; };
+  __nv_bfloat16* dG = (__nv_bfloat16*)take((size_t)BT * H4 * 2);
+  __nv_bfloat16* dGT = (__nv_bfloat16*)take((size_t)H4 * BTp * 2);
+  __nv_bfloat16* XT = (__nv_bfloat16*)take((size_t)maxI * BTp * 2);
+  float* dYa = (float*)take((size_t)BT * maxI * 4);
+  float* dYb = (float*)take((size_t)BT * maxI * 4);
+  float* dh_rec = (float*)take((size_t)B * H * 4);
+  float* dc = (float*)take((size_t)B * H * 4);
+  float* dWp = (float*)take((size_t)H4 * maxI * 4);
+  __nv_bfloat16* WT = (__nv_bfloat16*)take((size_t)maxI * H4 * 2);
+  float* partial = (float*)take((size_t)1024 * (H + 1) * 4);
+
+  // ---- head gradients (y_dim == 1): dl = dlogits [BT]
+  {
+    TapeView top = tape_layer(tape, layers - 1, H, B, T);
+    int nblocks = (int)std::min<int64_t>(1024, ceil_div(BT, 64));
+    int rows_per_block = (int)ceil_div(BT, nblocks);
+    nblocks = (int)ceil_div(BT, rows_per_block);
+    head_grad_partial_kernel<<<nblocks, 256, 0, st>>>(dlogits, top.hseq, BT, H, rows_per_block, partial);
+    AVVAD_LAUNCHED();
+    head_grad_final_kernel<<<(unsigned)ceil_div(H + 1, 256), 256, 0, st>>>(partial, nblocks, H, dW_head, db_head);
+    AVVAD_LAUNCHED();
+  }
+
+  const float* dY = nullptr;  // null: top layer takes dl * w_head on the fly
+  float* dX_out = dYa;
+  for (int l = layers - 1; l >= 0; --l) {
+    TapeView tv = tape_layer(tape, l, H, B, T);
+    const int64_t ld_in = (l == 0) ? ld0 : H;
+    const int I = (l == 0) ? input_size : H;
+    const __nv_bfloat16* Xin = (l == 0) ? (const __nv_bfloat16*)x_bf16 : tape_layer(tape, l - 1, H, B, T).hseq;
+
+    // W_hh'^T [H][4H] for the recurrent gradient GEMM
+    transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_hh[l], H4, H, H, WT);
+    AVVAD_LAUNCHED();
+    AVVAD_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
+    for (int t = (int)T - 1; t >= 0; --t) {
+      const int has_rec = (t < (int)T - 1) ? 1 : 0;
+      lstm_bwd_cell_kernel<<<(unsigned)ceil_div(B * H, 256), 256, 0, st>>>(tv.gates, tv.c, dY, dlogits, head_w32, dh_rec,
+                                                                          dc, lengths, (int)B, (int)T, H, t, has_rec, dG);
+      AVVAD_LAUNCHED();
+      if (t > 0) {
+        tc::EpiParams ep{};
+        ep.C = dh_rec;
+        ep.ldc = H;
+        int rc = tc::gemm_dispatch(dG + (int64_t)t * H4, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st);
+        if (rc) return rc;
+      }
+    }
+    // db (= db_ih = db_hh)
+    bias_grad_kernel<<<H4 / 64, 256, 0, st>>>(dG, BT, H, db[l]);
+    AVVAD_LAUNCHED();
+    // dG^T [4H][BTp]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H4, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(dG, BT, H4, H4, BTp, 0, (int)T, dGT);
+      AVVAD_LAUNCHED();
+    }
+    // dW_ih' = dG^T * X  -> [4H][ld_in]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(ld_in, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(Xin, BT, (int)ld_in, ld_in, BTp, 0, (int)T, XT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dWp;
+      ep.ldc = ld_in;
+      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, (int)ld_in, (int)BTp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * I, 256), 256, 0, st>>>(dWp, H, I, (int)ld_in, dW_ih[l]);
+      AVVAD_LAUNCHED();
+    }
+    // dW_hh' = dG^T * H_prev -> [4H][H]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(tv.hseq, BT, H, H, BTp, 1, (int)T, XT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dWp;
+      ep.ldc = H;
+      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, H, (int)BTp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(dWp, H, H, H, dW_hh[l]);
+      AVVAD_LAUNCHED();
+    }
+    // dX = dG * W_ih'  (needed below the top layer, or when the caller wants input gradients)
+    if (l > 0 || dx) {
+      transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * ld_in, 256), 256, 0, st>>>(w_ih[l], H4, (int)ld_in,
+                                                                                       (int)ld_in, WT);
+      AVVAD_LAUNCHED();
+      float* dst = (l == 0) ? dx : dX_out;
+      tc::EpiParams ep{};
+      ep.C = dst;
+      ep.ldc = (l == 0) ? I : ld_in;
+      // l == 0: only the first I (un-padded) columns are written (N guard in the epilogue)
+      int rc = tc::gemm_dispatch(dG, H4, WT, H4, BT, (l == 0) ? I : (int)ld_in, H4, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      dY = dst;
+      dX_out = (dX_out == dYa) ? dYb : dYa;
+    }
+  }
+  return AVVAD_OK;
+}
+}  // namespace avvad

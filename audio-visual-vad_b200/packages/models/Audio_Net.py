@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 
 from .utils import weights_init_normal
-from ._engine import E, EngineCache, check_inference_only, device_of
+from ._engine import E, EngineCache, LstmHeadFunction, device_of, lstm_params
 
 
 class DeepVAD_audio(nn.Module):
@@ -42,11 +42,16 @@ class DeepVAD_audio(nn.Module):
     def forward(self, x, lengths, return_posteriors=False):
         """x (B,T,513) standardised log-power, lengths -> logits (B,T,y_dim)."""
         device = device_of(x)
-        check_inference_only(self)
         eng = self._build(device)
         B, T, F = x.shape
         xb = eng["lstm"].new_input(B, T, device)
         E.pack_rows_bf16(x.detach().to(torch.float32).reshape(B * T, F).contiguous(), xb.view(B * T, -1), 0, False)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # training step: forward keeps a tape, loss.backward() runs BPTT on the device (SURVEY O1)
+            if self.y_dim != 1:
+                raise NotImplementedError("device-side BPTT is implemented for the VAD head (y_dim == 1)")
+            return LstmHeadFunction.apply(eng["lstm"], xb, lengths, x if x.requires_grad else None,
+                                          *lstm_params(self.lstm_audio, self.vad_audio))
         logits, post, dec, _ = eng["lstm"].forward(xb, lengths, want_post=return_posteriors,
                                                    want_dec=return_posteriors)
         if return_posteriors:

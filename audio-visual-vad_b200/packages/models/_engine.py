@@ -29,7 +29,7 @@ class EngineCache:
     def _signature(module: torch.nn.Module):
         sig = []
         for t in list(module.parameters()) + list(module.buffers()):
-            sig.append((t.data_ptr(), t._version))
+            sig.append((t.data_ptr(), t._version, getattr(t, "_avvad_gen", 0)))
         return tuple(sig)
 
     def get(self, module: torch.nn.Module, device: torch.device, builder):
@@ -41,6 +41,64 @@ class EngineCache:
         eng = builder(hit[1] if hit is not None else None)
         self.by_device[key] = (sig, eng)
         return eng
+
+
+class LstmHeadFunction(torch.autograd.Function):
+    """Differentiable LSTM + Linear head on libavvad: forward keeps a tape, backward runs BPTT on the device and
+    returns the gradients of the nn.LSTM / nn.Linear parameters in PyTorch's layout (and of the input when asked)."""
+
+    @staticmethod
+    def forward(ctx, lstm_engine, x_bf16, lengths, x_src, *params):
+        logits, tape = E.lstm_train_forward(lstm_engine, x_bf16, lengths)
+        ctx.lstm_engine = lstm_engine
+        ctx.tape = tape
+        ctx.n_params = len(params)
+        ctx.want_dx = x_src is not None and x_src.requires_grad
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        eng = ctx.lstm_engine
+        g = E.lstm_train_backward(eng, ctx.tape, dlogits, want_dx=ctx.want_dx)
+        ctx.tape = None
+        grads = []
+        for l in range(eng.layers):  # parameter order: weight_ih, weight_hh, bias_ih, bias_hh per layer, then head
+            grads += [g["weight_ih"][l], g["weight_hh"][l], g["bias"][l], g["bias"][l]]
+        grads += [g["head_w"], g["head_b"]]
+        return (None, None, None, g["dx"]) + tuple(grads)
+
+
+def lstm_params(lstm: torch.nn.LSTM, head: torch.nn.Linear):
+    ps = []
+    for l in range(lstm.num_layers):
+        ps += [getattr(lstm, f"weight_ih_l{l}"), getattr(lstm, f"weight_hh_l{l}"), getattr(lstm, f"bias_ih_l{l}"),
+               getattr(lstm, f"bias_hh_l{l}")]
+    return ps + [head.weight, head.bias]
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(lr, betas, eps) semantics (no weight decay / amsgrad) with the update done by libavvad."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p)
+                    st["exp_avg_sq"] = torch.zeros_like(p)
+                st["step"] += 1
+                E.adam_step(p.data, p.grad.contiguous(), st["exp_avg"], st["exp_avg_sq"], st["step"], group["lr"],
+                            group["betas"], group["eps"])
+                # the in-place kernel bypasses autograd's version counter: bump a generation tag so that the packed
+                # (bf16, gate-interleaved) weight caches of the engines are refreshed on the next forward
+                p._avvad_gen = getattr(p, "_avvad_gen", 0) + 1
 
 
 def check_inference_only(module: torch.nn.Module):

@@ -198,6 +198,24 @@ int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths
                        int32_t* dec, float* last_logits, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step of the LSTM + head: forward that keeps activations, BPTT, fused Adam
+ * replaces: autograd of packages/models/AV_Net.py:127-140 and torch.optim.Adam (scripts/train_AV_net.py:238,305-307).
+ * ---------------------------------------------------------------------------------------- */
+size_t avvad_lstm_tape_bytes(int layers, int hidden, int64_t B, int64_t T);
+int avvad_lstm_forward_train(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
+                             void* workspace, size_t workspace_bytes, void* tape, size_t tape_bytes, float* logits,
+                             void* stream);
+size_t avvad_lstm_backward_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T);
+/* dlogits f32 [B][T][1]; gradients fp32 in PyTorch layout: dW_ih[l] [4H][I_l], dW_hh[l] [4H][H], db[l] [4H] (bias_ih
+ * and bias_hh share it), dW_head [1][H], db_head [1]; dx optional f32 [B][T][input_size]. */
+int avvad_lstm_backward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T, void* tape,
+                        const float* dlogits, void* workspace, size_t workspace_bytes, float* const* dW_ih,
+                        float* const* dW_hh, float* const* db, float* dW_head, float* db_head, float* dx, void* stream);
+/* torch.optim.Adam update (no weight decay, no amsgrad): step >= 1 is the 1-based update count. */
+int avvad_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, int64_t step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Training-loop loss and metrics over padded batches
  * replaces: the per-utterance Python loops of scripts/train_AV_net.py:298-301 (sum over utterances of
  *           packages/models/utils.py:113 binary_cross_entropy) and :311-329 (packages/models/utils.py:164-203 f1_loss).
