@@ -204,6 +204,37 @@ class ResNet18Trunk:
                                                L.ptr(feat), L.ptr(feat_bf16), ld, col_off, L.stream_ptr()))
         return feat
 
+    def load_train(self, sd: Dict[str, torch.Tensor], device, prefix="features."):
+        """Un-folded weights + BN affine parameters for the batch-statistics (training-mode) forward."""
+        keep = []
+        for i, (ck, bk) in enumerate(RESNET_LAYER_KEYS):
+            w = _f32(sd[prefix + ck + ".weight"], device)
+            g = _f32(sd[prefix + bk + ".weight"], device)
+            b = _f32(sd[prefix + bk + ".bias"], device)
+            keep += [w, g, b]
+            L.check(L.lib().avvad_resnet18_set_conv_train(self.h, i, L.ptr(w), L.ptr(g), L.ptr(b), L.stream_ptr()))
+        torch.cuda.current_stream().synchronize()
+
+    def forward_train(self, frames: torch.Tensor, running: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
+                      feat_bf16: Optional[torch.Tensor] = None, col_off=0, want_f32=True, bn_eps=1e-5, momentum=0.1):
+        """Training-mode forward: batch statistics over all frames of the call; `running` = 20 (running_mean,
+        running_var) fp32 CUDA tensor pairs updated in place (the module's BatchNorm buffers)."""
+        L.require_cuda(frames)
+        frames = frames.contiguous()
+        n = frames.numel() // (67 * 67)
+        nbytes = L.lib().avvad_resnet18_train_workspace_bytes(n)
+        if not hasattr(self, "tws"):
+            self.tws = _Workspace()
+        ws = self.tws.get(nbytes, frames.device)
+        feat = torch.empty(n, 512, dtype=torch.float32, device=frames.device) if want_f32 else None
+        rm = _ptr_array([r[0] for r in running]) if running is not None else None
+        rv = _ptr_array([r[1] for r in running]) if running is not None else None
+        ld = feat_bf16.stride(-2) if feat_bf16 is not None else 0
+        L.check(L.lib().avvad_resnet18_forward_train(self.h, L.ptr(frames), n, L.ptr(ws), ws.numel(), bn_eps, momentum,
+                                                     rm, rv, L.ptr(feat), L.ptr(feat_bf16), ld, col_off,
+                                                     L.stream_ptr()))
+        return feat
+
     def forward_upto(self, frames: torch.Tensor, upto: int, shape: Tuple[int, int, int]) -> torch.Tensor:
         """Test hook: NHWC bf16 activation after conv layer `upto` (shape = (h, w, c))."""
         frames = frames.contiguous()
@@ -254,6 +285,29 @@ class Mcb:
         ld = out_bf16.stride(-2) if out_bf16 is not None else 0
         L.check(L.lib().avvad_mcb_forward(self.h, L.ptr(audio), L.ptr(video), rows, L.ptr(ws), ws.numel(),
                                           L.ptr(out_bf16), ld, L.ptr(out_f32), L.stream_ptr()))
+
+
+def mcb_forward_train(mcb: "Mcb", audio, video, gamma, beta, running_mean, running_var, out_bf16, momentum=0.1):
+    """Training-mode MCB fusion; returns the workspace (kept alive for mcb_backward_bn)."""
+    audio = audio.reshape(-1, 513).contiguous()
+    video = video.reshape(-1, 512).contiguous()
+    rows = audio.shape[0]
+    nbytes = L.lib().avvad_mcb_workspace_bytes(rows)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=audio.device)
+    ld = out_bf16.stride(-2)
+    L.check(L.lib().avvad_mcb_forward_train(mcb.h, L.ptr(audio), L.ptr(video), rows, L.ptr(ws), ws.numel(), L.ptr(gamma),
+                                            L.ptr(beta), momentum, L.ptr(running_mean), L.ptr(running_var),
+                                            L.ptr(out_bf16), ld, None, L.stream_ptr()))
+    return ws, rows
+
+
+def mcb_backward_bn(mcb: "Mcb", ws, rows, dx: torch.Tensor):
+    dx = dx.reshape(rows, -1).contiguous()
+    dg = torch.empty(1024, dtype=torch.float32, device=dx.device)
+    db = torch.empty(1024, dtype=torch.float32, device=dx.device)
+    L.check(L.lib().avvad_mcb_backward_bn(mcb.h, L.ptr(ws), L.ptr(dx), dx.stride(0), rows, L.ptr(dg), L.ptr(db),
+                                          L.stream_ptr()))
+    return dg, db
 
 
 class Lstm:

@@ -43,6 +43,10 @@ PROTOTYPES = {
     "avvad_resnet18_forward": (C.c_int, [VP, VP, C.c_int64, C.c_int64, VP, C.c_size_t, VP, VP, C.c_int64, C.c_int64,
                                          VP]),
     "avvad_resnet18_forward_upto": (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, C.c_size_t, VP, VP]),
+    "avvad_resnet18_set_conv_train": (C.c_int, [VP, C.c_int, VP, VP, VP, VP]),
+    "avvad_resnet18_train_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "avvad_resnet18_forward_train": (C.c_int, [VP, VP, C.c_int64, VP, C.c_size_t, C.c_float, C.c_float, VP, VP, VP, VP,
+                                               C.c_int64, C.c_int64, VP]),
     "avvad_gemm_bf16": (C.c_int, [VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                   C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -67,6 +71,9 @@ PROTOTYPES = {
     "avvad_wavenet_encoded_length": (C.c_int64, [VP, C.c_int64]),
     "avvad_wavenet_workspace_bytes": (C.c_size_t, [VP, C.c_int64, C.c_int64]),
     "avvad_wavenet_encode": (C.c_int, [VP, VP, C.c_int64, C.c_int64, VP, C.c_size_t, VP, VP]),
+    "avvad_mcb_forward_train": (C.c_int, [VP, VP, VP, C.c_int64, VP, C.c_size_t, VP, VP, C.c_float, VP, VP, VP, C.c_int64,
+                                          VP, VP]),
+    "avvad_mcb_backward_bn": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int64, VP, VP, VP]),
     "avvad_lstm_create": (C.c_int, [C.POINTER(VP), C.c_int, C.c_int, C.c_int, C.c_int]),
     "avvad_lstm_destroy": (None, [VP]),
     "avvad_lstm_set_layer": (C.c_int, [VP, C.c_int, VP, VP, VP, VP, VP]),

@@ -131,6 +131,90 @@ __global__ void mcb_apply_kernel(const float* __restrict__ y, const float* __res
   if (out_f32) out_f32[idx] = o;
 }
 
+// ---- training mode: BatchNorm1d with batch statistics over all rows, and the gradients of its affine parameters ----
+// v = y / norm;  stats over rows per channel (fp64 accumulation, one block per channel, fixed order)
+__global__ void __launch_bounds__(256) mcb_bn_stats_kernel(const float* __restrict__ y, const float* __restrict__ norm,
+                                                           int64_t rows, float eps, float momentum,
+                                                           float* __restrict__ mean_invstd,
+                                                           float* __restrict__ running_mean,
+                                                           float* __restrict__ running_var) {
+  __shared__ double s1[256], s2[256];
+  const int j = blockIdx.x;
+  const double inv = 1.0 / (double)norm[0];
+  double a = 0.0, b = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += 256) {
+    const double v = (double)y[r * kMcbOut + j] * inv;
+    a += v;
+    b += v * v;
+  }
+  s1[threadIdx.x] = a;
+  s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      s1[threadIdx.x] += s1[threadIdx.x + st];
+      s2[threadIdx.x] += s2[threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = s1[0] / (double)rows;
+    double var = s2[0] / (double)rows - mean * mean;
+    if (var < 0) var = 0;
+    mean_invstd[j] = (float)mean;
+    mean_invstd[kMcbOut + j] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+      running_mean[j] = (1.f - momentum) * running_mean[j] + momentum * (float)mean;
+      running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
+    }
+  }
+}
+__global__ void mcb_apply_train_kernel(const float* __restrict__ y, const float* __restrict__ norm,
+                                       const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int64_t rows, __nv_bfloat16* __restrict__ out_bf16,
+                                       int64_t ld_out, float* __restrict__ out_f32) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kMcbOut) return;
+  const int64_t r = idx / kMcbOut;
+  const int j = (int)(idx - r * kMcbOut);
+  const float v = y[idx] / norm[0];
+  const float o = (v - mean_invstd[j]) * mean_invstd[kMcbOut + j] * gamma[j] + beta[j];
+  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
+  if (out_f32) out_f32[idx] = o;
+}
+// dgamma[j] = sum_r dx[r][j] * xhat[r][j], dbeta[j] = sum_r dx[r][j]
+__global__ void __launch_bounds__(256) mcb_bn_grad_kernel(const float* __restrict__ y, const float* __restrict__ norm,
+                                                          const float* __restrict__ mean_invstd,
+                                                          const float* __restrict__ dx, int64_t ld_dx, int64_t rows,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double s1[256], s2[256];
+  const int j = blockIdx.x;
+  const float inv = 1.0f / norm[0];
+  const float mean = mean_invstd[j], istd = mean_invstd[kMcbOut + j];
+  double a = 0.0, b = 0.0;
+  for (int64_t r = threadIdx.x; r < rows; r += 256) {
+    const float g = dx[r * ld_dx + j];
+    const float xh = (y[r * kMcbOut + j] * inv - mean) * istd;
+    a += (double)g * xh;
+    b += (double)g;
+  }
+  s1[threadIdx.x] = a;
+  s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      s1[threadIdx.x] += s1[threadIdx.x + st];
+      s2[threadIdx.x] += s2[threadIdx.x + st];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    dgamma[j] = (float)s1[0];
+    dbeta[j] = (float)s2[0];
+  }
+}
+
 __global__ void bn_invstd_kernel(const float* __restrict__ var, float eps, float* __restrict__ invstd, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) invstd[i] = 1.0f / sqrtf(var[i] + eps);
@@ -218,7 +302,9 @@ extern "C" int avvad_mcb_load(avvad_mcb* h, const int64_t* h1, const float* s1, 
 
 extern "C" size_t avvad_mcb_workspace_bytes(int64_t rows) {
   if (rows <= 0) return 0;
-  return align_up((size_t)rows * kMcbOut * sizeof(float), 256) + align_up((size_t)rows * sizeof(float), 256) + 256;
+  // y (f32), per-row sums of squares, norm, [training] mean/invstd
+  return align_up((size_t)rows * kMcbOut * sizeof(float), 256) + align_up((size_t)rows * sizeof(float), 256) + 256 +
+         2 * kMcbOut * sizeof(float);
 }
 
 extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* video, int64_t rows, void* workspace,
@@ -254,6 +340,54 @@ extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* 
   mcb_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, h->bn_mean, h->bn_invstd, h->bn_gamma,
                                                                    h->bn_beta, rows, (__nv_bfloat16*)out_bf16, ld_out,
                                                                    out_f32);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+
+// Training-mode forward (AV_Net.py:119 with the module in train()): BatchNorm1d uses the batch statistics of this call
+// and the module's CURRENT affine parameters (gamma, beta: trainable, passed per call), and updates running_mean /
+// running_var in place (NULL = leave).  The workspace keeps y, the norm and the batch statistics for
+// avvad_mcb_backward_bn.
+extern "C" int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const float* video, int64_t rows,
+                                       void* workspace, size_t workspace_bytes, const float* gamma, const float* beta,
+                                       float momentum, float* running_mean, float* running_var, void* out_bf16,
+                                       int64_t ld_out, float* out_f32, void* stream) {
+  AVVAD_CHECK_ARG(h && audio && video && workspace && gamma && beta && rows > 0, "bad argument");
+  AVVAD_CHECK_ARG(out_bf16 || out_f32, "at least one output required");
+  if (!h->loaded) { set_error("mcb: not loaded"); return AVVAD_ERR_STATE; }
+  if (workspace_bytes < avvad_mcb_workspace_bytes(rows)) { set_error("mcb: workspace too small"); return AVVAD_ERR_WORKSPACE; }
+  const float2* tw = fft_twiddles_device();
+  if (!tw) { set_error("twiddle table allocation failed"); return AVVAD_ERR_CUDA; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* y = reinterpret_cast<float*>(workspace);
+  float* rowsq = reinterpret_cast<float*>((uint8_t*)workspace + align_up((size_t)rows * kMcbOut * sizeof(float), 256));
+  float* norm = reinterpret_cast<float*>((uint8_t*)rowsq + align_up((size_t)rows * sizeof(float), 256));
+  float* mean_invstd = norm + 64;
+  McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
+  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq);
+  AVVAD_LAUNCHED();
+  mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
+  AVVAD_LAUNCHED();
+  mcb_bn_stats_kernel<<<kMcbOut, 256, 0, st>>>(y, norm, rows, h->eps, momentum, mean_invstd, running_mean, running_var);
+  AVVAD_LAUNCHED();
+  const int64_t total = rows * kMcbOut;
+  mcb_apply_train_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, mean_invstd, gamma, beta, rows,
+                                                                         (__nv_bfloat16*)out_bf16, ld_out, out_f32);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+// dx: f32 [rows][ld_dx] gradient w.r.t. the BatchNorm output (first 1024 columns) -> dgamma, dbeta [1024].
+// `workspace` must be the one the matching avvad_mcb_forward_train call filled.
+extern "C" int avvad_mcb_backward_bn(avvad_mcb* h, void* workspace, const float* dx, int64_t ld_dx, int64_t rows,
+                                     float* dgamma, float* dbeta, void* stream) {
+  AVVAD_CHECK_ARG(h && workspace && dx && dgamma && dbeta && rows > 0 && ld_dx >= kMcbOut, "bad argument");
+  float* y = reinterpret_cast<float*>(workspace);
+  float* rowsq = reinterpret_cast<float*>((uint8_t*)workspace + align_up((size_t)rows * kMcbOut * sizeof(float), 256));
+  float* norm = reinterpret_cast<float*>((uint8_t*)rowsq + align_up((size_t)rows * sizeof(float), 256));
+  float* mean_invstd = norm + 64;
+  mcb_bn_grad_kernel<<<kMcbOut, 256, 0, (cudaStream_t)stream>>>(y, norm, mean_invstd, dx, ld_dx, rows, dgamma, dbeta);
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }

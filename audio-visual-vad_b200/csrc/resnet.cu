@@ -338,6 +338,98 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ act, int64_t n_
   }
 }
 
+// ---- training-mode BatchNorm (batch statistics) -------------------------------------------------------------
+// raw bf16 [M][C] -> per-channel sum / sum of squares (double atomics; one block per 256 rows)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int C,
+                                                       double* __restrict__ stats) {
+  const int64_t r0 = (int64_t)blockIdx.x * 256;
+  const int64_t r1 = (r0 + 256 < M) ? r0 + 256 : M;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f, ss = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const float v = __bfloat162float(raw[r * C + c]);
+      s += v;
+      ss += v * v;
+    }
+    atomicAdd(stats + c, (double)s);
+    atomicAdd(stats + C + c, (double)ss);
+  }
+}
+// mean / invstd for the apply pass; running statistics updated like nn.BatchNorm2d (momentum, unbiased variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t M, int C, float eps, float momentum,
+                                   float* __restrict__ mean_invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = stats[c] / (double)M;
+  double var = stats[C + c] / (double)M - mean * mean;
+  if (var < 0) var = 0;
+  mean_invstd[c] = (float)mean;
+  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+// out = act( (raw - mean) * invstd * gamma + beta (+ residual) ), 8 channels per thread
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int C,
+                                const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const __nv_bfloat16* __restrict__ residual, int relu,
+                                __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunks = C / 8;
+  if (idx >= M * chunks) return;
+  const int c0 = (int)(idx % chunks) * 8;
+  const int64_t off = (idx / chunks) * C + c0;
+  const uint4 v = *reinterpret_cast<const uint4*>(raw + off);
+  float x[8];
+  float2 t;
+  t = unpack_bf16x2(v.x); x[0] = t.x; x[1] = t.y;
+  t = unpack_bf16x2(v.y); x[2] = t.x; x[3] = t.y;
+  t = unpack_bf16x2(v.z); x[4] = t.x; x[5] = t.y;
+  t = unpack_bf16x2(v.w); x[6] = t.x; x[7] = t.y;
+  float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (residual) {
+    const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
+    t = unpack_bf16x2(rv.x); r[0] = t.x; r[1] = t.y;
+    t = unpack_bf16x2(rv.y); r[2] = t.x; r[3] = t.y;
+    t = unpack_bf16x2(rv.z); r[4] = t.x; r[5] = t.y;
+    t = unpack_bf16x2(rv.w); r[6] = t.x; r[7] = t.y;
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = c0 + q;
+    float y = (x[q] - mean_invstd[c]) * mean_invstd[C + c] * gamma[c] + beta[c] + r[q];
+    x[q] = relu ? fmaxf(y, 0.f) : y;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(x[0], x[1]);
+  o.y = pack_bf16x2(x[2], x[3]);
+  o.z = pack_bf16x2(x[4], x[5]);
+  o.w = pack_bf16x2(x[6], x[7]);
+  *reinterpret_cast<uint4*>(out + off) = o;
+}
+// raw (un-folded) weights: bf16 [O][R][S][I]; conv1: 3 channels summed, [64][64] with k = r*7+s
+__global__ void pack_conv_raw_kernel(const float* __restrict__ w, int cout, int cin, int k,
+                                     __nv_bfloat16* __restrict__ wp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * cin * k * k) return;
+  const int i = idx % cin;
+  const int s = (idx / cin) % k;
+  const int r = (idx / (cin * k)) % k;
+  const int o = idx / (cin * k * k);
+  wp[idx] = __float2bfloat16_rn(w[((o * cin + i) * k + r) * k + s]);
+}
+__global__ void pack_conv1_raw_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w1) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int o = idx / 64, k = idx % 64;
+  float v = 0.f;
+  if (k < 49) v = w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k];
+  w1[idx] = __float2bfloat16_rn(v);
+}
+
 }  // namespace avvad
 
 using namespace avvad;
@@ -350,6 +442,11 @@ struct avvad_resnet18 {
   __nv_bfloat16* w1s;  // conv1 folded bf16 [64][64] in packed-stem K order (TMA stem, default)
   bool set[20];
   bool smem_attr;
+  // training mode (batch-statistics BN): un-folded bf16 weights and BN affine parameters
+  __nv_bfloat16* wraw[20];
+  float* gamma[20];
+  float* beta[20];
+  bool set_train[20];
 };
 
 extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
@@ -359,6 +456,11 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     h->w[i] = nullptr;
     h->bias[i] = nullptr;
     h->set[i] = false;
+  }
+  for (int i = 0; i < 20; ++i) {
+    h->wraw[i] = nullptr;
+    h->gamma[i] = h->beta[i] = nullptr;
+    h->set_train[i] = false;
   }
   h->w1 = nullptr;
   h->w1b = nullptr;
@@ -384,6 +486,11 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
   for (int i = 0; i < 20; ++i) {
     cudaFree(h->w[i]);
     cudaFree(h->bias[i]);
+  }
+  for (int i = 0; i < 20; ++i) {
+    cudaFree(h->wraw[i]);
+    cudaFree(h->gamma[i]);
+    cudaFree(h->beta[i]);
   }
   cudaFree(h->w1);
   cudaFree(h->w1b);
@@ -650,5 +757,158 @@ extern "C" int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frame
   const int ho = (upto == 0) ? 17 : s.hout;
   const size_t bytes = (size_t)n_frames * ho * ho * s.cout * sizeof(__nv_bfloat16);
   AVVAD_CUDA(cudaMemcpyAsync(out_act, buf[last], bytes, cudaMemcpyDeviceToDevice, st));
+  return AVVAD_OK;
+}
+
+// =====================================================================================================================
+// Training-mode forward: BatchNorm uses batch statistics over ALL frames of the call (scripts/train_AV_net.py:253 puts
+// the frozen trunk's BN layers into train mode) and updates the running statistics in place.  Layer-major over the
+// whole batch: conv (raw, un-folded weights) -> per-channel statistics -> normalise + affine (+ residual) + ReLU.
+// =====================================================================================================================
+extern "C" int avvad_resnet18_set_conv_train(avvad_resnet18* h, int layer, const float* w, const float* gamma,
+                                             const float* beta, void* stream) {
+  AVVAD_CHECK_ARG(h && layer >= 0 && layer < 20 && w && gamma && beta, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const ConvSpec& s = kSpecs[layer];
+  const size_t wn = (layer == 0) ? 64 * 64 : (size_t)s.cout * s.cin * s.k * s.k;
+  if (!h->wraw[layer]) {
+    AVVAD_CUDA(cudaMalloc(&h->wraw[layer], wn * sizeof(__nv_bfloat16)));
+    AVVAD_CUDA(cudaMalloc(&h->gamma[layer], s.cout * sizeof(float)));
+    AVVAD_CUDA(cudaMalloc(&h->beta[layer], s.cout * sizeof(float)));
+  }
+  if (layer == 0)
+    pack_conv1_raw_kernel<<<16, 256, 0, st>>>(w, h->wraw[0]);
+  else
+    pack_conv_raw_kernel<<<(unsigned)ceil_div((int64_t)wn, 256), 256, 0, st>>>(w, s.cout, s.cin, s.k, h->wraw[layer]);
+  AVVAD_LAUNCHED();
+  AVVAD_CUDA(cudaMemcpyAsync(h->gamma[layer], gamma, s.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AVVAD_CUDA(cudaMemcpyAsync(h->beta[layer], beta, s.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  h->set_train[layer] = true;
+  return AVVAD_OK;
+}
+
+extern "C" size_t avvad_resnet18_train_workspace_bytes(int64_t n_frames) {
+  if (n_frames <= 0) return 0;
+  const size_t act = align_up((size_t)n_frames * kActBytesPerFrame, 1024);
+  const size_t stem = align_up((size_t)n_frames * kStemBytesPerFrame, 1024);
+  return 4 * act + 3 * stem + 64 * 1024;  // activations, raw / stem-output / im2col, statistics
+}
+
+namespace {
+struct TrainCtx {
+  avvad_resnet18* h;
+  int64_t n;
+  double* stats;        // [2*512]
+  float* mean_invstd;   // [2*512]
+  float bn_eps, momentum;
+  float* const* running_mean;
+  float* const* running_var;
+  cudaStream_t st;
+};
+
+// raw [M][C] -> out = act(bn(raw) (+res)); updates the running statistics of `layer`
+int bn_train(const TrainCtx& c, int layer, const __nv_bfloat16* raw, int64_t M, int C, const __nv_bfloat16* residual,
+             int relu, __nv_bfloat16* out) {
+  AVVAD_CUDA(cudaMemsetAsync(c.stats, 0, sizeof(double) * 2 * C, c.st));
+  bn_stats_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, c.st>>>(raw, M, C, c.stats);
+  AVVAD_LAUNCHED();
+  bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, c.st>>>(
+      c.stats, M, C, c.bn_eps, c.momentum, c.mean_invstd, c.running_mean ? c.running_mean[layer] : nullptr,
+      c.running_var ? c.running_var[layer] : nullptr);
+  AVVAD_LAUNCHED();
+  const int64_t total = M * (C / 8);
+  bn_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, c.st>>>(raw, M, C, c.mean_invstd, c.h->gamma[layer],
+                                                                   c.h->beta[layer], residual, relu, out);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+int conv_raw(const TrainCtx& c, int layer, const __nv_bfloat16* in, __nv_bfloat16* raw) {
+  const ConvSpec& s = kSpecs[layer];
+  return avvad_conv2d_nhwc_bf16(in, c.h->wraw[layer], nullptr, nullptr, raw, c.n, s.hin, s.hin, s.cin, s.cout, s.k, s.k,
+                                s.stride, s.pad, 0, c.st);
+}
+}  // namespace
+
+// running_mean / running_var: arrays of 20 device pointers (the module's BatchNorm buffers, updated in place with
+// `momentum`), or NULL to leave running statistics untouched.
+extern "C" int avvad_resnet18_forward_train(avvad_resnet18* h, const float* frames, int64_t n_frames, void* workspace,
+                                            size_t workspace_bytes, float bn_eps, float momentum,
+                                            float* const* running_mean, float* const* running_var, float* feat,
+                                            void* feat_bf16, int64_t ld_bf16, int64_t col_off, void* stream) {
+  AVVAD_CHECK_ARG(h && frames && workspace && n_frames > 0 && (feat || feat_bf16), "bad argument");
+  for (int i = 0; i < 20; ++i)
+    if (!h->set_train[i]) {
+      set_error("resnet18: training weights of conv layer " + std::to_string(i) + " not loaded");
+      return AVVAD_ERR_STATE;
+    }
+  if (workspace_bytes < avvad_resnet18_train_workspace_bytes(n_frames)) {
+    set_error("resnet18: training workspace too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = n_frames;
+  const size_t act = align_up((size_t)n * kActBytesPerFrame, 1024);
+  const size_t stem = align_up((size_t)n * kStemBytesPerFrame, 1024);
+  uint8_t* p = (uint8_t*)workspace;
+  __nv_bfloat16* buf[4];
+  for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>(p + i * act);
+  __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(p + 4 * act);            // raw conv output (largest: stem)
+  __nv_bfloat16* stem_out = reinterpret_cast<__nv_bfloat16*>(p + 4 * act + stem);
+  __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(p + 4 * act + 2 * stem);
+  double* stats = reinterpret_cast<double*>(p + 4 * act + 3 * stem);
+  float* mean_invstd = reinterpret_cast<float*>(p + 4 * act + 3 * stem + 16 * 1024);
+  TrainCtx c{h, n, stats, mean_invstd, bn_eps, momentum, running_mean, running_var, st};
+
+  // stem: im2col -> raw K=64 GEMM -> BN(batch stats) + ReLU -> max-pool
+  {
+    const int64_t M = n * 1156;
+    stem_im2col_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(frames, n, cols);
+    AVVAD_LAUNCHED();
+    tc::EpiParams ep{};
+    ep.C = raw;
+    ep.ldc = 64;
+    int rc = tc::gemm_dispatch(cols, 64, h->wraw[0], 64, M, 64, 64, ep, tc::EPI_BF16, 64, st);
+    if (rc) return rc;
+    rc = bn_train(c, 0, raw, M, 64, nullptr, 1, stem_out);
+    if (rc) return rc;
+    const int64_t total = n * 17 * 17 * 8;
+    maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem_out, n, 34, 17, 64, buf[0]);
+    AVVAD_LAUNCHED();
+  }
+  int cur = 0, layer = 1;
+  for (int stage = 0; stage < 4; ++stage) {
+    for (int blk = 0; blk < 2; ++blk) {
+      int o[3], k = 0;
+      for (int i = 0; i < 4; ++i)
+        if (i != cur) o[k++] = i;
+      const bool ds = (stage > 0 && blk == 0);
+      const int la = layer, lb = layer + 1, lds = layer + 2;
+      const ConvSpec& sa = kSpecs[la];
+      const int64_t Mo = n * sa.hout * sa.hout;
+      int rc = conv_raw(c, la, buf[cur], raw);
+      if (rc) return rc;
+      rc = bn_train(c, la, raw, Mo, sa.cout, nullptr, 1, buf[o[0]]);
+      if (rc) return rc;
+      const __nv_bfloat16* res = buf[cur];
+      if (ds) {
+        rc = conv_raw(c, lds, buf[cur], raw);
+        if (rc) return rc;
+        rc = bn_train(c, lds, raw, Mo, sa.cout, nullptr, 0, buf[o[1]]);
+        if (rc) return rc;
+        res = buf[o[1]];
+      }
+      rc = conv_raw(c, lb, buf[o[0]], raw);
+      if (rc) return rc;
+      rc = bn_train(c, lb, raw, Mo, sa.cout, res, 1, buf[o[2]]);
+      if (rc) return rc;
+      cur = o[2];
+      layer += ds ? 3 : 2;
+    }
+  }
+  const int64_t total = n * (512 / 8);
+  avgpool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(buf[cur], n, 9, 512, feat,
+                                                                 (__nv_bfloat16*)feat_bf16, ld_bf16, col_off);
+  AVVAD_LAUNCHED();
   return AVVAD_OK;
 }

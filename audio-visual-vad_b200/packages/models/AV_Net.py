@@ -6,7 +6,7 @@ import torchvision.models as models
 
 from .compact_bilinear_pooling import CompactBilinearPooling
 from .utils import weights_init_normal
-from ._engine import E, EngineCache, check_inference_only, device_of
+from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, device_of, lstm_params, trunk_bn_modules)
 
 
 class DeepVAD_AV(nn.Module):
@@ -57,6 +57,7 @@ class DeepVAD_AV(nn.Module):
                           "mcb": E.Mcb() if self.use_mcb else None}
             sd = self.state_dict()
             eng["trunk"].load(sd, device)
+            eng["trunk"].load_train(sd, device)
             eng["lstm"].load(sd, device, "lstm_merged", "vad_merged")
             if self.use_mcb:
                 eng["mcb"].load(sd, device, self.eps)
@@ -66,7 +67,6 @@ class DeepVAD_AV(nn.Module):
     def forward(self, audio, video, lengths, return_posteriors=False):
         """audio (B,T,513), video (B,T,67,67), lengths list / CPU / CUDA tensor -> logits (B,T,y_dim)."""
         device = device_of(audio, video)
-        check_inference_only(self)
         eng = self._build(device)
         batch, frames, height, width = video.size()
         M = batch * frames
@@ -74,12 +74,40 @@ class DeepVAD_AV(nn.Module):
         xv = x.view(M, x.shape[-1])
         vid = video.detach().to(torch.float32).reshape(M, height, width)
         aud = audio.detach().to(torch.float32).reshape(M, self.num_audio_ftrs).contiguous()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad and any(p.requires_grad for p in self.features.parameters()):
+            raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze "
+                                      "'features' as scripts/train_AV_net.py:241-245 does")
+        if need_grad and self.y_dim != 1:
+            raise NotImplementedError("device-side BPTT is implemented for the VAD head (y_dim == 1)")
+
+        # ---- video branch: batch-statistics BN while the module is in train() (train_AV_net.py:253), folded BN in eval()
+        def trunk(feat_bf16=None, col_off=0, want_f32=True):
+            if self.training:
+                bns = trunk_bn_modules(self.features)
+                out = eng["trunk"].forward_train(vid, [(b.running_mean, b.running_var) for b in bns],
+                                                 feat_bf16=feat_bf16, col_off=col_off, want_f32=want_f32)
+                for b in bns:
+                    b.num_batches_tracked += 1
+                return out
+            return eng["trunk"].forward(vid, feat_bf16=feat_bf16, col_off=col_off, want_f32=want_f32)
+
+        proxy = None
         if self.use_mcb:
-            feat = eng["trunk"].forward(vid)
-            eng["mcb"].forward(aud, feat, out_bf16=xv)
+            feat = trunk()
+            if self.training:
+                proxy = McbBnFunction.apply(eng["mcb"], aud, feat, x, self.mcb_bn, self.mcb_bn.weight, self.mcb_bn.bias)
+                self.mcb_bn.num_batches_tracked += 1
+            else:
+                if need_grad and (self.mcb_bn.weight.requires_grad or self.mcb_bn.bias.requires_grad):
+                    raise NotImplementedError("gradients of mcb_bn are implemented for train() mode")
+                eng["mcb"].forward(aud, feat, out_bf16=xv)
         else:
             E.pack_rows_bf16(aud, xv, 0, False)
-            eng["trunk"].forward(vid, feat_bf16=xv, col_off=self.num_audio_ftrs, want_f32=False)
+            trunk(feat_bf16=xv, col_off=self.num_audio_ftrs, want_f32=False)
+        if need_grad:
+            return LstmHeadFunction.apply(eng["lstm"], x, lengths, proxy,
+                                          *lstm_params(self.lstm_merged, self.vad_merged))
         logits, post, dec, _ = eng["lstm"].forward(x, lengths, want_post=return_posteriors,
                                                    want_dec=return_posteriors)
         if return_posteriors:

@@ -68,6 +68,31 @@ class LstmHeadFunction(torch.autograd.Function):
         return (None, None, None, g["dx"]) + tuple(grads)
 
 
+class McbBnFunction(torch.autograd.Function):
+    """Training-mode MCB fusion.  Fills the bf16 LSTM operand buffer (side effect) and returns a zero-storage fp32
+    proxy of its shape through which the LSTM's input gradient reaches the BatchNorm1d affine parameters (the only
+    trainable tensors upstream of the LSTM: the sketches are buffers and the ResNet is frozen)."""
+
+    @staticmethod
+    def forward(ctx, mcb_engine, audio, feat, x_bf16, bn, gamma, beta):
+        ws, rows = E.mcb_forward_train(mcb_engine, audio, feat, gamma.detach(), beta.detach(), bn.running_mean,
+                                       bn.running_var, x_bf16.view(-1, x_bf16.shape[-1]), momentum=bn.momentum)
+        ctx.mcb_engine, ctx.ws, ctx.rows = mcb_engine, ws, rows
+        B, T, _ = x_bf16.shape
+        return torch.zeros(1, device=x_bf16.device).expand(B, T, 1024)
+
+    @staticmethod
+    def backward(ctx, dx):
+        dg, db = E.mcb_backward_bn(ctx.mcb_engine, ctx.ws, ctx.rows, dx)
+        ctx.ws = None
+        return None, None, None, None, None, dg, db
+
+
+def trunk_bn_modules(features: torch.nn.Module):
+    """The 20 BatchNorm2d modules of the trunk in libavvad's conv-layer order."""
+    return [features.get_submodule(bk) for _, bk in E.RESNET_LAYER_KEYS]
+
+
 def lstm_params(lstm: torch.nn.LSTM, head: torch.nn.Linear):
     ps = []
     for l in range(lstm.num_layers):

@@ -133,6 +133,18 @@ int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_fra
 int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frames, int64_t n_frames, int upto,
                                 void* workspace, size_t workspace_bytes, void* out_act, void* stream);
 
+/* Training-mode forward: BatchNorm uses the batch statistics of this call (all n_frames frames) and
+ * updates running_mean / running_var (arrays of 20 device pointers in the conv layer order above; NULL = leave
+ * untouched) with `momentum`, as nn.BatchNorm2d does while scripts/train_AV_net.py:253 keeps the frozen trunk in
+ * train() mode.  avvad_resnet18_set_conv_train loads the un-folded conv weight and the BN affine parameters. */
+int avvad_resnet18_set_conv_train(avvad_resnet18* h, int layer, const float* w, const float* gamma, const float* beta,
+                                  void* stream);
+size_t avvad_resnet18_train_workspace_bytes(int64_t n_frames);
+int avvad_resnet18_forward_train(avvad_resnet18* h, const float* frames, int64_t n_frames, void* workspace,
+                                 size_t workspace_bytes, float bn_eps, float momentum, float* const* running_mean,
+                                 float* const* running_var, float* feat, void* feat_bf16, int64_t ld_bf16,
+                                 int64_t col_off, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * bf16 tensor-core GEMM  C[M][N] = A[M][K] * W[N][K]^T (+bias)   (tcgen05 / TMEM)
  * Exposed for tests and for the LSTM / head projections.  A, W bf16 row-major with K % 64 == 0
@@ -171,6 +183,16 @@ size_t avvad_mcb_workspace_bytes(int64_t rows);
 int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* video, int64_t rows,
                       void* workspace, size_t workspace_bytes, void* out_bf16, int64_t ld_out,
                       float* out_f32, void* stream);
+
+/* Training mode (module in train()): BatchNorm1d uses this call's batch statistics and the CURRENT gamma/beta, updates
+ * running_mean/var in place (NULL = leave); the workspace then carries what avvad_mcb_backward_bn needs to turn the
+ * gradient w.r.t. the BN output (dx, f32 [rows][ld_dx]) into dgamma / dbeta [1024]. */
+int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const float* video, int64_t rows, void* workspace,
+                            size_t workspace_bytes, const float* gamma, const float* beta, float momentum,
+                            float* running_mean, float* running_var, void* out_bf16, int64_t ld_out, float* out_f32,
+                            void* stream);
+int avvad_mcb_backward_bn(avvad_mcb* h, void* workspace, const float* dx, int64_t ld_dx, int64_t rows, float* dgamma,
+                          float* dbeta, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 2-layer (generic L) unidirectional LSTM over padded batches + Linear head (SURVEY R1,R2,H1,H2)

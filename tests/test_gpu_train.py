@@ -94,3 +94,67 @@ def test_two_training_steps_reduce_the_loss():
         opt.zero_grad()
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
+
+
+def test_trunk_train_mode_bn_matches_oracle():
+    """Batch-statistics BatchNorm: features and updated running statistics vs the fp32 oracle."""
+    sd = synth.seeded_state_dict(synth.model_spec("video"), seed=12)
+    frames = torch.randn(24, 67, 67, generator=torch.Generator().manual_seed(4))
+    ref = om.resnet18_trunk(frames, sd, training=True).numpy()
+    # oracle running-stat update of the stem BN (momentum 0.1, unbiased variance)
+    x0 = torch.nn.functional.conv2d(frames.unsqueeze(1).repeat(1, 3, 1, 1), sd["features.0.weight"], None, stride=2, padding=3)
+    rm_ref = 0.9 * sd["features.1.running_mean"] + 0.1 * x0.mean(dim=(0, 2, 3))
+    rv_ref = 0.9 * sd["features.1.running_var"] + 0.1 * x0.var(dim=(0, 2, 3), unbiased=True)
+    trunk = E.ResNet18Trunk()
+    trunk.load_train(sd, "cuda")
+    running = []
+    for _, bk in E.RESNET_LAYER_KEYS:
+        running.append((sd["features." + bk + ".running_mean"].clone().cuda(), sd["features." + bk + ".running_var"].clone().cuda()))
+    feat = trunk.forward_train(frames.cuda(), running).cpu().numpy()
+    st = err_stats(feat, ref)
+    assert st["rel_fro"] < 3e-2, st
+    assert np.allclose(running[0][0].cpu().numpy(), rm_ref.numpy(), atol=2e-3)
+    assert np.allclose(running[0][1].cpu().numpy(), rv_ref.numpy(), rtol=2e-2, atol=1e-3)
+
+
+@pytest.mark.parametrize("use_mcb", [False, True])
+def test_av_training_step_matches_autograd(use_mcb):
+    from packages.models.AV_Net import DeepVAD_AV
+    B, T = 3, 10
+    lens = [10, 7, 4]
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn(B, T, 513, generator=g)
+    v = torch.randn(B, T, 67, 67, generator=g)
+    y = (torch.rand(B, T, 1, generator=g) > 0.5).float()
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=use_mcb), seed=55)
+    # oracle: train-mode forward (batch-stat BN in trunk and mcb_bn), trainable = everything but the trunk
+    p = {k: (t.clone().requires_grad_(True) if (t.is_floating_point() and not k.startswith("features.")
+                                                  and "running" not in k and not k.startswith("mcb.sketch")) else t.clone())
+         for k, t in sd.items()}
+    logits_ref = om.deepvad_av_forward(a, v, lens, p, use_mcb=use_mcb, eps=1e-8, training=True)
+    loss_ref = om.batch_loss(logits_ref, y, lens, 1e-8)
+    loss_ref.backward()
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=use_mcb, eps=1e-8)
+    m.load_state_dict(sd)
+    for name, child in m.named_children():  # scripts/train_AV_net.py:241-245
+        if name == "features":
+            for q in child.parameters():
+                q.requires_grad = False
+    m = m.cuda().train()
+    logits = m(a.cuda(), v.cuda(), torch.tensor(lens).cuda())
+    loss, _, dl = E.batch_bce(logits, y.cuda(), lens, 1e-8, want_grad=True)
+    assert abs(loss.item() - loss_ref.item()) < 3e-2 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    logits.backward(dl)
+    names = ["lstm_merged.weight_ih_l0", "lstm_merged.weight_hh_l0", "lstm_merged.bias_ih_l0", "lstm_merged.weight_ih_l1",
+             "lstm_merged.weight_hh_l1", "vad_merged.weight"]
+    if use_mcb:
+        names += ["mcb_bn.weight", "mcb_bn.bias"]
+    report = {}
+    params = dict(m.named_parameters())
+    for k in names:
+        st = err_stats(params[k].grad.cpu().numpy(), p[k].grad.numpy())
+        report[k] = round(st["rel_fro"], 4)
+    print("AV grad rel errors:", report)
+    for k, e in report.items():
+        assert e < 6e-2, report
+    assert int(m.features[1].num_batches_tracked) == 1
