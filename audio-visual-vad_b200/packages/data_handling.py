@@ -1,0 +1,120 @@
+"""Dataset classes the three train scripts build (same names, constructor keywords and item tuples as
+packages/data_handling.py:192-495).  The per-utterance front end (peak-normalise -> STFT -> |.|^2 -> log) runs through
+packages.processing.stft.stft_pytorch, i.e. on the GPU: use num_workers=0 (or a 'spawn' worker context) with the
+spectrogram datasets, or the *Wav* variants + avvad.pipeline / collate_many2many_*_waveform to keep the workers CPU-only
+and do the whole front end batched on the device.  The legacy HDF5*/VideoFrames datasets are not provided."""
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from packages._io import load_wav, read_h5
+from packages.dataset.ntcd_timit import proc_noisy_clean_pair_dict, proc_video_audio_pair_dict
+from packages.processing.stft import stft_pytorch
+
+
+def _log_power(wave, ds):
+    """data_handling.py:441-457: x / max|x| -> STFT -> re^2 + im^2 -> log(. + eps), (513, T)."""
+    wave = wave / torch.max(torch.abs(wave))
+    tf = stft_pytorch(wave, fs=ds.fs, wlen_sec=ds.wlen_sec, win=ds.win, hop_percent=ds.hop_percent, center=ds.center,
+                      pad_mode=ds.pad_mode, pad_at_end=ds.pad_at_end)
+    return torch.log(tf[..., 0] ** 2 + tf[..., 1] ** 2 + ds.eps)
+
+
+class _StftConfig:
+    def _set_stft(self, fs, wlen_sec, win, hop_percent, center, pad_mode, pad_at_end, eps):
+        self.fs, self.wlen_sec, self.win, self.hop_percent = fs, wlen_sec, win, hop_percent
+        self.center, self.pad_mode, self.pad_at_end, self.eps = center, pad_mode, pad_at_end, eps
+
+
+class WavWholeSequenceSpectrogramLabeledFrames(Dataset):
+    """Video-only items (video (67,67,T), label (y_dim,T), length) (data_handling.py:192-229)."""
+
+    def __init__(self, input_video_dir, dataset_type, labels='vad_labels', upsampled=False, dct=False, norm_video=False):
+        self.dataset_type, self.input_video_dir, self.labels = dataset_type, input_video_dir, labels
+        self.video_file_paths, self.audio_file_paths = proc_video_audio_pair_dict(
+            input_video_dir=input_video_dir, dataset_type=dataset_type, labels=labels, upsampled=upsampled, dct=dct,
+            norm_video=norm_video)
+        self.dataset_len = len(self.video_file_paths)
+
+    def __getitem__(self, i):
+        data = read_h5(self.input_video_dir + self.video_file_paths[i], "X")
+        label = read_h5(self.input_video_dir + self.audio_file_paths[i], "Y")
+        return torch.Tensor(data), torch.Tensor(label), data.shape[-1]
+
+    def __len__(self):
+        return self.dataset_len
+
+
+class _NoisyBase(Dataset, _StftConfig):
+    def __init__(self, input_video_dir, dataset_type, dataset_size, labels='vad_labels', upsampled=False, fs=16000,
+                 wlen_sec=64e-3, win='hann', hop_percent=0.25, center=True, pad_mode='reflect', pad_at_end=True,
+                 eps=1e-8):
+        self.input_video_dir, self.dataset_type, self.dataset_size = input_video_dir, dataset_type, dataset_size
+        self.labels, self.upsampled = labels, upsampled
+        self._set_stft(fs, wlen_sec, win, hop_percent, center, pad_mode, pad_at_end, eps)
+        pairs = proc_noisy_clean_pair_dict(input_speech_dir=input_video_dir, dataset_type=dataset_type,
+                                           dataset_size=dataset_size, labels=labels, upsampled=upsampled)
+        self.noisy_clean_pair_paths = list(pairs.items())
+        self.dataset_len = len(self.noisy_clean_pair_paths)
+
+    def __len__(self):
+        return self.dataset_len
+
+    def _wave(self, i):
+        noisy, clean = self.noisy_clean_pair_paths[i]
+        wave, _ = load_wav(self.input_video_dir + noisy)
+        return wave[0], clean
+
+    def _video_path(self, clean):
+        p = clean.replace('Clean', 'matlab_raw').replace('_' + self.labels, '')
+        p = os.path.splitext(p)[0] + ('.h5' if self.upsampled else '_normvideo.h5')
+        return self.input_video_dir + p
+
+
+class NoisyWavWholeSequenceSpectrogramLabeledFrames(_NoisyBase):
+    """Audio-only items (log-power (513,T), label (y_dim,T), length) (data_handling.py:231-324)."""
+
+    def __getitem__(self, i):
+        wave, clean = self._wave(i)
+        data = _log_power(wave, self)
+        label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
+        n = min(data.shape[-1], label.shape[-1])  # the reference's longer-label branch overwrites data: not reproduced
+        return data[..., :n], label[..., :n] if label.shape[-1] > n else label, n
+
+
+class AudioVisualSequenceLabeledFrames(_NoisyBase):
+    """AV items (log-power (513,T), video (67,67,T), label (y_dim,T), length), all trimmed to the common length
+    (data_handling.py:387-495)."""
+
+    def __getitem__(self, i):
+        wave, clean = self._wave(i)
+        spec = _log_power(wave, self)
+        video = torch.Tensor(read_h5(self._video_path(clean), "X"))
+        label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
+        n = min(spec.shape[-1], video.shape[-1], label.shape[-1])
+        return spec[..., :n], video[..., :n], label[..., :n], n
+
+
+class AudioVisualSequenceWavLabeledFrames(_NoisyBase):
+    """Waveform variant (data_handling.py:497-566): (peak-normalised wave (N,), video, label, length, time_length);
+    pair with collate_many2many_AV_waveform and the on-device front end."""
+
+    def __getitem__(self, i):
+        wave, clean = self._wave(i)
+        wave = wave / torch.max(torch.abs(wave))
+        video = torch.Tensor(read_h5(self._video_path(clean), "X"))
+        label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
+        n = min(video.shape[-1], label.shape[-1])
+        return wave, video[..., :n], label[..., :n], n, wave.shape[-1]
+
+
+class NoisyWavWholeSequenceWavLabeledFrames(_NoisyBase):
+    """Waveform variant of the audio-only dataset (data_handling.py:326-385): (wave, label, time_length, tf_length)."""
+
+    def __getitem__(self, i):
+        wave, clean = self._wave(i)
+        wave = wave / torch.max(torch.abs(wave))
+        label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
+        return wave, label, wave.shape[-1], label.shape[-1]

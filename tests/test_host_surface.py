@@ -1,0 +1,89 @@
+"""CPU: the host-side part of the reference-compatible surface (imports, path builders, label generation, collate,
+metrics) -- what scripts/train_*_net.py and scripts/evaluate_*_net.py import at module top must import cleanly."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_script_level_imports_resolve():
+    from packages.models.utils import f1_loss, binary_cross_entropy  # noqa: F401
+    from packages.processing.stft import stft_pytorch  # noqa: F401
+    from packages.models.AV_Net import DeepVAD_AV  # noqa: F401
+    from packages.models.Audio_Net import DeepVAD_audio  # noqa: F401
+    from packages.models.Video_Net import DeepVAD_video  # noqa: F401
+    from packages.visualization import display_multiple_signals  # noqa: F401
+    from packages.dataset.ntcd_timit import proc_noisy_clean_pair_dict, speech_list, proc_video_audio_pair_dict  # noqa: F401
+    from packages.data_handling import (AudioVisualSequenceLabeledFrames, NoisyWavWholeSequenceSpectrogramLabeledFrames,  # noqa: F401
+                                        WavWholeSequenceSpectrogramLabeledFrames)
+    from packages.utils import count_parameters, collate_many2many_AV, collate_many2many_audio, collate_many2many_video  # noqa: F401
+    from packages.models.wavenet_autoencoder import wavenet_autoencoder  # noqa: F401
+    import packages.metrics  # noqa: F401
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    from avvad import synth
+    from packages.models.AV_Net import DeepVAD_AV
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models.Video_Net import DeepVAD_video
+    for mod, kind, kw in ((DeepVAD_AV(2, 1024, 1, use_mcb=True), "av", {"use_mcb": True}),
+                          (DeepVAD_AV(2, 1024, 1, use_mcb=False), "av", {"use_mcb": False}),
+                          (DeepVAD_audio(2, 1024, 1), "audio", {}), (DeepVAD_video(2, 1024, 1), "video", {})):
+        sd = mod.state_dict()
+        spec = synth.model_spec(kind, **kw)
+        assert list(sd.keys()) == list(spec.keys()) or set(sd.keys()) == set(spec.keys())
+        for k, (shape, dtype) in spec.items():
+            assert tuple(sd[k].shape) == tuple(shape) and sd[k].dtype == dtype, k
+    assert len(DeepVAD_AV(2, 1024, 1, use_mcb=True).state_dict()) == 144
+    assert "features" in dict(DeepVAD_AV(2, 1024, 1).named_children())
+
+
+def test_labels_reproduce_reference_files():
+    from packages.processing import target as tg
+    g = np.load(os.path.join(G, "golden_frontend_34M.npz"))
+    for utt in ("sa1", "sa2", "si494"):
+        x = g[utt + "_wav"].astype(np.float32) / 32768.0
+        x = x / np.abs(x).max()
+        vad = tg.clean_speech_VAD(x, fs=16000, wlen_sec=0.064, hop_percent=0.25, center=False)
+        assert np.array_equal(vad.astype(np.uint8), g[utt + "_vad"])
+
+
+def test_collate_matches_reference_golden():
+    from packages.utils import collate_many2many_AV
+    g = np.load(os.path.join(G, "ref_models.npz"))
+    a, v, t = g["collate_in_a"], g["collate_in_v"], g["collate_in_t"]
+    batch, oa, ov, ot = [], 0, 0, 0
+    for L in (5, 3, 4):
+        batch.append((torch.tensor(a[oa:oa + 513 * L]).view(513, L), torch.tensor(v[ov:ov + 4489 * L]).view(67, 67, L),
+                      torch.tensor(t[ot:ot + L]).view(1, L), L))
+        oa, ov, ot = oa + 513 * L, ov + 4489 * L, ot + L
+    lens, pa, pv, pt = collate_many2many_AV(batch)
+    assert np.array_equal(lens.numpy(), g["collate_lens"]) and np.array_equal(pa.numpy(), g["collate_a"])
+    assert np.array_equal(pv.numpy(), g["collate_v"]) and np.array_equal(pt.numpy(), g["collate_t"])
+
+
+def test_path_builders_on_the_reference_subset():
+    root = "/root/reference/data/subset/processed/"
+    if not os.path.isdir(root):
+        pytest.skip("reference data not present (GPU box)")
+    from packages.dataset.ntcd_timit import proc_noisy_clean_pair_dict, proc_video_audio_pair_dict
+    from packages.data_handling import WavWholeSequenceSpectrogramLabeledFrames
+    pairs = proc_noisy_clean_pair_dict(root, "test", "subset", "vad_labels", upsampled=False)
+    assert list(pairs.items())[0] == ("ntcd_timit/Noisy/Babble/-5/test/34M/sa1.wav", "ntcd_timit/Clean/test/34M/sa1_vad_labels.h5")
+    v, a = proc_video_audio_pair_dict(root, "test", "vad_labels", upsampled=True)
+    assert len(v) == 3 and v[0].endswith("sa1_upsampled.h5") and a[0].endswith("sa1_vad_labels.h5")
+    x, y, n = WavWholeSequenceSpectrogramLabeledFrames(root, "test", labels="vad_labels", upsampled=True)[0]
+    assert tuple(x.shape) == (67, 67, 317) and tuple(y.shape) == (1, 317) and n == 317
+
+
+def test_metrics_helpers():
+    from packages.metrics import energy_ratios, mean_confidence_interval
+    rng = np.random.default_rng(0)
+    s, n = rng.standard_normal(1000), 0.1 * rng.standard_normal(1000)
+    sdr, sir, sar = energy_ratios(s + n, s, n)
+    assert sdr > 15 and sir > 15
+    m, h = mean_confidence_interval([1.0, 2.0, 3.0, 4.0])
+    assert m == 2.5 and h > 0
