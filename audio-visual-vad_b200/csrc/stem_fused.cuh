@@ -16,7 +16,8 @@
 namespace avvad {
 namespace tc {
 
-constexpr int kStemThreads = 256;
+constexpr int kStemThreads = 512;
+constexpr int kStemPrefetch = (67 * 67 + kStemThreads - 1) / kStemThreads;  // pixels per thread
 constexpr int kImgPitchB = 80;                 // bf16 elements per padded image row (73 used)
 constexpr int kImgRows = 73;
 constexpr uint32_t kStemImgBytes = 12288;      // 73*80*2 = 11680, rounded
@@ -25,21 +26,21 @@ constexpr uint32_t kStemWBytes = 8192;
 constexpr uint32_t kStemConvBytes = 1156 * 128 + 512;  // + slack for the 4-row tail tile's unused rows
 constexpr uint32_t kStemSmem = 1024 + kStemABytes + kStemWBytes + kStemImgBytes + kStemConvBytes + 256 /*bias*/ + 64;
 
-template <int HALF>
-__device__ __forceinline__ void stem_build_half(const __nv_bfloat16* __restrict__ ip, uint32_t dst_row, int rsw) {
-  // k = HALF*32 + i, tap (fr, fs) = (k / 7, k % 7), value = ip[fr*80 + fs]; k >= 49 -> 0
-  uint32_t w[16];
+template <int PART>
+__device__ __forceinline__ void stem_build_quarter(const __nv_bfloat16* __restrict__ ip, uint32_t dst_row, int rsw) {
+  // k = PART*16 + i, tap (fr, fs) = (k / 7, k % 7), value = ip[fr*80 + fs]; k >= 49 -> 0
+  uint32_t w[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int k0 = HALF * 32 + 2 * i, k1 = k0 + 1;
+  for (int i = 0; i < 8; ++i) {
+    const int k0 = PART * 16 + 2 * i, k1 = k0 + 1;
     uint32_t lo = 0, hi = 0;
     if (k0 < 49) lo = *reinterpret_cast<const unsigned short*>(ip + (k0 / 7) * kImgPitchB + (k0 % 7));
     if (k1 < 49) hi = *reinterpret_cast<const unsigned short*>(ip + (k1 / 7) * kImgPitchB + (k1 % 7));
     w[i] = lo | (hi << 16);
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = HALF * 4 + j;
+  for (int j = 0; j < 2; ++j) {
+    const int c = PART * 2 + j;
     const uint32_t dst = dst_row + (uint32_t)((c ^ rsw) << 4);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w[4 * j]), "r"(w[4 * j + 1]),
                  "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
@@ -91,14 +92,29 @@ stem_fused_kernel(const float* __restrict__ frames, int64_t n_frames, const __nv
   const uint32_t w_lo = desc_lo(sW);
 
   uint32_t uses0 = 0, uses1 = 0;  // completed-phase counters of the two MMA barriers
-  const int q = warp & 3, chalf = warp >> 2;  // epilogue: TMEM lane quarter, 32-column half
+  const int q = warp & 3, cgrp = warp >> 2;  // epilogue: TMEM lane quarter, 16-column group
+
+  // the pixels of a frame are fetched into registers one frame ahead (while the previous frame is being pooled)
+  float pf[kStemPrefetch];
+  auto prefetch = [&](int64_t f) {
+    const float* src = frames + f * (67 * 67);
+#pragma unroll
+    for (int j = 0; j < kStemPrefetch; ++j) {
+      const int i = tid + j * kStemThreads;
+      pf[j] = (i < 67 * 67) ? __ldg(src + i) : 0.f;
+    }
+  };
+  if ((int64_t)blockIdx.x < n_frames) prefetch(blockIdx.x);
 
   for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
-    // ---- 1. frame -> padded bf16 image
-    const float* src = frames + f * (67 * 67);
-    for (int i = tid; i < 67 * 67; i += kStemThreads) {
-      const int r = i / 67, c = i - r * 67;
-      img[(r + 3) * kImgPitchB + c + 3] = __float2bfloat16_rn(__ldg(src + i));
+    // ---- 1. prefetched frame -> padded bf16 image (the previous frame's last im2col tile has been built)
+#pragma unroll
+    for (int j = 0; j < kStemPrefetch; ++j) {
+      const int i = tid + j * kStemThreads;
+      if (i < 67 * 67) {
+        const int r = i / 67, c = i - r * 67;
+        img[(r + 3) * kImgPitchB + c + 3] = __float2bfloat16_rn(pf[j]);
+      }
     }
     __syncthreads();
 
@@ -106,17 +122,21 @@ stem_fused_kernel(const float* __restrict__ frames, int64_t n_frames, const __nv
 #pragma unroll 1
     for (int t = 0; t <= 10; ++t) {
       if (t < 10) {
-        const int r = tid >> 1;
+        const int r = tid >> 2;
         const int m = t * 128 + r;
         const int mm = m < 1156 ? m : 1155;  // tail rows: any valid address, results are ignored
         const int oh = mm / 34, ow = mm - oh * 34;
         const __nv_bfloat16* ip = img + (2 * oh) * kImgPitchB + 2 * ow;
         const uint32_t dst_row = sA + (uint32_t)(t & 1) * 16384u + (uint32_t)(((r >> 3) << 10) + ((r & 7) << 7));
-        if (tid & 1)
-          stem_build_half<1>(ip, dst_row, r & 7);
-        else
-          stem_build_half<0>(ip, dst_row, r & 7);
+        switch (tid & 3) {
+          case 0: stem_build_quarter<0>(ip, dst_row, r & 7); break;
+          case 1: stem_build_quarter<1>(ip, dst_row, r & 7); break;
+          case 2: stem_build_quarter<2>(ip, dst_row, r & 7); break;
+          default: stem_build_quarter<3>(ip, dst_row, r & 7); break;
+        }
         fence_proxy_async();
+      } else if (f + gridDim.x < n_frames) {
+        prefetch(f + gridDim.x);  // t == 10: all tiles of this frame are built; fetch the next frame's pixels now
       }
       __syncthreads();
       if (t < 10 && tid == 0) {
@@ -140,24 +160,24 @@ stem_fused_kernel(const float* __restrict__ frames, int64_t n_frames, const __nv
           ++uses0;
         }
         tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(tmem_acc + (uint32_t)(tp & 7) * 64u + (uint32_t)chalf * 32u + ((uint32_t)(q * 32) << 16), v);
+        uint32_t v[16];
+        tmem_ld16(tmem_acc + (uint32_t)(tp & 7) * 64u + (uint32_t)cgrp * 16u + ((uint32_t)(q * 32) << 16), v);
         tmem_ld_wait();
         const int m = tp * 128 + q * 32 + lane;
         if (m < 1156) {
           uint8_t* crow = conv + m * 128;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             float x[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              x[e] = fmaxf(__uint_as_float(v[8 * c + e]) + bias_s[chalf * 32 + 8 * c + e], 0.f);
+              x[e] = fmaxf(__uint_as_float(v[8 * c + e]) + bias_s[cgrp * 16 + 8 * c + e], 0.f);
             uint4 o;
             o.x = pack_bf16x2(x[0], x[1]);
             o.y = pack_bf16x2(x[2], x[3]);
             o.z = pack_bf16x2(x[4], x[5]);
             o.w = pack_bf16x2(x[6], x[7]);
-            const int chunk = chalf * 4 + c;
+            const int chunk = cgrp * 2 + c;
             *reinterpret_cast<uint4*>(crow + ((chunk ^ (m & 7)) << 4)) = o;
           }
         }

@@ -74,7 +74,8 @@ class DeepVAD_AV(nn.Module):
         xv = x.view(M, x.shape[-1])
         vid = video.detach().to(torch.float32).reshape(M, height, width)
         aud = audio.detach().to(torch.float32).reshape(M, self.num_audio_ftrs).contiguous()
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        # eval() forward is inference only (detached logits, folded BN); the autograd path is the train() step
+        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad and any(p.requires_grad for p in self.features.parameters()):
             raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze "
                                       "'features' as scripts/train_AV_net.py:241-245 does")
@@ -99,8 +100,6 @@ class DeepVAD_AV(nn.Module):
                 proxy = McbBnFunction.apply(eng["mcb"], aud, feat, x, self.mcb_bn, self.mcb_bn.weight, self.mcb_bn.bias)
                 self.mcb_bn.num_batches_tracked += 1
             else:
-                if need_grad and (self.mcb_bn.weight.requires_grad or self.mcb_bn.bias.requires_grad):
-                    raise NotImplementedError("gradients of mcb_bn are implemented for train() mode")
                 eng["mcb"].forward(aud, feat, out_bf16=xv)
         else:
             E.pack_rows_bf16(aud, xv, 0, False)
