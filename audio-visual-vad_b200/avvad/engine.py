@@ -147,6 +147,25 @@ def conv2d_nhwc_bf16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tens
     return out
 
 
+def conv2d_nhwc_bf16_dual(x: torch.Tensor, x2: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
+                          stride: int, pad: int, k: int, stride2: int, relu=False) -> torch.Tensor:
+    """out = act(conv_kxk(x; w[:, :k*k*Cin]) + conv_1x1_stride2(x2; w[:, k*k*Cin:]) + bias) in one implicit GEMM."""
+    L.require_cuda(x, x2, w)
+    x, x2, w = x.contiguous(), x2.contiguous(), w.contiguous()
+    n, H, W, Cin = x.shape
+    _, H2, W2, Cin2 = x2.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == k * k * Cin + Cin2
+    OH = (H + 2 * pad - k) // stride + 1
+    OW = (W + 2 * pad - k) // stride + 1
+    out = torch.empty(n, OH, OW, Cout, dtype=torch.bfloat16, device=x.device)
+    b = _f32(bias, x.device) if bias is not None else None
+    L.check(L.lib().avvad_conv2d_nhwc_bf16_dual(L.ptr(x), L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(out), n, H, W, Cin, H2, W2,
+                                                Cin2, stride2, Cout, k, k, stride, pad, 1 if relu else 0,
+                                                L.stream_ptr()))
+    return out
+
+
 def pack_rows_bf16(src: torch.Tensor, dst: torch.Tensor, col_off: int, zero_tail: bool):
     """dst[m, col_off:col_off+cols] = bf16(src[m, :]) (dst is a (rows, ld) bf16 operand buffer)."""
     rows, cols = src.shape

@@ -324,6 +324,29 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
                     (cudaStream_t)stream);
 }
 
+extern "C" int avvad_conv2d_nhwc_bf16_dual(const void* in, const void* in2, const void* w, const float* bias, void* out,
+                                           int64_t n, int H, int W, int Cin, int H2, int W2, int Cin2, int stride2,
+                                           int Cout, int R, int S, int stride, int pad, int relu, void* stream) {
+  AVVAD_CHECK_ARG(in && in2 && w && out, "null pointer");
+  AVVAD_CHECK_ARG(n > 0 && H > 0 && W > 0 && H2 > 0 && W2 > 0 && R > 0 && S > 0 && stride > 0 && stride2 > 0 && pad >= 0,
+                  "bad conv shape");
+  AVVAD_CHECK_ARG(Cin % 64 == 0 && Cin2 % 64 == 0 && Cout % 32 == 0, "Cin, Cin2 multiples of 64 and Cout of 32");
+  if (!tc::use_tma()) {
+    set_error("dual-operand convolution needs the TMA engine");
+    return AVVAD_ERR_STATE;
+  }
+  tc::EpiParams ep{};
+  ep.bias = bias;
+  ep.C = out;
+  ep.ldc = Cout;
+  ep.relu = relu;
+  tc::SecondOperand so;
+  so.in2 = (const __nv_bfloat16*)in2;
+  so.H2 = H2; so.W2 = W2; so.Cin2 = Cin2; so.stride2 = stride2;
+  return tc::launch_tma_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, W, Cin, Cout, R, S, stride,
+                             pad, bn_override(), (cudaStream_t)stream, 0, 0.0, &so);
+}
+
 extern "C" int avvad_pack_rows_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t col_off,
                                     int64_t rows, int64_t cols, int zero_tail, void* stream) {
   AVVAD_CHECK_ARG(src && dst && rows > 0 && cols > 0 && col_off >= 0 && col_off + cols <= ld_dst, "bad argument");

@@ -166,17 +166,25 @@ static int pick_bn(int N, int hint) {
 
 int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
                     int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st, int cat,
-                    double flops_override) {
+                    double flops_override, const SecondOperand* second) {
   const int OH = (H + 2 * pad - R) / stride + 1;
   const int OW = (W + 2 * pad - S) / stride + 1;
   const int KE = (Cin % 64 == 0) ? 64 : 16;  // 16-channel inputs (packed stem) use 32-byte K blocks
   AVVAD_CHECK_ARG(OW <= 128 && Cin % KE == 0, "TMA conv: OW <= 128 and Cin % 64 == 0 (or Cin == 16) required");
   AVVAD_CHECK_ARG(KE == 64 || Cout == 64, "16-channel TMA conv supports Cout == 64 only");
+  const bool dual = second && second->in2;
+  if (dual) {
+    AVVAD_CHECK_ARG(KE == 64 && second->Cin2 % 64 == 0 && second->stride2 >= 1, "second operand: Cin2 % 64 == 0 required");
+    AVVAD_CHECK_ARG((second->H2 - 1) / second->stride2 + 1 == OH && (second->W2 - 1) / second->stride2 + 1 == OW,
+                    "second operand: output grid mismatch");
+  }
   TmaGeom g{};
   g.mode = 1;
   g.OH = OH; g.OW = OW; g.stride = stride; g.pad = pad; g.S = S; g.cpb = Cin / KE; g.KB = R * S * (Cin / KE);
   g.n_frames = n;
   g.N = Cout;
+  g.KB2 = dual ? second->Cin2 / 64 : 0;
+  g.stride2 = dual ? second->stride2 : 1;
   const int bn = pick_bn(Cout, bn_hint);
   g.n_tiles = (Cout + bn - 1) / bn;
   // choose up to two (band height, frames per tile) phases maximising the fill of the 128 accumulator rows
@@ -222,8 +230,20 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
     int rc = encode4(&maps.a[p], in, dims, strides, box, estr, KE == 16);
     if (rc) return rc;
     g.bytesA[p] = (uint32_t)F * hb * OW * (uint32_t)(KE * 2);
+    if (dual) {
+      const int s2 = second->stride2;
+      const uint64_t dims2[4] = {(uint64_t)second->Cin2, (uint64_t)second->W2, (uint64_t)second->H2, (uint64_t)n};
+      const uint64_t strides2[3] = {(uint64_t)second->Cin2 * 2, (uint64_t)second->W2 * second->Cin2 * 2,
+                                    (uint64_t)second->H2 * second->W2 * second->Cin2 * 2};
+      const uint32_t estr2[4] = {1, (uint32_t)s2, (uint32_t)s2, 1};
+      const uint32_t box2[4] = {64, (uint32_t)((OW - 1) * s2 + 1), (uint32_t)((hb - 1) * s2 + 1), (uint32_t)F};
+      rc = encode4(&maps.a2[p], second->in2, dims2, strides2, box2, estr2, false);
+      if (rc) return rc;
+    } else {
+      maps.a2[p] = maps.a[p];
+    }
   }
-  const int K = R * S * Cin;
+  const int K = R * S * Cin + (dual ? second->Cin2 : 0);
   int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)KE, (uint32_t)bn, KE == 16);
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * (uint32_t)(KE * 2);
@@ -255,6 +275,7 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
   int rc = encode4(&maps.a[0], A, dims, strides, box, estr);
   if (rc) return rc;
   maps.a[1] = maps.a[0];
+  maps.a2[0] = maps.a2[1] = maps.a[0];
   g.bytesA[0] = g.bytesA[1] = 128u * 128u;
   rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)bn);
   if (rc) return rc;

@@ -8,7 +8,15 @@
 //                     the map's traversal strides) and a 2-D box {64, BN} of the packed weights for B.  Both land
 //                     in the canonical K-major SWIZZLE_128B layout the UMMA descriptors expect.
 //   warp 1          : TMEM allocation; lane 0 issues tcgen05.mma / tcgen05.commit (as in gemm_tc.cuh).
-//   warps 2-5       : epilogue (TMEM -> registers -> bias / residual / ReLU / LSTM cell -> global).
+//   warps 2-9       : epilogue (TMEM -> registers -> bias / residual / ReLU / LSTM cell -> global).  Two warps per
+//                     TMEM lane quarter split the 32-column chunks of a tile; the residual of a thread's chunks is
+//                     requested BEFORE the wait on the accumulator and the bias sits in shared memory, so no global
+//                     latency is left on the drain path.
+//
+// K-concatenated second operand (ResNet downsample blocks): after the KB blocks of the main convolution the producer
+// appends KB2 blocks of a 1x1 / stride-s2 convolution over a SECOND activation tensor (maps.a2) into the same
+// accumulator -- out = conv3x3(y) + conv1x1_s2(x) + bias -- so the downsample branch costs neither a launch nor an
+// output/residual round trip.  The packed weight rows are [9*C | Cin2] wide.
 //
 // An output tile is F whole frames x a band of hb output rows (F*hb*OW <= 128 accumulator rows).  Up to two
 // "phases" with different (hb, F) cover a frame (e.g. 17x17: two 7-row bands per frame + one 3-row band over
@@ -22,7 +30,9 @@
 namespace avvad {
 namespace tc {
 
-constexpr int kTmaThreads = 192;
+constexpr int kTmaThreads = 320;
+constexpr int kTmaEpiWarps = 8;
+constexpr int kTmaBiasSmem = 1024;  // bias entries staged in shared memory (N <= this), else read through L1
 
 struct TmaGeom {
   int mode;             // 0 = plain GEMM rows, 1 = convolution boxes
@@ -31,6 +41,7 @@ struct TmaGeom {
   int64_t tiles0;       // m-tiles of phase 0 (conv)
   int h0[2], hb[2], nb[2], F[2];  // per phase: first output row, band height, bands per frame, frames per tile
   int OH, OW, stride, pad, S, cpb, KB;
+  int KB2, stride2;     // K-concatenated 1x1 / stride2 / pad 0 second operand (0 = none)
   int64_t n_frames;     // conv: frames in this launch; gemm: M
   int N;
   uint32_t bytesA[2];   // TMA box bytes per phase
@@ -39,6 +50,7 @@ struct TmaGeom {
 
 struct TmaMaps {
   CUtensorMap a[2];
+  CUtensorMap a2[2];  // second operand (per phase), valid when TmaGeom::KB2 > 0
   CUtensorMap b;
 };
 
@@ -84,7 +96,7 @@ struct TmaCfg {
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
   static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? 3 : 4));
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + kTmaBiasSmem * 4;
   // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
   static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
 };
@@ -115,7 +127,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TmaGeom& g, int64_t tile,
 }
 
 template <int BN, int KE>
-__global__ void __launch_bounds__(kTmaThreads)
+__global__ void __launch_bounds__(kTmaThreads, TmaCfg<BN, KE>::kCtasPerSm)
 tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaGeom g, const EpiParams ep,
               const int epi_mode) {
   using C = TmaCfg<BN, KE>;
@@ -138,13 +150,22 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar0 + 8 * (2 * S + a), 1);      // tmem full
-      mbar_init(bar0 + 8 * (2 * S + 2 + a), 4);  // tmem empty: one arrival per epilogue warp
+      mbar_init(bar0 + 8 * (2 * S + 2 + a), kTmaEpiWarps);  // tmem empty: one arrival per epilogue warp
     }
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.a[1]);
+    if (g.KB2 > 0) {
+      tma_prefetch_desc(&maps.a2[0]);
+      tma_prefetch_desc(&maps.a2[1]);
+    }
     tma_prefetch_desc(&maps.b);
   }
+  // bias -> shared memory (behind the barriers and the TMEM slot); zero when absent
+  float* bias_s = reinterpret_cast<float*>(smem + S * C::kStageBytes + 256);
+  const bool bias_in_smem = g.N <= kTmaBiasSmem;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < g.N; i += kTmaThreads) bias_s[i] = ep.bias ? ep.bias[i] : 0.f;
   if (warp == 1) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
     tmem_relinquish();
@@ -184,6 +205,16 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             }
           }
         }
+        for (int kb2 = 0; kb2 < g.KB2; ++kb2, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1u;
+          mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+          const uint32_t full = bar0 + 8 * s;
+          const uint32_t sa = base + s * C::kStageBytes;
+          mbar_arrive_expect_tx(full, bytes);
+          tma_load_4d(sa, &maps.a2[t.phase], kb2 * KE, 0, t.hstart * g.stride2, (int)t.n0, full);
+          tma_load_2d(sa + C::kABytes, &maps.b, (g.KB + kb2) * KE, t.n_base, full);
+        }
       }
     }
   } else if (warp == 1) {
@@ -196,7 +227,8 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + acc * BN;
-        for (int kb = 0; kb < g.KB; ++kb, ++it) {
+        const int kb_total = g.KB + g.KB2;
+        for (int kb = 0; kb < kb_total; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1u;
           mbar_wait(bar0 + 8 * s, ph);
@@ -215,8 +247,12 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       }
     }
   } else {
-    // ================= epilogue warps 2..5 =================
-    const int q = warp & 3;
+    // ================= epilogue warps 2..9 =================
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;   // chunk parity handled by this warp
+    constexpr int kJ = BN / 32;         // 32-column chunks per tile
+    constexpr int kMine = (kJ + 1) / 2;  // chunks per warp
+    const bool fast = (epi_mode == EPI_BF16) && bias_in_smem && (g.N % 32 == 0);
     uint32_t tl = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord t = decode_tile(g, tile, BN);
@@ -237,16 +273,80 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         if (f < g.F[t.phase] && t.n0 + f < g.n_frames && oh < g.OH)
           m = ((t.n0 + f) * g.OH + oh) * g.OW + ww;
       }
-      mbar_wait(bar0 + 8 * (2 * S + acc), aph);
-      tc_fence_after();
       const uint32_t t_row = tmem_acc + acc * BN + ((uint32_t)(q * 32) << 16);
+      if (fast) {
+        // residual of this thread's chunks: in flight while the tile's MMAs run
+        uint4 rb[kMine][4];
+        const bool has_res = (ep.residual != nullptr) && (m >= 0);
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < kMine; ++i) {
+            const int n0 = t.n_base + (2 * i + half) * 32;
+            if (2 * i + half < kJ && n0 < g.N) {
+              const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + m * ep.ldc + n0);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
+            }
+          }
+        }
+        mbar_wait(bar0 + 8 * (2 * S + acc), aph);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < kMine; ++i) {
+          const int j = 2 * i + half;
+          if (j < kJ) {  // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(t_row + j * 32, v);
+            tmem_ld_wait();
+            const int n0 = t.n_base + j * 32;
+            if (m >= 0 && n0 < g.N) {
+              float f32[32];
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 b4 = bp[c];
+                f32[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + b4.x;
+                f32[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b4.y;
+                f32[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b4.z;
+                f32[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b4.w;
+              }
+              if (has_res) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float2 a = unpack_bf16x2(rb[i][c].x), b2 = unpack_bf16x2(rb[i][c].y);
+                  const float2 c2 = unpack_bf16x2(rb[i][c].z), d2 = unpack_bf16x2(rb[i][c].w);
+                  f32[8 * c + 0] += a.x;  f32[8 * c + 1] += a.y;  f32[8 * c + 2] += b2.x; f32[8 * c + 3] += b2.y;
+                  f32[8 * c + 4] += c2.x; f32[8 * c + 5] += c2.y; f32[8 * c + 6] += d2.x; f32[8 * c + 7] += d2.y;
+                }
+              }
+              if (ep.relu) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) f32[c] = fmaxf(f32[c], 0.f);
+              }
+              uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + m * ep.ldc + n0);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint4 o;
+                o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
+                o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
+                o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
+                o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
+                cp[c] = o;
+              }
+            }
+          }
+        }
+      } else {
+        mbar_wait(bar0 + 8 * (2 * S + acc), aph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t v[32];
-        tmem_ld32(t_row + j * 32, v);
-        tmem_ld_wait();
-        const int n0 = t.n_base + j * 32;
-        if (m >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m, n0, g.N);
+        for (int j = half; j < kJ; j += 2) {
+          uint32_t v[32];
+          tmem_ld32(t_row + j * 32, v);
+          tmem_ld_wait();
+          const int n0 = t.n_base + j * 32;
+          if (m >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m, n0, g.N);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -264,9 +364,15 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
 
 // host side (gemm_tma.cu)
 bool tma_available();
+// Optional K-concatenated second operand: `in2` NHWC [n][H2][W2][Cin2] convolved 1x1 / stride2 / pad 0 (same output
+// grid required); the weight rows are then [R*S*Cin | Cin2] wide.
+struct SecondOperand {
+  const __nv_bfloat16* in2 = nullptr;
+  int H2 = 0, W2 = 0, Cin2 = 0, stride2 = 1;
+};
 int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int W,
                     int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st, int cat = 0,
-                    double flops_override = 0.0);
+                    double flops_override = 0.0, const SecondOperand* second = nullptr);
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                     const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 

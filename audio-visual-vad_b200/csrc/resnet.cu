@@ -307,6 +307,20 @@ conv1_pool_kernel(const float* __restrict__ frames, const float* __restrict__ w1
   }
 }
 
+// Downsample blocks: out = relu(conv_b(y) + bn_b + conv_ds(x) + bn_ds).  Both folded convolutions share the output
+// grid, so the 1x1/stride-2 branch is appended to conv_b's K dimension: wf[o] = [ w_b[o][9*C] | w_ds[o][Cin] ],
+// bias = bias_b + bias_ds, and one implicit GEMM accumulates both (gemm_tma.cuh, "second operand").
+__global__ void concat_ds_kernel(const __nv_bfloat16* __restrict__ wb, const __nv_bfloat16* __restrict__ wds,
+                                 const float* __restrict__ bb, const float* __restrict__ bds, int cout, int kb, int kds,
+                                 __nv_bfloat16* __restrict__ wf, float* __restrict__ bf) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kt = kb + kds;
+  if (idx < cout) bf[idx] = bb[idx] + bds[idx];
+  if (idx >= cout * kt) return;
+  const int o = idx / kt, k = idx - o * kt;
+  wf[idx] = (k < kb) ? wb[o * kb + k] : wds[o * kds + (k - kb)];
+}
+
 // ---- global average pool over the 3x3x512 map -----------------------------------------------------------
 __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ act, int64_t n_frames, int hw, int C,
                                float* __restrict__ feat, __nv_bfloat16* __restrict__ feat_bf16, int64_t ld_bf16,
@@ -442,6 +456,10 @@ struct avvad_resnet18 {
   __nv_bfloat16* w1s;  // conv1 folded bf16 [64][64] in packed-stem K order (TMA stem, default)
   bool set[20];
   bool smem_attr;
+  // downsample blocks (stages 2-4): conv_b weights with the 1x1 branch appended along K, summed folded biases
+  __nv_bfloat16* wf[3];
+  float* bf[3];
+  bool fused_ready;
   // training mode (batch-statistics BN): un-folded bf16 weights and BN affine parameters
   __nv_bfloat16* wraw[20];
   float* gamma[20];
@@ -466,6 +484,11 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
   h->w1b = nullptr;
   h->w1s = nullptr;
   h->smem_attr = false;
+  for (int i = 0; i < 3; ++i) {
+    h->wf[i] = nullptr;
+    h->bf[i] = nullptr;
+  }
+  h->fused_ready = false;
   for (int i = 0; i < 20; ++i) {
     const ConvSpec& s = kSpecs[i];
     AVVAD_CUDA(cudaMalloc(&h->bias[i], sizeof(float) * s.cout));
@@ -495,6 +518,10 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
   cudaFree(h->w1);
   cudaFree(h->w1b);
   cudaFree(h->w1s);
+  for (int i = 0; i < 3; ++i) {
+    cudaFree(h->wf[i]);
+    cudaFree(h->bf[i]);
+  }
   delete h;
 }
 
@@ -518,6 +545,39 @@ extern "C" int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float
   }
   AVVAD_LAUNCHED();
   h->set[layer] = true;
+  h->fused_ready = false;
+  return AVVAD_OK;
+}
+
+// 0 disables the K-concatenated downsample branch (separate 1x1 launch + residual add, the pre-fusion path)
+static bool fuse_ds() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_FUSE_DS");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0 && tc::tma_available();
+}
+
+static const int kDsBlocks[3][2] = {{6, 7}, {11, 12}, {16, 17}};  // (conv_b, downsample) layer indices of stages 2-4
+
+static int build_fused(avvad_resnet18* h, cudaStream_t st) {
+  if (h->fused_ready) return AVVAD_OK;
+  for (int i = 0; i < 3; ++i) {
+    const int lb = kDsBlocks[i][0], lds = kDsBlocks[i][1];
+    const ConvSpec& sb = kSpecs[lb];
+    const ConvSpec& sd = kSpecs[lds];
+    const int kb = sb.k * sb.k * sb.cin, kds = sd.cin;
+    const size_t total = (size_t)sb.cout * (kb + kds);
+    if (!h->wf[i]) {
+      AVVAD_CUDA(cudaMalloc(&h->wf[i], total * sizeof(__nv_bfloat16)));
+      AVVAD_CUDA(cudaMalloc(&h->bf[i], sb.cout * sizeof(float)));
+    }
+    concat_ds_kernel<<<(unsigned)ceil_div((int64_t)total, 256), 256, 0, st>>>(h->w[lb], h->w[lds], h->bias[lb],
+                                                                             h->bias[lds], sb.cout, kb, kds, h->wf[i],
+                                                                             h->bf[i]);
+    AVVAD_LAUNCHED();
+  }
+  h->fused_ready = true;
   return AVVAD_OK;
 }
 
@@ -561,6 +621,10 @@ static int stem_mode() {
 
 static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4],
                            __nv_bfloat16* stem, int upto, int* last, cudaStream_t st) {
+  if (fuse_ds()) {
+    int frc = build_fused(h, st);
+    if (frc) return frc;
+  }
   if (stem_mode() == 0) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -679,6 +743,27 @@ static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __
       if (rc) return rc;
       if (upto == la) { *last = o[0]; return AVVAD_OK; }
       const __nv_bfloat16* res = buf[cur];
+      if (ds && fuse_ds() && upto != lds) {
+        // conv_b with the downsample branch appended along K: no 1x1 launch, no residual round trip
+        const ConvSpec& sb = kSpecs[lb];
+        const ConvSpec& sd = kSpecs[lds];
+        tc::EpiParams ep{};
+        ep.bias = h->bf[stage - 1];
+        ep.C = buf[o[2]];
+        ep.ldc = sb.cout;
+        ep.relu = 1;
+        tc::SecondOperand so;
+        so.in2 = buf[cur];
+        so.H2 = sd.hin; so.W2 = sd.hin; so.Cin2 = sd.cin; so.stride2 = sd.stride;
+        rc = tc::launch_tma_conv(buf[o[0]], h->wf[stage - 1], ep, n, sb.hin, sb.hin, sb.cin, sb.cout, sb.k, sb.k, sb.stride,
+                                 sb.pad, 0, st, 0, 0.0, &so);
+        if (rc) return rc;
+        cur = o[2];
+        *last = cur;
+        if (upto == lb) return AVVAD_OK;
+        layer += 3;
+        continue;
+      }
       if (ds) {
         rc = run_conv(h, lds, buf[cur], nullptr, buf[o[1]], n, 0, st);
         if (rc) return rc;

@@ -160,6 +160,14 @@ int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float* bias, con
                            void* out, int64_t n, int H, int W, int Cin, int Cout, int R, int S,
                            int stride, int pad, int relu, void* stream);
 
+/* Same convolution with a second operand appended along K (ResNet downsample blocks, torchvision BasicBlock with
+ * `downsample`: out = relu(bn2(conv2(y)) + bn_ds(conv1x1_s2(x))), AV_Net.py:25-30 via torchvision resnet18):
+ *   out = act( conv_{RxS,stride,pad}(in; w[:, :R*S*Cin]) + conv_{1x1,stride2,0}(in2; w[:, R*S*Cin:]) + bias )
+ * in2 [n][H2][W2][Cin2]; w [Cout][R*S*Cin + Cin2]; both convolutions must produce the same OH x OW grid. */
+int avvad_conv2d_nhwc_bf16_dual(const void* in, const void* in2, const void* w, const float* bias, void* out,
+                                int64_t n, int H, int W, int Cin, int H2, int W2, int Cin2, int stride2, int Cout,
+                                int R, int S, int stride, int pad, int relu, void* stream);
+
 /* f32 -> bf16 row repack: dst[m][col_off + j] = bf16(src[m][j]) for j < cols; optional zero fill of
  * [col_off+cols, ld_dst) when zero_tail != 0. */
 int avvad_pack_rows_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t col_off,

@@ -68,3 +68,44 @@ def test_conv_matches_fp32_reference(H, Cin, Cout, k, stride, pad):
     st = err_stats(got.cpu().numpy(), ref.cpu().numpy())
     assert st["max"] < 3e-2 * max(1.0, st["ref_absmax"]), st
     assert st["rel_fro"] < 6e-3, st
+
+
+DUALS = [  # (H, C, H2, Cin2) -- conv_b of the three downsample blocks with the 1x1/stride-2 branch appended along K
+    (9, 128, 17, 64), (5, 256, 9, 128), (3, 512, 5, 256),
+]
+
+
+@pytest.mark.parametrize("H,C,H2,Cin2", DUALS)
+def test_dual_operand_conv_matches_two_fp32_convs(H, C, H2, Cin2):
+    n = 19
+    g = torch.Generator(device="cuda").manual_seed(H * 10 + C)
+    y = torch.randn(n, H, H, C, device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randn(n, H2, H2, Cin2, device="cuda", generator=g).to(torch.bfloat16)
+    wb = (torch.randn(C, 3, 3, C, device="cuda", generator=g) * (2.0 / (9 * C)) ** 0.5).to(torch.bfloat16)
+    wd = (torch.randn(C, 1, 1, Cin2, device="cuda", generator=g) * (2.0 / Cin2) ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(C, device="cuda", generator=g) * 0.1
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        ref = torch.nn.functional.conv2d(y.float().permute(0, 3, 1, 2), wb.float().permute(0, 3, 1, 2), bias, padding=1)
+        ref = ref + torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wd.float().permute(0, 3, 1, 2), stride=2)
+    ref = torch.relu(ref.permute(0, 2, 3, 1))
+    w = torch.cat([wb.reshape(C, -1), wd.reshape(C, -1)], dim=1)
+    got = E.conv2d_nhwc_bf16_dual(y, x, w, bias, 1, 1, 3, 2, relu=True).float()
+    st = err_stats(got.cpu().numpy(), ref.cpu().numpy())
+    assert st["max"] < 3e-2 * max(1.0, st["ref_absmax"]), st
+    assert st["rel_fro"] < 6e-3, st
+
+
+def test_dual_operand_conv_exact_on_small_integers():
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, H, C, H2, Cin2 = 7, 9, 128, 17, 64
+    y = torch.randint(-2, 3, (n, H, H, C), device="cuda", generator=g).to(torch.bfloat16)
+    x = torch.randint(-2, 3, (n, H2, H2, Cin2), device="cuda", generator=g).to(torch.bfloat16)
+    wb = torch.randint(-1, 2, (C, 3, 3, C), device="cuda", generator=g).to(torch.bfloat16)
+    wd = torch.randint(-1, 2, (C, 1, 1, Cin2), device="cuda", generator=g).to(torch.bfloat16)
+    with torch.backends.cudnn.flags(allow_tf32=False):
+        ref = torch.nn.functional.conv2d(y.float().permute(0, 3, 1, 2), wb.float().permute(0, 3, 1, 2), padding=1)
+        ref = ref + torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wd.float().permute(0, 3, 1, 2), stride=2)
+    w = torch.cat([wb.reshape(C, -1), wd.reshape(C, -1)], dim=1)
+    got = E.conv2d_nhwc_bf16_dual(y, x, w, None, 1, 1, 3, 2).float()
+    # |sum| <= 9*128*2 + 64*2 < 2^12: exactly representable in bf16 only below 256, so compare after bf16 rounding
+    assert torch.equal(got, ref.permute(0, 2, 3, 1).to(torch.bfloat16).float())
