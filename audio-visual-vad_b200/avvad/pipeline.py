@@ -36,6 +36,9 @@ class AVVADPipeline:
                 self.mcb = E.Mcb()
                 self.mcb.load(state_dict, self.device, eps)
         self._bufs = {}
+        self.piece = 32            # utterances per video piece (upload / upsample / trunk granularity)
+        self._copy_stream = None
+        self._events = []
 
     def _buf(self, name, shape, dtype):
         t = self._bufs.get(name)
@@ -50,42 +53,89 @@ class AVVADPipeline:
         return [min(E.stft_num_frames(n), E.upsampled_length(f)) for n, f in zip(n_samples, n_src)]
 
     def infer_device(self, wave: torch.Tensor, n_samples, video_u8: torch.Tensor, n_src, lengths=None,
-                     t_max: Optional[int] = None):
+                     t_max: Optional[int] = None, _video_ready=None, _wave_ready=None):
         """wave (B,N) f32 and video (B,F,67,67) u8/f32 already on the device.
-        Returns (logits, posteriors, decisions), each (B,t_max,y_dim) on the device."""
+        Returns (logits, posteriors, decisions), each (B,t_max,y_dim) on the device.
+
+        The video branch runs in pieces of ``self.piece`` utterances (frames of an utterance are independent for
+        the trunk); ``_video_ready[k]`` / ``_wave_ready`` are optional CUDA events the current stream waits on
+        before touching piece k / the waveforms (used by :meth:`infer_host` to overlap the uploads)."""
         B = wave.shape[0]
         if lengths is None:
             lengths = self.frame_counts(n_samples, n_src)
         if t_max is None:
             t_max = max(lengths)
         dev = self.device
+        cur = torch.cuda.current_stream(dev)
         lens = E._i32(lengths, dev)
-        audio = self._buf("audio", (B, t_max, 513), torch.float32)
-        E.frontend_logpower(wave, n_samples, lens, t_max, self.audio_mean, self.audio_std, self.eps, True, out=audio)
-        frames = self._buf("frames", (B, t_max, 67, 67), torch.float32)
-        E.upsample_gather(video_u8, n_src, lens, t_max, self.video_mean, self.video_std, self.eps, True, out=frames)
+        ns, nsrc = E._i32(n_samples, dev), E._i32(n_src, dev)
         M = B * t_max
+        audio = self._buf("audio", (B, t_max, 513), torch.float32)
         x = self._buf("x", (B, t_max, self.lstm.ld), torch.bfloat16)
         xv = x.view(M, self.lstm.ld)
-        if self.use_mcb:
-            feat = self._buf("feat", (M, 512), torch.float32)
-            self.trunk.forward(frames.view(M, 67, 67), feat=feat)
-            self.mcb.forward(audio.view(M, 513), feat, out_bf16=xv)
-        else:
+        feat = self._buf("feat", (M, 512), torch.float32) if self.use_mcb else None
+        if not self.use_mcb:
             x.zero_()
-            E.pack_rows_bf16(audio.view(M, 513), xv, 0, False)
-            self.trunk.forward(frames.view(M, 67, 67), feat_bf16=xv, col_off=513, want_f32=False)
+        P = max(1, min(self.piece, B))
+        frames = self._buf("frames", (P, t_max, 67, 67), torch.float32)
+
+        def front_end():
+            if _wave_ready is not None:
+                cur.wait_event(_wave_ready)
+            E.frontend_logpower(wave, ns, lens, t_max, self.audio_mean, self.audio_std, self.eps, True, out=audio)
+            if not self.use_mcb:
+                E.pack_rows_bf16(audio.view(M, 513), xv, 0, False)
+
+        if _wave_ready is None:
+            front_end()
+        for k, b0 in enumerate(range(0, B, P)):
+            b1 = min(B, b0 + P)
+            if _video_ready is not None:
+                cur.wait_event(_video_ready[k])
+            fr = frames[: b1 - b0]
+            E.upsample_gather(video_u8[b0:b1], nsrc[b0:b1], lens[b0:b1], t_max, self.video_mean, self.video_std,
+                              self.eps, True, out=fr)
+            m0, m1 = b0 * t_max, b1 * t_max
+            if self.use_mcb:
+                self.trunk.forward(fr.view(m1 - m0, 67, 67), feat=feat[m0:m1])
+            else:
+                self.trunk.forward(fr.view(m1 - m0, 67, 67), feat_bf16=xv[m0:m1], col_off=513, want_f32=False)
+            if k == 0 and _wave_ready is not None:
+                front_end()  # the waveforms arrive behind the first video piece
+        if self.use_mcb:
+            self.mcb.forward(audio.view(M, 513), feat, out_bf16=xv)
         logits, post, dec, _ = self.lstm.forward(x, lens, want_post=True, want_dec=True)
         return logits, post, dec
 
-    def infer_host(self, wave_pinned: torch.Tensor, n_samples, video_pinned: torch.Tensor, n_src):
-        """Host (pinned) buffers in, host posteriors/decisions out: H2D copies, the whole device path and
-        the D2H read-back are enqueued on the current stream (this is what bench.py's `e2e` times)."""
+    def infer_host(self, wave_pinned: torch.Tensor, n_samples, video_pinned: torch.Tensor, n_src, lengths=None,
+                   t_max: Optional[int] = None):
+        """Host (pinned) buffers in, host posteriors/decisions out.  The uploads run on a copy stream -- first video
+        piece, waveforms, remaining video pieces -- while the current stream computes piece by piece, so only the
+        first piece's upload is exposed; the D2H read-back is inside the call (this is what bench.py's `e2e` times)."""
+        dev = self.device
+        B = wave_pinned.shape[0]
         w = self._buf("wave_dev", tuple(wave_pinned.shape), wave_pinned.dtype)
         v = self._buf("video_dev", tuple(video_pinned.shape), video_pinned.dtype)
-        w.copy_(wave_pinned, non_blocking=True)
-        v.copy_(video_pinned, non_blocking=True)
-        _, post, dec = self.infer_device(w, n_samples, v, n_src)
+        cur = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        P = max(1, min(self.piece, B))
+        n_pieces = (B + P - 1) // P
+        while len(self._events) < n_pieces + 1:
+            self._events.append(torch.cuda.Event())
+        ew, ev = self._events[0], self._events[1:n_pieces + 1]
+        cs.wait_stream(cur)  # earlier consumers of the staging buffers
+        with torch.cuda.stream(cs):
+            for k, b0 in enumerate(range(0, B, P)):
+                b1 = min(B, b0 + P)
+                v[b0:b1].copy_(video_pinned[b0:b1], non_blocking=True)
+                ev[k].record(cs)
+                if k == 0:
+                    w.copy_(wave_pinned, non_blocking=True)
+                    ew.record(cs)
+        _, post, dec = self.infer_device(w, n_samples, v, n_src, lengths=lengths, t_max=t_max, _video_ready=ev,
+                                         _wave_ready=ew)
         hp = self._bufs.get("post_host")
         if hp is None or hp.shape != post.shape:
             hp = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
@@ -94,5 +144,5 @@ class AVVADPipeline:
         hd = self._bufs["dec_host"]
         hp.copy_(post, non_blocking=True)
         hd.copy_(dec, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return hp, hd

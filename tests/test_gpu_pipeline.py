@@ -20,8 +20,8 @@ def _inputs(B, seed=0):
     return ns, nf, waves, vids
 
 
-@pytest.mark.parametrize("use_mcb", [False, True])
-def test_pipeline_matches_reference_port(use_mcb):
+@pytest.mark.parametrize("use_mcb,piece", [(False, 32), (True, 32), (True, 3), (False, 1)])
+def test_pipeline_matches_reference_port(use_mcb, piece):
     B = 4
     ns, nf, waves, vids = _inputs(B)
     mean, std = synth.synth_audio_stats(0)
@@ -36,6 +36,7 @@ def test_pipeline_matches_reference_port(use_mcb):
     assert rlens == lens
 
     pipe = AVVADPipeline(sd, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD, use_mcb=use_mcb)
+    pipe.piece = piece  # utterances per upload/trunk piece: 32 = one piece, 3 and 1 exercise the overlapped path
     wave = torch.zeros(B, max(ns))
     vid = torch.zeros(B, max(nf), 67, 67, dtype=torch.uint8)
     for i in range(B):
