@@ -223,6 +223,29 @@ class ResNet18Trunk:
                                                L.ptr(feat), L.ptr(feat_bf16), ld, col_off, L.stream_ptr()))
         return feat
 
+    def forward_u8(self, src: torch.Tensor, n_src, n_out, t_max: int, mean=0.0, std=1.0, eps=1e-8, standardise=True,
+                   feat: Optional[torch.Tensor] = None, feat_bf16: Optional[torch.Tensor] = None, col_off=0,
+                   want_f32=True, num=FPS_NUM, den=FPS_DEN):
+        """Trunk fed from the 30 fps u8 source frames (B,F,67,67): the 30->62.5 fps gather, standardisation and
+        collate padding happen while a frame is staged in shared memory (== upsample_gather + forward, bit for bit)."""
+        L.require_cuda(src)
+        assert src.dtype == torch.uint8 and src.dim() == 4 and src.shape[-2:] == (67, 67)
+        src = src.contiguous()
+        B, F = src.shape[:2]
+        dev = src.device
+        a, b = _i32(n_src, dev), _i32(n_out, dev)
+        n = B * t_max
+        nbytes = L.lib().avvad_resnet18_workspace_bytes(n, self.chunk)
+        ws = self.ws.get(nbytes, dev)
+        if feat is None and want_f32:
+            feat = torch.empty(n, 512, dtype=torch.float32, device=dev)
+        ld = feat_bf16.stride(-2) if feat_bf16 is not None else 0
+        L.check(L.lib().avvad_resnet18_forward_u8(self.h, L.ptr(src), L.ptr(a), L.ptr(b), B, F, t_max, num, den,
+                                                  float(mean), float(std), float(eps), 1 if standardise else 0,
+                                                  self.chunk, L.ptr(ws), ws.numel(), L.ptr(feat), L.ptr(feat_bf16), ld,
+                                                  col_off, L.stream_ptr()))
+        return feat
+
     def load_train(self, sd: Dict[str, torch.Tensor], device, prefix="features."):
         """Un-folded weights + BN affine parameters for the batch-statistics (training-mode) forward."""
         keep = []

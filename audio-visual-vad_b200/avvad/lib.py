@@ -42,6 +42,9 @@ PROTOTYPES = {
     "avvad_resnet18_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "avvad_resnet18_forward": (C.c_int, [VP, VP, C.c_int64, C.c_int64, VP, C.c_size_t, VP, VP, C.c_int64, C.c_int64,
                                          VP]),
+    "avvad_resnet18_forward_u8": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64, VP, C.c_size_t, VP, VP,
+                                            C.c_int64, C.c_int64, VP]),
     "avvad_resnet18_forward_upto": (C.c_int, [VP, VP, C.c_int64, C.c_int, VP, C.c_size_t, VP, VP]),
     "avvad_resnet18_set_conv_train": (C.c_int, [VP, C.c_int, VP, VP, VP, VP]),
     "avvad_resnet18_train_workspace_bytes": (C.c_size_t, [C.c_int64]),

@@ -37,6 +37,7 @@ class AVVADPipeline:
                 self.mcb.load(state_dict, self.device, eps)
         self._bufs = {}
         self.piece = 32            # utterances per video piece (upload / upsample / trunk granularity)
+        self.fuse_gather = True    # u8 video: gather + standardise inside the stem (False: separate fp32 gather)
         self._copy_stream = None
         self._events = []
 
@@ -77,7 +78,8 @@ class AVVADPipeline:
         if not self.use_mcb:
             x.zero_()
         P = max(1, min(self.piece, B))
-        frames = self._buf("frames", (P, t_max, 67, 67), torch.float32)
+        fused = self.fuse_gather and video_u8.dtype == torch.uint8
+        frames = None if fused else self._buf("frames", (P, t_max, 67, 67), torch.float32)
 
         def front_end():
             if _wave_ready is not None:
@@ -92,14 +94,19 @@ class AVVADPipeline:
             b1 = min(B, b0 + P)
             if _video_ready is not None:
                 cur.wait_event(_video_ready[k])
-            fr = frames[: b1 - b0]
-            E.upsample_gather(video_u8[b0:b1], nsrc[b0:b1], lens[b0:b1], t_max, self.video_mean, self.video_std,
-                              self.eps, True, out=fr)
             m0, m1 = b0 * t_max, b1 * t_max
-            if self.use_mcb:
-                self.trunk.forward(fr.view(m1 - m0, 67, 67), feat=feat[m0:m1])
+            if fused:  # gather + standardise + collate padding inside the stem kernel
+                kw = dict(feat=feat[m0:m1]) if self.use_mcb else dict(feat_bf16=xv[m0:m1], col_off=513, want_f32=False)
+                self.trunk.forward_u8(video_u8[b0:b1], nsrc[b0:b1], lens[b0:b1], t_max, self.video_mean,
+                                      self.video_std, self.eps, True, **kw)
             else:
-                self.trunk.forward(fr.view(m1 - m0, 67, 67), feat_bf16=xv[m0:m1], col_off=513, want_f32=False)
+                fr = frames[: b1 - b0]
+                E.upsample_gather(video_u8[b0:b1], nsrc[b0:b1], lens[b0:b1], t_max, self.video_mean, self.video_std,
+                                  self.eps, True, out=fr)
+                if self.use_mcb:
+                    self.trunk.forward(fr.view(m1 - m0, 67, 67), feat=feat[m0:m1])
+                else:
+                    self.trunk.forward(fr.view(m1 - m0, 67, 67), feat_bf16=xv[m0:m1], col_off=513, want_f32=False)
             if k == 0 and _wave_ready is not None:
                 front_end()  # the waveforms arrive behind the first video piece
         if self.use_mcb:

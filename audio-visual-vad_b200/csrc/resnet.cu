@@ -14,6 +14,7 @@
 
 #include "gemm_tma.cuh"
 #include "stem_fused.cuh"
+#include "stem_s2d.cuh"
 
 namespace avvad {
 
@@ -35,8 +36,6 @@ static const ConvSpec kSpecs[20] = {
 constexpr int64_t kFrameHW = 67 * 67;
 constexpr int64_t kActBytesPerFrame = 17 * 17 * 64 * 2;  // largest NHWC bf16 activation (after the pool)
 constexpr int64_t kStemBytesPerFrame = 34 * 34 * 64 * 2;  // conv1 output before the pool
-constexpr int64_t kPackBytesPerFrame = 37 * 34 * 16 * 2;  // packed stem input T[37][34][16] bf16
-constexpr int64_t kStemSubChunk = 512;                    // 512 * 148 KB = 76 MB: conv1 -> pool stays L2-resident
 
 // ---- weight folding / packing ----------------------------------------------------------------------
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
@@ -61,8 +60,14 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
 
 // conv1 for the tensor-core stem: same folding, bf16 [64 out][64 k] with k = r*7+s (49..63 zero)
 __global__ void pack_conv1_tc_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                     const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ w1b) {
+                                     const float* __restrict__ beta, const float* __restrict__ mean,
+                                     const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ w1b,
+                                     float* __restrict__ bias) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 64) {
+    const float sc = gamma[idx] / sqrtf(var[idx] + eps);
+    bias[idx] = beta[idx] - mean[idx] * sc;
+  }
   if (idx >= 64 * 64) return;
   const int o = idx / 64, k = idx % 64;
   float v = 0.f;
@@ -71,37 +76,6 @@ __global__ void pack_conv1_tc_kernel(const float* __restrict__ w, const float* _
     v = (w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k]) * sc;
   }
   w1b[idx] = __float2bfloat16_rn(v);
-}
-
-// Stem input packing (space-to-depth with the horizontal window baked in):
-//   T[n][y][x][j*4 + b*2 + d] = P[2y+b][2(x+j)+d],  P = frame zero-padded by 3,  y in [0,37), x in [0,34), j in [0,4)
-// so the 7x7/stride-2 convolution becomes a 4x1 / stride-1 convolution over 16 "channels":
-//   out[oh][ow][o] = sum_{a<4} sum_{k<16} W'[o][a*16+k] * T[oh+a][ow][k],  W'[o][a*16 + j*4+b*2+d] = w[o][2a+b][2j+d]
-// and each filter row `a` is one 32-byte K16 slice that a TMA box can fetch.
-__global__ void stem_pack_kernel(const float* __restrict__ frames, int64_t n_frames, __nv_bfloat16* __restrict__ T) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = n_frames * 37 * 34;
-  if (idx >= total) return;
-  const int x = (int)(idx % 34);
-  const int y = (int)((idx / 34) % 37);
-  const int64_t n = idx / (34 * 37);
-  const float* f = frames + n * (67 * 67);
-  uint32_t pk[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int r = 2 * y + b - 3;
-      const int c0 = 2 * (x + j) - 3;
-      const bool rok = (unsigned)r < 67u;
-      const float v0 = (rok && (unsigned)c0 < 67u) ? __ldg(f + r * 67 + c0) : 0.f;
-      const float v1 = (rok && (unsigned)(c0 + 1) < 67u) ? __ldg(f + r * 67 + c0 + 1) : 0.f;
-      pk[j * 2 + b] = pack_bf16x2(v0, v1);
-    }
-  }
-  uint4* o = reinterpret_cast<uint4*>(T + idx * 16);
-  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 // Stem im2col rows: A[m][r*7+s] = frame[2oh-3+r][2ow-3+s] (zero outside), m = (n*34+oh)*34+ow, bf16 [M][64]
@@ -137,23 +111,6 @@ __global__ void stem_im2col_kernel(const float* __restrict__ frames, int64_t n_f
     }
     o[c] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-}
-
-// conv1 weights for the packed stem: bf16 [64 out][64 k], k = a*16 + j*4 + b*2 + d  <->  tap (r=2a+b, s=2j+d)
-__global__ void pack_conv1_s2d_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                      const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ w1s) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 64 * 64) return;
-  const int o = idx / 64, k = idx % 64;
-  const int a = k / 16, j = (k % 16) / 4, b = (k % 4) / 2, d = k % 2;
-  const int r = 2 * a + b, s = 2 * j + d;
-  float v = 0.f;
-  if (r < 7 && s < 7) {
-    const float sc = gamma[o] / sqrtf(var[o] + eps);
-    const int tap = r * 7 + s;
-    v = (w[(o * 3 + 0) * 49 + tap] + w[(o * 3 + 1) * 49 + tap] + w[(o * 3 + 2) * 49 + tap]) * sc;
-  }
-  w1s[idx] = __float2bfloat16_rn(v);
 }
 
 // NHWC bf16 3x3 / stride 2 / pad 1 max pool (inputs are post-ReLU, so clipping the window == -inf padding)
@@ -193,118 +150,6 @@ __global__ void maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int64_
   r.z = pack_bf16x2(m[4], m[5]);
   r.w = pack_bf16x2(m[6], m[7]);
   *reinterpret_cast<uint4*>(out + ((f * OH + ph) * OH + pw) * C + ch * 8) = r;
-}
-
-// conv1: fold 3 identical input channels and the BN scale -> fp32 [49][64] (tap-major, channel-minor)
-__global__ void pack_conv1_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, const float* __restrict__ mean,
-                                  const float* __restrict__ var, float eps, float* __restrict__ w1,
-                                  float* __restrict__ bias) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < 64) {
-    const float sc = gamma[idx] / sqrtf(var[idx] + eps);
-    bias[idx] = beta[idx] - mean[idx] * sc;
-  }
-  if (idx >= 49 * 64) return;
-  const int o = idx % 64, tap = idx / 64;
-  const float sc = gamma[o] / sqrtf(var[o] + eps);
-  const float sum = w[(o * 3 + 0) * 49 + tap] + w[(o * 3 + 1) * 49 + tap] + w[(o * 3 + 2) * 49 + tap];
-  w1[idx] = sum * sc;
-}
-
-// ---- conv1 + BN + ReLU + maxpool, one CTA per frame ---------------------------------------------------
-constexpr int kC1Threads = 256;
-constexpr int kImgPitch = 76;
-constexpr size_t kC1Smem = (73 * kImgPitch + 49 * 64 + 64) * sizeof(float) + 1156 * 64 * sizeof(__nv_bfloat16);
-
-__global__ void __launch_bounds__(kC1Threads)
-conv1_pool_kernel(const float* __restrict__ frames, const float* __restrict__ w1, const float* __restrict__ bias,
-                  __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t c1_smem[];
-  float* img = reinterpret_cast<float*>(c1_smem);  // [73][76], 3-pixel zero border
-  float* wsm = img + 73 * kImgPitch;               // [49][64]
-  float* bsm = wsm + 49 * 64;                      // [64]
-  __nv_bfloat16* cv = reinterpret_cast<__nv_bfloat16*>(bsm + 64);  // conv+ReLU output [34*34][64]
-
-  const int tid = threadIdx.x;
-  const float* f = frames + (int64_t)blockIdx.x * kFrameHW;
-  for (int i = tid; i < 73 * kImgPitch; i += kC1Threads) {
-    const int r = i / kImgPitch - 3, c = i % kImgPitch - 3;
-    img[i] = (r >= 0 && r < 67 && c >= 0 && c < 67) ? f[r * 67 + c] : 0.f;
-  }
-  for (int i = tid; i < 49 * 64; i += kC1Threads) wsm[i] = w1[i];
-  if (tid < 64) bsm[tid] = bias[tid];
-  __syncthreads();
-
-#pragma unroll 1
-  for (int cg = 0; cg < 4; ++cg) {
-    for (int p = tid; p < 1156; p += kC1Threads) {
-      const int oh = p / 34, ow = p - oh * 34;
-      float acc[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) acc[q] = bsm[cg * 16 + q];
-      const float* ip = img + (2 * oh) * kImgPitch + 2 * ow;
-#pragma unroll
-      for (int r = 0; r < 7; ++r) {
-#pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const float x = ip[r * kImgPitch + s];
-          const float4* w4 = reinterpret_cast<const float4*>(wsm + (r * 7 + s) * 64 + cg * 16);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 w = w4[q];
-            acc[4 * q + 0] = fmaf(x, w.x, acc[4 * q + 0]);
-            acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
-            acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
-          }
-        }
-      }
-      uint4 o0, o1;
-      o0.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-      o0.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-      o0.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-      o0.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-      o1.x = pack_bf16x2(fmaxf(acc[8], 0.f), fmaxf(acc[9], 0.f));
-      o1.y = pack_bf16x2(fmaxf(acc[10], 0.f), fmaxf(acc[11], 0.f));
-      o1.z = pack_bf16x2(fmaxf(acc[12], 0.f), fmaxf(acc[13], 0.f));
-      o1.w = pack_bf16x2(fmaxf(acc[14], 0.f), fmaxf(acc[15], 0.f));
-      uint4* dst = reinterpret_cast<uint4*>(cv + p * 64 + cg * 16);
-      dst[0] = o0;
-      dst[1] = o1;
-    }
-  }
-  __syncthreads();
-
-  // 3x3 / stride 2 / pad 1 max pool; inputs are >= 0 so clipping the window equals -inf padding
-  __nv_bfloat16* o = out + (int64_t)blockIdx.x * 289 * 64;
-  for (int item = tid; item < 289 * 8; item += kC1Threads) {
-    const int pp = item >> 3, ch = item & 7;
-    const int ph = pp / 17, pw = pp - ph * 17;
-    float m[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) m[q] = 0.f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int y = 2 * ph + dy;
-      if (y < 0 || y >= 34) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int x = 2 * pw + dx;
-        if (x < 0 || x >= 34) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(cv + (y * 34 + x) * 64 + ch * 8);
-        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-        m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
-        m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
-      }
-    }
-    uint4 r;
-    r.x = pack_bf16x2(m[0], m[1]);
-    r.y = pack_bf16x2(m[2], m[3]);
-    r.z = pack_bf16x2(m[4], m[5]);
-    r.w = pack_bf16x2(m[6], m[7]);
-    *reinterpret_cast<uint4*>(o + pp * 64 + ch * 8) = r;
-  }
 }
 
 // Downsample blocks: out = relu(conv_b(y) + bn_b + conv_ds(x) + bn_ds).  Both folded convolutions share the output
@@ -451,11 +296,8 @@ using namespace avvad;
 struct avvad_resnet18 {
   __nv_bfloat16* w[20];
   float* bias[20];
-  float* w1;  // conv1 folded fp32 [49][64] (direct-conv stem, AVVAD_STEM=simt)
-  __nv_bfloat16* w1b;  // conv1 folded bf16 [64][64], k = r*7+s (cp.async stem, AVVAD_STEM=cpasync)
-  __nv_bfloat16* w1s;  // conv1 folded bf16 [64][64] in packed-stem K order (TMA stem, default)
+  __nv_bfloat16* w1b;  // conv1 folded bf16 [64][64], k = r*7+s (3 input channels summed)
   bool set[20];
-  bool smem_attr;
   // downsample blocks (stages 2-4): conv_b weights with the 1x1 branch appended along K, summed folded biases
   __nv_bfloat16* wf[3];
   float* bf[3];
@@ -480,10 +322,7 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     h->gamma[i] = h->beta[i] = nullptr;
     h->set_train[i] = false;
   }
-  h->w1 = nullptr;
   h->w1b = nullptr;
-  h->w1s = nullptr;
-  h->smem_attr = false;
   for (int i = 0; i < 3; ++i) {
     h->wf[i] = nullptr;
     h->bf[i] = nullptr;
@@ -493,9 +332,7 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     const ConvSpec& s = kSpecs[i];
     AVVAD_CUDA(cudaMalloc(&h->bias[i], sizeof(float) * s.cout));
     if (i == 0) {
-      AVVAD_CUDA(cudaMalloc(&h->w1, sizeof(float) * 49 * 64));
       AVVAD_CUDA(cudaMalloc(&h->w1b, sizeof(__nv_bfloat16) * 64 * 64));
-      AVVAD_CUDA(cudaMalloc(&h->w1s, sizeof(__nv_bfloat16) * 64 * 64));
     } else {
       AVVAD_CUDA(cudaMalloc(&h->w[i], sizeof(__nv_bfloat16) * (size_t)s.cout * s.cin * s.k * s.k));
     }
@@ -515,9 +352,7 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
     cudaFree(h->gamma[i]);
     cudaFree(h->beta[i]);
   }
-  cudaFree(h->w1);
   cudaFree(h->w1b);
-  cudaFree(h->w1s);
   for (int i = 0; i < 3; ++i) {
     cudaFree(h->wf[i]);
     cudaFree(h->bf[i]);
@@ -533,11 +368,7 @@ extern "C" int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float
   cudaStream_t st = (cudaStream_t)stream;
   const ConvSpec& s = kSpecs[layer];
   if (layer == 0) {
-    pack_conv1_kernel<<<(49 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, h->w1, h->bias[0]);
-    AVVAD_LAUNCHED();
-    pack_conv1_tc_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, var, bn_eps, h->w1b);
-    AVVAD_LAUNCHED();
-    pack_conv1_s2d_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, var, bn_eps, h->w1s);
+    pack_conv1_tc_kernel<<<(64 * 64 + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, h->w1b, h->bias[0]);
   } else {
     const int total = s.cout * s.cin * s.k * s.k;
     pack_conv_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, gamma, beta, mean, var, bn_eps, s.cout, s.cin, s.k,
@@ -589,10 +420,7 @@ static int64_t chunk_of(int64_t n_frames, int64_t chunk) {
 extern "C" size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk_frames) {
   if (n_frames <= 0) return 0;
   const int64_t mc = chunk_of(n_frames, chunk_frames);
-  const int64_t sub = mc < kStemSubChunk ? mc : kStemSubChunk;
-  (void)sub;
-  return (size_t)(4 * align_up((size_t)mc * kActBytesPerFrame, 1024)) +
-         align_up((size_t)kStemSubChunk * 2 * kStemBytesPerFrame, 1024);  // stem output + im2col rows, <= 512 frames each
+  return (size_t)(4 * align_up((size_t)mc * kActBytesPerFrame, 1024));  // four rotating NHWC activation buffers
 }
 
 static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const __nv_bfloat16* residual,
@@ -604,28 +432,81 @@ static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const
 
 // Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
 // Returns the buffer index holding the last produced activation in *last.
-// 0 = fused stem kernel (default), 1 = direct fp32 conv, 2 = cp.async im2col producer, 3 = K16/SWIZZLE_32B boxes,
-// 4 = im2col pack + TMA GEMM + separate pool
+// 1 (default) = image-as-operand stem (stem_s2d.cuh); 0 = im2col-in-shared-memory stem (stem_fused.cuh, fp32 frames only)
 static int stem_mode() {
   static int v = [] {
     const char* e = getenv("AVVAD_STEM");
-    if (e && std::string(e) == "simt") return 1;
-    if (e && std::string(e) == "cpasync") return 2;
-    if (e && std::string(e) == "k16") return tc::tma_available() ? 3 : 2;
-    if (e && std::string(e) == "gemm") return 4;
-    if (e && std::string(e) == "fused") return 0;
-    return 0;
+    return (e && std::string(e) == "fused") ? 0 : 1;
   }();
   return v;
 }
 
-static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __nv_bfloat16* const buf[4],
-                           __nv_bfloat16* stem, int upto, int* last, cudaStream_t st) {
+// Video source of one trunk call: fp32 frames (already standardised) or u8 frames at the source rate + the gather
+struct StemInput {
+  const float* frames = nullptr;  // [n][67*67]
+  const uint8_t* src = nullptr;   // [B][f_max][67*67]
+  const int32_t* n_src = nullptr;
+  const int32_t* n_out = nullptr;
+  int f_max = 0, t_max = 0, num = 0, den = 0, standardise = 0;
+  float mean = 0.f, denom = 1.f;
+  StemInput advance(int64_t f0) const {  // the same source seen from frame f0 on (chunking)
+    StemInput r = *this;
+    r.first = first + f0;
+    return r;
+  }
+  int64_t first = 0;  // global index of the first frame of this (sub-)call
+};
+
+static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+  });
+  AVVAD_CUDA(attr_err);
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  tc::StemS2Params p{};
+  p.n_frames = n;
+  p.w1b = h->w1b;
+  p.bias = h->bias[0];
+  p.out = out;
+  const int64_t batches = (n + tc::kS2FramesPerBatch - 1) / tc::kS2FramesPerBatch;
+  const unsigned grid = (unsigned)(batches < num_sms ? batches : num_sms);
+  void* tok = nullptr;
+  tc::prof_begin(st, &tok);
+  if (in.src) {
+    // frame n of this launch is global frame in.first + n = (b, k); shift the per-utterance arrays so that the kernel's
+    // n / t_max arithmetic stays local: only whole-utterance offsets are representable, so pass `first` through
+    p.src = in.src; p.n_src = in.n_src; p.n_out = in.n_out;
+    p.f_max = in.f_max; p.t_max = in.t_max; p.num = in.num; p.den = in.den;
+    p.mean = in.mean; p.denom = in.denom; p.standardise = in.standardise;
+    p.first = in.first;
+    tc::stem_s2d_kernel<1><<<grid, tc::kS2Threads, tc::kS2Smem, st>>>(p);
+  } else {
+    p.frames = in.frames + in.first * kFrameHW;
+    tc::stem_s2d_kernel<0><<<grid, tc::kS2Threads, tc::kS2Smem, st>>>(p);
+  }
+  AVVAD_LAUNCHED();
+  tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
+  return AVVAD_OK;
+}
+
+static int run_trunk_chunk(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* const buf[4], int upto,
+                           int* last, cudaStream_t st) {
   if (fuse_ds()) {
     int frc = build_fused(h, st);
     if (frc) return frc;
   }
-  if (stem_mode() == 0) {
+  if (stem_mode() == 1 || in.src) {
+    int rc = launch_stem_s2d(h, in, n, buf[0], st);
+    if (rc) return rc;
+  } else {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -641,85 +522,10 @@ static int run_trunk_chunk(avvad_resnet18* h, const float* frames, int64_t n, __
     const unsigned grid = (unsigned)(n < num_sms ? n : num_sms);
     void* tok = nullptr;
     tc::prof_begin(st, &tok);
-    tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(frames, n, h->w1b, h->bias[0], buf[0]);
+    tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(in.frames + in.first * kFrameHW, n, h->w1b,
+                                                                         h->bias[0], buf[0]);
     AVVAD_LAUNCHED();
     tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
-  } else if (stem_mode() == 4) {
-    // stem = im2col pack (bandwidth kernel) -> plain K=64 tcgen05 GEMM fed by 16 KB contiguous TMA boxes with fused
-    // bias+ReLU -> max-pool; 256-frame sub-chunks keep both 38 MB intermediates L2-resident.
-    static const int64_t kSub = [] {
-      const char* e = getenv("AVVAD_STEM_SUB");
-      int64_t v = e ? atoll(e) : 256;
-      return (v >= 64 && v <= 512) ? v : 256;  // workspace holds 512 frames of stem output + 512 of im2col rows
-    }();
-    __nv_bfloat16* cols = stem + kSub * (kStemBytesPerFrame / 2);
-    for (int64_t f0 = 0; f0 < n; f0 += kSub) {
-      const int64_t nn = (n - f0 < kSub) ? (n - f0) : kSub;
-      const int64_t M = nn * 1156;
-      stem_im2col_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(frames + f0 * kFrameHW, nn, cols);
-      AVVAD_LAUNCHED();
-      tc::EpiParams ep{};
-      ep.bias = h->bias[0];
-      ep.C = stem;
-      ep.ldc = 64;
-      ep.relu = 1;
-      int rc = tc::gemm_dispatch(cols, 64, h->w1b, 64, M, 64, 64, ep, tc::EPI_BF16, 64, st);
-      if (rc) return rc;
-      const int64_t total = nn * 17 * 17 * 8;
-      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
-                                                                          buf[0] + f0 * 17 * 17 * 64);
-      AVVAD_LAUNCHED();
-    }
-  } else if (stem_mode() == 3) {
-    // stem on TMA boxes: pack -> 4x1 conv over 16 packed channels (K16 / SWIZZLE_32B) -> bias+ReLU -> max-pool,
-    // sub-chunked so the 34x34x64 intermediate stays in L2.  The pack buffer lives behind the stem scratch.
-    __nv_bfloat16* packed = stem + kStemSubChunk * (kStemBytesPerFrame / 2);
-    for (int64_t f0 = 0; f0 < n; f0 += kStemSubChunk) {
-      const int64_t nn = (n - f0 < kStemSubChunk) ? (n - f0) : kStemSubChunk;
-      const int64_t tot = nn * 37 * 34;
-      stem_pack_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(frames + f0 * kFrameHW, nn, packed);
-      AVVAD_LAUNCHED();
-      tc::EpiParams ep{};
-      ep.bias = h->bias[0];
-      ep.C = stem;
-      ep.ldc = 64;
-      ep.relu = 1;
-      int rc = tc::launch_tma_conv(packed, h->w1s, ep, nn, 37, 34, 16, 64, 4, 1, 1, 0, 64, st, 3,
-                                   2.0 * (double)nn * 1156 * 64 * 49);
-      if (rc) return rc;
-      const int64_t total = nn * 17 * 17 * 8;
-      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
-                                                                          buf[0] + f0 * 17 * 17 * 64);
-      AVVAD_LAUNCHED();
-    }
-  } else if (stem_mode() == 1) {
-    if (!h->smem_attr) {
-      AVVAD_CUDA(cudaFuncSetAttribute(conv1_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC1Smem));
-      h->smem_attr = true;
-    }
-    conv1_pool_kernel<<<(unsigned)n, kC1Threads, kC1Smem, st>>>(frames, h->w1, h->bias[0], buf[0]);
-    AVVAD_LAUNCHED();
-  } else {
-    // stem on the tensor cores: im2col(7x7/2) producer -> tcgen05 GEMM (K 49->64) -> bias+ReLU -> bf16, then a
-    // bandwidth max-pool; sub-chunked so the 34x34x64 intermediate stays in L2
-    for (int64_t f0 = 0; f0 < n; f0 += kStemSubChunk) {
-      const int64_t nn = (n - f0 < kStemSubChunk) ? (n - f0) : kStemSubChunk;
-      tc::AParams ap{};
-      ap.A = reinterpret_cast<const __nv_bfloat16*>(h->w1b);  // unused by the stem producer (alignment check only)
-      ap.A32 = frames + f0 * kFrameHW;
-      ap.H = 67; ap.W = 67; ap.OH = 34; ap.OW = 34;
-      tc::EpiParams ep{};
-      ep.bias = h->bias[0];
-      ep.C = stem;
-      ep.ldc = 64;
-      ep.relu = 1;
-      int rc = tc::launch(tc::A_CONV1, ap, h->w1b, 64, nn * 34 * 34, 64, 64, ep, tc::EPI_BF16, 64, st);
-      if (rc) return rc;
-      const int64_t total = nn * 17 * 17 * 8;
-      maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem, nn, 34, 17, 64,
-                                                                          buf[0] + f0 * 17 * 17 * 64);
-      AVVAD_LAUNCHED();
-    }
   }
   int cur = 0;
   *last = cur;
@@ -790,10 +596,9 @@ static int check_loaded(avvad_resnet18* h) {
   return AVVAD_OK;
 }
 
-extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_frames, int64_t chunk_frames,
-                                      void* workspace, size_t workspace_bytes, float* feat, void* feat_bf16,
-                                      int64_t ld_bf16, int64_t col_off, void* stream) {
-  AVVAD_CHECK_ARG(h && frames && workspace && n_frames > 0, "bad argument");
+static int forward_common(avvad_resnet18* h, const StemInput& in, int64_t n_frames, int64_t chunk_frames,
+                          void* workspace, size_t workspace_bytes, float* feat, void* feat_bf16, int64_t ld_bf16,
+                          int64_t col_off, cudaStream_t st) {
   AVVAD_CHECK_ARG(feat || feat_bf16, "at least one output required");
   int rc = check_loaded(h);
   if (rc) return rc;
@@ -801,16 +606,14 @@ extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, in
     set_error("resnet18: workspace too small");
     return AVVAD_ERR_WORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
   const int64_t mc = chunk_of(n_frames, chunk_frames);
   const size_t bsz = align_up((size_t)mc * kActBytesPerFrame, 1024);
   __nv_bfloat16* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
-  __nv_bfloat16* stem = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + 4 * bsz);
   for (int64_t f0 = 0; f0 < n_frames; f0 += mc) {
     const int64_t n = (n_frames - f0 < mc) ? (n_frames - f0) : mc;
     int last = 0;
-    rc = run_trunk_chunk(h, frames + f0 * kFrameHW, n, buf, stem, 20, &last, st);
+    rc = run_trunk_chunk(h, in.advance(f0), n, buf, 20, &last, st);
     if (rc) return rc;
     const int64_t total = n * (512 / 8);
     avgpool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
@@ -819,6 +622,34 @@ extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, in
     AVVAD_LAUNCHED();
   }
   return AVVAD_OK;
+}
+
+extern "C" int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_frames, int64_t chunk_frames,
+                                      void* workspace, size_t workspace_bytes, float* feat, void* feat_bf16,
+                                      int64_t ld_bf16, int64_t col_off, void* stream) {
+  AVVAD_CHECK_ARG(h && frames && workspace && n_frames > 0, "bad argument");
+  StemInput in;
+  in.frames = frames;
+  return forward_common(h, in, n_frames, chunk_frames, workspace, workspace_bytes, feat, feat_bf16, ld_bf16, col_off,
+                        (cudaStream_t)stream);
+}
+
+// Same trunk fed straight from the 30 fps u8 source frames: output frame (b, k), k < t_max, is source frame
+// upsample_src_index(k, n_src[b]) standardised as (v - mean) / (std + eps) when k < n_out[b], else the collate zero
+// frame -- exactly what avvad_upsample_gather writes, without the fp32 (B, t_max, 67, 67) round trip through HBM.
+extern "C" int avvad_resnet18_forward_u8(avvad_resnet18* h, const uint8_t* src, const int32_t* n_src,
+                                         const int32_t* n_out, int32_t B, int32_t f_max, int32_t t_max, int32_t num,
+                                         int32_t den, float mean, float stdv, float eps, int standardise,
+                                         int64_t chunk_frames, void* workspace, size_t workspace_bytes, float* feat,
+                                         void* feat_bf16, int64_t ld_bf16, int64_t col_off, void* stream) {
+  AVVAD_CHECK_ARG(h && src && n_src && n_out && workspace, "null pointer");
+  AVVAD_CHECK_ARG(B > 0 && f_max > 0 && t_max > 0 && num > 0 && den > 0, "non-positive size");
+  StemInput in;
+  in.src = src; in.n_src = n_src; in.n_out = n_out;
+  in.f_max = f_max; in.t_max = t_max; in.num = num; in.den = den;
+  in.mean = mean; in.denom = stdv + eps; in.standardise = standardise;
+  return forward_common(h, in, (int64_t)B * t_max, chunk_frames, workspace, workspace_bytes, feat, feat_bf16, ld_bf16,
+                        col_off, (cudaStream_t)stream);
 }
 
 extern "C" int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frames, int64_t n_frames, int upto,
@@ -834,9 +665,10 @@ extern "C" int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frame
   const size_t bsz = align_up((size_t)n_frames * kActBytesPerFrame, 1024);
   __nv_bfloat16* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + i * bsz);
-  __nv_bfloat16* stem = reinterpret_cast<__nv_bfloat16*>((uint8_t*)workspace + 4 * bsz);
   int last = 0;
-  rc = run_trunk_chunk(h, frames, n_frames, buf, stem, upto, &last, st);
+  StemInput in;
+  in.frames = frames;
+  rc = run_trunk_chunk(h, in, n_frames, buf, upto, &last, st);
   if (rc) return rc;
   const ConvSpec& s = kSpecs[upto];
   const int ho = (upto == 0) ? 17 : s.hout;

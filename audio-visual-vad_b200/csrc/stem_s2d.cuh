@@ -66,6 +66,7 @@ struct StemS2Params {
   float mean, denom;  // standardisation (v - mean) / denom; denom = std + eps
   int standardise;
   int64_t n_frames;
+  int64_t first;             // mode 1: global index of local frame 0 (chunked calls)
   const __nv_bfloat16* w1b;  // folded conv1 weights [64][64], k = fr*7 + fs
   const float* bias;         // folded BN bias [64]
   __nv_bfloat16* out;        // [n_frames][17][17][64]
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         if (MODE == 0) {
           f32 = p.frames + n * (67 * 67);
         } else {
-          const int b = (int)(n / p.t_max), k = (int)(n - (int64_t)b * p.t_max);
+          const int64_t ng = p.first + n;
+          const int b = (int)(ng / p.t_max), k = (int)(ng - (int64_t)b * p.t_max);
           const int F = p.n_src[b], T = p.n_out[b];
           if (k < T && F > 0) u8 = p.src + ((int64_t)b * p.f_max + s2_src_index(k, F, p.num, p.den)) * (67 * 67);
           zero_pair = (uint32_t)lut[0] * 0x10001u;
@@ -190,18 +192,19 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
           const int r = item / 37, q = item - r * 37;
           const int c0 = 2 * q - 3, c1 = c0 + 1;
           uint32_t lo = 0u, hi = 0u;
+          const bool ok0 = (unsigned)c0 < 67u, ok1 = (unsigned)c1 < 67u;
           if (MODE == 0) {
-            const float v0 = (c0 >= 0) ? __ldg(f32 + r * 67 + c0) : 0.f;
-            const float v1 = (c1 < 67) ? __ldg(f32 + r * 67 + c1) : 0.f;
+            const float v0 = ok0 ? __ldg(f32 + r * 67 + c0) : 0.f;
+            const float v1 = ok1 ? __ldg(f32 + r * 67 + c1) : 0.f;
             const uint32_t pk = pack_bf16x2(v0, v1);
-            lo = (c0 >= 0) ? (pk & 0xFFFFu) : 0u;
-            hi = (c1 < 67) ? (pk >> 16) : 0u;
+            lo = ok0 ? (pk & 0xFFFFu) : 0u;
+            hi = ok1 ? (pk >> 16) : 0u;
           } else if (u8) {
-            if (c0 >= 0) lo = lut[__ldg(u8 + r * 67 + c0)];
-            if (c1 < 67) hi = lut[__ldg(u8 + r * 67 + c1)];
+            if (ok0) lo = lut[__ldg(u8 + r * 67 + c0)];
+            if (ok1) hi = lut[__ldg(u8 + r * 67 + c1)];
           } else {
-            lo = (c0 >= 0) ? (zero_pair & 0xFFFFu) : 0u;
-            hi = (c1 < 67) ? (zero_pair >> 16) : 0u;
+            lo = ok0 ? (zero_pair & 0xFFFFu) : 0u;
+            hi = ok1 ? (zero_pair >> 16) : 0u;
           }
           const uint32_t w = lo | (hi << 16);
           const int pr = r + 3;  // padded row

@@ -128,6 +128,18 @@ int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_fra
                            float* feat, void* feat_bf16, int64_t ld_bf16, int64_t col_off,
                            void* stream);
 
+/* The same trunk fed straight from the 30 fps u8 source frames (rows U + A4 + V1/V2 of SURVEY 8a in one pass):
+ * output frame (b, k), k < t_max, is source frame avvad_upsample_index(k, n_src[b]) standardised as
+ * (v - mean) / (std + eps) when k < n_out[b] and the collate zero frame otherwise -- bit-identical to
+ * avvad_upsample_gather followed by avvad_resnet18_forward, without the fp32 (B, t_max, 67, 67) tensor.
+ * src : u8 [B][f_max][67][67] device.  Outputs as avvad_resnet18_forward with n_frames = B * t_max
+ * (workspace: avvad_resnet18_workspace_bytes(B * t_max, chunk_frames)). */
+int avvad_resnet18_forward_u8(avvad_resnet18* h, const uint8_t* src, const int32_t* n_src,
+                              const int32_t* n_out, int32_t B, int32_t f_max, int32_t t_max, int32_t num,
+                              int32_t den, float mean, float std, float eps, int standardise,
+                              int64_t chunk_frames, void* workspace, size_t workspace_bytes, float* feat,
+                              void* feat_bf16, int64_t ld_bf16, int64_t col_off, void* stream);
+
 /* Test hook: run the trunk up to and including conv layer `upto` (see order above; 0 = conv1 +
  * maxpool) and copy that activation (bf16 NHWC) to out_act. */
 int avvad_resnet18_forward_upto(avvad_resnet18* h, const float* frames, int64_t n_frames, int upto,

@@ -172,3 +172,52 @@ def test_av_larger_batch_decisions_agree_with_oracle():
     sure = np.abs(rp - 0.5) > POST_TOL
     assert ((rp > 0.5).astype(np.int32) == dec.cpu().numpy())[sure].all()
     assert agree >= 0.99, agree
+
+
+def _stem_reference(frames, sd):
+    """fp32 torch: conv1 (3 identical channels) + BN(eval) + ReLU + maxpool, on bf16-rounded inputs."""
+    import torch.nn.functional as F
+    x = frames.to(torch.bfloat16).float()[:, None].repeat(1, 3, 1, 1)
+    y = F.conv2d(x, sd["features.0.weight"], stride=2, padding=3)
+    y = F.batch_norm(y, sd["features.1.running_mean"], sd["features.1.running_var"], sd["features.1.weight"],
+                     sd["features.1.bias"], training=False, eps=1e-5)
+    return F.max_pool2d(torch.relu(y), 3, 2, 1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 37, 301])
+def test_stem_image_as_operand_matches_fp32(n):
+    """Every output pixel of the stem (incl. the edge tile's pooled column 16, odd batch tails and both frames of a
+    batch) against fp32 conv+BN+ReLU+maxpool."""
+    sd = _sd("video", 5)
+    g = torch.Generator().manual_seed(n)
+    frames = torch.randn(n, 67, 67, generator=g)
+    ref = _stem_reference(frames, sd).permute(0, 2, 3, 1).numpy()
+    trunk = E.ResNet18Trunk()
+    trunk.load(sd, "cuda")
+    got = trunk.forward_upto(frames.cuda(), 0, (17, 17, 64)).float().cpu().numpy()
+    st = err_stats(got, ref)
+    assert st["rel_fro"] < 8e-3, st
+    assert st["max"] < 3e-2 * max(1.0, st["ref_absmax"]), st
+    # per pooled column: a wrong anchor / shift mapping shows up as one bad column, not as noise
+    col_err = np.abs(got - ref).max(axis=(0, 1, 3))
+    assert col_err.max() < 3e-2 * max(1.0, st["ref_absmax"]), col_err
+
+
+def test_trunk_from_u8_source_equals_gather_then_trunk():
+    """avvad_resnet18_forward_u8 (gather + standardise + padding inside the stem) is bit-identical to
+    avvad_upsample_gather followed by avvad_resnet18_forward, ragged lengths and chunking included."""
+    sd = _sd("video", 9)
+    trunk = E.ResNet18Trunk()
+    trunk.load(sd, "cuda")
+    B, F = 5, 23
+    n_src = [23, 17, 1, 20, 0]
+    t_max = 50
+    n_out = [48, 35, 2, 50, 0]
+    g = torch.Generator().manual_seed(3)
+    src = torch.randint(0, 256, (B, F, 67, 67), generator=g, dtype=torch.uint8).cuda()
+    frames = E.upsample_gather(src, n_src, n_out, t_max, synth.VIDEO_MEAN, synth.VIDEO_STD, 1e-8, True)
+    for chunk in (2048, 64, 7):
+        trunk.chunk = chunk
+        a = trunk.forward(frames.view(B * t_max, 67, 67))
+        b = trunk.forward_u8(src, n_src, n_out, t_max, synth.VIDEO_MEAN, synth.VIDEO_STD, 1e-8, True)
+        assert torch.equal(a, b), (chunk, (a - b).abs().max().item())
