@@ -17,19 +17,23 @@
 // as a separate transposed plane.  Horizontally pooled rows go to a 32-row shared-memory ring; the vertical 3-row
 // maximum is taken from there and written to global memory as the pooled 17x17x64 bf16 map.
 //
-// Seven tcgen05.mma (128 x 256 x 16) per tile of 16 image rows; a batch of 2 frames is 5 such tiles + 1 edge tile.
+// Seven tcgen05.mma (128 x 256 x 16) per tile of 16 image rows + one "bias step" (A = ones, B = folded BN bias split
+// into a bf16 high and low part), so the accumulator already holds conv + bias and the epilogue is max / ReLU / pack
+// only; a batch of 2 frames is 5 such tiles + 1 edge tile.
 //
-//   warps 0-3  : builders  (global -> planes; double-buffered batches)
-//   warp  4    : TMEM alloc; lane 0 issues the MMAs
-//   warps 5-12 : epilogue  (TMEM -> horizontal pool -> ring; then vertical pool -> global)
+//   warps 0-7  : builders  (global -> registers one frame ahead -> planes; double-buffered batches)
+//   warp  8    : TMEM alloc; lane 0 issues the MMAs
+//   warps 9-16 : epilogue  (TMEM -> horizontal pool -> ring; then vertical pool -> global)
 #pragma once
 #include "gemm_tc.cuh"
 
 namespace avvad {
 namespace tc {
 
-constexpr int kS2Builders = 128;
-constexpr int kS2Threads = 128 + 32 + 256;
+constexpr int kS2Builders = 256;
+constexpr int kS2BuilderWarps = kS2Builders / 32;
+constexpr int kS2Items = (67 * 37 + kS2Builders - 1) / kS2Builders;  // (row, pixel pair) items per builder thread and frame
+constexpr int kS2Threads = kS2Builders + 32 + 256;
 constexpr int kS2FramesPerBatch = 2;
 constexpr int kS2RowsPerFrame = 37;                    // plane rows per frame: y = 0..36 (34 outputs + 3 filter-row halo)
 constexpr int kS2Pitch = 160;                          // bytes per plane row: 80 bf16 pixels (73 used)
@@ -40,14 +44,16 @@ constexpr uint32_t kS2EdgeChunkBytes = kS2EdgeRows * 16;         // one 8-pixel 
 constexpr uint32_t kS2EdgePlaneBytes = 2 * kS2EdgeChunkBytes;    // chunks 0,1
 constexpr uint32_t kS2BufBytes = 2 * kS2PlaneBytes + 2 * kS2EdgePlaneBytes;  // one batch buffer: 35,008
 constexpr uint32_t kS2WStepBytes = 256 * 32;           // one filter row: N=256 x K=16 bf16
-constexpr uint32_t kS2WBytes = 7 * kS2WStepBytes;      // 57,344
+constexpr uint32_t kS2WBytes = 8 * kS2WStepBytes;      // 7 filter rows + the bias step: 65,536
+constexpr uint32_t kS2OnesBytes = 128 * 32;            // 128 x 16 bf16 ones: A operand of the bias step
 constexpr int kS2RingRows = 32;
 constexpr uint32_t kS2RingRowBytes = 16 * 128;         // 16 pooled columns x 64 ch bf16
 constexpr uint32_t kS2RingBytes = kS2RingRows * kS2RingRowBytes;  // 65,536
 constexpr uint32_t kS2EdgeHpBytes = 80 * 128;          // pooled column 16 of every stream row of the batch
-// layout: [buf0][buf1][W][ring][edge_hp][lut 512][bias 256][barriers 128]
+// layout: [buf0][buf1][W][ones][ring][edge_hp][lut 512][bias 256][barriers 128]
 constexpr uint32_t kS2OffW = 2 * kS2BufBytes;
-constexpr uint32_t kS2OffRing = kS2OffW + kS2WBytes;
+constexpr uint32_t kS2OffOnes = kS2OffW + kS2WBytes;
+constexpr uint32_t kS2OffRing = kS2OffOnes + kS2OnesBytes;
 constexpr uint32_t kS2OffEdgeHp = kS2OffRing + kS2RingBytes;
 constexpr uint32_t kS2OffLut = kS2OffEdgeHp + kS2EdgeHpBytes;
 constexpr uint32_t kS2OffBias = kS2OffLut + 512;
@@ -106,6 +112,13 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   return r;
 }
 
+// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -138,6 +151,20 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
                          (uint32_t)(n & 7) * 16u + (uint32_t)(e & 7) * 2u;
     *reinterpret_cast<__nv_bfloat16*>(smem + off) = v;
   }
+  // bias step: B[n][0] = bf16(bias), B[n][1] = bf16(bias - hi) (together ~16 mantissa bits), other columns zero
+  for (int idx = tid; idx < 256 * 16; idx += kS2Threads) {
+    const int e = idx & 15, n = idx >> 4;
+    const float bv = p.bias[n & 63];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (e == 0) v = hi;
+    if (e == 1) v = __float2bfloat16_rn(bv - __bfloat162float(hi));
+    const uint32_t off = kS2OffW + 7u * kS2WStepBytes + (uint32_t)(n >> 3) * 256u + (uint32_t)(e >> 3) * 128u +
+                         (uint32_t)(n & 7) * 16u + (uint32_t)(e & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(smem + off) = v;
+  }
+  for (uint32_t i = tid; i < kS2OnesBytes / 4; i += kS2Threads)
+    reinterpret_cast<uint32_t*>(smem + kS2OffOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
   if (tid < 64) bias_s[tid] = p.bias[tid];
   if (MODE == 1 && tid < 256) {
     float v = (float)tid;
@@ -154,7 +181,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
     }
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kS2BuilderWarps) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     tmem_relinquish();
   }
@@ -164,63 +191,87 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kS2BuilderWarps) {
     // ======================= builders =======================
+    // item j of a thread = (source row r, pixel pair q): padded pixels 2q, 2q+1 <-> source columns 2q-3, 2q-2.
+    // The pixels of a frame are fetched into registers one frame ahead, so the global latency overlaps the wait for
+    // a free batch buffer and the stores of the previous frame.
+    uint32_t px[kS2Items];  // MODE 0: packed bf16 pair; MODE 1: packed lut indices (lo | hi << 8), bit 16/17 = column valid
+    auto fetch = [&](int64_t n) {
+      if (n >= p.n_frames) return;
+      if (MODE == 0) {
+        const float* f32 = p.frames + n * (67 * 67);
+#pragma unroll
+        for (int j = 0; j < kS2Items; ++j) {
+          const int item = tid + j * kS2Builders;
+          const int r = item / 37, q = item - r * 37;
+          const int c0 = 2 * q - 3, c1 = c0 + 1;
+          const bool ok0 = (unsigned)c0 < 67u && r < 67, ok1 = (unsigned)c1 < 67u && r < 67;
+          const float v0 = ok0 ? __ldg(f32 + r * 67 + c0) : 0.f;
+          const float v1 = ok1 ? __ldg(f32 + r * 67 + c1) : 0.f;
+          px[j] = pack_bf16x2(v0, v1);  // bf16(0) == 0 keeps the border pixels zero
+        }
+      } else {
+        const int64_t ng = p.first + n;
+        const int b = (int)(ng / p.t_max), k = (int)(ng - (int64_t)b * p.t_max);
+        const int F = p.n_src[b], T = p.n_out[b];
+        const bool live = (k < T && F > 0);
+        const uint8_t* u8 = live ? p.src + ((int64_t)b * p.f_max + s2_src_index(k, F, p.num, p.den)) * (67 * 67) : p.src;
+#pragma unroll
+        for (int j = 0; j < kS2Items; ++j) {
+          const int item = tid + j * kS2Builders;
+          const int r = item / 37, q = item - r * 37;
+          const int c0 = 2 * q - 3, c1 = c0 + 1;
+          const bool ok0 = (unsigned)c0 < 67u && r < 67, ok1 = (unsigned)c1 < 67u && r < 67;
+          uint32_t lo = 0u, hi = 0u;  // collate zero frame: source value 0
+          if (live && ok0) lo = __ldg(u8 + r * 67 + c0);
+          if (live && ok1) hi = __ldg(u8 + r * 67 + c1);
+          px[j] = lo | (hi << 8) | (ok0 ? 0x10000u : 0u) | (ok1 ? 0x20000u : 0u);
+        }
+      }
+    };
+    auto store = [&](uint8_t* bufp, int fi) {
+#pragma unroll
+      for (int j = 0; j < kS2Items; ++j) {
+        const int item = tid + j * kS2Builders;
+        const int r = item / 37, q = item - r * 37;
+        if (r >= 67) continue;
+        uint32_t w;
+        if (MODE == 0) {
+          w = px[j];
+        } else {
+          const uint32_t lo = (px[j] & 0x10000u) ? (uint32_t)lut[px[j] & 0xFFu] : 0u;
+          const uint32_t hi = (px[j] & 0x20000u) ? (uint32_t)lut[(px[j] >> 8) & 0xFFu] : 0u;
+          w = lo | (hi << 16);
+        }
+        const int pr = r + 3;  // padded row
+        const int yy = fi * kS2RowsPerFrame + (pr >> 1);
+        uint8_t* plane = bufp + (uint32_t)(pr & 1) * kS2PlaneBytes;
+        *reinterpret_cast<uint32_t*>(plane + yy * kS2Pitch + 4 * q) = w;
+        if (q >= 30) {  // pixels 60..73: the edge anchor's two chunks, transposed (rows 16 bytes apart)
+          uint8_t* edge = bufp + 2 * kS2PlaneBytes + (uint32_t)(pr & 1) * kS2EdgePlaneBytes;
+          *reinterpret_cast<uint32_t*>(edge + (uint32_t)((q - 30) >> 2) * kS2EdgeChunkBytes + yy * 16 + 4 * ((q - 30) & 3)) = w;
+        }
+      }
+    };
     uint32_t it = 0;
+    fetch((int64_t)blockIdx.x * kS2FramesPerBatch);
     for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
       mbar_wait(BAR(2 + buf), ((it >> 1) & 1u) ^ 1u);
       uint8_t* bufp = smem + buf * kS2BufBytes;
+#pragma unroll
       for (int fi = 0; fi < kS2FramesPerBatch; ++fi) {
         const int64_t n = bi * kS2FramesPerBatch + fi;
-        if (n >= p.n_frames) break;
-        const float* f32 = nullptr;
-        const uint8_t* u8 = nullptr;
-        uint32_t zero_pair = 0u;
-        if (MODE == 0) {
-          f32 = p.frames + n * (67 * 67);
-        } else {
-          const int64_t ng = p.first + n;
-          const int b = (int)(ng / p.t_max), k = (int)(ng - (int64_t)b * p.t_max);
-          const int F = p.n_src[b], T = p.n_out[b];
-          if (k < T && F > 0) u8 = p.src + ((int64_t)b * p.f_max + s2_src_index(k, F, p.num, p.den)) * (67 * 67);
-          zero_pair = (uint32_t)lut[0] * 0x10001u;
-        }
-        // item = (source row r, pixel pair q): padded pixels 2q, 2q+1 <-> source columns 2q-3, 2q-2
-#pragma unroll 4
-        for (int item = tid; item < 67 * 37; item += kS2Builders) {
-          const int r = item / 37, q = item - r * 37;
-          const int c0 = 2 * q - 3, c1 = c0 + 1;
-          uint32_t lo = 0u, hi = 0u;
-          const bool ok0 = (unsigned)c0 < 67u, ok1 = (unsigned)c1 < 67u;
-          if (MODE == 0) {
-            const float v0 = ok0 ? __ldg(f32 + r * 67 + c0) : 0.f;
-            const float v1 = ok1 ? __ldg(f32 + r * 67 + c1) : 0.f;
-            const uint32_t pk = pack_bf16x2(v0, v1);
-            lo = ok0 ? (pk & 0xFFFFu) : 0u;
-            hi = ok1 ? (pk >> 16) : 0u;
-          } else if (u8) {
-            if (ok0) lo = lut[__ldg(u8 + r * 67 + c0)];
-            if (ok1) hi = lut[__ldg(u8 + r * 67 + c1)];
-          } else {
-            lo = ok0 ? (zero_pair & 0xFFFFu) : 0u;
-            hi = ok1 ? (zero_pair >> 16) : 0u;
-          }
-          const uint32_t w = lo | (hi << 16);
-          const int pr = r + 3;  // padded row
-          const int yy = fi * kS2RowsPerFrame + (pr >> 1);
-          uint8_t* plane = bufp + (uint32_t)(pr & 1) * kS2PlaneBytes;
-          *reinterpret_cast<uint32_t*>(plane + yy * kS2Pitch + 4 * q) = w;
-          if (q >= 30 && q < 38) {  // pixels 60..75: the edge anchor's two chunks, transposed (rows 16 bytes apart)
-            uint8_t* edge = bufp + 2 * kS2PlaneBytes + (uint32_t)(pr & 1) * kS2EdgePlaneBytes;
-            *reinterpret_cast<uint32_t*>(edge + (uint32_t)((q - 30) >> 2) * kS2EdgeChunkBytes + yy * 16 + 4 * ((q - 30) & 3)) = w;
-          }
-        }
+        if (n < p.n_frames) store(bufp, fi);
+        // next frame of this CTA: the second of this batch, or the first of the next one
+        const int64_t nn = (fi + 1 < kS2FramesPerBatch) ? n + 1 : (bi + gridDim.x) * kS2FramesPerBatch;
+        if (fi + 1 < kS2FramesPerBatch || bi + gridDim.x < n_batches) fetch(nn);
       }
       fence_proxy_async();
       mbar_arrive(BAR(0 + buf));
     }
-  } else if (warp == 4) {
+  } else if (warp == kS2BuilderWarps) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(256);
@@ -240,6 +291,9 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
           mbar_wait(BAR(6 + acc), ((g >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d = tmem_acc + acc * 256u;
+          // bias step: ones (128 x 16, core matrices [r/8][k/8]: SBO 256, LBO 128) x bias rows
+          umma_f16_ns(d, desc_lo_ns(base + kS2OffOnes, 128u), b_hi, desc_lo_ns(base + kS2OffW + 7u * kS2WStepBytes, 128u),
+                      b_hi, idesc, 0);
 #pragma unroll
           for (int fr = 0; fr < 7; ++fr) {
             const int a = fr >> 1, b = fr & 1;
@@ -253,7 +307,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
               a_hi = a_hi_main;
             }
             const uint32_t b_lo = desc_lo_ns(base + kS2OffW + (uint32_t)fr * kS2WStepBytes, 128u);
-            umma_f16_ns(d, a_lo, a_hi, b_lo, b_hi, idesc, fr != 0);
+            umma_f16_ns(d, a_lo, a_hi, b_lo, b_hi, idesc, 1);
           }
           umma_commit(BAR(4 + acc));
         }
@@ -261,11 +315,11 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
       }
     }
   } else {
-    // ======================= epilogue: warps 5..12 =======================
-    const int ew = warp - 5;           // 0..7
+    // ======================= epilogue: the last 8 warps =======================
+    const int ew = warp - (kS2BuilderWarps + 1);  // 0..7
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = ew >> 2;          // channel half: [32*half, 32*half + 32)
-    const int etid = tid - 160;        // 0..255
+    const int etid = tid - (kS2Builders + 32);  // 0..255
     const int L = q * 32 + lane;       // accumulator row
     uint8_t* ring = smem + kS2OffRing;
     uint8_t* edge_hp = smem + kS2OffEdgeHp;
@@ -298,7 +352,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
                 const float x0 = fmaxf(fmaxf(__uint_as_float(v1[2 * c]), __uint_as_float(v2[2 * c])), __uint_as_float(v3[2 * c]));
                 const float x1 = fmaxf(fmaxf(__uint_as_float(v1[2 * c + 1]), __uint_as_float(v2[2 * c + 1])),
                                        __uint_as_float(v3[2 * c + 1]));
-                o[c] = pack_bf16x2(fmaxf(x0 + bias_s[ch0 + 2 * c], 0.f), fmaxf(x1 + bias_s[ch0 + 2 * c + 1], 0.f));
+                o[c] = pack_relu_bf16x2(x0, x1);
               }
               uint8_t* rowp = edge_hp + L * 128;
               const int k0 = ch0 >> 3;
@@ -334,13 +388,12 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
               const float s0 = __uint_as_float(v0[c + h]), s1 = __uint_as_float(v1[c + h]);
               const float s2 = __uint_as_float(v2[c + h]), s3 = __uint_as_float(v3[c + h]);
               float left = __shfl_up_sync(0xffffffffu, s3, 1);  // conv column 4i-1 (lane L-1 is anchor i-1 of the same row)
-              if (i == 0) left = s0;
-              const float bch = bias_s[ch0 + c + h];
-              pa[h] = fmaxf(fmaxf(fmaxf(left, s0), s1) + bch, 0.f);
-              pb[h] = fmaxf(fmaxf(fmaxf(s1, s2), s3) + bch, 0.f);
+              left = (i == 0) ? s0 : left;
+              pa[h] = fmaxf(fmaxf(left, s0), s1);  // accumulators already hold conv + bias; max commutes with ReLU / rounding
+              pb[h] = fmaxf(fmaxf(s1, s2), s3);
             }
-            oa[c >> 1] = pack_bf16x2(pa[0], pa[1]);
-            ob[c >> 1] = pack_bf16x2(pb[0], pb[1]);
+            oa[c >> 1] = pack_relu_bf16x2(pa[0], pa[1]);
+            ob[c >> 1] = pack_relu_bf16x2(pb[0], pb[1]);
           }
           if (yy < n_rows) {
             const int k0 = ch0 >> 3;  // 16-byte chunk index of these channels within the 128-byte pixel
@@ -357,39 +410,46 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         if (lane == 0) mbar_arrive(BAR(6 + acc));
         named_bar_sync(1, 256);  // this tile's ring rows are visible to all epilogue warps
 
-        // vertical pool: every odd conv row y = 2ph+1 inside this tile completes pooled row ph (rows y-2, y-1, y)
-        for (int item = etid; item < 8 * 17 * 8; item += 256) {
-          const int ch = item & 7;
-          const int pw = (item >> 3) % 17;
-          const int rr = (item >> 3) / 17;  // 0..7: the rr-th odd/even pair of this tile
-          // stream rows of the tile: 16t .. 16t+15; frame fi = yy / 37, y = yy % 37
-          // enumerate candidate rows: yy = 16t + 2*rr + {0,1}; the one with odd y < 34 is the trigger
+        // vertical pool: every odd conv row y = 2ph+1 inside this tile completes pooled row ph (rows y-2, y-1, y).
+        // thread = (16-byte channel chunk ch, row pair rr of the tile, column group pg); columns pg, pg+4, ...
+        {
+          const int ch = etid & 7, rr = (etid >> 3) & 7, pg = etid >> 6;
+          // candidate stream rows 16t + 2rr + {0,1}: the one whose in-frame row y is odd is the trigger
           int ys = 16 * t + 2 * rr;
-          int fi = ys / kS2RowsPerFrame;
+          int fi = (ys >= kS2RowsPerFrame) ? 1 : 0;
           int y = ys - fi * kS2RowsPerFrame;
           if ((y & 1) == 0) {
             ++ys; ++y;
             if (y == kS2RowsPerFrame) { y = 0; ++fi; }
           }
-          if (!(y & 1) || y > 33 || ys >= n_rows || fi >= nf) continue;
-          const int ph = y >> 1;
-          uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+          if ((y & 1) && y <= 33 && ys < n_rows && fi < nf) {
+            const int ph = y >> 1;
+            const uint8_t* r0 = ring + (uint32_t)(ys & (kS2RingRows - 1)) * kS2RingRowBytes;
+            const uint8_t* r1 = ring + (uint32_t)((ys - 1) & (kS2RingRows - 1)) * kS2RingRowBytes;
+            const uint8_t* r2 = ring + (uint32_t)((ys - 2) & (kS2RingRows - 1)) * kS2RingRowBytes;
+            const bool top = (y >= 2);  // pooled row 0 has no conv row -1
+            __nv_bfloat16* orow = p.out + ((bi * kS2FramesPerBatch + fi) * 17 + ph) * (17 * 64) + ch * 8;
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const int yr = y - dy;  // conv row (>= 0 since y >= 1; row -1 of ph = 0 is simply absent)
-            if (yr < 0) continue;
-            const int ysr = ys - dy;
-            uint4 v;
-            if (pw < 16) {
-              v = *reinterpret_cast<const uint4*>(ring + (uint32_t)(ysr & (kS2RingRows - 1)) * kS2RingRowBytes + pw * 128 +
-                                                  ((ch ^ (pw >> 1)) << 4));
-            } else {
-              v = *reinterpret_cast<const uint4*>(edge_hp + ysr * 128 + ((ch ^ (ysr & 7)) << 4));
+            for (int pw = pg; pw < 17; pw += 4) {
+              uint4 a, b, c;
+              if (pw < 16) {
+                const uint32_t off = (uint32_t)pw * 128u + (uint32_t)((ch ^ (pw >> 1)) << 4);
+                a = *reinterpret_cast<const uint4*>(r0 + off);
+                b = *reinterpret_cast<const uint4*>(r1 + off);
+                c = top ? *reinterpret_cast<const uint4*>(r2 + off) : b;
+              } else {
+                a = *reinterpret_cast<const uint4*>(edge_hp + ys * 128 + ((ch ^ (ys & 7)) << 4));
+                b = *reinterpret_cast<const uint4*>(edge_hp + (ys - 1) * 128 + ((ch ^ ((ys - 1) & 7)) << 4));
+                c = top ? *reinterpret_cast<const uint4*>(edge_hp + (ys - 2) * 128 + ((ch ^ ((ys - 2) & 7)) << 4)) : b;
+              }
+              uint4 m;
+              m.x = bf16x2_max(bf16x2_max(a.x, b.x), c.x);
+              m.y = bf16x2_max(bf16x2_max(a.y, b.y), c.y);
+              m.z = bf16x2_max(bf16x2_max(a.z, b.z), c.z);
+              m.w = bf16x2_max(bf16x2_max(a.w, b.w), c.w);
+              *reinterpret_cast<uint4*>(orow + pw * 64) = m;
             }
-            m0 = bf16x2_max(m0, v.x); m1 = bf16x2_max(m1, v.y); m2 = bf16x2_max(m2, v.z); m3 = bf16x2_max(m3, v.w);
           }
-          const int64_t n = bi * kS2FramesPerBatch + fi;
-          *reinterpret_cast<uint4*>(p.out + ((n * 17 + ph) * 17 + pw) * 64 + ch * 8) = make_uint4(m0, m1, m2, m3);
         }
         named_bar_sync(1, 256);  // ring rows of tile t-1 may be overwritten by tile t+1 from here on
       }
@@ -398,7 +458,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kS2BuilderWarps) {
     __syncwarp();
     tmem_dealloc(tmem_acc, 512);
   }
