@@ -230,7 +230,7 @@ LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
   w.hbuf[1] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.c = (float*)take((size_t)B * H * sizeof(float));
   w.hlast = (__nv_bfloat16*)take((size_t)B * H * 2);
-  w.counters = (unsigned int*)take(256);
+  w.counters = (unsigned int*)take(4096);  // per-CTA step flags of the persistent recurrence
   w.total = off;
   return w;
 }
@@ -257,7 +257,7 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
                                      float* c_out = nullptr) {
   *done = false;
   const int H = h->H;
-  if (!persist_mode() || H % 64 != 0 || H > 1024 || T < 1) return AVVAD_OK;
+  if (!persist_mode() || H % 64 != 0 || H > 1024 || 4 * H / 64 > tc::kLstmMaxSlices || T < 1) return AVVAD_OK;
   static int num_sms = [] {
     int dev = 0, v = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
@@ -275,7 +275,7 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [smem] {
-    attr_err = cudaFuncSetAttribute(tc::lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_err = cudaFuncSetAttribute(tc::lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   AVVAD_CUDA(attr_err);
   const int64_t Bg = (int64_t)max_ms * 128;
@@ -300,9 +300,14 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     g.hseq = hs;
     g.lengths = lengths + g0;
     g.counters = counters;
+    static int variant = [] {
+      const char* e = getenv("AVVAD_LSTM_VARIANT");
+      return e ? atoi(e) : 0;
+    }();
+    g.variant = variant;
     g.gates_out = gates_out ? gates_out + g0 * T * 4 * H : nullptr;
     g.c_out = c_out ? c_out + g0 * T * H : nullptr;
-    AVVAD_CUDA(cudaMemsetAsync(counters, 0, 256, st));
+    AVVAD_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
     void* args[2] = {(void*)&maps, (void*)&g};
     void* tok = nullptr;
     tc::prof_begin(st, &tok);
