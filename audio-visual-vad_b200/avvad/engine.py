@@ -6,6 +6,7 @@ parameter storage.  All arithmetic of the hot path happens inside libavvad.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -184,7 +185,7 @@ class ResNet18Trunk:
         L.check(L.lib().avvad_resnet18_create(C.byref(h)))
         self.h = h
         self.ws = _Workspace()
-        self.chunk = 2048
+        self.chunk = int(os.environ.get("AVVAD_CHUNK", "24576"))  # frames per trunk pass (buffers: 4 x chunk x 37 KB)
 
     def __del__(self):
         try:

@@ -8,6 +8,7 @@ CPU-STFT evaluation loop: scripts/evaluate_AV_net.py:141-250); the reference-com
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -36,7 +37,7 @@ class AVVADPipeline:
                 self.mcb = E.Mcb()
                 self.mcb.load(state_dict, self.device, eps)
         self._bufs = {}
-        self.piece = 32            # utterances per video piece (upload / upsample / trunk granularity)
+        self.piece = int(os.environ.get("AVVAD_PIECE", "64"))  # utterances per video piece (upload / trunk granularity)
         self.fuse_gather = True    # u8 video: gather + standardise inside the stem (False: separate fp32 gather)
         self._copy_stream = None
         self._events = []

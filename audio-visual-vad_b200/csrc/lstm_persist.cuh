@@ -57,6 +57,15 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 // generic <-> async proxy ordering for global memory only (h is written with st.global and read back by TMA)
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// hardware tanh (MUFU.TANH, |err| ~ 5e-4 abs, below the bf16 rounding of h) and sigmoid(x) = 0.5 tanh(x/2) + 0.5: one
+// special-function instruction per gate on the recurrence's critical path
+__device__ __forceinline__ float tanh_hw(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_hw(float x) { return fmaf(0.5f, tanh_hw(0.5f * x), 0.5f); }
+
 __global__ void __launch_bounds__(kLstmThreads)
 lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -205,12 +214,23 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int o = u * 4;
-          const float gi = sigmoidf_fast(__uint_as_float(v[o + 0]) + x[u].x);
-          const float gf = sigmoidf_fast(__uint_as_float(v[o + 1]) + x[u].y);
-          const float gg = tanhf_fast(__uint_as_float(v[o + 2]) + x[u].z);
-          const float go = sigmoidf_fast(__uint_as_float(v[o + 3]) + x[u].w);
-          c[u] = gf * c[u] + gi * gg;
-          hv[u] = go * tanhf_fast(c[u]);
+          float gi, gf, gg, go, tc;
+          if (g.variant & 8) {  // exp-based activations (the pre-MUFU.TANH path, kept for A/B accuracy checks)
+            gi = sigmoidf_fast(__uint_as_float(v[o + 0]) + x[u].x);
+            gf = sigmoidf_fast(__uint_as_float(v[o + 1]) + x[u].y);
+            gg = tanhf_fast(__uint_as_float(v[o + 2]) + x[u].z);
+            go = sigmoidf_fast(__uint_as_float(v[o + 3]) + x[u].w);
+            c[u] = gf * c[u] + gi * gg;
+            tc = tanhf_fast(c[u]);
+          } else {
+            gi = sigmoid_hw(__uint_as_float(v[o + 0]) + x[u].x);
+            gf = sigmoid_hw(__uint_as_float(v[o + 1]) + x[u].y);
+            gg = tanh_hw(__uint_as_float(v[o + 2]) + x[u].z);
+            go = sigmoid_hw(__uint_as_float(v[o + 3]) + x[u].w);
+            c[u] = gf * c[u] + gi * gg;
+            tc = tanh_hw(c[u]);
+          }
+          hv[u] = go * tc;
           if (gsave) {
             uint2 pk;
             pk.x = pack_bf16x2(gi, gf);

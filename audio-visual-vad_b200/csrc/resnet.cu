@@ -497,91 +497,115 @@ static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __
   return AVVAD_OK;
 }
 
+static int launch_stem(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st) {
+  if (stem_mode() == 1 || in.src) return launch_stem_s2d(h, in, n, out, st);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)tc::kStemSmem);
+  });
+  AVVAD_CUDA(attr_err);
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const unsigned grid = (unsigned)(n < num_sms ? n : num_sms);
+  void* tok = nullptr;
+  tc::prof_begin(st, &tok);
+  tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(in.frames + in.first * kFrameHW, n, h->w1b,
+                                                                       h->bias[0], out);
+  AVVAD_LAUNCHED();
+  tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
+  return AVVAD_OK;
+}
+
+// per-frame elements of a stage's input / output activation and its tensor-core MACs per frame
+static const int64_t kStageIn[4] = {17 * 17 * 64, 17 * 17 * 64, 9 * 9 * 128, 5 * 5 * 256};
+static const int64_t kStageOut[4] = {17 * 17 * 64, 9 * 9 * 128, 5 * 5 * 256, 3 * 3 * 512};
+static const double kStageMac[4] = {42614784.0, 42467328.0, 52428800.0, 75497472.0};
+
+// Runs the trunk on one chunk; stops after layer `upto` (20 = run everything).  Returns the buffer index holding the
+// last produced activation in *last.  Stage s = torchvision layer(s+1): two BasicBlocks, the first of stages 1-3 with
+// a stride-2 conv_a and a 1x1 downsample branch (K-concatenated into conv_b unless AVVAD_FUSE_DS=0).
 static int run_trunk_chunk(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* const buf[4], int upto,
                            int* last, cudaStream_t st) {
   if (fuse_ds()) {
     int frc = build_fused(h, st);
     if (frc) return frc;
   }
-  if (stem_mode() == 1 || in.src) {
-    int rc = launch_stem_s2d(h, in, n, buf[0], st);
-    if (rc) return rc;
-  } else {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-      attr_err = cudaFuncSetAttribute(tc::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::kStemSmem);
-    });
-    AVVAD_CUDA(attr_err);
-    static int num_sms = [] {
-      int dev = 0, v = 148;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-      return v > 0 ? v : 148;
-    }();
-    const unsigned grid = (unsigned)(n < num_sms ? n : num_sms);
-    void* tok = nullptr;
-    tc::prof_begin(st, &tok);
-    tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(in.frames + in.first * kFrameHW, n, h->w1b,
-                                                                         h->bias[0], buf[0]);
-    AVVAD_LAUNCHED();
-    tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
-  }
+  // Note: running layer1/layer2 depth-first over L2-sized slices of the chunk was measured SLOWER (each persistent
+  // launch pays a prologue and a tail; 512-frame slices cost +15 % on the convolutions), larger chunks are faster:
+  // chunk 2048 -> 20288 frames = 36.3 -> 33.3 ms of convolutions per 81,152 frames.
+  const bool whole = upto < 20;  // layer-by-layer test hook: per-launch profiling records
   int cur = 0;
   *last = cur;
-  if (upto == 0) return AVVAD_OK;
-  // one profiling record for the chunk's 19 implicit-GEMM convolutions (216,633,600 - 3,625,216 MAC per frame)
-  void* gtok = nullptr;
-  if (upto >= 20) tc::prof_group_begin(st, &gtok);
-  struct GroupEnd {
-    cudaStream_t st; void* tok; double flops;
-    ~GroupEnd() { tc::prof_group_end(st, tok, 0, flops); }
-  } group_end{st, gtok, 2.0 * (double)n * (216633600.0 - 1156.0 * 64.0 * 49.0)};
   int layer = 1;
   for (int stage = 0; stage < 4; ++stage) {
-    for (int blk = 0; blk < 2; ++blk) {
-      int o[3], k = 0;
-      for (int i = 0; i < 4; ++i)
-        if (i != cur) o[k++] = i;
-      const bool ds = (stage > 0 && blk == 0);
-      const int la = layer, lb = layer + 1, lds = layer + 2;
-      int rc = run_conv(h, la, buf[cur], nullptr, buf[o[0]], n, 1, st);
-      if (rc) return rc;
-      if (upto == la) { *last = o[0]; return AVVAD_OK; }
-      const __nv_bfloat16* res = buf[cur];
-      if (ds && fuse_ds() && upto != lds) {
-        // conv_b with the downsample branch appended along K: no 1x1 launch, no residual round trip
-        const ConvSpec& sb = kSpecs[lb];
-        const ConvSpec& sd = kSpecs[lds];
-        tc::EpiParams ep{};
-        ep.bias = h->bf[stage - 1];
-        ep.C = buf[o[2]];
-        ep.ldc = sb.cout;
-        ep.relu = 1;
-        tc::SecondOperand so;
-        so.in2 = buf[cur];
-        so.H2 = sd.hin; so.W2 = sd.hin; so.Cin2 = sd.cin; so.stride2 = sd.stride;
-        rc = tc::launch_tma_conv(buf[o[0]], h->wf[stage - 1], ep, n, sb.hin, sb.hin, sb.cin, sb.cout, sb.k, sb.k, sb.stride,
-                                 sb.pad, 0, st, 0, 0.0, &so);
+    {
+      const int64_t f0 = 0, nn = n;
+      if (stage == 0) {
+        int rc = launch_stem(h, in.advance(f0), nn, buf[0] + f0 * kStageIn[0], st);
+        if (rc) return rc;
+        if (upto == 0) return AVVAD_OK;
+      }
+      // one profiling record per stage: its convolution launches and their algorithmic FLOPs
+      void* gtok = nullptr;
+      if (!whole) tc::prof_group_begin(st, &gtok);
+      struct GroupEnd {
+        cudaStream_t st; void* tok; double flops;
+        ~GroupEnd() { tc::prof_group_end(st, tok, 0, flops); }
+      } group_end{st, gtok, 2.0 * (double)nn * kStageMac[stage]};
+      for (int blk = 0; blk < 2; ++blk) {
+        int o[3], k = 0;
+        for (int i = 0; i < 4; ++i)
+          if (i != cur) o[k++] = i;
+        const bool ds = (stage > 0 && blk == 0);
+        const int la = layer, lb = layer + 1, lds = layer + 2;
+        // the block input has the stage-input geometry only for the first block of the stage
+        const __nv_bfloat16* xin = buf[cur] + f0 * (blk == 0 ? kStageIn[stage] : kStageOut[stage]);
+        __nv_bfloat16* y0 = buf[o[0]] + f0 * kStageOut[stage];
+        __nv_bfloat16* y1 = buf[o[1]] + f0 * kStageOut[stage];
+        __nv_bfloat16* y2 = buf[o[2]] + f0 * kStageOut[stage];
+        int rc = run_conv(h, la, xin, nullptr, y0, nn, 1, st);
+        if (rc) return rc;
+        if (upto == la) { *last = o[0]; return AVVAD_OK; }
+        const __nv_bfloat16* res = xin;
+        if (ds && fuse_ds() && upto != lds) {
+          // conv_b with the downsample branch appended along K: no 1x1 launch, no residual round trip
+          const ConvSpec& sb = kSpecs[lb];
+          const ConvSpec& sd = kSpecs[lds];
+          tc::EpiParams ep{};
+          ep.bias = h->bf[stage - 1];
+          ep.C = y2;
+          ep.ldc = sb.cout;
+          ep.relu = 1;
+          tc::SecondOperand so;
+          so.in2 = xin;
+          so.H2 = sd.hin; so.W2 = sd.hin; so.Cin2 = sd.cin; so.stride2 = sd.stride;
+          rc = tc::launch_tma_conv(y0, h->wf[stage - 1], ep, nn, sb.hin, sb.hin, sb.cin, sb.cout, sb.k, sb.k, sb.stride,
+                                   sb.pad, 0, st, 0, 0.0, &so);
+          if (rc) return rc;
+          cur = o[2];
+          *last = cur;
+          if (upto == lb) return AVVAD_OK;
+          layer += 3;
+          continue;
+        }
+        if (ds) {
+          rc = run_conv(h, lds, xin, nullptr, y1, nn, 0, st);
+          if (rc) return rc;
+          if (upto == lds) { *last = o[1]; return AVVAD_OK; }
+          res = y1;
+        }
+        rc = run_conv(h, lb, y0, res, y2, nn, 1, st);
         if (rc) return rc;
         cur = o[2];
         *last = cur;
         if (upto == lb) return AVVAD_OK;
-        layer += 3;
-        continue;
+        layer += ds ? 3 : 2;
       }
-      if (ds) {
-        rc = run_conv(h, lds, buf[cur], nullptr, buf[o[1]], n, 0, st);
-        if (rc) return rc;
-        if (upto == lds) { *last = o[1]; return AVVAD_OK; }
-        res = buf[o[1]];
-      }
-      rc = run_conv(h, lb, buf[o[0]], res, buf[o[2]], n, 1, st);
-      if (rc) return rc;
-      cur = o[2];
-      *last = cur;
-      if (upto == lb) return AVVAD_OK;
-      layer += ds ? 3 : 2;
     }
   }
   return AVVAD_OK;
