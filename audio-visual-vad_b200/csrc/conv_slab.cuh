@@ -93,91 +93,117 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      if (RESIDENT_B) {
-        // all weight K blocks, once (n_tiles == 1 in this mode)
+    // ================= TMA producer (warp-converged; one elected lane issues) =================
+    if (RESIDENT_B) {
+      // all weight K blocks, once (n_tiles == 1 in this mode)
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(BAR(kBarBFull), (uint32_t)KB * b_tile);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_base + kb * b_tile, &maps.b, kb * BK, 0, BAR(kBarBFull));
       }
-      uint32_t si = 0, bi = 0;  // slab / weight-ring counters
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const int n_base = (int)(tile % g.n_tiles) * BN;
-        const int64_t mt = tile / g.n_tiles;
-        const int band = (int)(mt % g.nb);
-        const int n0 = (int)((mt / g.nb) * g.F);
-        const int hstart = band * g.hb;
-        for (int cb = 0; cb < g.cpb; ++cb, ++si) {
-          const int sb = si & 1;
-          mbar_wait(BAR(2 + sb), ((si >> 1) & 1u) ^ 1u);
+      __syncwarp();
+    }
+    uint32_t si = 0, bi = 0;  // slab / weight-ring counters
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int n_base = (int)(tile % g.n_tiles) * BN;
+      const int64_t mt = tile / g.n_tiles;
+      const int band = (int)(mt % g.nb);
+      const int n0 = (int)((mt / g.nb) * g.F);
+      const int hstart = band * g.hb;
+      for (int cb = 0; cb < g.cpb; ++cb, ++si) {
+        const int sb = si & 1;
+        mbar_wait(BAR(2 + sb), ((si >> 1) & 1u) ^ 1u);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(BAR(0 + sb), g.slab_tx);
           tma_load_4d(base + sb * slab_bytes, &maps.a, cb * BK, -1, hstart - 1, n0, BAR(0 + sb));
-          if (!RESIDENT_B) {
-            for (int tap = 0; tap < 9; ++tap, ++bi) {
-              const int bs = bi % g.b_stages;
-              mbar_wait(BAR(kBarBEmpty + bs), ((bi / g.b_stages) & 1u) ^ 1u);
+        }
+        __syncwarp();
+        if (!RESIDENT_B) {
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const int bs = bi % g.b_stages;
+            mbar_wait(BAR(kBarBEmpty + bs), ((bi / g.b_stages) & 1u) ^ 1u);
+            if (elect_one_sync()) {
               mbar_arrive_expect_tx(BAR(kBarBFull + bs), b_tile);
               tma_load_2d(w_base + bs * b_tile, &maps.b, (tap * g.cpb + cb) * BK, n_base, BAR(kBarBFull + bs));
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t si = 0, bi = 0, tl = 0;
-      if (RESIDENT_B) {
-        mbar_wait(BAR(kBarBFull), 0);
+    // ================= MMA issuer (warp-converged; one elected lane issues MMAs and commits) =================
+    constexpr uint32_t idesc = make_idesc(BN);
+    uint32_t si = 0, bi = 0, tl = 0;
+    if (RESIDENT_B) {
+      mbar_wait(BAR(kBarBFull), 0);
+      tc_fence_after();
+    }
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(BAR(6 + acc), aph ^ 1u);
+      tc_fence_after();
+      for (int cb = 0; cb < g.cpb; ++cb, ++si) {
+        const int sb = si & 1;
+        mbar_wait(BAR(0 + sb), (si >> 1) & 1u);
         tc_fence_after();
-      }
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-        mbar_wait(BAR(6 + acc), aph ^ 1u);
-        tc_fence_after();
-        for (int cb = 0; cb < g.cpb; ++cb, ++si) {
-          const int sb = si & 1;
-          mbar_wait(BAR(0 + sb), (si >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t slab_lo = desc_lo(base + sb * slab_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            uint32_t w_lo;
-            int bs = 0;
-            if (RESIDENT_B) {
-              w_lo = desc_lo(w_base + (uint32_t)(tap * g.cpb + cb) * b_tile);
-            } else {
-              bs = bi % g.b_stages;
-              mbar_wait(BAR(kBarBFull + bs), (bi / g.b_stages) & 1u);
-              tc_fence_after();
-              w_lo = desc_lo(w_base + bs * b_tile);
+        const uint32_t slab_lo = desc_lo(base + sb * slab_bytes);
+        if (RESIDENT_B) {
+          // every tap of this channel block in one elected region: 9 x mb x 4 MMAs issued back to back
+          if (elect_one_sync()) {
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t w_lo = desc_lo(w_base + (uint32_t)(tap * g.cpb + cb) * b_tile);
+              const int fr = tap / 3, fs = tap - fr * 3;
+              // descriptor low words count 16-byte units: one slab row = 8, one accumulator block (128 rows) = 1024
+              uint32_t a_lo = slab_lo + (uint32_t)(fr * g.Wp + fs) * 8u;
+              uint32_t d_tmem = tmem_acc + acc * acc_cols;
+              const uint32_t first = (cb | tap) != 0;
+              for (int m = 0; m < g.mb; ++m, a_lo += 1024u, d_tmem += BN) {
+                umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
+                umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
+                umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
+                umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+              }
             }
-            const int fr = tap / 3, fs = tap - fr * 3;
-            // descriptor low words count 16-byte units: one slab row = 8, one accumulator block (128 rows) = 1024
-            uint32_t a_lo = slab_lo + (uint32_t)(fr * g.Wp + fs) * 8u;
-            uint32_t d_tmem = tmem_acc + acc * acc_cols;
-            const uint32_t first = (cb | tap) != 0;
-            for (int m = 0; m < g.mb; ++m, a_lo += 1024u, d_tmem += BN) {
-              umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
-              umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
-              umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
-              umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
-            }
-            if (!RESIDENT_B) {
-              umma_commit(BAR(kBarBEmpty + bs));
-              ++bi;
-            }
+            umma_commit(BAR(2 + sb));
+            if (cb == g.cpb - 1) umma_commit(BAR(4 + acc));
           }
-          umma_commit(BAR(2 + sb));
+          __syncwarp();
+        } else {
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const int bs = bi % g.b_stages;
+            mbar_wait(BAR(kBarBFull + bs), (bi / g.b_stages) & 1u);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              const uint32_t w_lo = desc_lo(w_base + bs * b_tile);
+              const int fr = tap / 3, fs = tap - fr * 3;
+              uint32_t a_lo = slab_lo + (uint32_t)(fr * g.Wp + fs) * 8u;
+              uint32_t d_tmem = tmem_acc + acc * acc_cols;
+              const uint32_t first = (cb | tap) != 0;
+              for (int m = 0; m < g.mb; ++m, a_lo += 1024u, d_tmem += BN) {
+                umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
+                umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
+                umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
+                umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+              }
+              umma_commit(BAR(kBarBEmpty + bs));
+              if (tap == 8) {
+                umma_commit(BAR(2 + sb));
+                if (cb == g.cpb - 1) umma_commit(BAR(4 + acc));
+              }
+            }
+            __syncwarp();
+          }
         }
-        umma_commit(BAR(4 + acc));
       }
     }
   } else {
     // ================= epilogue: warps 2..9 =================
     // A tile has mb * (BN/32) units of 128 rows x 32 columns; unit u = (m, j) is handled by the four warps of
-    // group (u & 1) (one TMEM lane quarter each).  The residual of every unit a thread owns is requested BEFORE
-    // the wait on the accumulator, so its latency hides behind the tile's MMAs; the folded-BN bias sits in smem.
+    // group (u & 1) (one TMEM lane quarter each).  The position -> (frame, y, x) mapping of a thread's rows is the
+    // same for every tile, so it is computed once; per tile only the frame / band base is added.  The residual of
+    // every unit a thread owns is requested BEFORE the wait on the accumulator (and pinned behind it), so its latency
+    // hides behind the tile's MMAs; the folded-BN bias sits in smem; ReLU is fused into the bf16 pack.
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;  // 0 or 1
     uint32_t tl = 0;
@@ -185,6 +211,31 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
     constexpr int kJ = BN / 32;
     constexpr int kMaxUnits = 4;  // per warp and tile (mb * kJ <= 8)
     const float* bias_s = reinterpret_cast<const float*>(smem + (bar0 - base) + 8 * 24 + 16);
+    const int units = g.mb * kJ;
+    // tile-invariant part: local output offset (elements) and the (frame, row) of each owned unit row; -1 = padding
+    int loc[kMaxUnits], lf[kMaxUnits], ly[kMaxUnits], ncol[kMaxUnits];
+#pragma unroll
+    for (int i = 0; i < kMaxUnits; ++i) {
+      const int u = grp + 2 * i;
+      loc[i] = -1; lf[i] = 0; ly[i] = 0; ncol[i] = 0;
+      if (u < units) {
+        const int m = u / kJ, j = u - m * kJ;
+        const int p = m * 128 + q * 32 + lane;  // position in the padded grid of the slab
+        const int f = p / per_frame;
+        const int rem = p - f * per_frame;
+        const int y = rem / g.Wp;
+        const int x = rem - y * g.Wp;
+        ncol[i] = j * 32;
+        if (f < g.F && y < g.hb && x < g.OW) {
+          loc[i] = ((f * g.OH + y) * g.OW + x) * (int)ep.ldc + j * 32;
+          lf[i] = f;
+          ly[i] = y;
+        }
+      }
+    }
+    const __nv_bfloat16* resp = ep.residual;
+    __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.C);
+    const bool relu = ep.relu != 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
       const int64_t mt = tile / g.n_tiles;
@@ -192,65 +243,73 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
       const int64_t n0 = (mt / g.nb) * g.F;
       const int hstart = band * g.hb;
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      const int units = g.mb * kJ;
-      int64_t mo[kMaxUnits];
-      uint4 rb[kMaxUnits][4];
+      const int64_t tile_off = ((n0 * g.OH + hstart) * g.OW) * ep.ldc + n_base;
+      bool ok[kMaxUnits];
+      uint4 rb[kMaxUnits][4] = {};
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
-        const int u = grp + 2 * i;
-        mo[i] = -1;
-        if (u < units) {
-          const int m = u / kJ, j = u - m * kJ;
-          const int p = m * 128 + q * 32 + lane;  // position in the padded grid of the slab
-          const int f = p / per_frame;
-          const int rem = p - f * per_frame;
-          const int y = rem / g.Wp;
-          const int x = rem - y * g.Wp;
-          if (f < g.F && y < g.hb && x < g.OW && n0 + f < g.n_frames && hstart + y < g.OH)
-            mo[i] = ((n0 + f) * g.OH + hstart + y) * g.OW + x;
-          if (mo[i] >= 0 && ep.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + mo[i] * ep.ldc + n_base + j * 32);
+        ok[i] = loc[i] >= 0 && n0 + lf[i] < g.n_frames && hstart + ly[i] < g.OH;
+        if (ok[i] && resp) {
+          const uint4* rp = reinterpret_cast<const uint4*>(resp + tile_off + loc[i]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
-          }
+          for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
         }
       }
       mbar_wait(BAR(4 + acc), aph);
       tc_fence_after();
+      // pin the prefetched residual registers behind the wait: without this the compiler hoists the bf16 unpack
+      // right behind the loads and every unit's load latency is paid synchronously before the wait
+#pragma unroll
+      for (int i = 0; i < kMaxUnits; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          asm volatile("" : "+r"(rb[i][c].x), "+r"(rb[i][c].y), "+r"(rb[i][c].z), "+r"(rb[i][c].w));
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
         const int u = grp + 2 * i;
         if (u < units) {  // warp-uniform
-          const int m = u / kJ, j = u - m * kJ;
+          const int m = u / kJ;
           uint32_t v[32];
-          tmem_ld32(tmem_acc + acc * acc_cols + (uint32_t)m * BN + (uint32_t)j * 32 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld32(tmem_acc + acc * acc_cols + (uint32_t)m * BN + (uint32_t)ncol[i] + ((uint32_t)(q * 32) << 16), v);
           tmem_ld_wait();
-          if (mo[i] >= 0) {
-            const int nc = n_base + j * 32;
+          if (ok[i]) {
+            const int nc = n_base + ncol[i];
             float f32[32];
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + nc);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) f32[c] = __uint_as_float(v[c]) + bias_s[nc + c];
-            if (ep.residual) {
+            for (int c = 0; c < 8; ++c) {
+              const float4 b4 = bp[c];
+              f32[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + b4.x;
+              f32[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b4.y;
+              f32[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b4.z;
+              f32[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b4.w;
+            }
+            if (resp) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const float2 a = unpack_bf16x2(rb[i][c].x), b2 = unpack_bf16x2(rb[i][c].y);
-                const float2 c2 = unpack_bf16x2(rb[i][c].z), d2 = unpack_bf16x2(rb[i][c].w);
-                f32[8 * c + 0] += a.x;  f32[8 * c + 1] += a.y;  f32[8 * c + 2] += b2.x; f32[8 * c + 3] += b2.y;
-                f32[8 * c + 4] += c2.x; f32[8 * c + 5] += c2.y; f32[8 * c + 6] += d2.x; f32[8 * c + 7] += d2.y;
+                const uint32_t w[4] = {rb[i][c].x, rb[i][c].y, rb[i][c].z, rb[i][c].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {  // bf16 -> f32 is a 16-bit shift / mask
+                  f32[8 * c + 2 * e + 0] += __uint_as_float(w[e] << 16);
+                  f32[8 * c + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                }
               }
             }
-            if (ep.relu) {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) f32[c] = fmaxf(f32[c], 0.f);
-            }
-            uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + mo[i] * ep.ldc + nc);
+            uint4* cp = reinterpret_cast<uint4*>(outp + tile_off + loc[i]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint4 o;
-              o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
-              o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
-              o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
-              o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
+              if (relu) {
+                o.x = pack_relu_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
+                o.y = pack_relu_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
+                o.z = pack_relu_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
+                o.w = pack_relu_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
+              } else {
+                o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
+                o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
+                o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
+                o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
+              }
               cp[c] = o;
             }
           }

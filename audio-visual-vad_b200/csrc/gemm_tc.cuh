@@ -171,6 +171,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// One elected lane of a fully converged warp (deterministic for a given mask).  Issuing tcgen05.mma / commit / TMA from
+// `if (elect_one_sync())` inside warp-uniform control flow lets the compiler keep descriptors in uniform registers and
+// emit the instructions back to back; the older `if (lane == 0) { whole loop }` form made every issue pay ~10-20
+// scalar instructions (R2UR, ELECT, BRA.U.ANY loops), which was the bound for N <= 128 tiles (48-64 cycle MMAs).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int BN, int AMODE = A_PLAIN>

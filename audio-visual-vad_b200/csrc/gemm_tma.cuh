@@ -176,17 +176,17 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(g, tile, BN);
-        const uint32_t bytes = g.bytesA[t.phase] + g.bytesB;
-        int tap = 0, cb = 0, fr = 0, fs = 0;
-        for (int kb = 0; kb < g.KB; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+    // ================= TMA producer (warp-converged; one elected lane issues) =================
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(g, tile, BN);
+      const uint32_t bytes = g.bytesA[t.phase] + g.bytesB;
+      int cb = 0, fr = 0, fs = 0;
+      for (int kb = 0; kb < g.KB; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+        if (elect_one_sync()) {
           const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
           mbar_arrive_expect_tx(full, bytes);
@@ -196,43 +196,46 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             tma_load_4d(sa, &maps.a[t.phase], cb * KE, fs - g.pad, t.hstart * g.stride + fr - g.pad, (int)t.n0, full);
           }
           tma_load_2d(sa + C::kABytes, &maps.b, kb * KE, t.n_base, full);
-          if (++cb == g.cpb) {
-            cb = 0;
-            ++tap;
-            if (++fs == g.S) {
-              fs = 0;
-              ++fr;
-            }
+        }
+        __syncwarp();
+        if (++cb == g.cpb) {
+          cb = 0;
+          if (++fs == g.S) {
+            fs = 0;
+            ++fr;
           }
         }
-        for (int kb2 = 0; kb2 < g.KB2; ++kb2, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+      }
+      for (int kb2 = 0; kb2 < g.KB2; ++kb2, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
+        if (elect_one_sync()) {
           const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
           mbar_arrive_expect_tx(full, bytes);
           tma_load_4d(sa, &maps.a2[t.phase], kb2 * KE, 0, t.hstart * g.stride2, (int)t.n0, full);
           tma_load_2d(sa + C::kABytes, &maps.b, (g.KB + kb2) * KE, t.n_base, full);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, tl = 0;
-      for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-        mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
+    // ================= MMA issuer (warp-converged; one elected lane issues MMAs and commits) =================
+    constexpr uint32_t idesc = make_idesc(BN);
+    uint32_t it = 0, tl = 0;
+    const int kb_total = g.KB + g.KB2;
+    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_acc + acc * BN;
+      for (int kb = 0; kb < kb_total; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1u;
+        mbar_wait(bar0 + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_acc + acc * BN;
-        const int kb_total = g.KB + g.KB2;
-        for (int kb = 0; kb < kb_total; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          mbar_wait(bar0 + 8 * s, ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t a_lo = desc_lo(base + s * C::kStageBytes);
           const uint32_t b_lo = a_lo + (C::kABytes >> 4);
           umma_f16_lo2(d_tmem, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
@@ -242,8 +245,9 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             umma_f16_lo2(d_tmem, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
           }
           umma_commit(bar0 + 8 * (S + s));
+          if (kb == kb_total - 1) umma_commit(bar0 + 8 * (2 * S + acc));
         }
-        umma_commit(bar0 + 8 * (2 * S + acc));
+        __syncwarp();
       }
     }
   } else {
@@ -276,7 +280,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       const uint32_t t_row = tmem_acc + acc * BN + ((uint32_t)(q * 32) << 16);
       if (fast) {
         // residual of this thread's chunks: in flight while the tile's MMAs run
-        uint4 rb[kMine][4];
+        uint4 rb[kMine][4] = {};
         const bool has_res = (ep.residual != nullptr) && (m >= 0);
         if (has_res) {
 #pragma unroll
@@ -291,6 +295,13 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         }
         mbar_wait(bar0 + 8 * (2 * S + acc), aph);
         tc_fence_after();
+        // pin the prefetched residual behind the wait (otherwise the unpack is hoisted right behind the loads and their
+        // latency is paid before the wait instead of under the tile's MMAs)
+#pragma unroll
+        for (int i = 0; i < kMine; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("" : "+r"(rb[i][c].x), "+r"(rb[i][c].y), "+r"(rb[i][c].z), "+r"(rb[i][c].w));
 #pragma unroll
         for (int i = 0; i < kMine; ++i) {
           const int j = 2 * i + half;

@@ -155,16 +155,17 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(64);
-      mbar_wait(BAR(kBarW), 0);
-      tc_fence_after();
-      uint32_t it = 0;
-      for (int t = 1; t < g.T; ++t) {
-        for (int kb = 0; kb < g.KB; ++kb, ++it) {
-          const int s = it % kLstmStages;
-          mbar_wait(BAR(s), (it / kLstmStages) & 1u);
-          tc_fence_after();
+    // MMA issuer (warp-converged; one elected lane issues the MMAs and commits)
+    constexpr uint32_t idesc = make_idesc(64);
+    mbar_wait(BAR(kBarW), 0);
+    tc_fence_after();
+    uint32_t it = 0;
+    for (int t = 1; t < g.T; ++t) {
+      for (int kb = 0; kb < g.KB; ++kb, ++it) {
+        const int s = it % kLstmStages;
+        mbar_wait(BAR(s), (it / kLstmStages) & 1u);
+        tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t a_lo = desc_lo(sA + s * 16384u);
           const uint32_t b_lo = desc_lo(sW + kb * 8192u);
           umma_f16_lo(tmem_acc, a_lo, b_lo, idesc, kb != 0);
@@ -172,8 +173,9 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
           umma_f16_lo(tmem_acc, a_lo + 4, b_lo + 4, idesc, 1);
           umma_f16_lo(tmem_acc, a_lo + 6, b_lo + 6, idesc, 1);
           umma_commit(BAR(kLstmStages + s));
+          if (kb == g.KB - 1) umma_commit(BAR(kBarT));
         }
-        umma_commit(BAR(kBarT));
+        __syncwarp();
       }
     }
   } else {

@@ -112,13 +112,6 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   return r;
 }
 
-// {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -272,24 +265,24 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
       mbar_arrive(BAR(0 + buf));
     }
   } else if (warp == kS2BuilderWarps) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(256);
-      const uint32_t a_hi_main = desc_hi_ns(kS2Pitch), a_hi_edge = desc_hi_ns(128), b_hi = desc_hi_ns(256);
-      uint32_t it = 0, g = 0;  // batch / tile counters of this CTA
-      for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x, ++it) {
-        const uint32_t buf = it & 1u;
-        const int nf = (int)((p.n_frames - bi * kS2FramesPerBatch) < kS2FramesPerBatch
-                                 ? (p.n_frames - bi * kS2FramesPerBatch)
-                                 : kS2FramesPerBatch);
-        const int n_main = (nf * kS2RowsPerFrame + 15) / 16;
-        mbar_wait(BAR(0 + buf), (it >> 1) & 1u);
+    // ======================= MMA issuer (warp-converged; one elected lane issues) =======================
+    constexpr uint32_t idesc = make_idesc(256);
+    const uint32_t a_hi_main = desc_hi_ns(kS2Pitch), a_hi_edge = desc_hi_ns(128), b_hi = desc_hi_ns(256);
+    uint32_t it = 0, g = 0;  // batch / tile counters of this CTA
+    for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const int nf = (int)((p.n_frames - bi * kS2FramesPerBatch) < kS2FramesPerBatch
+                               ? (p.n_frames - bi * kS2FramesPerBatch)
+                               : kS2FramesPerBatch);
+      const int n_main = (nf * kS2RowsPerFrame + 15) / 16;
+      mbar_wait(BAR(0 + buf), (it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t bufa = base + buf * kS2BufBytes;
+      for (int t = -1; t < n_main; ++t, ++g) {  // t = -1: edge tile
+        const uint32_t acc = g & 1u;
+        mbar_wait(BAR(6 + acc), ((g >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t bufa = base + buf * kS2BufBytes;
-        for (int t = -1; t < n_main; ++t, ++g) {  // t = -1: edge tile
-          const uint32_t acc = g & 1u;
-          mbar_wait(BAR(6 + acc), ((g >> 1) & 1u) ^ 1u);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t d = tmem_acc + acc * 256u;
           // bias step: ones (128 x 16, core matrices [r/8][k/8]: SBO 256, LBO 128) x bias rows
           umma_f16_ns(d, desc_lo_ns(base + kS2OffOnes, 128u), b_hi, desc_lo_ns(base + kS2OffW + 7u * kS2WStepBytes, 128u),
@@ -310,8 +303,9 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
             umma_f16_ns(d, a_lo, a_hi, b_lo, b_hi, idesc, 1);
           }
           umma_commit(BAR(4 + acc));
+          if (t == n_main - 1) umma_commit(BAR(2 + buf));  // all MMAs reading this batch buffer have completed
         }
-        umma_commit(BAR(2 + buf));  // all MMAs reading this batch buffer have completed
+        __syncwarp();
       }
     }
   } else {

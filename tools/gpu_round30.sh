@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "40576 128" "81152 256" "27051 86" "20288 64"; do
+for cfg in "24576 64"; do
 set -- $cfg
-AVVAD_SUB1=100000 AVVAD_SUB2=100000 AVVAD_CHUNK=$1 AVVAD_PIECE=$2 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.log 2>&1; echo "chunk=$1 piece=$2 exit=$?"
+AVVAD_CHUNK=$1 AVVAD_PIECE=$2 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s.log 2>&1; echo "chunk=$1 piece=$2 exit=$?"
 python - <<PY
 import json
 l=[x for x in open('gpurun_out/bench_s.log') if x.startswith('{')][-1]
