@@ -109,10 +109,10 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
     sa[i] = make_float2(v0 * w, 0.f);
   }
   __syncthreads();
-  fft1024_smem(sa, sb, stw, tid);
+  const float2* spec = fft1024_smem(sa, sb, stw, tid);
 
   for (int k = tid; k < 513; k += kFftThreads) {
-    const float2 z = sa[k];
+    const float2 z = spec[k];
     if (MODE == 0) {
       const float la = logf(z.x * z.x + z.y * z.y + eps);
       out[((int64_t)b * t_max + t) * 513 + k] = mean ? (la - mean[k]) / (stdv[k] + eps) : la;

@@ -59,31 +59,32 @@ mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video,
     sa[j] = make_float2(px, py);
   }
   __syncthreads();
-  fft1024_smem(sa, sb, stw, tid);
+  float2* z1 = fft1024_smem(sa, sb, stw, tid);  // result buffer (the other one is free scratch)
+  float2* z2 = (z1 == sa) ? sb : sa;
 
   // P[k] = X[k]*Y[k]; store conj(P) so that a second forward FFT yields N * ifft(P)
   for (int k = tid; k <= 512; k += kFftThreads) {
     if (k == 0 || k == 512) {
-      const float2 z = sa[k];
-      sa[k] = make_float2(z.x * z.y, 0.f);
+      const float2 z = z1[k];
+      z1[k] = make_float2(z.x * z.y, 0.f);
     } else {
-      const float2 zk = sa[k];
-      const float2 zn = sa[kFftN - k];
+      const float2 zk = z1[k];
+      const float2 zn = z1[kFftN - k];
       const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       const float2 Y = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
       const float2 P = cmul(X, Y);
-      sa[k] = make_float2(P.x, -P.y);        // conj(P[k])
-      sa[kFftN - k] = make_float2(P.x, P.y);  // conj(P[N-k]) = P[k]
+      z1[k] = make_float2(P.x, -P.y);        // conj(P[k])
+      z1[kFftN - k] = make_float2(P.x, P.y);  // conj(P[N-k]) = P[k]
     }
   }
   __syncthreads();
-  fft1024_smem(sa, sb, stw, tid);
+  const float2* res = fft1024_smem(z1, z2, stw, tid);
 
   float ss = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int j = tid + q * kFftThreads;
-    const float p = sa[j].x * (1.0f / kFftN);
+    const float p = res[j].x * (1.0f / kFftN);
     // torch.sign(p) * sqrt(|p| + eps)   (sign(0) = 0)
     const float r = sqrtf(fabsf(p) + eps);
     const float y = (p > 0.f) ? r : ((p < 0.f) ? -r : 0.f);
