@@ -108,6 +108,21 @@ def upsample_gather(src: torch.Tensor, n_src, n_out, t_max: int, mean=0.0, std=1
     return out
 
 
+def feature_gather(feat_src: torch.Tensor, feat_pad: torch.Tensor, n_src, n_out, t_max: int,
+                   out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None, col_off=0,
+                   num=FPS_NUM, den=FPS_DEN):
+    """(B,F,C) fp32 source-rate features -> (B*t_max, C) at 62.5 fps (same index map as upsample_gather); rows past
+    n_out[b] get `feat_pad` (the feature of the collate zero frame)."""
+    L.require_cuda(feat_src, feat_pad)
+    B, F, Cc = feat_src.shape
+    dev = feat_src.device
+    a, b = _i32(n_src, dev), _i32(n_out, dev)
+    ld = out_bf16.stride(-2) if out_bf16 is not None else 0
+    L.check(L.lib().avvad_feature_gather(L.ptr(feat_src.contiguous()), L.ptr(feat_pad.contiguous()), L.ptr(a), L.ptr(b),
+                                         B, F, t_max, Cc, num, den, L.ptr(out_f32), L.ptr(out_bf16), ld, col_off,
+                                         L.stream_ptr()))
+
+
 def upsample_index(n_src: int, n_out: int, device="cuda", num=FPS_NUM, den=FPS_DEN) -> torch.Tensor:
     out = torch.empty(n_out, dtype=torch.int32, device=device)
     L.check(L.lib().avvad_upsample_index(n_src, n_out, num, den, L.ptr(out), L.stream_ptr()))

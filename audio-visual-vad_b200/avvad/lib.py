@@ -54,6 +54,8 @@ PROTOTYPES = {
                                   C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "avvad_feature_gather": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       VP, VP, C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16_dual": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64] + [C.c_int] * 13 + [VP]),
     "avvad_pack_rows_bf16": (C.c_int, [VP, C.c_int64, VP, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, VP]),
     "avvad_mcb_create": (C.c_int, [C.POINTER(VP)]),

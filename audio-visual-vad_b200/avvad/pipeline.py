@@ -39,6 +39,12 @@ class AVVADPipeline:
         self._bufs = {}
         self.piece = int(os.environ.get("AVVAD_PIECE", "64"))  # utterances per video piece (upload / trunk granularity)
         self.fuse_gather = True    # u8 video: gather + standardise inside the stem (False: separate fp32 gather)
+        # Optional: run the trunk on the 30 fps SOURCE frames and gather the 512-d features to 62.5 fps.  The eval-mode
+        # trunk is a pure per-frame function and the upsampled sequence only duplicates frames, so the result is
+        # bit-identical with 2.09x less convolution work.  Off by default: the headline benchmark keeps the
+        # reference's order (every 62.5 fps frame through the ResNet).
+        self.dedup_video = False
+        self._feat_pad = None
         self._copy_stream = None
         self._events = []
 
@@ -96,7 +102,19 @@ class AVVADPipeline:
             if _video_ready is not None:
                 cur.wait_event(_video_ready[k])
             m0, m1 = b0 * t_max, b1 * t_max
-            if fused:  # gather + standardise + collate padding inside the stem kernel
+            if fused and self.dedup_video:
+                Fm = video_u8.shape[1]
+                if self._feat_pad is None:  # trunk feature of the collate zero frame (input independent)
+                    z = torch.zeros(1, 1, 67, 67, dtype=torch.uint8, device=dev)
+                    self._feat_pad = self.trunk.forward_u8(z, [0], [0], 1, self.video_mean, self.video_std, self.eps,
+                                                           True, num=1, den=1).clone()
+                fs = self._buf("feat_src", (P * Fm, 512), torch.float32)[: (b1 - b0) * Fm]
+                self.trunk.forward_u8(video_u8[b0:b1], nsrc[b0:b1], nsrc[b0:b1], Fm, self.video_mean, self.video_std,
+                                      self.eps, True, feat=fs, num=1, den=1)
+                E.feature_gather(fs.view(b1 - b0, Fm, 512), self._feat_pad, nsrc[b0:b1], lens[b0:b1], t_max,
+                                 out_f32=feat[m0:m1] if self.use_mcb else None,
+                                 out_bf16=None if self.use_mcb else xv[m0:m1], col_off=513)
+            elif fused:  # gather + standardise + collate padding inside the stem kernel
                 kw = dict(feat=feat[m0:m1]) if self.use_mcb else dict(feat_bf16=xv[m0:m1], col_off=513, want_f32=False)
                 self.trunk.forward_u8(video_u8[b0:b1], nsrc[b0:b1], lens[b0:b1], t_max, self.video_mean,
                                       self.video_std, self.eps, True, **kw)

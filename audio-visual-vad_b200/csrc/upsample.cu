@@ -32,6 +32,36 @@ __global__ void upsample_kernel(const SrcT* __restrict__ src, const int32_t* __r
   }
 }
 
+// Feature-level form of the same gather: out[b][k][:] = feat_src[b][src(k)][:] for k < n_out[b], else feat_pad[:]
+// (the trunk feature of the collate zero frame).  8 channels per thread.
+__global__ void feature_gather_kernel(const float* __restrict__ feat_src, const float* __restrict__ feat_pad,
+                                      const int32_t* __restrict__ n_src, const int32_t* __restrict__ n_out, int f_max,
+                                      int t_max, int C, int num, int den, int64_t total, float* __restrict__ out_f32,
+                                      __nv_bfloat16* __restrict__ out_bf16, int64_t ld_bf16, int64_t col_off) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int chunks = C / 8;
+  const int ch = (int)(idx % chunks) * 8;
+  const int64_t row = idx / chunks;  // b * t_max + k
+  const int b = (int)(row / t_max), k = (int)(row - (int64_t)b * t_max);
+  const int F = n_src[b], T = n_out[b];
+  const float* s = (k < T && F > 0) ? feat_src + ((int64_t)b * f_max + upsample_src_index(k, F, num, den)) * C + ch
+                                    : feat_pad + ch;
+  const float4 a = *reinterpret_cast<const float4*>(s);
+  const float4 c = *reinterpret_cast<const float4*>(s + 4);
+  if (out_f32) {
+    float4* o = reinterpret_cast<float4*>(out_f32 + row * C + ch);
+    o[0] = a;
+    o[1] = c;
+  }
+  if (out_bf16) {
+    __nv_bfloat16* o = out_bf16 + row * ld_bf16 + col_off + ch;  // col_off may be odd (513): scalar stores
+    o[0] = __float2bfloat16_rn(a.x); o[1] = __float2bfloat16_rn(a.y); o[2] = __float2bfloat16_rn(a.z);
+    o[3] = __float2bfloat16_rn(a.w); o[4] = __float2bfloat16_rn(c.x); o[5] = __float2bfloat16_rn(c.y);
+    o[6] = __float2bfloat16_rn(c.z); o[7] = __float2bfloat16_rn(c.w);
+  }
+}
+
 __global__ void upsample_index_kernel(int n_src, int n_out, int num, int den, int32_t* __restrict__ out) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n_out) out[k] = upsample_src_index(k, n_src, num, den);
@@ -71,6 +101,20 @@ extern "C" int avvad_upsample_index(int32_t n_src, int32_t n_out, int32_t num, i
   AVVAD_CHECK_ARG(out_idx && n_src > 0 && n_out > 0 && num > 0 && den > 0, "bad argument");
   upsample_index_kernel<<<(unsigned)ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(n_src, n_out, num, den,
                                                                                           out_idx);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+extern "C" int avvad_feature_gather(const float* feat_src, const float* feat_pad, const int32_t* n_src,
+                                    const int32_t* n_out, int32_t B, int32_t f_max, int32_t t_max, int32_t C,
+                                    int32_t num, int32_t den, float* out_f32, void* out_bf16, int64_t ld_bf16,
+                                    int64_t col_off, void* stream) {
+  AVVAD_CHECK_ARG(feat_src && feat_pad && n_src && n_out && (out_f32 || out_bf16), "null pointer");
+  AVVAD_CHECK_ARG(B > 0 && f_max > 0 && t_max > 0 && C > 0 && C % 8 == 0 && num > 0 && den > 0, "bad size");
+  const int64_t total = (int64_t)B * t_max * (C / 8);
+  feature_gather_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      feat_src, feat_pad, n_src, n_out, f_max, t_max, C, num, den, total, out_f32, (__nv_bfloat16*)out_bf16, ld_bf16,
+      col_off);
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }

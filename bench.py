@@ -76,7 +76,7 @@ def synth_weights(B: int, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -90,7 +90,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
@@ -295,12 +295,26 @@ def run_ours(args, rank, world, local_rank):
     # host clock around a synchronised region (covers enqueue + copies + kernels); never below the device time
     e2e_ms = max(1e3 * (time.perf_counter() - t0), g0.elapsed_time(g1))
 
+    # ---- variant (reported separately, NOT the headline): trunk on the 30 fps source frames + feature gather ----
+    pipe.dedup_video = True
+    for _ in range(2):
+        step_device()
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.steps):
+        step_device()
+    d1.record()
+    barrier()
+    dedup_ms = d0.elapsed_time(d1)
+    pipe.dedup_video = False
+
     if world > 1:
         import torch.distributed as dist
 
-        t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_ms, dedup_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+        ms, e2e_ms, dedup_ms = float(t[0]), float(t[1]), float(t[2])
 
     frames_per_step = B * T_FRAMES * world
     value = frames_per_step * args.steps / (ms / 1e3)
@@ -324,8 +338,9 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor",
-                     "kernel": "tcgen05 implicit-GEMM convolutions of the ResNet-18 trunk (19 layers: tc_tma_kernel "
-                               "<BN=128/256> TMA-box im2col, tc_slab_kernel<64> for layer1)",
+                     "kernel": "tcgen05 implicit-GEMM convolutions of the ResNet-18 trunk (19 layers in 16 launches per pass: "
+                               "tc_slab_kernel<64> for layer1, tc_tma_kernel<BN=128/256> TMA-box im2col for layer2-4 "
+                               "with the downsample 1x1 branches K-concatenated into conv_b)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
                      # dram__bytes_read+write per conv launch, averaged over the 19 launches of one 2048-frame chunk
@@ -336,6 +351,12 @@ def run_ours(args, rank, world, local_rank):
                      "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
                      "flops_per_launch_avg": conv_flops / conv_n if conv_n else None},
+        "variants": {"dedup_video": {
+            "value": frames_per_step * args.steps / (dedup_ms / 1e3), "unit": "frames/s",
+            "ms_per_step": dedup_ms / args.steps,
+            "note": "NOT the headline: ResNet on the 152 source frames per utterance + index-exact gather of the 512-d "
+                    "features to 317 frames; bit-identical posteriors (tests/test_gpu_pipeline.py), 2.09x less "
+                    "convolution work than the reference's order (every upsampled frame through the ResNet)"}},
         "breakdown_ms_per_step": {"conv_tc": conv_ms / args.steps, "gemm_tc": gemm_ms / args.steps,
                                   "lstm_step_tc": lstm_ms / args.steps, "stem_tc": stem_ms / args.steps, "lstm_step_launches": int(lstm_n / args.steps),
                                   "lstm_step_tflops": (lstm_flops / (lstm_ms / 1e3) / 1e12) if lstm_ms > 0 else None,
@@ -361,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")

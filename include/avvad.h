@@ -92,6 +92,15 @@ int avvad_upsample_gather(const void* src, int src_is_f32, const int32_t* n_src,
                           float mean, float std, float eps, int standardise, float* out, void* stream);
 
 /* Just the index map (i32 [n_out]) -- exposed so callers/tests can check it bit-exactly. */
+/* Feature-level form of the same gather (optional "dedup" path of the pipeline): the eval-mode trunk is a pure
+ * per-frame function and the 62.5 fps sequence is a duplication of the 30 fps one, so the trunk may run on the source
+ * frames and its 512-d features be gathered instead:
+ *   out[b][k][:] = feat_src[b][avvad_upsample_index(k, n_src[b])][:]  for k < n_out[b],  feat_pad[:] otherwise
+ * (feat_pad = trunk feature of the collate zero frame).  Writes f32 [B][t_max][C] and/or bf16 rows at column col_off. */
+int avvad_feature_gather(const float* feat_src, const float* feat_pad, const int32_t* n_src, const int32_t* n_out,
+                         int32_t B, int32_t f_max, int32_t t_max, int32_t C, int32_t num, int32_t den,
+                         float* out_f32, void* out_bf16, int64_t ld_bf16, int64_t col_off, void* stream);
+
 int avvad_upsample_index(int32_t n_src, int32_t n_out, int32_t num, int32_t den, int32_t* out_idx,
                          void* stream);
 

@@ -54,3 +54,32 @@ def test_pipeline_matches_reference_port(use_mcb, piece):
     for b in range(B):
         if lens[b] < tmax:
             assert np.allclose(post[b, lens[b]:], 1.0 / (1.0 + np.exp(-bias)), atol=1e-6)
+
+
+@pytest.mark.parametrize("use_mcb", [False, True])
+def test_dedup_video_is_bit_identical(use_mcb):
+    """Trunk on the 30 fps source frames + feature gather == trunk on every upsampled frame (ragged lengths, padded
+    frames included): the optional dedup path must not change a single bit of the posteriors."""
+    B = 5
+    ns, nf, waves, vids = _inputs(B, seed=7)
+    nf[2] = 20  # a short video: many collate-padded frames
+    vids[2] = vids[2][:20]
+    mean, std = synth.synth_audio_stats(0)
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=use_mcb), seed=5)
+    wave = torch.zeros(B, max(ns))
+    vid = torch.zeros(B, max(nf), 67, 67, dtype=torch.uint8)
+    for i in range(B):
+        wave[i, : ns[i]] = torch.from_numpy(waves[i])
+        vid[i, : nf[i]] = torch.from_numpy(vids[i])
+    wave, vid = wave.cuda(), vid.cuda()
+    lens = [min(a, b) for a, b in zip(AVVADPipeline.frame_counts(ns, nf), [AVVADPipeline.frame_counts(ns, nf)[i] for i in range(B)])]
+    tmax = max(lens) + 3  # a few all-padding columns as well
+    outs = []
+    for dedup in (False, True):
+        pipe = AVVADPipeline(sd, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD, use_mcb=use_mcb)
+        pipe.dedup_video = dedup
+        pipe.piece = 2
+        logits, post, dec = pipe.infer_device(wave, ns, vid, nf, lengths=lens, t_max=tmax)
+        outs.append((logits.clone(), post.clone(), dec.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
