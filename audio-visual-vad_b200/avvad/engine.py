@@ -130,6 +130,85 @@ def upsample_index(n_src: int, n_out: int, device="cuda", num=FPS_NUM, den=FPS_D
 
 
 # ---------------------------------------------------------------------------------------------
+# data preparation on the device
+# ---------------------------------------------------------------------------------------------
+def dct_roi_decode(dct: torch.Tensor, mode="per_frame", want_raw=False):
+    """(F, 4489) fp32 DCT rows of an NTCD-TIMIT .mat file -> mouth-ROI frames.
+    mode "per_frame": u8 (F,67,67), per-frame min-max + rot90(.,3) (the variant behind the shipped *_upsampled.h5);
+    mode "global": fp32 (F,67,67), the script as shipped (global min, largest per-row range)."""
+    L.require_cuda(dct)
+    dct = dct.to(torch.float32).contiguous()
+    F = dct.shape[0]
+    dev = dct.device
+    if mode == "per_frame":
+        out = torch.empty(F, 67, 67, dtype=torch.uint8, device=dev)
+        raw = torch.empty(F, 67, 67, dtype=torch.float32, device=dev) if want_raw else None
+        L.check(L.lib().avvad_dct_roi_decode(L.ptr(dct), F, 0, L.ptr(out), L.ptr(raw), None, 0, L.stream_ptr()))
+        return (out, raw) if want_raw else out
+    ws = torch.empty(L.lib().avvad_dct_roi_workspace_bytes(F), dtype=torch.uint8, device=dev)
+    out = torch.empty(F, 67, 67, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_dct_roi_decode(L.ptr(dct), F, 1, None, L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    return out
+
+
+def vad_labels(wave: torch.Tensor, n_samples, n_frames, t_max: int, nfft=1024, hop=256, vad_threshold=1.70):
+    """clean_speech_VAD (center=False) for a batch of (B,N) fp32 waveforms -> (B,t_max) fp32 0/1."""
+    L.require_cuda(wave)
+    wave = wave.contiguous()
+    B, dev = wave.shape[0], wave.device
+    ns, nf = _i32(n_samples, dev), _i32(n_frames, dev)
+    energy = torch.empty(B, t_max, dtype=torch.float32, device=dev)
+    labels = torch.empty(B, t_max, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_vad_labels(L.ptr(wave), wave.stride(0), L.ptr(ns), L.ptr(nf), B, t_max, nfft, hop,
+                                     float(vad_threshold), L.ptr(energy), L.ptr(labels), L.stream_ptr()))
+    return labels
+
+
+def ibm_labels(stft_ft2: torch.Tensor, n_frames, eps=1e-8, ibm_threshold=50.0):
+    """clean_speech_IBM on (B,513,T,2) STFTs (layout of `stft`) -> (B,513,T) fp32 0/1."""
+    L.require_cuda(stft_ft2)
+    stft_ft2 = stft_ft2.contiguous()
+    B, bins, T, _ = stft_ft2.shape
+    dev = stft_ft2.device
+    nf = _i32(n_frames, dev)
+    db = torch.empty(B, bins, T, dtype=torch.float32, device=dev)
+    mx = torch.empty(B, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, bins, T, dtype=torch.float32, device=dev)
+    L.check(L.lib().avvad_ibm_labels(L.ptr(stft_ft2), L.ptr(nf), B, T, bins, float(eps), float(ibm_threshold), L.ptr(db),
+                                     L.ptr(mx), L.ptr(mask), L.stream_ptr()))
+    return mask
+
+
+class RunningStats:
+    """Per-bin mean / empirical std over a dataset (create_audio_train_files.py:273-280,365-368), accumulated on the
+    device in fp64 batch by batch."""
+
+    def __init__(self, bins: int, device="cuda"):
+        self.bins = bins
+        self.sum = torch.zeros(bins, dtype=torch.float64, device=device)
+        self.sumsq = torch.zeros(bins, dtype=torch.float64, device=device)
+        self.n = 0
+
+    def update(self, x: torch.Tensor, n_frames):
+        """x (B,T,bins) fp32; only frames t < n_frames[b] count."""
+        L.require_cuda(x)
+        x = x.contiguous()
+        B, T, bins = x.shape
+        assert bins == self.bins
+        nf = _i32(n_frames, x.device)
+        L.check(L.lib().avvad_stats_accumulate(L.ptr(x), L.ptr(nf), B, T, bins, L.ptr(self.sum), L.ptr(self.sumsq),
+                                               L.stream_ptr()))
+        self.n += int(torch.clamp(nf, max=T).sum().item())
+
+    def finalize(self):
+        mean = torch.empty(self.bins, dtype=torch.float32, device=self.sum.device)
+        std = torch.empty(self.bins, dtype=torch.float32, device=self.sum.device)
+        L.check(L.lib().avvad_stats_finalize(L.ptr(self.sum), L.ptr(self.sumsq), float(self.n), self.bins, L.ptr(mean),
+                                             L.ptr(std), L.stream_ptr()))
+        return mean, std
+
+
+# ---------------------------------------------------------------------------------------------
 # generic tensor-core ops (exposed for tests)
 # ---------------------------------------------------------------------------------------------
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, out_bf16=False, relu=False):

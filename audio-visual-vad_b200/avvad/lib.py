@@ -54,6 +54,13 @@ PROTOTYPES = {
                                   C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int, VP]),
+    "avvad_dct_roi_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "avvad_dct_roi_decode": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, VP, C.c_size_t, VP]),
+    "avvad_vad_labels": (C.c_int, [VP, C.c_int64, VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, VP, VP,
+                                   VP]),
+    "avvad_ibm_labels": (C.c_int, [VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, VP, VP, VP, VP]),
+    "avvad_stats_accumulate": (C.c_int, [VP, VP, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
+    "avvad_stats_finalize": (C.c_int, [VP, VP, C.c_double, C.c_int32, VP, VP, VP]),
     "avvad_feature_gather": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        VP, VP, C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16_dual": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64] + [C.c_int] * 13 + [VP]),

@@ -167,6 +167,38 @@ int avvad_resnet18_forward_train(avvad_resnet18* h, const float* frames, int64_t
                                  int64_t col_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data preparation on the device
+ *
+ * avvad_dct_roi_decode: NTCD-TIMIT `.mat` rows (67x67 2-D DCT coefficients per 30 fps frame) -> mouth-ROI frames.
+ *   replaces: scripts/create_video_train_files_upsampled.py:137-162, packages/processing/video.py:5-24
+ *   (scipy idct(idct(x).T).T in float64, normalisation, np.rot90(., 3)).
+ *   dct [n_frames][67*67] f32.  mode 0: per-frame min-max -> u8 [n_frames][67][67] in out_u8 (the variant that produced
+ *   the reference's shipped *_upsampled.h5 files), optional raw decode (un-rotated, f32) in out_f32.
+ *   mode 1: the script as shipped: (A - A.min()) / max_row_range * 255 over ALL frames of the call, rotated, f32 in
+ *   out_f32; needs avvad_dct_roi_workspace_bytes(n_frames).
+ * avvad_vad_labels: packages/processing/target.py:5-48 (clean_speech_VAD, center=False): fp32 frame energies summed
+ *   in the reference's order, label = energy > 10^vad_threshold * min(energy) (fp64 compare).  labels [B][t_max] f32.
+ * avvad_ibm_labels: target.py:50-70 (clean_speech_IBM) on an STFT [B][bins][t_max][2] (avvad_stft layout):
+ *   20*log10(|X|+eps) > max - ibm_threshold per utterance.  mask [B][bins][t_max] f32; scratch db same size, max [B].
+ * avvad_stats_accumulate / _finalize: scripts/create_audio_train_files.py:273-280,365-368: per-bin running sum and sum
+ *   of squares (fp64, caller-zeroed accumulators) over the valid frames of x [B][t_max][bins]; mean = S/n,
+ *   std = sqrt((Q - n*mean^2)/(n-1)).
+ * ---------------------------------------------------------------------------------------- */
+size_t avvad_dct_roi_workspace_bytes(int64_t n_frames);
+int avvad_dct_roi_decode(const float* dct, int64_t n_frames, int mode, uint8_t* out_u8, float* out_f32,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int avvad_vad_labels(const float* wave, int64_t wave_stride, const int32_t* n_samples, const int32_t* n_frames,
+                     int32_t B, int32_t t_max, int32_t nfft, int32_t hop, double vad_threshold,
+                     float* energy_scratch, float* labels, void* stream);
+int avvad_ibm_labels(const float* stft_ft2, const int32_t* n_frames, int32_t B, int32_t t_max, int32_t bins,
+                     float eps, float ibm_threshold, float* db_scratch, float* max_scratch, float* mask,
+                     void* stream);
+int avvad_stats_accumulate(const float* x, const int32_t* n_frames, int32_t B, int32_t t_max, int32_t bins,
+                           double* sum, double* sumsq, void* stream);
+int avvad_stats_finalize(const double* sum, const double* sumsq, double n, int32_t bins, float* mean, float* std,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * bf16 tensor-core GEMM  C[M][N] = A[M][K] * W[N][K]^T (+bias)   (tcgen05 / TMEM)
  * Exposed for tests and for the LSTM / head projections.  A, W bf16 row-major with K % 64 == 0
  * and 16-byte aligned rows; C f32 or bf16.
