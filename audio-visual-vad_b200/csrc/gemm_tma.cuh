@@ -32,7 +32,12 @@ namespace tc {
 
 constexpr int kTmaThreads = 320;
 constexpr int kTmaEpiWarps = 8;
-constexpr int kTmaBiasSmem = 1024;  // bias entries staged in shared memory (N <= this), else read through L1
+// bias entries staged in shared memory (N <= this), else read through L1: the BN = 256 configuration runs one CTA per
+// SM and can afford the 4096 columns of the LSTM input projection, the two-CTA configurations keep 1024
+template <int BN>
+struct TmaBias {
+  static constexpr int kEntries = (BN == 256) ? 4096 : 1024;
+};
 
 struct TmaGeom {
   int mode;             // 0 = plain GEMM rows, 1 = convolution boxes
@@ -96,7 +101,7 @@ struct TmaCfg {
   static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
   static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? 3 : 4));
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + kTmaBiasSmem * 4;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + TmaBias<BN>::kEntries * 4;
   // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
   static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
 };
@@ -163,7 +168,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
   }
   // bias -> shared memory (behind the barriers and the TMEM slot); zero when absent
   float* bias_s = reinterpret_cast<float*>(smem + S * C::kStageBytes + 256);
-  const bool bias_in_smem = g.N <= kTmaBiasSmem;
+  const bool bias_in_smem = g.N <= TmaBias<BN>::kEntries;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < g.N; i += kTmaThreads) bias_s[i] = ep.bias ? ep.bias[i] : 0.f;
   if (warp == 1) {
@@ -257,6 +262,8 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     constexpr int kJ = BN / 32;         // 32-column chunks per tile
     constexpr int kMine = (kJ + 1) / 2;  // chunks per warp
     const bool fast = (epi_mode == EPI_BF16) && bias_in_smem && (g.N % 32 == 0);
+    const bool fast32 = (epi_mode == EPI_F32) && bias_in_smem && (g.N % 32 == 0) && (ep.ldc % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
     uint32_t tl = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const TileCoord t = decode_tile(g, tile, BN);
@@ -344,6 +351,31 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
                 o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
                 cp[c] = o;
               }
+            }
+          }
+        }
+      } else if (fast32) {
+        // fp32 output (LSTM input projection): smem bias, 8 x 16-byte stores per 32-column chunk
+        mbar_wait(bar0 + 8 * (2 * S + acc), aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = half; j < kJ; j += 2) {
+          uint32_t v[32];
+          tmem_ld32(t_row + j * 32, v);
+          tmem_ld_wait();
+          const int n0 = t.n_base + j * 32;
+          if (m >= 0 && n0 < g.N) {
+            const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
+            float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + m * ep.ldc + n0);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 b4 = bp[c];
+              float4 o = make_float4(__uint_as_float(v[4 * c + 0]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
+                                     __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
+              if (ep.relu) {
+                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              }
+              cp[c] = o;
             }
           }
         }

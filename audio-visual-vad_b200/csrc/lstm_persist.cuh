@@ -13,6 +13,11 @@
 //   warps 2-9: have already fetched xproj[b][t][their 32 columns] (independent of h), wait for the accumulator,
 //            apply the gate non-linearities, update c (registers), store h_t as bf16 (zero beyond the sequence
 //            length); after a named barrier one thread fences and publishes the CTA's flag.
+// Cluster mode (g.cluster = 2, 4 or 8 CTAs with the same batch slice): every CTA needs ALL of h_{t-1}[128 rows], so
+// without help the 64 column slices of a batch slice read the same 256 KB from L2 each step (32 MB per step).  In a
+// cluster, K block kb is fetched once by CTA (kb % cluster) and TMA-multicast into the same ring slot of all members;
+// a slot is recycled when every member's MMA has committed it (tcgen05.commit multicast onto the members' `empty`
+// barriers, count = cluster).
 // Reference semantics: nn.LSTM inside packages/models/AV_Net.py:128-137 (gates i,f,g,o; zero initial state).
 #pragma once
 #include "gemm_tma.cuh"
@@ -34,6 +39,7 @@ struct LstmGeom {
   // training only (may be null): post-activation gates (i,f,g,o per unit, bf16 [B][T][4H]) and cell states (f32 [B][T][H])
   __nv_bfloat16* gates_out;
   float* c_out;
+  int cluster;  // CTAs per cluster sharing h through TMA multicast (1 = none)
   int variant;  // tuning knob (AVVAD_LSTM_VARIANT): bit 0 = every thread fences before the barrier, bit 1 = back-off between polls
 };
 
@@ -47,6 +53,29 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%2, %3, %4}], [%5], %6;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -89,7 +118,7 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < kLstmStages; ++s) {
       mbar_init(BAR(s), 1);
-      mbar_init(BAR(kLstmStages + s), 1);
+      mbar_init(BAR(kLstmStages + s), (uint32_t)g.cluster);  // every cluster member's MMA releases the slot
     }
     mbar_init(BAR(kBarW), 1);
     mbar_init(BAR(kBarT), 1);
@@ -105,6 +134,10 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  const int CL = g.cluster;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+  if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts onto them
 
   if (warp == 0) {
     if (lane == 0) {
@@ -112,10 +145,40 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       mbar_arrive_expect_tx(BAR(kBarW), w_bytes);
       for (int kb = 0; kb < g.KB; ++kb) tma_load_2d(sW + kb * 8192u, &maps.w, kb * 64, ns * 64, BAR(kBarW));
     }
+    uint32_t it = 0;
+    if (CL > 1) {
+      // cluster mode: slots are armed in K order by every member; the member that owns kb waits for its four producer
+      // flags (lanes 0,1 read the two flag pairs), fences once and multicasts the box to all members
+      for (int t = 1; t < g.T; ++t) {
+        const unsigned int target = (unsigned int)t;
+        for (int kb = 0; kb < g.KB; ++kb, ++it) {
+          const int s = it % kLstmStages;
+          mbar_wait(BAR(kLstmStages + s), ((it / kLstmStages) & 1u) ^ 1u);
+          if (elect_one_sync()) mbar_arrive_expect_tx(BAR(s), 16384u);
+          __syncwarp();
+          if ((uint32_t)(kb % CL) == crank) {
+            const unsigned long long* fp = reinterpret_cast<const unsigned long long*>(flags + 4 * kb) + (lane & 1);
+            uint32_t spins = 0;
+            for (;;) {
+              unsigned long long fv;
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fv) : "l"(fp) : "memory");
+              const bool ok = ((unsigned int)fv >= target) && ((unsigned int)(fv >> 32) >= target);
+              if ((__ballot_sync(0xffffffffu, ok) & 3u) == 3u) break;
+              if (++spins > (1u << 26)) __trap();
+            }
+            if (elect_one_sync()) {
+              asm volatile("fence.acq_rel.gpu;" ::: "memory");
+              fence_proxy_async_global();
+              tma_load_3d_mc(sA + s * 16384u, &maps.h, kb * 64, t - 1, ms * 128, BAR(s), cmask);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else {
     // lane l watches the flags of slices 2l and 2l+1; K block kb is produced by slices 4kb .. 4kb+3 = lanes 2kb, 2kb+1
     const int f0 = 2 * lane, f1 = 2 * lane + 1;
     const unsigned long long* fpair = reinterpret_cast<const unsigned long long*>(flags + f0);  // both flags in one load
-    uint32_t it = 0;
     for (int t = 1; t < g.T; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
       const unsigned int target = (unsigned int)t;
       bool ok = false;
@@ -154,6 +217,7 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
         }
       }
     }
+    }
   } else if (warp == 1) {
     // MMA issuer (warp-converged; one elected lane issues the MMAs and commits)
     constexpr uint32_t idesc = make_idesc(64);
@@ -172,7 +236,10 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
           umma_f16_lo(tmem_acc, a_lo + 2, b_lo + 2, idesc, 1);
           umma_f16_lo(tmem_acc, a_lo + 4, b_lo + 4, idesc, 1);
           umma_f16_lo(tmem_acc, a_lo + 6, b_lo + 6, idesc, 1);
-          umma_commit(BAR(kLstmStages + s));
+          if (CL > 1)
+            umma_commit_mc(BAR(kLstmStages + s), cmask);
+          else
+            umma_commit(BAR(kLstmStages + s));
           if (kb == g.KB - 1) umma_commit(BAR(kBarT));
         }
         __syncwarp();
@@ -270,6 +337,7 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no member exits while peers may still arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_acc, 64);
