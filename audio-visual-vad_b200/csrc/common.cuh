@@ -61,6 +61,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread and instruction; the
+// address must be 32-byte aligned
+struct alignas(32) u32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ void st_global_256(void* p, const u32x8& x) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]),
+               "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7])
+               : "memory");
+}
+__device__ __forceinline__ u32x8 ld_global_256(const void* p) {
+  u32x8 x;
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x.v[0]), "=r"(x.v[1]), "=r"(x.v[2]), "=r"(x.v[3]), "=r"(x.v[4]), "=r"(x.v[5]), "=r"(x.v[6]),
+                 "=r"(x.v[7])
+               : "l"(p));
+  return x;
+}
+
 // {bf16(max(lo,0)), bf16(max(hi,0))} in one instruction (F2FP.RELU)
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   uint32_t r;

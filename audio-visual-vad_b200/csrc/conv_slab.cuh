@@ -245,14 +245,13 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       const int64_t tile_off = ((n0 * g.OH + hstart) * g.OW) * ep.ldc + n_base;
       bool ok[kMaxUnits];
-      uint4 rb[kMaxUnits][4] = {};
+      u32x8 rb[kMaxUnits][2] = {};  // activations are 128-byte rows at 1 KB aligned bases: 256-bit accesses are legal
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
         ok[i] = loc[i] >= 0 && n0 + lf[i] < g.n_frames && hstart + ly[i] < g.OH;
         if (ok[i] && resp) {
-          const uint4* rp = reinterpret_cast<const uint4*>(resp + tile_off + loc[i]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
+          rb[i][0] = ld_global_256(resp + tile_off + loc[i]);
+          rb[i][1] = ld_global_256(resp + tile_off + loc[i] + 16);
         }
       }
       mbar_wait(BAR(4 + acc), aph);
@@ -262,8 +261,9 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          asm volatile("" : "+r"(rb[i][c].x), "+r"(rb[i][c].y), "+r"(rb[i][c].z), "+r"(rb[i][c].w));
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) asm volatile("" : "+r"(rb[i][c].v[e]));
 #pragma unroll
       for (int i = 0; i < kMaxUnits; ++i) {
         const int u = grp + 2 * i;
@@ -286,31 +286,21 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
             }
             if (resp) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const uint32_t w[4] = {rb[i][c].x, rb[i][c].y, rb[i][c].z, rb[i][c].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {  // bf16 -> f32 is a 16-bit shift / mask
-                  f32[8 * c + 2 * e + 0] += __uint_as_float(w[e] << 16);
-                  f32[8 * c + 2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                }
+              for (int e = 0; e < 16; ++e) {  // bf16 -> f32 is a 16-bit shift / mask
+                const uint32_t w = rb[i][e >> 3].v[e & 7];
+                f32[2 * e + 0] += __uint_as_float(w << 16);
+                f32[2 * e + 1] += __uint_as_float(w & 0xFFFF0000u);
               }
             }
-            uint4* cp = reinterpret_cast<uint4*>(outp + tile_off + loc[i]);
+            __nv_bfloat16* cp = outp + tile_off + loc[i];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 o;
-              if (relu) {
-                o.x = pack_relu_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
-                o.y = pack_relu_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
-                o.z = pack_relu_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
-                o.w = pack_relu_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
-              } else {
-                o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
-                o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
-                o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
-                o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
-              }
-              cp[c] = o;
+            for (int c = 0; c < 2; ++c) {
+              u32x8 o;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                o.v[e] = relu ? pack_relu_bf16x2(f32[16 * c + 2 * e], f32[16 * c + 2 * e + 1])
+                              : pack_bf16x2(f32[16 * c + 2 * e], f32[16 * c + 2 * e + 1]);
+              st_global_256(cp + 16 * c, o);
             }
           }
         }

@@ -312,7 +312,9 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
   ep.C = out;
   ep.ldc = Cout;
   ep.relu = relu;
-  if (tc::use_tma() && tc::slab_supported(H, W, Cin, Cout, R, S, stride, pad))
+  // the slab epilogue uses 256-bit residual loads / output stores: rows must be 32-byte aligned
+  const bool aligned32 = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0;
+  if (tc::use_tma() && aligned32 && tc::slab_supported(H, W, Cin, Cout, R, S, stride, pad))
     return tc::launch_slab_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, Cin, Cout,
                                 (cudaStream_t)stream);
   if (tc::use_tma() && OW <= 128)

@@ -114,14 +114,16 @@ int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, u
   return encode2(m, ptr, K, N, K * 2, 64, bn);
 }
 
-template <int BN, int KE = 64>
-static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep, int epi_mode, int cat, double flops,
+template <int BN, int KE = 64, int MB = 1>
+static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {
-  using C = TmaCfg<BN, KE>;
+  using C = TmaCfg<BN, KE, MB>;
+  g.total_tiles = ((g.m_tiles + MB - 1) / MB) * g.n_tiles;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN, KE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN, KE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)C::kSmemBytes);
   });
   if (attr_err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));
@@ -133,11 +135,17 @@ static int launch_bn(const TmaMaps& maps, const TmaGeom& g, const EpiParams& ep,
     return n > 0 ? n : 148;
   }();
   if (g.total_tiles <= 0) return AVVAD_OK;
+  static int epi_debug = [] {
+    const char* e = getenv("AVVAD_EPI_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  EpiParams epd = ep;
+  epd.debug = epi_debug;
   const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
   const unsigned grid = (unsigned)(g.total_tiles < resident ? g.total_tiles : resident);
   void* tok = nullptr;
   prof_begin(st, &tok);
-  tc_tma_kernel<BN, KE><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, ep, epi_mode);
+  tc_tma_kernel<BN, KE, MB><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, epd, epi_mode);
   AVVAD_LAUNCHED();
   prof_end(st, tok, cat, flops);
   return AVVAD_OK;
@@ -147,7 +155,15 @@ static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiPara
                     double flops, cudaStream_t st) {
   switch (bn) {
     case 64: return launch_bn<64>(maps, g, ep, epi_mode, cat, flops, st);
-    case 128: return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
+    case 128: {
+      // two accumulator blocks per weight box unless AVVAD_MB=1 (see TmaCfg)
+      static int mb2 = [] {
+        const char* e = getenv("AVVAD_MB");
+        return (e && atoi(e) == 1) ? 0 : 1;
+      }();
+      if (mb2 && epi_mode != EPI_LSTM) return launch_bn<128, 64, 2>(maps, g, ep, epi_mode, cat, flops, st);
+      return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
+    }
     case 256: return launch_bn<256>(maps, g, ep, epi_mode, cat, flops, st);
   }
   set_error("bad BN");
@@ -217,7 +233,8 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
   int64_t tiles1 = 0;
   g.h0[1] = bnb0 * bh0; g.hb[1] = brem > 0 ? brem : 1; g.nb[1] = 1; g.F[1] = bF1;
   if (brem > 0) tiles1 = (n + bF1 - 1) / bF1;
-  g.total_tiles = (g.tiles0 + tiles1) * g.n_tiles;
+  g.m_tiles = g.tiles0 + tiles1;
+  g.total_tiles = g.m_tiles * g.n_tiles;
 
   TmaMaps maps;
   const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)n};
@@ -264,8 +281,9 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
   g.N = N;
   int bn = pick_bn(N, bn_hint);
   g.n_tiles = (N + bn - 1) / bn;
-  g.total_tiles = ((M + BM - 1) / BM) * g.n_tiles;
-  g.tiles0 = g.total_tiles;
+  g.m_tiles = (M + BM - 1) / BM;
+  g.total_tiles = g.m_tiles * g.n_tiles;
+  g.tiles0 = g.m_tiles;
   g.hb[0] = g.hb[1] = 1; g.nb[0] = g.nb[1] = 1; g.F[0] = g.F[1] = 1; g.OW = 128; g.OH = 1;
   TmaMaps maps;
   const uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};

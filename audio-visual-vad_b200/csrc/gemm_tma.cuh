@@ -42,7 +42,8 @@ struct TmaBias {
 struct TmaGeom {
   int mode;             // 0 = plain GEMM rows, 1 = convolution boxes
   int n_tiles;          // tiles along N
-  int64_t total_tiles;  // all (m, n) tiles
+  int64_t total_tiles;  // all (super m, n) tiles of the launch
+  int64_t m_tiles;      // 128-row blocks (both phases)
   int64_t tiles0;       // m-tiles of phase 0 (conv)
   int h0[2], hb[2], nb[2], F[2];  // per phase: first output row, band height, bands per frame, frames per tile
   int OH, OW, stride, pad, S, cpb, KB;
@@ -92,30 +93,37 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // KE = bf16 elements per K block: 64 (128-byte rows, SWIZZLE_128B, four K16 UMMAs per block) or 16 (32-byte rows,
 // SWIZZLE_32B, one UMMA per block -- used by the stem convolution whose packed input has 16 "channels").
-template <int BN, int KE = 64>
+// MB = accumulator blocks (128 rows each) per tile that share one weight box per K block.  A 128x128 tile moves
+// 32 KB through L2 -> SMEM per 256 MMA cycles (128 B/clk/SM, more than L2 delivers to 148 SMs at once: the N = 128
+// layers sat at 51-57 % tensor activity with L2 at 62-65 %); MB = 2 makes it 48 KB per 512 cycles (96 B/clk), the
+// ratio of the 128x256 tiles.  TMEM: 2 (double buffer) x MB x BN columns <= 512.
+template <int BN, int KE = 64, int MB = 1>
 struct TmaCfg {
   static constexpr uint32_t kRowBytes = KE * 2;
   static constexpr uint32_t kABytes = BM * kRowBytes;
   static constexpr uint32_t kBBytes = BN * kRowBytes;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
+  static constexpr uint32_t kStageBytes = MB * kABytes + kBBytes;
+  static constexpr int kCtasPerSm = (BN == 256 || MB > 1) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
-  static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? 3 : 4));
+  static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? (MB > 1 ? 4 : 3) : 4));
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + TmaBias<BN>::kEntries * 4;
   // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
   static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
+  static_assert(2 * MB * BN <= 512, "TMEM: two accumulator stages of MB x BN columns");
 };
 
 struct TileCoord {
-  int phase, n_base;
+  int phase;
   int64_t n0;   // conv: first frame; gemm: first row
   int hstart;   // conv: first output row of the band
+  bool valid;   // false: block index past the last m-tile (operands of the last valid block are loaded, nothing is stored)
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const TmaGeom& g, int64_t tile, int BN) {
+// m-tile index -> coordinates (clamped to the last m-tile)
+__device__ __forceinline__ TileCoord decode_block(const TmaGeom& g, int64_t mt) {
   TileCoord t;
-  t.n_base = (int)(tile % g.n_tiles) * BN;
-  int64_t mt = tile / g.n_tiles;
+  t.valid = mt < g.m_tiles;
+  if (!t.valid) mt = g.m_tiles - 1;
   if (g.mode == 0) {
     t.phase = 0;
     t.n0 = mt * BM;
@@ -131,13 +139,14 @@ __device__ __forceinline__ TileCoord decode_tile(const TmaGeom& g, int64_t tile,
   return t;
 }
 
-template <int BN, int KE>
-__global__ void __launch_bounds__(kTmaThreads, TmaCfg<BN, KE>::kCtasPerSm)
+template <int BN, int KE, int MB>
+__global__ void __launch_bounds__(kTmaThreads, TmaCfg<BN, KE, MB>::kCtasPerSm)
 tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaGeom g, const EpiParams ep,
               const int epi_mode) {
-  using C = TmaCfg<BN, KE>;
+  using C = TmaCfg<BN, KE, MB>;
   constexpr int S = C::kStages;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kAccCols = MB * BN;       // columns of one accumulator stage
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -180,12 +189,20 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
+  // tile = (n-tile fastest, super m-tile); super m-tile sm covers m-tiles sm*MB .. sm*MB + MB-1
   if (warp == 0) {
     // ================= TMA producer (warp-converged; one elected lane issues) =================
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(g, tile, BN);
-      const uint32_t bytes = g.bytesA[t.phase] + g.bytesB;
+      const int n_base = (int)(tile % g.n_tiles) * BN;
+      const int64_t sm = tile / g.n_tiles;
+      TileCoord t[MB];
+      uint32_t bytes = g.bytesB;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        t[mb] = decode_block(g, sm * MB + mb);
+        bytes += g.bytesA[t[mb].phase];
+      }
       int cb = 0, fr = 0, fs = 0;
       for (int kb = 0; kb < g.KB; ++kb, ++it) {
         const int s = it % S;
@@ -195,12 +212,16 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
           mbar_arrive_expect_tx(full, bytes);
-          if (g.mode == 0) {
-            tma_load_4d(sa, &maps.a[0], kb * KE, (int)t.n0, 0, 0, full);
-          } else {
-            tma_load_4d(sa, &maps.a[t.phase], cb * KE, fs - g.pad, t.hstart * g.stride + fr - g.pad, (int)t.n0, full);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            if (g.mode == 0) {
+              tma_load_4d(sa + mb * C::kABytes, &maps.a[0], kb * KE, (int)t[mb].n0, 0, 0, full);
+            } else {
+              tma_load_4d(sa + mb * C::kABytes, &maps.a[t[mb].phase], cb * KE, fs - g.pad,
+                          t[mb].hstart * g.stride + fr - g.pad, (int)t[mb].n0, full);
+            }
           }
-          tma_load_2d(sa + C::kABytes, &maps.b, kb * KE, t.n_base, full);
+          tma_load_2d(sa + MB * C::kABytes, &maps.b, kb * KE, n_base, full);
         }
         __syncwarp();
         if (++cb == g.cpb) {
@@ -219,8 +240,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
           mbar_arrive_expect_tx(full, bytes);
-          tma_load_4d(sa, &maps.a2[t.phase], kb2 * KE, 0, t.hstart * g.stride2, (int)t.n0, full);
-          tma_load_2d(sa + C::kABytes, &maps.b, (g.KB + kb2) * KE, t.n_base, full);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb)
+            tma_load_4d(sa + mb * C::kABytes, &maps.a2[t[mb].phase], kb2 * KE, 0, t[mb].hstart * g.stride2,
+                        (int)t[mb].n0, full);
+          tma_load_2d(sa + MB * C::kABytes, &maps.b, (g.KB + kb2) * KE, n_base, full);
         }
         __syncwarp();
       }
@@ -234,20 +258,25 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_acc + acc * BN;
+      const uint32_t d_tmem = tmem_acc + acc * kAccCols;
       for (int kb = 0; kb < kb_total; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(bar0 + 8 * s, ph);
         tc_fence_after();
         if (elect_one_sync()) {
-          const uint32_t a_lo = desc_lo(base + s * C::kStageBytes);
-          const uint32_t b_lo = a_lo + (C::kABytes >> 4);
-          umma_f16_lo2(d_tmem, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
-          if (KE == 64) {
-            umma_f16_lo2(d_tmem, a_lo + 2, b_lo + 2, idesc, 1, C::kDescHiWord);
-            umma_f16_lo2(d_tmem, a_lo + 4, b_lo + 4, idesc, 1, C::kDescHiWord);
-            umma_f16_lo2(d_tmem, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
+          const uint32_t a0 = desc_lo(base + s * C::kStageBytes);
+          const uint32_t b_lo = a0 + ((MB * C::kABytes) >> 4);
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint32_t a_lo = a0 + ((mb * C::kABytes) >> 4);
+            const uint32_t d = d_tmem + mb * BN;
+            umma_f16_lo2(d, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
+            if (KE == 64) {
+              umma_f16_lo2(d, a_lo + 2, b_lo + 2, idesc, 1, C::kDescHiWord);
+              umma_f16_lo2(d, a_lo + 4, b_lo + 4, idesc, 1, C::kDescHiWord);
+              umma_f16_lo2(d, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
+            }
           }
           umma_commit(bar0 + 8 * (S + s));
           if (kb == kb_total - 1) umma_commit(bar0 + 8 * (2 * S + acc));
@@ -259,136 +288,169 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     // ================= epilogue warps 2..9 =================
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;   // chunk parity handled by this warp
-    constexpr int kJ = BN / 32;         // 32-column chunks per tile
-    constexpr int kMine = (kJ + 1) / 2;  // chunks per warp
+    constexpr int kJ = BN / 32;         // 32-column chunks per accumulator block
+    constexpr int kMine = (kJ + 1) / 2;  // chunks per warp and block
     const bool fast = (epi_mode == EPI_BF16) && bias_in_smem && (g.N % 32 == 0);
     const bool fast32 = (epi_mode == EPI_F32) && bias_in_smem && (g.N % 32 == 0) && (ep.ldc % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
     uint32_t tl = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
-      const TileCoord t = decode_tile(g, tile, BN);
+      const int n_base = (int)(tile % g.n_tiles) * BN;
+      const int64_t sm = tile / g.n_tiles;
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      // output row of accumulator row r = q*32 + lane
+      // output row of accumulator row r = q*32 + lane of every block
       const int r = q * 32 + lane;
-      int64_t m = -1;
-      if (g.mode == 0) {
-        if (t.n0 + r < g.n_frames) m = t.n0 + r;
-      } else {
-        const int hb = g.hb[t.phase];
-        const int per_frame = hb * g.OW;
-        const int f = r / per_frame;
-        const int rem = r - f * per_frame;
-        const int hh = rem / g.OW;
-        const int ww = rem - hh * g.OW;
-        const int oh = t.hstart + hh;
-        if (f < g.F[t.phase] && t.n0 + f < g.n_frames && oh < g.OH)
-          m = ((t.n0 + f) * g.OH + oh) * g.OW + ww;
+      int64_t m[MB];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const TileCoord t = decode_block(g, sm * MB + mb);
+        m[mb] = -1;
+        if (!t.valid) continue;
+        if (g.mode == 0) {
+          if (t.n0 + r < g.n_frames) m[mb] = t.n0 + r;
+        } else {
+          const int hb = g.hb[t.phase];
+          const int per_frame = hb * g.OW;
+          const int f = r / per_frame;
+          const int rem = r - f * per_frame;
+          const int hh = rem / g.OW;
+          const int ww = rem - hh * g.OW;
+          const int oh = t.hstart + hh;
+          if (f < g.F[t.phase] && t.n0 + f < g.n_frames && oh < g.OH)
+            m[mb] = ((t.n0 + f) * g.OH + oh) * g.OW + ww;
+        }
       }
-      const uint32_t t_row = tmem_acc + acc * BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t t_row = tmem_acc + acc * kAccCols + ((uint32_t)(q * 32) << 16);
       if (fast) {
         // residual of this thread's chunks: in flight while the tile's MMAs run
-        uint4 rb[kMine][4] = {};
-        const bool has_res = (ep.residual != nullptr) && (m >= 0);
-        if (has_res) {
+        u32x8 rb[MB * kMine][2] = {};
+        const bool wide = ((reinterpret_cast<uintptr_t>(ep.C) | reinterpret_cast<uintptr_t>(ep.residual)) & 31) == 0 &&
+                          (ep.ldc % 16 == 0);  // 32-byte aligned rows: 256-bit loads / stores
+        if (ep.residual) {
 #pragma unroll
-          for (int i = 0; i < kMine; ++i) {
-            const int n0 = t.n_base + (2 * i + half) * 32;
-            if (2 * i + half < kJ && n0 < g.N) {
-              const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + m * ep.ldc + n0);
+          for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-              for (int c = 0; c < 4; ++c) rb[i][c] = rp[c];
+            for (int i = 0; i < kMine; ++i) {
+              const int n0 = n_base + (2 * i + half) * 32;
+              if (m[mb] >= 0 && 2 * i + half < kJ && n0 < g.N) {
+                const __nv_bfloat16* rp = ep.residual + m[mb] * ep.ldc + n0;
+                if (wide) {
+                  rb[mb * kMine + i][0] = ld_global_256(rp);
+                  rb[mb * kMine + i][1] = ld_global_256(rp + 16);
+                } else {
+                  const uint4* r4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const uint4 t4 = r4[c];
+                    rb[mb * kMine + i][c >> 1].v[4 * (c & 1) + 0] = t4.x;
+                    rb[mb * kMine + i][c >> 1].v[4 * (c & 1) + 1] = t4.y;
+                    rb[mb * kMine + i][c >> 1].v[4 * (c & 1) + 2] = t4.z;
+                    rb[mb * kMine + i][c >> 1].v[4 * (c & 1) + 3] = t4.w;
+                  }
+                }
+              }
             }
-          }
         }
         mbar_wait(bar0 + 8 * (2 * S + acc), aph);
         tc_fence_after();
         // pin the prefetched residual behind the wait (otherwise the unpack is hoisted right behind the loads and their
         // latency is paid before the wait instead of under the tile's MMAs)
 #pragma unroll
-        for (int i = 0; i < kMine; ++i)
+        for (int i = 0; i < MB * kMine; ++i)
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            asm volatile("" : "+r"(rb[i][c].x), "+r"(rb[i][c].y), "+r"(rb[i][c].z), "+r"(rb[i][c].w));
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < kMine; ++i) {
-          const int j = 2 * i + half;
-          if (j < kJ) {  // warp-uniform
-            uint32_t v[32];
-            tmem_ld32(t_row + j * 32, v);
-            tmem_ld_wait();
-            const int n0 = t.n_base + j * 32;
-            if (m >= 0 && n0 < g.N) {
-              float f32[32];
-              const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
+            for (int e = 0; e < 8; ++e) asm volatile("" : "+r"(rb[i][c].v[e]));
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 b4 = bp[c];
-                f32[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + b4.x;
-                f32[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b4.y;
-                f32[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b4.z;
-                f32[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b4.w;
-              }
-              if (has_res) {
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float2 a = unpack_bf16x2(rb[i][c].x), b2 = unpack_bf16x2(rb[i][c].y);
-                  const float2 c2 = unpack_bf16x2(rb[i][c].z), d2 = unpack_bf16x2(rb[i][c].w);
-                  f32[8 * c + 0] += a.x;  f32[8 * c + 1] += a.y;  f32[8 * c + 2] += b2.x; f32[8 * c + 3] += b2.y;
-                  f32[8 * c + 4] += c2.x; f32[8 * c + 5] += c2.y; f32[8 * c + 6] += d2.x; f32[8 * c + 7] += d2.y;
+          for (int i = 0; i < kMine; ++i) {
+            const int j = 2 * i + half;
+            if (j < kJ) {  // warp-uniform
+              uint32_t v[32];
+              tmem_ld32(t_row + mb * BN + j * 32, v);
+              tmem_ld_wait();
+              const int n0 = n_base + j * 32;
+              if (m[mb] >= 0 && n0 < g.N) {
+                float f32[32];
+                const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b4 = bp[c];
+                  f32[4 * c + 0] = __uint_as_float(v[4 * c + 0]) + b4.x;
+                  f32[4 * c + 1] = __uint_as_float(v[4 * c + 1]) + b4.y;
+                  f32[4 * c + 2] = __uint_as_float(v[4 * c + 2]) + b4.z;
+                  f32[4 * c + 3] = __uint_as_float(v[4 * c + 3]) + b4.w;
                 }
-              }
-              if (ep.relu) {
+                if (ep.residual) {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) f32[c] = fmaxf(f32[c], 0.f);
-              }
-              uint4* cp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.C) + m * ep.ldc + n0);
+                  for (int e = 0; e < 16; ++e) {  // bf16 -> f32 is a 16-bit shift / mask
+                    const uint32_t w = rb[mb * kMine + i][e >> 3].v[e & 7];
+                    f32[2 * e + 0] += __uint_as_float(w << 16);
+                    f32[2 * e + 1] += __uint_as_float(w & 0xFFFF0000u);
+                  }
+                }
+                __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(ep.C) + m[mb] * ep.ldc + n0;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint4 o;
-                o.x = pack_bf16x2(f32[8 * c + 0], f32[8 * c + 1]);
-                o.y = pack_bf16x2(f32[8 * c + 2], f32[8 * c + 3]);
-                o.z = pack_bf16x2(f32[8 * c + 4], f32[8 * c + 5]);
-                o.w = pack_bf16x2(f32[8 * c + 6], f32[8 * c + 7]);
-                cp[c] = o;
+                for (int c = 0; c < 2; ++c) {
+                  u32x8 o;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    o.v[e] = ep.relu ? pack_relu_bf16x2(f32[16 * c + 2 * e], f32[16 * c + 2 * e + 1])
+                                     : pack_bf16x2(f32[16 * c + 2 * e], f32[16 * c + 2 * e + 1]);
+                  if ((ep.debug & 1) && o.v[0] != 0x12345678u) continue;
+                  if (wide) {
+                    st_global_256(cp + 16 * c, o);
+                  } else {
+                    uint4* c4 = reinterpret_cast<uint4*>(cp + 16 * c);
+                    c4[0] = make_uint4(o.v[0], o.v[1], o.v[2], o.v[3]);
+                    c4[1] = make_uint4(o.v[4], o.v[5], o.v[6], o.v[7]);
+                  }
+                }
               }
             }
           }
-        }
       } else if (fast32) {
         // fp32 output (LSTM input projection): smem bias, 8 x 16-byte stores per 32-column chunk
         mbar_wait(bar0 + 8 * (2 * S + acc), aph);
         tc_fence_after();
-#pragma unroll 1
-        for (int j = half; j < kJ; j += 2) {
-          uint32_t v[32];
-          tmem_ld32(t_row + j * 32, v);
-          tmem_ld_wait();
-          const int n0 = t.n_base + j * 32;
-          if (m >= 0 && n0 < g.N) {
-            const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
-            float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + m * ep.ldc + n0);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 b4 = bp[c];
-              float4 o = make_float4(__uint_as_float(v[4 * c + 0]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
-                                     __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
-              if (ep.relu) {
-                o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll 1
+          for (int j = half; j < kJ; j += 2) {
+            uint32_t v[32];
+            tmem_ld32(t_row + mb * BN + j * 32, v);
+            tmem_ld_wait();
+            const int n0 = n_base + j * 32;
+            if (m[mb] >= 0 && n0 < g.N) {
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
+              float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + m[mb] * ep.ldc + n0);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 b4 = bp[c];
+                float4 o = make_float4(__uint_as_float(v[4 * c + 0]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
+                                       __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
+                if (ep.relu) {
+                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                cp[c] = o;
               }
-              cp[c] = o;
             }
           }
         }
       } else {
         mbar_wait(bar0 + 8 * (2 * S + acc), aph);
         tc_fence_after();
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll 1
-        for (int j = half; j < kJ; j += 2) {
-          uint32_t v[32];
-          tmem_ld32(t_row + j * 32, v);
-          tmem_ld_wait();
-          const int n0 = t.n_base + j * 32;
-          if (m >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m, n0, g.N);
+          for (int j = half; j < kJ; j += 2) {
+            uint32_t v[32];
+            tmem_ld32(t_row + mb * BN + j * 32, v);
+            tmem_ld_wait();
+            const int n0 = n_base + j * 32;
+            if (m[mb] >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m[mb], n0, g.N);
+          }
         }
       }
       tc_fence_before();
