@@ -35,7 +35,6 @@ static const ConvSpec kSpecs[20] = {
 };
 constexpr int64_t kFrameHW = 67 * 67;
 constexpr int64_t kActBytesPerFrame = 17 * 17 * 64 * 2;  // largest NHWC bf16 activation (after the pool)
-constexpr int64_t kStemBytesPerFrame = 34 * 34 * 64 * 2;  // conv1 output before the pool
 
 // ---- weight folding / packing ----------------------------------------------------------------------
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
@@ -76,80 +75,6 @@ __global__ void pack_conv1_tc_kernel(const float* __restrict__ w, const float* _
     v = (w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k]) * sc;
   }
   w1b[idx] = __float2bfloat16_rn(v);
-}
-
-// Stem im2col rows: A[m][r*7+s] = frame[2oh-3+r][2ow-3+s] (zero outside), m = (n*34+oh)*34+ow, bf16 [M][64]
-// (columns 49..63 zero).  128-byte rows make the following K=64 GEMM a stream of 16 KB contiguous TMA boxes.
-__global__ void stem_im2col_kernel(const float* __restrict__ frames, int64_t n_frames, __nv_bfloat16* __restrict__ A) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_frames * 1156) return;
-  const int64_t n = m / 1156;
-  const int rem = (int)(m - n * 1156);
-  const int oh = rem / 34, ow = rem - oh * 34;
-  const float* f = frames + n * (67 * 67);
-  const int ih0 = 2 * oh - 3, iw0 = 2 * ow - 3;
-  float v[50];
-#pragma unroll
-  for (int r = 0; r < 7; ++r) {
-    const int ih = ih0 + r;
-    const bool rok = (unsigned)ih < 67u;
-#pragma unroll
-    for (int c = 0; c < 7; ++c) {
-      const int iw = iw0 + c;
-      v[r * 7 + c] = (rok && (unsigned)iw < 67u) ? __ldg(f + ih * 67 + iw) : 0.f;
-    }
-  }
-  v[49] = 0.f;
-  uint4* o = reinterpret_cast<uint4*>(A + m * 64);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t w[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int k = c * 8 + q * 2;
-      w[q] = (k < 50) ? pack_bf16x2(v[k], k + 1 < 50 ? v[k + 1] : 0.f) : 0u;
-    }
-    o[c] = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-// NHWC bf16 3x3 / stride 2 / pad 1 max pool (inputs are post-ReLU, so clipping the window == -inf padding)
-__global__ void maxpool_nhwc_kernel(const __nv_bfloat16* __restrict__ in, int64_t n_frames, int H, int OH, int C,
-                                    __nv_bfloat16* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int chunks = C / 8;
-  const int64_t total = n_frames * OH * OH * chunks;
-  if (idx >= total) return;
-  const int ch = (int)(idx % chunks);
-  int64_t pp = idx / chunks;
-  const int pw = (int)(pp % OH);
-  pp /= OH;
-  const int ph = (int)(pp % OH);
-  const int64_t f = pp / OH;
-  float m[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) m[q] = 0.f;
-  const __nv_bfloat16* base = in + f * H * H * C + ch * 8;
-#pragma unroll
-  for (int dy = -1; dy <= 1; ++dy) {
-    const int y = 2 * ph + dy;
-    if (y < 0 || y >= H) continue;
-#pragma unroll
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int x = 2 * pw + dx;
-      if (x < 0 || x >= H) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(base + ((int64_t)y * H + x) * C);
-      const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
-      m[0] = fmaxf(m[0], a.x); m[1] = fmaxf(m[1], a.y); m[2] = fmaxf(m[2], b.x); m[3] = fmaxf(m[3], b.y);
-      m[4] = fmaxf(m[4], c.x); m[5] = fmaxf(m[5], c.y); m[6] = fmaxf(m[6], d.x); m[7] = fmaxf(m[7], d.y);
-    }
-  }
-  uint4 r;
-  r.x = pack_bf16x2(m[0], m[1]);
-  r.y = pack_bf16x2(m[2], m[3]);
-  r.z = pack_bf16x2(m[4], m[5]);
-  r.w = pack_bf16x2(m[6], m[7]);
-  *reinterpret_cast<uint4*>(out + ((f * OH + ph) * OH + pw) * C + ch * 8) = r;
 }
 
 // Downsample blocks: out = relu(conv_b(y) + bn_b + conv_ds(x) + bn_ds).  Both folded convolutions share the output
@@ -198,76 +123,112 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ act, int64_t n_
 }
 
 // ---- training-mode BatchNorm (batch statistics) -------------------------------------------------------------
-// raw bf16 [M][C] -> per-channel sum / sum of squares (double atomics; one block per 256 rows)
+// raw bf16 [M][C] -> per-channel sum / sum of squares.  A block owns kStatRows consecutive rows; thread = (8-channel
+// group, row lane): 16-byte loads, many rows in flight, fp32 partial sums per thread, shared-memory tree over the row
+// lanes, one fp64 atomic per channel and block.
+constexpr int kStatRows = 2048;
 __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int C,
                                                        double* __restrict__ stats) {
-  const int64_t r0 = (int64_t)blockIdx.x * 256;
-  const int64_t r1 = (r0 + 256 < M) ? r0 + 256 : M;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float s = 0.f, ss = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      const float v = __bfloat162float(raw[r * C + c]);
-      s += v;
-      ss += v * v;
+  extern __shared__ float st_sm[];  // [lanes][2*C] partial sums
+  const int groups = C / 8;                 // 8, 16, 32 or 64
+  const int lanes = 256 / groups;           // row lanes: 32, 16, 8 or 4
+  const int gidx = threadIdx.x % groups, ln = threadIdx.x / groups;
+  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
+  const int64_t r1 = (r0 + kStatRows < M) ? r0 + kStatRows : M;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t r = r0 + ln; r < r1; r += lanes) {
+    const uint4 v = *reinterpret_cast<const uint4*>(raw + r * C + gidx * 8);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
+      s[2 * e] += a; q[2 * e] = fmaf(a, a, q[2 * e]);
+      s[2 * e + 1] += b; q[2 * e + 1] = fmaf(b, b, q[2 * e + 1]);
     }
-    atomicAdd(stats + c, (double)s);
-    atomicAdd(stats + C + c, (double)ss);
+  }
+  float* mine = st_sm + (size_t)ln * 2 * C + gidx * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mine[e] = s[e];
+    mine[C + e] = q[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)st_sm[(size_t)l * 2 * C + c];
+    atomicAdd(stats + c, acc);
   }
 }
-// mean / invstd for the apply pass; running statistics updated like nn.BatchNorm2d (momentum, unbiased variance)
+// per-channel scale / shift for the apply pass: y = x*a + b with a = invstd*gamma, b = beta - mean*a; running statistics
+// updated like nn.BatchNorm2d (momentum, unbiased variance)
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t M, int C, float eps, float momentum,
-                                   float* __restrict__ mean_invstd, float* __restrict__ running_mean,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale_shift, float* __restrict__ running_mean,
                                    float* __restrict__ running_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[c] / (double)M;
   double var = stats[C + c] / (double)M - mean * mean;
   if (var < 0) var = 0;
-  mean_invstd[c] = (float)mean;
-  mean_invstd[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  // same fp32 operation order as before the scale/shift refactoring is not required: (x-mean)*invstd*gamma+beta is
+  // evaluated as x*a + b in fp32 from fp64-derived a, b
+  const double a = (1.0 / sqrt(var + (double)eps)) * (double)gamma[c];
+  scale_shift[c] = (float)a;
+  scale_shift[C + c] = (float)((double)beta[c] - mean * a);
   if (running_mean) {
     const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
 }
-// out = act( (raw - mean) * invstd * gamma + beta (+ residual) ), 8 channels per thread
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int C,
-                                const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const __nv_bfloat16* __restrict__ residual, int relu,
-                                __nv_bfloat16* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int chunks = C / 8;
-  if (idx >= M * chunks) return;
-  const int c0 = (int)(idx % chunks) * 8;
-  const int64_t off = (idx / chunks) * C + c0;
-  const uint4 v = *reinterpret_cast<const uint4*>(raw + off);
-  float x[8];
-  float2 t;
-  t = unpack_bf16x2(v.x); x[0] = t.x; x[1] = t.y;
-  t = unpack_bf16x2(v.y); x[2] = t.x; x[3] = t.y;
-  t = unpack_bf16x2(v.z); x[4] = t.x; x[5] = t.y;
-  t = unpack_bf16x2(v.w); x[6] = t.x; x[7] = t.y;
-  float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (residual) {
-    const uint4 rv = *reinterpret_cast<const uint4*>(residual + off);
-    t = unpack_bf16x2(rv.x); r[0] = t.x; r[1] = t.y;
-    t = unpack_bf16x2(rv.y); r[2] = t.x; r[3] = t.y;
-    t = unpack_bf16x2(rv.z); r[4] = t.x; r[5] = t.y;
-    t = unpack_bf16x2(rv.w); r[6] = t.x; r[7] = t.y;
+// out = act(raw * a + b (+ residual)); 8 channels per thread, the block's scale/shift staged in shared memory,
+// kApplyRows rows per thread so the per-channel constants are read once
+constexpr int kApplyRows = 4;
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ raw, int64_t M, int C,
+                                                       const float* __restrict__ scale_shift,
+                                                       const __nv_bfloat16* __restrict__ residual, int relu,
+                                                       __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float ss_sm[];  // [2*C]
+  for (int i = threadIdx.x; i < 2 * C; i += 256) ss_sm[i] = scale_shift[i];
+  __syncthreads();
+  const int groups = C / 8;
+  const int rows_per_block = (256 / groups) * kApplyRows;
+  const int gidx = threadIdx.x % groups, ln = threadIdx.x / groups;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = ss_sm[gidx * 8 + e];
+    b[e] = ss_sm[C + gidx * 8 + e];
+  }
+  const int64_t base = (int64_t)blockIdx.x * rows_per_block + ln;
+  uint4 v[kApplyRows], rv[kApplyRows];
+#pragma unroll
+  for (int k = 0; k < kApplyRows; ++k) {
+    const int64_t r = base + (int64_t)k * (256 / groups);
+    if (r < M) {
+      v[k] = *reinterpret_cast<const uint4*>(raw + r * C + gidx * 8);
+      if (residual) rv[k] = *reinterpret_cast<const uint4*>(residual + r * C + gidx * 8);
+    }
   }
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int c = c0 + q;
-    float y = (x[q] - mean_invstd[c]) * mean_invstd[C + c] * gamma[c] + beta[c] + r[q];
-    x[q] = relu ? fmaxf(y, 0.f) : y;
+  for (int k = 0; k < kApplyRows; ++k) {
+    const int64_t r = base + (int64_t)k * (256 / groups);
+    if (r >= M) continue;
+    const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+    const uint32_t rw[4] = {rv[k].x, rv[k].y, rv[k].z, rv[k].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float y0 = fmaf(__uint_as_float(w[e] << 16), a[2 * e], b[2 * e]);
+      float y1 = fmaf(__uint_as_float(w[e] & 0xFFFF0000u), a[2 * e + 1], b[2 * e + 1]);
+      if (residual) {
+        y0 += __uint_as_float(rw[e] << 16);
+        y1 += __uint_as_float(rw[e] & 0xFFFF0000u);
+      }
+      o[e] = relu ? pack_relu_bf16x2(y0, y1) : pack_bf16x2(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(out + r * C + gidx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  uint4 o;
-  o.x = pack_bf16x2(x[0], x[1]);
-  o.y = pack_bf16x2(x[2], x[3]);
-  o.z = pack_bf16x2(x[4], x[5]);
-  o.w = pack_bf16x2(x[6], x[7]);
-  *reinterpret_cast<uint4*>(out + off) = o;
 }
 // raw (un-folded) weights: bf16 [O][R][S][I]; conv1: 3 channels summed, [64][64] with k = r*7+s
 __global__ void pack_conv_raw_kernel(const float* __restrict__ w, int cout, int cin, int k,
@@ -279,6 +240,20 @@ __global__ void pack_conv_raw_kernel(const float* __restrict__ w, int cout, int 
   const int r = (idx / (cin * k)) % k;
   const int o = idx / (cin * k * k);
   wp[idx] = __float2bfloat16_rn(w[((o * cin + i) * k + r) * k + s]);
+}
+// conv1 for the training stem: three input channels summed, fp32 [64][49]; and the fold of the batch scale
+__global__ void pack_conv1_raw32_kernel(const float* __restrict__ w, float* __restrict__ w32) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 49) return;
+  const int o = idx / 49, k = idx % 49;
+  w32[idx] = w[(o * 3 + 0) * 49 + k] + w[(o * 3 + 1) * 49 + k] + w[(o * 3 + 2) * 49 + k];
+}
+__global__ void fold_conv1_kernel(const float* __restrict__ w32, const float* __restrict__ scale_shift,
+                                  __nv_bfloat16* __restrict__ w1fold) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int o = idx / 64, k = idx % 64;
+  w1fold[idx] = __float2bfloat16_rn(k < 49 ? w32[o * 49 + k] * scale_shift[o] : 0.f);
 }
 __global__ void pack_conv1_raw_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w1) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +279,8 @@ struct avvad_resnet18 {
   bool fused_ready;
   // training mode (batch-statistics BN): un-folded bf16 weights and BN affine parameters
   __nv_bfloat16* wraw[20];
+  float* w1raw32;        // conv1 raw weights, three input channels summed, fp32 [64][49]
+  __nv_bfloat16* w1fold;  // conv1 weights with the batch scale folded in (training stem, second pass)
   float* gamma[20];
   float* beta[20];
   bool set_train[20];
@@ -328,6 +305,8 @@ extern "C" int avvad_resnet18_create(avvad_resnet18** out) {
     h->bf[i] = nullptr;
   }
   h->fused_ready = false;
+  h->w1raw32 = nullptr;
+  h->w1fold = nullptr;
   for (int i = 0; i < 20; ++i) {
     const ConvSpec& s = kSpecs[i];
     AVVAD_CUDA(cudaMalloc(&h->bias[i], sizeof(float) * s.cout));
@@ -353,6 +332,8 @@ extern "C" void avvad_resnet18_destroy(avvad_resnet18* h) {
     cudaFree(h->beta[i]);
   }
   cudaFree(h->w1b);
+  cudaFree(h->w1raw32);
+  cudaFree(h->w1fold);
   for (int i = 0; i < 3; ++i) {
     cudaFree(h->wf[i]);
     cudaFree(h->bf[i]);
@@ -457,13 +438,19 @@ struct StemInput {
   int64_t first = 0;  // global index of the first frame of this (sub-)call
 };
 
-static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st) {
+// w / bias: the conv1 operands of this launch (folded eval-mode weights by default); stats != NULL selects the
+// statistics-only first pass of the training stem (fp32 frames)
+static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st,
+                           const __nv_bfloat16* w = nullptr, const float* bias = nullptr, double* stats = nullptr) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::kS2Smem);
   });
   AVVAD_CUDA(attr_err);
   static int num_sms = [] {
@@ -473,9 +460,10 @@ static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __
   }();
   tc::StemS2Params p{};
   p.n_frames = n;
-  p.w1b = h->w1b;
-  p.bias = h->bias[0];
+  p.w1b = w ? w : h->w1b;
+  p.bias = w ? bias : h->bias[0];
   p.out = out;
+  p.stats = stats;
   const int64_t batches = (n + tc::kS2FramesPerBatch - 1) / tc::kS2FramesPerBatch;
   const unsigned grid = (unsigned)(batches < num_sms ? batches : num_sms);
   void* tok = nullptr;
@@ -488,6 +476,9 @@ static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __
     p.mean = in.mean; p.denom = in.denom; p.standardise = in.standardise;
     p.first = in.first;
     tc::stem_s2d_kernel<1><<<grid, tc::kS2Threads, tc::kS2Smem, st>>>(p);
+  } else if (stats) {
+    p.frames = in.frames + in.first * kFrameHW;
+    tc::stem_s2d_kernel<0, true><<<grid, tc::kS2Threads, tc::kS2Smem, st>>>(p);
   } else {
     p.frames = in.frames + in.first * kFrameHW;
     tc::stem_s2d_kernel<0><<<grid, tc::kS2Threads, tc::kS2Smem, st>>>(p);
@@ -717,9 +708,15 @@ extern "C" int avvad_resnet18_set_conv_train(avvad_resnet18* h, int layer, const
     AVVAD_CUDA(cudaMalloc(&h->gamma[layer], s.cout * sizeof(float)));
     AVVAD_CUDA(cudaMalloc(&h->beta[layer], s.cout * sizeof(float)));
   }
-  if (layer == 0)
+  if (layer == 0) {
+    if (!h->w1raw32) {
+      AVVAD_CUDA(cudaMalloc(&h->w1raw32, 64 * 49 * sizeof(float)));
+      AVVAD_CUDA(cudaMalloc(&h->w1fold, 64 * 64 * sizeof(__nv_bfloat16)));
+    }
+    pack_conv1_raw32_kernel<<<13, 256, 0, st>>>(w, h->w1raw32);
+    AVVAD_LAUNCHED();
     pack_conv1_raw_kernel<<<16, 256, 0, st>>>(w, h->wraw[0]);
-  else
+  } else
     pack_conv_raw_kernel<<<(unsigned)ceil_div((int64_t)wn, 256), 256, 0, st>>>(w, s.cout, s.cin, s.k, h->wraw[layer]);
   AVVAD_LAUNCHED();
   AVVAD_CUDA(cudaMemcpyAsync(h->gamma[layer], gamma, s.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -731,8 +728,7 @@ extern "C" int avvad_resnet18_set_conv_train(avvad_resnet18* h, int layer, const
 extern "C" size_t avvad_resnet18_train_workspace_bytes(int64_t n_frames) {
   if (n_frames <= 0) return 0;
   const size_t act = align_up((size_t)n_frames * kActBytesPerFrame, 1024);
-  const size_t stem = align_up((size_t)n_frames * kStemBytesPerFrame, 1024);
-  return 4 * act + 3 * stem + 64 * 1024;  // activations, raw / stem-output / im2col, statistics
+  return 5 * act + 64 * 1024;  // four rotating activations, one raw conv output, statistics
 }
 
 namespace {
@@ -751,15 +747,17 @@ struct TrainCtx {
 int bn_train(const TrainCtx& c, int layer, const __nv_bfloat16* raw, int64_t M, int C, const __nv_bfloat16* residual,
              int relu, __nv_bfloat16* out) {
   AVVAD_CUDA(cudaMemsetAsync(c.stats, 0, sizeof(double) * 2 * C, c.st));
-  bn_stats_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, c.st>>>(raw, M, C, c.stats);
+  const int lanes = 256 / (C / 8);
+  bn_stats_kernel<<<(unsigned)ceil_div(M, kStatRows), 256, (size_t)lanes * 2 * C * sizeof(float), c.st>>>(raw, M, C,
+                                                                                                        c.stats);
   AVVAD_LAUNCHED();
   bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, c.st>>>(
-      c.stats, M, C, c.bn_eps, c.momentum, c.mean_invstd, c.running_mean ? c.running_mean[layer] : nullptr,
-      c.running_var ? c.running_var[layer] : nullptr);
+      c.stats, M, C, c.bn_eps, c.momentum, c.h->gamma[layer], c.h->beta[layer], c.mean_invstd,
+      c.running_mean ? c.running_mean[layer] : nullptr, c.running_var ? c.running_var[layer] : nullptr);
   AVVAD_LAUNCHED();
-  const int64_t total = M * (C / 8);
-  bn_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, c.st>>>(raw, M, C, c.mean_invstd, c.h->gamma[layer],
-                                                                   c.h->beta[layer], residual, relu, out);
+  const int rows_per_block = lanes * kApplyRows;
+  bn_apply_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 2 * C * sizeof(float), c.st>>>(
+      raw, M, C, c.mean_invstd, residual, relu, out);
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }
@@ -790,32 +788,31 @@ extern "C" int avvad_resnet18_forward_train(avvad_resnet18* h, const float* fram
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = n_frames;
   const size_t act = align_up((size_t)n * kActBytesPerFrame, 1024);
-  const size_t stem = align_up((size_t)n * kStemBytesPerFrame, 1024);
   uint8_t* p = (uint8_t*)workspace;
   __nv_bfloat16* buf[4];
   for (int i = 0; i < 4; ++i) buf[i] = reinterpret_cast<__nv_bfloat16*>(p + i * act);
-  __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(p + 4 * act);            // raw conv output (largest: stem)
-  __nv_bfloat16* stem_out = reinterpret_cast<__nv_bfloat16*>(p + 4 * act + stem);
-  __nv_bfloat16* cols = reinterpret_cast<__nv_bfloat16*>(p + 4 * act + 2 * stem);
-  double* stats = reinterpret_cast<double*>(p + 4 * act + 3 * stem);
-  float* mean_invstd = reinterpret_cast<float*>(p + 4 * act + 3 * stem + 16 * 1024);
+  __nv_bfloat16* raw = reinterpret_cast<__nv_bfloat16*>(p + 4 * act);  // raw conv output (largest: layer1)
+  double* stats = reinterpret_cast<double*>(p + 5 * act);
+  float* mean_invstd = reinterpret_cast<float*>(p + 5 * act + 16 * 1024);  // scale [C] | shift [C]
   TrainCtx c{h, n, stats, mean_invstd, bn_eps, momentum, running_mean, running_var, st};
 
-  // stem: im2col -> raw K=64 GEMM -> BN(batch stats) + ReLU -> max-pool
+  // stem, two passes of the image-as-operand kernel (no 34x34x64 tensor in HBM):
+  //   1. raw conv1 (un-folded weights, no bias) -> per-channel batch statistics only
+  //   2. batch scale folded into the weights, batch shift as bias -> conv + BN + ReLU + max-pool as in eval mode
   {
-    const int64_t M = n * 1156;
-    stem_im2col_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, st>>>(frames, n, cols);
-    AVVAD_LAUNCHED();
-    tc::EpiParams ep{};
-    ep.C = raw;
-    ep.ldc = 64;
-    int rc = tc::gemm_dispatch(cols, 64, h->wraw[0], 64, M, 64, 64, ep, tc::EPI_BF16, 64, st);
+    StemInput sin;
+    sin.frames = frames;
+    AVVAD_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * 64, st));
+    int rc = launch_stem_s2d(h, sin, n, nullptr, st, h->wraw[0], nullptr, stats);
     if (rc) return rc;
-    rc = bn_train(c, 0, raw, M, 64, nullptr, 1, stem_out);
-    if (rc) return rc;
-    const int64_t total = n * 17 * 17 * 8;
-    maxpool_nhwc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(stem_out, n, 34, 17, 64, buf[0]);
+    bn_finalize_kernel<<<1, 128, 0, st>>>(stats, n * 1156, 64, bn_eps, momentum, h->gamma[0], h->beta[0], mean_invstd,
+                                          running_mean ? running_mean[0] : nullptr,
+                                          running_var ? running_var[0] : nullptr);
     AVVAD_LAUNCHED();
+    fold_conv1_kernel<<<16, 256, 0, st>>>(h->w1raw32, mean_invstd, h->w1fold);
+    AVVAD_LAUNCHED();
+    rc = launch_stem_s2d(h, sin, n, buf[0], st, h->w1fold, mean_invstd + 64);
+    if (rc) return rc;
   }
   int cur = 0, layer = 1;
   for (int stage = 0; stage < 4; ++stage) {

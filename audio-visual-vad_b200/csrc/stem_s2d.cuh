@@ -74,8 +74,9 @@ struct StemS2Params {
   int64_t n_frames;
   int64_t first;             // mode 1: global index of local frame 0 (chunked calls)
   const __nv_bfloat16* w1b;  // folded conv1 weights [64][64], k = fr*7 + fs
-  const float* bias;         // folded BN bias [64]
+  const float* bias;         // folded BN bias [64] (NULL = zero)
   __nv_bfloat16* out;        // [n_frames][17][17][64]
+  double* stats;             // STATS kernels: per-channel sum [64] and sum of squares [64] of the conv1 outputs
 };
 
 // un-swizzled K-major descriptor: low word = addr>>4 | (LBO>>4)<<16, high word = SBO>>4 | version 1 | layout 0
@@ -112,7 +113,11 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   return r;
 }
 
-template <int MODE>
+// STATS = true: training-mode first pass.  Same operand staging and MMAs, but the epilogue only accumulates the
+// per-channel sum and sum of squares of the 34x34 conv1 outputs of every frame (batch statistics of the BatchNorm that
+// follows conv1); nothing is pooled or written.  The second pass is the normal kernel with the batch scale folded
+// into the weights and the batch shift as bias.
+template <int MODE, bool STATS = false>
 __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
   // bias step: B[n][0] = bf16(bias), B[n][1] = bf16(bias - hi) (together ~16 mantissa bits), other columns zero
   for (int idx = tid; idx < 256 * 16; idx += kS2Threads) {
     const int e = idx & 15, n = idx >> 4;
-    const float bv = p.bias[n & 63];
+    const float bv = p.bias ? p.bias[n & 63] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
     __nv_bfloat16 v = __float2bfloat16_rn(0.f);
     if (e == 0) v = hi;
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
   }
   for (uint32_t i = tid; i < kS2OnesBytes / 4; i += kS2Threads)
     reinterpret_cast<uint32_t*>(smem + kS2OffOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs
-  if (tid < 64) bias_s[tid] = p.bias[tid];
+  if (tid < 64) bias_s[tid] = p.bias ? p.bias[tid] : 0.f;
   if (MODE == 1 && tid < 256) {
     float v = (float)tid;
     if (p.standardise) v = (v - p.mean) / p.denom;
@@ -318,6 +323,70 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
     uint8_t* ring = smem + kS2OffRing;
     uint8_t* edge_hp = smem + kS2OffEdgeHp;
     uint32_t g = 0;
+    if (STATS) {
+      // per-thread running sums of this thread's 32 channels over all its rows and tiles; reduced once at the end
+      float sa[32], sq[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sa[c] = sq[c] = 0.f;
+      for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x) {
+        const int nf = (int)((p.n_frames - bi * kS2FramesPerBatch) < kS2FramesPerBatch
+                                 ? (p.n_frames - bi * kS2FramesPerBatch)
+                                 : kS2FramesPerBatch);
+        const int n_rows = nf * kS2RowsPerFrame;
+        const int n_main = (n_rows + 15) / 16;
+        for (int t = -1; t < n_main; ++t, ++g) {
+          const uint32_t acc = g & 1u;
+          mbar_wait(BAR(4 + acc), (g >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t t_row = tmem_acc + acc * 256u + ((uint32_t)(q * 32) << 16);
+          // stream row of this accumulator row and the shifts that are distinct conv outputs
+          const int yy = (t < 0) ? L : 16 * t + (L >> 3);
+          const int y = yy % kS2RowsPerFrame;
+          const bool live = (yy < n_rows) && (y < 34) && (t >= 0 || L < 80);
+          const int s_first = (t < 0) ? 2 : 0;  // edge tile: conv columns 30,31 (s = 0,1) belong to the main tiles
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {
+            const int ch0 = half * 32 + pass * 16;
+#pragma unroll
+            for (int sft = 0; sft < 4; ++sft) {
+              uint32_t v[16];
+              tmem_ld16(t_row + (uint32_t)sft * 64u + ch0, v);
+              tmem_ld_wait();
+              if (live && sft >= s_first) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  const float x = __uint_as_float(v[c]);
+                  if (pass == 0) {
+                    sa[c] += x;
+                    sq[c] = fmaf(x, x, sq[c]);
+                  } else {
+                    sa[16 + c] += x;
+                    sq[16 + c] = fmaf(x, x, sq[16 + c]);
+                  }
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(6 + acc));
+        }
+      }
+      // warp reduction over the 32 rows of the quarter, then one fp64 atomic per channel and warp
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float a = sa[c], b = sq[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (lane == 0) {
+          atomicAdd(p.stats + half * 32 + c, (double)a);
+          atomicAdd(p.stats + 64 + half * 32 + c, (double)b);
+        }
+      }
+    } else
     for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x) {
       const int nf = (int)((p.n_frames - bi * kS2FramesPerBatch) < kS2FramesPerBatch
                                ? (p.n_frames - bi * kS2FramesPerBatch)
