@@ -118,7 +118,10 @@ template <int BN, int KE = 64, int MB = 1>
 static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {
   using C = TmaCfg<BN, KE, MB>;
-  g.total_tiles = ((g.m_tiles + MB - 1) / MB) * g.n_tiles;
+  if (g.ksplit < 1) g.ksplit = 1;
+  if (g.ksplit == 1) g.kb_split = g.KB;
+  g.m_supers = (g.m_tiles + MB - 1) / MB;
+  g.total_tiles = g.m_supers * g.n_tiles * g.ksplit;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -270,9 +273,14 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
 }
 
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
-                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
+                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st, int ksplit, int64_t split_stride) {
   AVVAD_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0, "TMA gemm: K % 64, lda % 8, ldw % 8 required");
+  AVVAD_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (epi_mode == EPI_F32 && !ep.bias && !ep.relu)),
+                  "split-K needs fp32 output without bias / ReLU");
   TmaGeom g{};
+  g.ksplit = ksplit;
+  g.kb_split = (K / 64 + ksplit - 1) / ksplit;
+  g.split_stride = split_stride;
   g.mode = 0;
   g.KB = K / 64;
   g.cpb = g.KB;  // never wraps

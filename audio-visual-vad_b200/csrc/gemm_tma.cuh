@@ -48,6 +48,11 @@ struct TmaGeom {
   int h0[2], hb[2], nb[2], F[2];  // per phase: first output row, band height, bands per frame, frames per tile
   int OH, OW, stride, pad, S, cpb, KB;
   int KB2, stride2;     // K-concatenated 1x1 / stride2 / pad 0 second operand (0 = none)
+  // split-K (plain GEMM, fp32 output, no bias): split s covers K blocks [s*kb_split, (s+1)*kb_split) and writes its
+  // partial product to C + s*split_stride; the consumer sums the partials (tiny-M GEMMs such as the BPTT step would
+  // otherwise run on 32 CTAs with a 64-block K loop each)
+  int ksplit, kb_split;
+  int64_t split_stride, m_supers;
   int64_t n_frames;     // conv: frames in this launch; gemm: M
   int N;
   uint32_t bytesA[2];   // TMA box bytes per phase
@@ -195,7 +200,10 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
-      const int64_t sm = tile / g.n_tiles;
+      const int64_t sm = (tile / g.n_tiles) % g.m_supers;
+      const int split = (int)(tile / (g.n_tiles * g.m_supers));
+      const int kb0 = split * g.kb_split;
+      const int kb1 = (kb0 + g.kb_split < g.KB) ? kb0 + g.kb_split : g.KB;
       TileCoord t[MB];
       uint32_t bytes = g.bytesB;
 #pragma unroll
@@ -204,7 +212,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         bytes += g.bytesA[t[mb].phase];
       }
       int cb = 0, fr = 0, fs = 0;
-      for (int kb = 0; kb < g.KB; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {  // conv mode: kb0 = 0, kb1 = KB
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
@@ -253,9 +261,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     // ================= MMA issuer (warp-converged; one elected lane issues MMAs and commits) =================
     constexpr uint32_t idesc = make_idesc(BN);
     uint32_t it = 0, tl = 0;
-    const int kb_total = g.KB + g.KB2;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+      const int split = (int)(tile / (g.n_tiles * g.m_supers));
+      const int kbs = split * g.kb_split;
+      const int kb_total = ((kbs + g.kb_split < g.KB) ? g.kb_split : g.KB - kbs) + g.KB2;
       mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_acc + acc * kAccCols;
@@ -296,7 +306,8 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     uint32_t tl = 0;
     for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
-      const int64_t sm = tile / g.n_tiles;
+      const int64_t sm = (tile / g.n_tiles) % g.m_supers;
+      const int64_t c_off = (tile / (g.n_tiles * g.m_supers)) * g.split_stride;  // split-K partial (fp32 paths)
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       // output row of accumulator row r = q*32 + lane of every block
       const int r = q * 32 + lane;
@@ -424,7 +435,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             const int n0 = n_base + j * 32;
             if (m[mb] >= 0 && n0 < g.N) {
               const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
-              float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + m[mb] * ep.ldc + n0);
+              float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + c_off + m[mb] * ep.ldc + n0);
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 const float4 b4 = bp[c];
@@ -449,7 +460,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             tmem_ld32(t_row + mb * BN + j * 32, v);
             tmem_ld_wait();
             const int n0 = n_base + j * 32;
-            if (m[mb] >= 0 && n0 < g.N) epilogue_chunk(ep, epi_mode, v, m[mb], n0, g.N);
+            if (m[mb] >= 0 && n0 < g.N) {
+              EpiParams e2 = ep;
+              if (epi_mode == EPI_F32) e2.C = reinterpret_cast<float*>(ep.C) + c_off;
+              epilogue_chunk(e2, epi_mode, v, m[mb], n0, g.N);
+            }
           }
         }
       }
@@ -479,7 +494,8 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
                     int Cin, int Cout, int R, int S, int stride, int pad, int bn_hint, cudaStream_t st, int cat = 0,
                     double flops_override = 0.0, const SecondOperand* second = nullptr);
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
-                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
+                    const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st, int ksplit = 1,
+                    int64_t split_stride = 0);
 
 }  // namespace tc
 }  // namespace avvad

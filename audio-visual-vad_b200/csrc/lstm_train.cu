@@ -13,7 +13,7 @@
 // Gradients are returned in PyTorch's layout (gate-major rows i,f,g,o), fp32.
 #include <vector>
 
-#include "gemm_tc.cuh"
+#include "gemm_tma.cuh"
 
 namespace avvad {
 
@@ -26,6 +26,7 @@ __global__ void lstm_bwd_cell_kernel(const __nv_bfloat16* __restrict__ gates, co
                                      const float* __restrict__ w_head, const float* __restrict__ dh_rec,
                                      float* __restrict__ dc, const int32_t* __restrict__ lengths, int B, int T, int H,
                                      int t, int has_rec, __nv_bfloat16* __restrict__ dG) {
+  // dh_rec holds `has_rec` split-K partial products [has_rec][B][H] of the recurrent GEMM of step t+1
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int b = idx / H, u = idx - b * H;
@@ -41,7 +42,7 @@ __global__ void lstm_bwd_cell_kernel(const __nv_bfloat16* __restrict__ gates, co
   const float c = cst[row * H + u];
   const float cp = t > 0 ? cst[(row - 1) * H + u] : 0.f;
   float dh = dY ? dY[row * H + u] : dl[row] * w_head[u];
-  if (has_rec) dh += dh_rec[idx];
+  for (int sp = 0; sp < has_rec; ++sp) dh += dh_rec[(int64_t)sp * B * H + idx];
   const float tc = tanhf(c);
   const float d_o = dh * tc * go * (1.f - go);
   const float dcc = dh * go * (1.f - tc * tc) + dc[idx];
@@ -99,21 +100,38 @@ __global__ void deinterleave_w_kernel(const float* __restrict__ dwp, int H, int 
   out[idx] = dwp[(int64_t)(4 * u + g) * ldw + i];
 }
 
-// db[g*H+u] = sum_r dG[r][4u+g]   (one block per 64 interleaved columns; fixed-order reduction)
-__global__ void __launch_bounds__(256) bias_grad_kernel(const __nv_bfloat16* __restrict__ dG, int64_t R, int H,
-                                                        float* __restrict__ db) {
-  __shared__ float sm[4][64];
-  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int part = threadIdx.x >> 6;
-  float acc = 0.f;
-  for (int64_t r = part; r < R; r += 4) acc += __bfloat162float(dG[r * 4 * H + col]);
-  sm[part][threadIdx.x & 63] = acc;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    const float t = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
-    const int u = col >> 2, g = col & 3;
-    db[g * H + u] = t;
+// db[g*H+u] = sum_r dG[r][4u+g].  Two deterministic stages: (column block of 256, row chunk) partial sums with 16-byte
+// loads (thread = 8 columns x one of 8 row lanes), then a fixed-order sum over the row chunks.
+constexpr int kBiasChunks = 64;
+__global__ void __launch_bounds__(256) bias_grad_partial_kernel(const __nv_bfloat16* __restrict__ dG, int64_t R, int H4,
+                                                                float* __restrict__ partial) {
+  __shared__ float sm[8][256];
+  const int grp = threadIdx.x & 31, ln = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + grp * 8;
+  const int64_t rows_per = (R + kBiasChunks - 1) / kBiasChunks;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per;
+  const int64_t r1 = (r0 + rows_per < R) ? r0 + rows_per : R;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t r = r0 + ln; r < r1; r += 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(dG + r * H4 + col);
+    acc[0] += bf16lo(v.x); acc[1] += bf16hi(v.x); acc[2] += bf16lo(v.y); acc[3] += bf16hi(v.y);
+    acc[4] += bf16lo(v.z); acc[5] += bf16hi(v.z); acc[6] += bf16lo(v.w); acc[7] += bf16hi(v.w);
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sm[ln][grp * 8 + e] = acc[e];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) t += sm[l][threadIdx.x];
+  partial[(int64_t)blockIdx.y * H4 + blockIdx.x * 256 + threadIdx.x] = t;
+}
+__global__ void bias_grad_final_kernel(const float* __restrict__ partial, int H, float* __restrict__ db) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= 4 * H) return;
+  float t = 0.f;
+  for (int c = 0; c < kBiasChunks; ++c) t += partial[(int64_t)c * 4 * H + col];
+  const int u = col >> 2, g = col & 3;
+  db[g * H + u] = t;
 }
 
 // y_dim == 1 head: dW[u] = sum_r dl[r] * h[r][u]; db = sum_r dl[r].  Two-stage deterministic reduction.
@@ -186,6 +204,8 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
                        float* dx, cudaStream_t st);
+constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
+
 size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T);
 
 struct TapeView {
@@ -213,7 +233,7 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)4 * H * BTp * 2, 256);         // dG^T
   s += align_up((size_t)maxI * BTp * 2, 256);          // X^T / H_prev^T
   s += 2 * align_up((size_t)BT * maxI * 4, 256);       // dY ping-pong (f32)
-  s += 2 * align_up((size_t)B * H * 4, 256);           // dh_rec, dc
+  s += (kBpttSplit + 1) * align_up((size_t)B * H * 4, 256);  // dh_rec split-K partials, dc
   s += align_up((size_t)4 * H * maxI * 4, 256);        // dW' (interleaved)
   s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
@@ -237,7 +257,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   __nv_bfloat16* XT = (__nv_bfloat16*)take((size_t)maxI * BTp * 2);
   float* dYa = (float*)take((size_t)BT * maxI * 4);
   float* dYb = (float*)take((size_t)BT * maxI * 4);
-  float* dh_rec = (float*)take((size_t)B * H * 4);
+  float* dh_rec = (float*)take((size_t)kBpttSplit * align_up((size_t)B * H * 4, 256));
   float* dc = (float*)take((size_t)B * H * 4);
   float* dWp = (float*)take((size_t)H4 * maxI * 4);
   __nv_bfloat16* WT = (__nv_bfloat16*)take((size_t)maxI * H4 * 2);
@@ -268,7 +288,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     AVVAD_LAUNCHED();
     AVVAD_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
     for (int t = (int)T - 1; t >= 0; --t) {
-      const int has_rec = (t < (int)T - 1) ? 1 : 0;
+      const int has_rec = (t < (int)T - 1) ? kBpttSplit : 0;  // number of partial products to sum
       lstm_bwd_cell_kernel<<<(unsigned)ceil_div(B * H, 256), 256, 0, st>>>(tv.gates, tv.c, dY, dlogits, head_w32, dh_rec,
                                                                           dc, lengths, (int)B, (int)T, H, t, has_rec, dG);
       AVVAD_LAUNCHED();
@@ -276,12 +296,16 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
         tc::EpiParams ep{};
         ep.C = dh_rec;
         ep.ldc = H;
-        int rc = tc::gemm_dispatch(dG + (int64_t)t * H4, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st);
+        // M = B is tiny: split K = 4H over kBpttSplit CTAs per output tile so the step fills the GPU
+        int rc = tc::launch_tma_gemm(dG + (int64_t)t * H4, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st,
+                                     kBpttSplit, (int64_t)B * H);
         if (rc) return rc;
       }
     }
     // db (= db_ih = db_hh)
-    bias_grad_kernel<<<H4 / 64, 256, 0, st>>>(dG, BT, H, db[l]);
+    bias_grad_partial_kernel<<<dim3(H4 / 256, kBiasChunks), 256, 0, st>>>(dG, BT, H4, dWp);  // dWp is free here
+    AVVAD_LAUNCHED();
+    bias_grad_final_kernel<<<(unsigned)ceil_div(H4, 256), 256, 0, st>>>(dWp, H, db[l]);
     AVVAD_LAUNCHED();
     // dG^T [4H][BTp]
     {
