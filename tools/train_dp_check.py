@@ -29,6 +29,7 @@ def main():
     from packages.models.AV_Net import DeepVAD_AV
 
     out = {"world": world}
+    quick = os.environ.get("AVVAD_TRAIN_QUICK") == "1"  # profiling: one warm-up + one timed AV step only
     # ---- 1. gradient equivalence (audio-only)
     B, T = 8 * world, 40
     g = torch.Generator().manual_seed(0)
@@ -69,14 +70,14 @@ def main():
     v = torch.randn(Bl, Tt, 67, 67, device=dev)
     tgt = (torch.rand(Bl, Tt, 1, device=dev) > 0.5).float()
     ln = torch.full((Bl,), Tt, dtype=torch.int32, device=dev)
-    for _ in range(2):
+    for _ in range(1 if quick else 2):
         loss = tr.step((a, v), tgt, ln)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    steps = 3
+    steps = 1 if quick else 3
     for _ in range(steps):
         loss = tr.step((a, v), tgt, ln)
     e1.record()
