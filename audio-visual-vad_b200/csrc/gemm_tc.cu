@@ -96,100 +96,19 @@ void prof_end(cudaStream_t st, void* tok, int cat, double flops) {
   delete r;
 }
 
-static bool use_tma() {
-  static int v = [] {
-    const char* e = getenv("AVVAD_TMA");
-    if (e && atoi(e) == 0) return 0;
-    return tma_available() ? 1 : 0;
-  }();
-  return v != 0;
-}
-
-// Plain GEMM through whichever operand-staging engine is active (TMA by default, cp.async with AVVAD_TMA=0).
+// Plain GEMM on the TMA-fed engine.  cuTensorMapEncodeTiled is fetched from the driver at run time; a driver without
+// it cannot run this library (there is no second engine).
 int gemm_dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                   const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
-  if (use_tma()) return launch_tma_gemm(A, lda, Wt, ldw, M, N, K, ep, epi_mode, bn_hint, st);
-  AParams ap{};
-  ap.A = A;
-  ap.lda = lda;
-  return launch(A_PLAIN, ap, Wt, ldw, M, N, K, ep, epi_mode, bn_hint, st);
-}
-
-template <int BN, int AMODE>
-static int launch_t(const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int KB,
-                    const EpiParams& ep, int epi_mode, cudaStream_t st) {
-  using C = Cfg<BN, AMODE>;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_gemm_kernel<BN, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::kSmemBytes);
-  });
-  if (attr_err != cudaSuccess) {
-    set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));
+  if (!tma_available()) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable: libavvad needs a CUDA 12 driver");
     return AVVAD_ERR_CUDA;
   }
-  const int n_tiles = (int)ceil_div(N, BN);
-  const int64_t m_tiles = ceil_div(M, BM);
-  const int64_t tiles = m_tiles * n_tiles;
-  if (tiles <= 0) return AVVAD_OK;
-  AVVAD_CHECK_ARG(tiles < (1ll << 31), "too many tiles");
-  ProfRec rec{};
-  bool prof = false;
-  {
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    prof = g_prof_on && t_group_depth == 0;
-    if (prof) {
-      rec.beg = prof_event();
-      rec.end = prof_event();
-    }
-  }
-  if (prof) cudaEventRecord(rec.beg, st);
-  static int num_sms = [] {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
-  const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
-  const unsigned grid = (unsigned)(tiles < resident ? tiles : resident);
-  tc_gemm_kernel<BN, AMODE><<<grid, kThreads, C::kSmemBytes, st>>>(ap, Wt, ldw, M, N, KB, n_tiles, tiles, ep,
-                                                                    epi_mode);
-  AVVAD_LAUNCHED();
-  if (prof) {
-    cudaEventRecord(rec.end, st);
-    rec.cat = (AMODE == A_CONV) ? 0 : (AMODE == A_CONV1 ? 3 : (epi_mode == EPI_LSTM ? 2 : 1));
-    rec.flops = 2.0 * (double)M * (double)N * (double)KB * BK;
-    std::lock_guard<std::mutex> lk(g_prof_mu);
-    g_prof.push_back(rec);
-  }
-  return AVVAD_OK;
-}
-
-int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
-           const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st) {
   AVVAD_CHECK_ARG(K > 0 && K % BK == 0, "K must be a positive multiple of 64");
-  AVVAD_CHECK_ARG((reinterpret_cast<uintptr_t>(ap.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0,
+  AVVAD_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0,
                   "operands must be 16-byte aligned");
-  if (amode == A_CONV1) {
-    AVVAD_CHECK_ARG(K == 64 && N == 64 && ap.A32, "stem conv expects K=64 (49 padded), N=64");
-    return launch_t<64, A_CONV1>(ap, Wt, ldw, M, N, 1, ep, epi_mode, st);
-  }
-  AVVAD_CHECK_ARG(ldw % 8 == 0 && (amode != A_PLAIN || ap.lda % 8 == 0), "leading dimensions must be multiples of 8");
-  const int KB = K / BK;
-  int bn = bn_hint;
-  if (bn != 64 && bn != 128 && bn != 256) bn = (N <= 64) ? 64 : 128;
   if (epi_mode == EPI_LSTM) AVVAD_CHECK_ARG(N % 32 == 0, "LSTM epilogue needs N % 32 == 0");
-#define AVVAD_TC_CASE(BNV)                                                                           \
-  case BNV:                                                                                          \
-    return amode == A_PLAIN ? launch_t<BNV, A_PLAIN>(ap, Wt, ldw, M, N, KB, ep, epi_mode, st)        \
-                            : launch_t<BNV, A_CONV>(ap, Wt, ldw, M, N, KB, ep, epi_mode, st);
-  switch (bn) {
-    AVVAD_TC_CASE(64)
-    AVVAD_TC_CASE(128)
-    AVVAD_TC_CASE(256)
-  }
-#undef AVVAD_TC_CASE
-  return AVVAD_ERR_ARG;
+  return launch_tma_gemm(A, lda, Wt, ldw, M, N, K, ep, epi_mode, bn_hint, st);
 }
 
 __global__ void pack_rows_kernel(const float* __restrict__ src, int64_t ld_src, __nv_bfloat16* __restrict__ dst,
@@ -276,9 +195,6 @@ extern "C" int avvad_gemm_bf16(const void* A, int64_t lda, const void* W, int64_
                                int64_t ldc, int c_is_bf16, int relu, int64_t M, int64_t N, int64_t K, void* stream) {
   AVVAD_CHECK_ARG(A && W && Cp, "null pointer");
   AVVAD_CHECK_ARG(M > 0 && N > 0 && N < (1 << 30), "bad M/N");
-  tc::AParams ap{};
-  ap.A = (const __nv_bfloat16*)A;
-  ap.lda = lda;
   tc::EpiParams ep{};
   ep.bias = bias;
   ep.C = Cp;
@@ -297,33 +213,24 @@ extern "C" int avvad_conv2d_nhwc_bf16(const void* in, const void* w, const float
   const int OH = (H + 2 * pad - R) / stride + 1;
   const int OW = (W + 2 * pad - S) / stride + 1;
   AVVAD_CHECK_ARG(OH > 0 && OW > 0, "empty output");
-  tc::AParams ap{};
-  ap.A = (const __nv_bfloat16*)in;
-  ap.H = H; ap.W = W; ap.Cin = Cin; ap.OH = OH; ap.OW = OW; ap.R = R; ap.S = S; ap.stride = stride; ap.pad = pad;
-  ap.cpb = Cin / 64;
-  static int use_ca = [] {
-    const char* e = getenv("AVVAD_CA");
-    return e ? atoi(e) : 0;
-  }();
-  ap.use_ca = use_ca;
   tc::EpiParams ep{};
   ep.bias = bias;
   ep.residual = (const __nv_bfloat16*)residual;
   ep.C = out;
   ep.ldc = Cout;
   ep.relu = relu;
+  if (!tc::tma_available()) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable: libavvad needs a CUDA 12 driver");
+    return AVVAD_ERR_CUDA;
+  }
+  AVVAD_CHECK_ARG(OW <= 128, "output width above 128 is not supported by the TMA box tiling");
   // the slab epilogue uses 256-bit residual loads / output stores: rows must be 32-byte aligned
   const bool aligned32 = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 31) == 0;
-  if (tc::use_tma() && aligned32 && tc::slab_supported(H, W, Cin, Cout, R, S, stride, pad))
+  if (aligned32 && tc::slab_supported(H, W, Cin, Cout, R, S, stride, pad))
     return tc::launch_slab_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, Cin, Cout,
                                 (cudaStream_t)stream);
-  if (tc::use_tma() && OW <= 128)
-    return tc::launch_tma_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, W, Cin, Cout, R, S,
-                               stride, pad, bn_override(), (cudaStream_t)stream);
-  const int64_t M = n * OH * OW;
-  const int K = R * S * Cin;
-  return tc::launch(tc::A_CONV, ap, (const __nv_bfloat16*)w, K, M, Cout, K, ep, tc::EPI_BF16, bn_override(),
-                    (cudaStream_t)stream);
+  return tc::launch_tma_conv((const __nv_bfloat16*)in, (const __nv_bfloat16*)w, ep, n, H, W, Cin, Cout, R, S, stride,
+                             pad, bn_override(), (cudaStream_t)stream);
 }
 
 extern "C" int avvad_conv2d_nhwc_bf16_dual(const void* in, const void* in2, const void* w, const float* bias, void* out,
@@ -333,9 +240,9 @@ extern "C" int avvad_conv2d_nhwc_bf16_dual(const void* in, const void* in2, cons
   AVVAD_CHECK_ARG(n > 0 && H > 0 && W > 0 && H2 > 0 && W2 > 0 && R > 0 && S > 0 && stride > 0 && stride2 > 0 && pad >= 0,
                   "bad conv shape");
   AVVAD_CHECK_ARG(Cin % 64 == 0 && Cin2 % 64 == 0 && Cout % 32 == 0, "Cin, Cin2 multiples of 64 and Cout of 32");
-  if (!tc::use_tma()) {
-    set_error("dual-operand convolution needs the TMA engine");
-    return AVVAD_ERR_STATE;
+  if (!tc::tma_available()) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable: libavvad needs a CUDA 12 driver");
+    return AVVAD_ERR_CUDA;
   }
   tc::EpiParams ep{};
   ep.bias = bias;

@@ -1,19 +1,7 @@
-// bf16 tensor-core engine for sm_100a: C[M][N] = A[M][K] * W[N][K]^T with fp32 accumulation in TMEM.
-//
-// Persistent CTAs (one or two per SM) loop over 128 x BN output tiles with three warp roles:
-//   warps 0-3 (128 threads) : operand producers.  They gather 128-byte K-slices (64 bf16) of A rows and
-//                             W rows with 16-byte cp.async (zero-filling out-of-image taps / tail rows)
-//                             into the canonical K-major SWIZZLE_128B shared-memory layout, then
-//                             fence.proxy.async + mbarrier-arrive so the tensor core may read them.
-//                             The A "row" is either a plain matrix row (GEMM) or an im2col row of an
-//                             NHWC convolution (tap-major K order), so convolutions never materialise
-//                             im2col in HBM.  The ring runs ahead across tile boundaries.
-//   warp 4                  : allocates TMEM (2 accumulator stages of BN fp32 columns); its lane 0 issues
-//                             tcgen05.mma (UMMA 128 x BN x 16, kind::f16, bf16 operands from shared-memory
-//                             descriptors) and tcgen05.commit to free ring stages / publish an accumulator.
-//   warps 5-8 (128 threads) : epilogue.  tcgen05.ld TMEM -> registers -> fused bias / residual / ReLU / LSTM
-//                             cell -> global, overlapped with the next tile's main loop.
-// Pipeline: kStages-deep ring of {A 16 KB, W BN*128 B} stages (full/empty mbarriers) + tmem full/empty.
+// Shared pieces of the bf16 tensor-core engine for sm_100a (C[M][N] = A[M][K] * W[N][K]^T, fp32 accumulation in TMEM):
+// PTX wrappers (mbarrier, tcgen05.alloc / mma / commit / ld, UMMA descriptors), the epilogue parameter block and the
+// generic per-chunk epilogue (bias / residual / ReLU / LSTM cell).  The kernels live in gemm_tma.cuh (TMA-fed
+// implicit GEMM), conv_slab.cuh (3x3 slab convolution), stem_s2d.cuh (stem) and lstm_persist.cuh (recurrence).
 #pragma once
 #include "common.cuh"
 
@@ -22,20 +10,7 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per K block = 128 bytes = one swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 288;  // 4 producer warps + 1 MMA warp + 4 epilogue warps
-constexpr int kLag = 2;  // cp.async groups in flight before a stage is published
-
-enum AMode { A_PLAIN = 0, A_CONV = 1, A_CONV1 = 2 };
 enum EpiMode { EPI_BF16 = 0, EPI_F32 = 1, EPI_LSTM = 2 };
-
-struct AParams {
-  const __nv_bfloat16* A;  // plain: [M][lda]; conv: NHWC input [n][H][W][Cin]
-  const float* A32;        // A_CONV1: fp32 single-channel frames [n][H][W] (7x7 / stride 2 / pad 3 im2col, K 49 -> 64)
-  int64_t lda;
-  int H, W, Cin, OH, OW, R, S, stride, pad, cpb;  // conv only; cpb = Cin / 64
-  int use_ca;                                     // conv only: cache A gathers in L1 (tap re-reads)
-};
 
 struct EpiParams {
   const float* bias;              // [N] or null
@@ -86,18 +61,6 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
                : "memory");
@@ -186,17 +149,6 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-template <int BN, int AMODE = A_PLAIN>
-struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 3 : ((BN == 128) ? 3 : 4);
-  static constexpr uint32_t kABytes = BM * 128;
-  static constexpr uint32_t kBBytes = BN * 128;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  // resident CTAs per SM: shared memory (227 KB) and TMEM (512 columns, 2*BN per CTA) permitting
-  static constexpr int kCtasPerSm = (BN == 256) ? 1 : 2;
-};
 
 // ---- epilogue for one 32-column chunk held by one thread (row m, columns n0..n0+31) ----------------
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, const uint32_t (&v)[32], int64_t m,
@@ -312,258 +264,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, co
   }
 }
 
-// ---- the kernel -------------------------------------------------------------------------------------
-// Persistent and warp-specialised: every CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x, n-tile
-// fastest so concurrently running CTAs share A rows in L2).  The operand ring runs across tile boundaries and the
-// accumulator is double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int AMODE>
-__global__ void __launch_bounds__(kThreads)
-tc_gemm_kernel(AParams ap, const __nv_bfloat16* __restrict__ Wt, int64_t ldw, int64_t M, int N, int KB,
-               int n_tiles, int64_t total_tiles, EpiParams ep, int epi_mode) {
-  using C = Cfg<BN, AMODE>;
-  constexpr int S = C::kStages;
-  constexpr uint32_t kTmemCols = 2 * BN;  // two accumulator stages (BN in {64,128,256} -> power of two >= 32)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
-  // barriers: full[s] = bar0+8s | empty[s] = bar0+8(S+s) | tfull[a] = bar0+8(2S+a) | tempty[a] = bar0+8(2S+2+a)
-  const uint32_t bar0 = base + S * C::kStageBytes;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + S * C::kStageBytes + 8 * (2 * S + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bar0 + 8 * s, kProducerThreads);
-      mbar_init(bar0 + 8 * (S + s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar0 + 8 * (2 * S + a), 1);
-      mbar_init(bar0 + 8 * (2 * S + 2 + a), 4);  // one arrival per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 4) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
-
-  if (warp < 4) {
-    // ================= producers =================
-    const int p = threadIdx.x;
-    const int chunk = p & 7;
-    const int r0 = p >> 3;  // this thread feeds rows r0 + 16 i
-    const uint32_t sw_off = (uint32_t)(((r0 >> 3) << 10) + ((r0 & 7) << 7) + ((chunk ^ (r0 & 7)) << 4));
-    uint32_t it = 0;  // global K-block counter of this CTA (ring position)
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_base = (int)(tile % n_tiles) * BN;
-      const int64_t m_base = (tile / n_tiles) * BM;
-      const __nv_bfloat16* wrow = Wt + (int64_t)(n_base + r0) * ldw + chunk * 8;
-
-      if (AMODE == A_CONV1) {
-        // Stem convolution (7x7 / stride 2 / pad 3 on an fp32 single-channel frame, K 49 -> 64, one K block per
-        // tile): thread p builds im2col row p with read-only loads (L1 serves the overlap between neighbouring
-        // rows) and stores its 8 swizzled 16-byte chunks.
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1u;
-        mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
-        const uint32_t stage = base + s * C::kStageBytes;
-        const uint32_t sb = stage + C::kABytes + sw_off;
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-          const bool ok = (n_base + r0 + 16 * i) < N;
-          cp_async16(sb + i * 2048, ok ? (const void*)(wrow + (int64_t)i * 16 * ldw) : (const void*)Wt, ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        const int64_t m = m_base + p;
-        uint32_t pk[32];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) pk[q] = 0u;
-        if (m < M) {
-          const int ohw = ap.OH * ap.OW;
-          const int64_t n = m / ohw;
-          const int rem = (int)(m - n * ohw);
-          const int oh = rem / ap.OW, ow = rem - oh * ap.OW;
-          const float* img = ap.A32 + n * ap.H * ap.W;
-          const int ih0 = oh * 2 - 3, iw0 = ow * 2 - 3;
-          float vals[50];
-#pragma unroll
-          for (int r = 0; r < 7; ++r) {
-            const int ih = ih0 + r;
-            const bool rok = (unsigned)ih < (unsigned)ap.H;
-#pragma unroll
-            for (int c = 0; c < 7; ++c) {
-              const int iw = iw0 + c;
-              vals[r * 7 + c] = (rok && (unsigned)iw < (unsigned)ap.W) ? __ldg(img + ih * ap.W + iw) : 0.f;
-            }
-          }
-          vals[49] = 0.f;
-#pragma unroll
-          for (int q = 0; q < 25; ++q) pk[q] = pack_bf16x2(vals[2 * q], vals[2 * q + 1]);
-        }
-        const uint32_t rowoff = (uint32_t)(((p >> 3) << 10) + ((p & 7) << 7));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t dst = stage + rowoff + (uint32_t)((c ^ (p & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[4 * c]), "r"(pk[4 * c + 1]),
-                       "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3])
-                       : "memory");
-        }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(bar0 + 8 * s);
-        ++it;
-        continue;
-      }
-
-      // per-row state for the 8 A rows this thread feeds
-      int64_t a_off[8];
-      int ihw0[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t m = m_base + r0 + 16 * i;
-        if (AMODE == A_PLAIN) {
-          a_off[i] = (m < M) ? m * ap.lda + chunk * 8 : -1;
-          ihw0[i] = 0;
-        } else {
-          if (m < M) {
-            const int ohw = ap.OH * ap.OW;
-            const int64_t n = m / ohw;
-            const int rem = (int)(m - n * ohw);
-            const int oh = rem / ap.OW;
-            const int ow = rem - oh * ap.OW;
-            a_off[i] = n * ap.H * ap.W;  // pixel index of the frame origin
-            const int ih0 = oh * ap.stride - ap.pad, iw0 = ow * ap.stride - ap.pad;
-            ihw0[i] = (int)(((uint32_t)(ih0 + 1024) << 16) | (uint32_t)(iw0 + 1024));
-          } else {
-            a_off[i] = -1;
-            ihw0[i] = 0;
-          }
-        }
-      }
-
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1u;
-        mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
-        const uint32_t sa = base + s * C::kStageBytes + sw_off;
-        const uint32_t sb = sa + C::kABytes;
-        if (AMODE == A_PLAIN) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = a_off[i] >= 0;
-            cp_async16(sa + i * 2048, ok ? (const void*)(ap.A + a_off[i] + (int64_t)kb * BK) : (const void*)ap.A,
-                       ok ? 16u : 0u);
-          }
-        } else {
-          const int tap = kb / ap.cpb;
-          const int cb = kb - tap * ap.cpb;
-          const int fr = tap / ap.S;
-          const int fs = tap - fr * ap.S;
-          const int coff = cb * BK + chunk * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int ih = (int)((uint32_t)ihw0[i] >> 16) - 1024 + fr;
-            const int iw = (int)((uint32_t)ihw0[i] & 0xFFFFu) - 1024 + fs;
-            const bool ok = (a_off[i] >= 0) && ((unsigned)ih < (unsigned)ap.H) && ((unsigned)iw < (unsigned)ap.W);
-            const int64_t off = (a_off[i] + (int64_t)ih * ap.W + iw) * ap.Cin + coff;
-            cp_async16(sa + i * 2048, ok ? (const void*)(ap.A + off) : (const void*)ap.A, ok ? 16u : 0u);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < BN / 16; ++i) {
-          const bool ok = (n_base + r0 + 16 * i) < N;
-          cp_async16(sb + i * 2048,
-                     ok ? (const void*)(wrow + (int64_t)i * 16 * ldw + (int64_t)kb * BK) : (const void*)Wt,
-                     ok ? 16u : 0u);
-        }
-        cp_async_commit();
-        if (it >= (uint32_t)kLag) {
-          cp_async_wait<kLag>();
-          fence_proxy_async();
-          mbar_arrive(bar0 + 8 * ((it - kLag) % S));
-        }
-      }
-    }
-    if (AMODE != A_CONV1 && it > 0) {
-      // drain: publish the last min(kLag, it) stages
-      if (it >= 2) {
-        cp_async_wait<1>();
-        fence_proxy_async();
-        mbar_arrive(bar0 + 8 * ((it - 2) % S));
-      }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(bar0 + 8 * ((it - 1) % S));
-    }
-  } else if (warp == 4) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      uint32_t it = 0, tl = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-        mbar_wait(bar0 + 8 * (2 * S + 2 + acc), aph ^ 1u);  // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_acc + acc * BN;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1u;
-          mbar_wait(bar0 + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = base + s * C::kStageBytes;
-          const uint32_t sb = sa + C::kABytes;
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(d_tmem, make_sw128_desc(sa + k * 32), make_sw128_desc(sb + k * 32), idesc, (kb | k) != 0);
-          umma_commit(bar0 + 8 * (S + s));
-        }
-        umma_commit(bar0 + 8 * (2 * S + acc));
-      }
-    }
-  } else {
-    // ================= epilogue warps 5..8 =================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    uint32_t tl = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const int n_base = (int)(tile % n_tiles) * BN;
-      const int64_t m_base = (tile / n_tiles) * BM;
-      const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-      mbar_wait(bar0 + 8 * (2 * S + acc), aph);
-      tc_fence_after();
-      const int64_t m = m_base + q * 32 + lane;
-      const uint32_t t_row = tmem_acc + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t v[32];
-        tmem_ld32(t_row + j * 32, v);
-        tmem_ld_wait();
-        const int n0 = n_base + j * 32;
-        if (m < M && n0 < N) epilogue_chunk(ep, epi_mode, v, m, n0, N);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (2 * S + 2 + acc));
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    __syncwarp();
-    tmem_dealloc(tmem_acc, kTmemCols);
-  }
-}
-
 // ---- host-side launcher -----------------------------------------------------------------------------
-int launch(int amode, const AParams& ap, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
-           const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st);
 int prof_begin(cudaStream_t st, void** tok);
 void prof_end(cudaStream_t st, void* tok, int cat, double flops);
 int prof_group_begin(cudaStream_t st, void** tok);

@@ -13,7 +13,6 @@
 #include <mutex>
 
 #include "gemm_tma.cuh"
-#include "stem_fused.cuh"
 #include "stem_s2d.cuh"
 
 namespace avvad {
@@ -413,15 +412,6 @@ static int run_conv(avvad_resnet18* h, int layer, const __nv_bfloat16* in, const
 
 // Runs conv layers in execution order on one chunk; stops after layer `upto` (20 = run everything).
 // Returns the buffer index holding the last produced activation in *last.
-// 1 (default) = image-as-operand stem (stem_s2d.cuh); 0 = im2col-in-shared-memory stem (stem_fused.cuh, fp32 frames only)
-static int stem_mode() {
-  static int v = [] {
-    const char* e = getenv("AVVAD_STEM");
-    return (e && std::string(e) == "fused") ? 0 : 1;
-  }();
-  return v;
-}
-
 // Video source of one trunk call: fp32 frames (already standardised) or u8 frames at the source rate + the gather
 struct StemInput {
   const float* frames = nullptr;  // [n][67*67]
@@ -489,27 +479,7 @@ static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __
 }
 
 static int launch_stem(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st) {
-  if (stem_mode() == 1 || in.src) return launch_stem_s2d(h, in, n, out, st);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc::stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)tc::kStemSmem);
-  });
-  AVVAD_CUDA(attr_err);
-  static int num_sms = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  const unsigned grid = (unsigned)(n < num_sms ? n : num_sms);
-  void* tok = nullptr;
-  tc::prof_begin(st, &tok);
-  tc::stem_fused_kernel<<<grid, tc::kStemThreads, tc::kStemSmem, st>>>(in.frames + in.first * kFrameHW, n, h->w1b,
-                                                                       h->bias[0], out);
-  AVVAD_LAUNCHED();
-  tc::prof_end(st, tok, 3, 2.0 * (double)n * 1156 * 64 * 49);
-  return AVVAD_OK;
+  return launch_stem_s2d(h, in, n, out, st);
 }
 
 // per-frame elements of a stage's input / output activation and its tensor-core MACs per frame
