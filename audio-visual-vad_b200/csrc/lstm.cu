@@ -199,11 +199,12 @@ struct TapeView {
 };
 TapeView tape_layer(void* tape, int l, int H, int64_t B, int64_t T);
 int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
-                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const __nv_bfloat16* head_w16,
+                       const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
                        float* dx, cudaStream_t st);
-size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T);
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T);
 }  // namespace avvad
 
 namespace {
@@ -516,7 +517,7 @@ extern "C" int avvad_lstm_forward_train(avvad_lstm* h, const void* x_bf16, const
 
 extern "C" size_t avvad_lstm_backward_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T) {
   if (!h || B <= 0 || T <= 0) return 0;
-  return lstm_backward_workspace(h->layers, h->input_size, h->ld0, h->H, B, T);
+  return lstm_backward_workspace(h->layers, h->input_size, h->ld0, h->H, h->y_dim, B, T);
 }
 
 // dlogits f32 [B][T][1] (e.g. from avvad_bce_loss).  Gradients in PyTorch layout, fp32: dW_ih[l] [4H][I_l],
@@ -528,7 +529,8 @@ extern "C" int avvad_lstm_backward(avvad_lstm* h, const void* x_bf16, const int3
                                    float* db_head, float* dx, void* stream) {
   AVVAD_CHECK_ARG(h && x_bf16 && lengths && tape && dlogits && workspace && dW_ih && dW_hh && db && dW_head && db_head,
                   "null pointer");
-  return lstm_backward_impl(h->layers, h->input_size, h->ld0, h->H, h->y_dim, h->w_ih, h->w_hh, h->head_w32, x_bf16,
+  return lstm_backward_impl(h->layers, h->input_size, h->ld0, h->H, h->y_dim, h->w_ih, h->w_hh, h->head_w32,
+                            h->head_w16, x_bf16,
                             lengths, B, T, tape, dlogits, workspace, workspace_bytes, dW_ih, dW_hh, db, dW_head, db_head,
                             dx, (cudaStream_t)stream);
 }

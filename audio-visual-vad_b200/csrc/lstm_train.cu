@@ -134,6 +134,28 @@ __global__ void bias_grad_final_kernel(const float* __restrict__ partial, int H,
   db[g * H + u] = t;
 }
 
+// W_head bf16 [y][H] -> W_head^T as the GEMM's B operand [N = H][K = yp] (zero columns past y)
+__global__ void head_wt_kernel(const __nv_bfloat16* __restrict__ w, int y, int H, int yp, __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)H * yp) return;
+  const int u = (int)(idx / yp), k = (int)(idx - (int64_t)u * yp);
+  out[idx] = (k < y) ? w[(int64_t)k * H + u] : __float2bfloat16_rn(0.f);
+}
+// out[c] = sum_r x[r][c]  (fp32, 64 columns per block, fixed-order reduction over four row lanes)
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ x, int64_t R, int Ccols,
+                                                         float* __restrict__ out) {
+  __shared__ float sm[4][64];
+  const int col = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int part = threadIdx.x >> 6;
+  float acc = 0.f;
+  if (col < Ccols)
+    for (int64_t r = part; r < R; r += 4) acc += x[r * Ccols + col];
+  sm[part][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (threadIdx.x < 64 && col < Ccols)
+    out[col] = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
+}
+
 // y_dim == 1 head: dW[u] = sum_r dl[r] * h[r][u]; db = sum_r dl[r].  Two-stage deterministic reduction.
 __global__ void __launch_bounds__(256) head_grad_partial_kernel(const float* __restrict__ dl,
                                                                 const __nv_bfloat16* __restrict__ h, int64_t R, int H,
@@ -200,13 +222,14 @@ extern "C" int avvad_adam_step(float* param, const float* grad, float* exp_avg, 
 namespace avvad {
 // exposed to lstm.cu
 int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
-                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const __nv_bfloat16* head_w16,
+                       const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
                        float* dx, cudaStream_t st);
 constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
 
-size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T);
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T);
 
 struct TapeView {
   __nv_bfloat16* gates;
@@ -224,7 +247,9 @@ TapeView tape_layer(void* tape, int l, int H, int64_t B, int64_t T) {
   return v;
 }
 
-size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int64_t B, int64_t T) {
+static int64_t head_pad(int y_dim) { return ((int64_t)y_dim + 63) / 64 * 64; }
+
+size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T) {
   (void)layers; (void)input_size;
   const int64_t BT = B * T, BTp = (BT + 63) / 64 * 64;
   const int64_t maxI = ld0 > H ? ld0 : H;
@@ -237,16 +262,24 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)4 * H * maxI * 4, 256);        // dW' (interleaved)
   s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
+  if (y_dim > 1) {
+    const int64_t yp = head_pad(y_dim);
+    s += align_up((size_t)BT * yp * 2, 256);           // dlogits bf16, padded columns
+    s += align_up((size_t)yp * BTp * 2, 256);          // its transpose
+    s += align_up((size_t)H * yp * 2, 256);            // W_head^T bf16 [H][yp]
+  }
   return s + 1024;
 }
 
 int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
-                       __nv_bfloat16* const* w_hh, const float* head_w32, const void* x_bf16, const int32_t* lengths,
+                       __nv_bfloat16* const* w_hh, const float* head_w32, const __nv_bfloat16* head_w16,
+                       const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
                        float* dx, cudaStream_t st) {
-  AVVAD_CHECK_ARG(y_dim == 1, "LSTM backward currently supports y_dim == 1 (the VAD head)");
-  AVVAD_CHECK_ARG(workspace_bytes >= lstm_backward_workspace(layers, input_size, ld0, H, B, T), "workspace too small");
+  AVVAD_CHECK_ARG(y_dim >= 1, "bad y_dim");
+  AVVAD_CHECK_ARG(workspace_bytes >= lstm_backward_workspace(layers, input_size, ld0, H, y_dim, B, T),
+                  "workspace too small");
   const int64_t BT = B * T, BTp = (BT + 63) / 64 * 64;
   const int64_t maxI = ld0 > H ? ld0 : H;
   const int H4 = 4 * H;
@@ -263,8 +296,9 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   __nv_bfloat16* WT = (__nv_bfloat16*)take((size_t)maxI * H4 * 2);
   float* partial = (float*)take((size_t)1024 * (H + 1) * 4);
 
-  // ---- head gradients (y_dim == 1): dl = dlogits [BT]
-  {
+  const float* dY_head = nullptr;  // y_dim > 1: gradient of the top layer's output through the head (GEMM)
+  if (y_dim == 1) {
+    // ---- head gradients (y_dim == 1): dl = dlogits [BT]
     TapeView top = tape_layer(tape, layers - 1, H, B, T);
     int nblocks = (int)std::min<int64_t>(1024, ceil_div(BT, 64));
     int rows_per_block = (int)ceil_div(BT, nblocks);
@@ -273,10 +307,48 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     AVVAD_LAUNCHED();
     head_grad_final_kernel<<<(unsigned)ceil_div(H + 1, 256), 256, 0, st>>>(partial, nblocks, H, dW_head, db_head);
     AVVAD_LAUNCHED();
+  } else {
+    // ---- head gradients (IBM head, y_dim = 513): three GEMMs on bf16 copies of dlogits
+    //   dY_top [BT][H]   = dL [BT][yp] * W_head [yp][H]
+    //   dW_head [y][H]   = dL^T [yp][BT] * h_top [BT][H]
+    //   db_head [y]      = column sums of dL (fp32)
+    const int64_t yp = head_pad(y_dim);
+    __nv_bfloat16* dl16 = (__nv_bfloat16*)take((size_t)BT * yp * 2);
+    __nv_bfloat16* dlT = (__nv_bfloat16*)take((size_t)yp * BTp * 2);
+    __nv_bfloat16* WTh = (__nv_bfloat16*)take((size_t)H * yp * 2);
+    TapeView top = tape_layer(tape, layers - 1, H, B, T);
+    int rc = avvad_pack_rows_bf16(dlogits, y_dim, dl16, yp, 0, BT, y_dim, 1, st);
+    if (rc) return rc;
+    head_wt_kernel<<<(unsigned)ceil_div((int64_t)H * yp, 256), 256, 0, st>>>(head_w16, y_dim, H, (int)yp, WTh);
+    AVVAD_LAUNCHED();
+    {
+      tc::EpiParams ep{};
+      ep.C = dYa;
+      ep.ldc = H;
+      rc = tc::gemm_dispatch(dl16, yp, WTh, yp, BT, H, (int)yp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      dY_head = dYa;
+    }
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(yp, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(dl16, BT, (int)yp, yp, BTp, 0, (int)T, dlT);
+      AVVAD_LAUNCHED();
+      dim3 grid2((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H, 32));
+      transpose_bf16_kernel<<<grid2, dim3(32, 8), 0, st>>>(top.hseq, BT, H, H, BTp, 0, (int)T, XT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dWp;
+      ep.ldc = H;
+      rc = tc::gemm_dispatch(dlT, BTp, XT, BTp, yp, H, (int)BTp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      AVVAD_CUDA(cudaMemcpyAsync(dW_head, dWp, (size_t)y_dim * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    colsum_f32_kernel<<<(unsigned)ceil_div(y_dim, 64), 256, 0, st>>>(dlogits, BT, y_dim, db_head);
+    AVVAD_LAUNCHED();
   }
 
-  const float* dY = nullptr;  // null: top layer takes dl * w_head on the fly
-  float* dX_out = dYa;
+  const float* dY = dY_head;  // null (y_dim == 1): the top layer takes dl * w_head on the fly
+  float* dX_out = dY_head ? dYb : dYa;
   for (int l = layers - 1; l >= 0; --l) {
     TapeView tv = tape_layer(tape, l, H, B, T);
     const int64_t ld_in = (l == 0) ? ld0 : H;

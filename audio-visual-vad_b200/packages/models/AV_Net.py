@@ -79,8 +79,6 @@ class DeepVAD_AV(nn.Module):
         if need_grad and any(p.requires_grad for p in self.features.parameters()):
             raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze "
                                       "'features' as scripts/train_AV_net.py:241-245 does")
-        if need_grad and self.y_dim != 1:
-            raise NotImplementedError("device-side BPTT is implemented for the VAD head (y_dim == 1)")
 
         # ---- video branch: batch-statistics BN while the module is in train() (train_AV_net.py:253), folded BN in eval()
         def trunk(feat_bf16=None, col_off=0, want_f32=True):

@@ -48,8 +48,6 @@ class DeepVAD_audio(nn.Module):
         E.pack_rows_bf16(x.detach().to(torch.float32).reshape(B * T, F).contiguous(), xb.view(B * T, -1), 0, False)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # training step: forward keeps a tape, loss.backward() runs BPTT on the device
-            if self.y_dim != 1:
-                raise NotImplementedError("device-side BPTT is implemented for the VAD head (y_dim == 1)")
             return LstmHeadFunction.apply(eng["lstm"], xb, lengths, x if x.requires_grad else None,
                                           *lstm_params(self.lstm_audio, self.vad_audio))
         logits, post, dec, _ = eng["lstm"].forward(xb, lengths, want_post=return_posteriors,

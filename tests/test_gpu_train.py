@@ -158,3 +158,33 @@ def test_av_training_step_matches_autograd(use_mcb):
     for k, e in report.items():
         assert e < 6e-2, report
     assert int(m.features[1].num_batches_tracked) == 1
+
+
+def test_ibm_head_training_gradients_match_autograd():
+    """labels = 'ibm_labels' (y_dim = 513, scripts/train_AV_net.py:65-66): the head backward is three GEMMs instead of
+    the rank-1 VAD path; loss and every gradient against fp32 autograd of the oracle."""
+    from packages.models.Audio_Net import DeepVAD_audio
+    B, T = 4, 20
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, 513, generator=g)
+    y = (torch.rand(B, T, 513, generator=g) > 0.5).float()
+    lens = [20, 13, 20, 6]
+    sd = synth.seeded_state_dict(synth.model_spec("audio", y_dim=513), seed=31)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref_logits = om.deepvad_audio_forward(x, lens, p)
+    ref_loss = om.batch_loss(ref_logits, y, lens, 1e-8)
+    ref_loss.backward()
+    m = DeepVAD_audio(2, 1024, 513)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    logits = m(x.cuda(), lens)
+    assert logits.shape == (B, T, 513) and logits.requires_grad
+    loss, per, dl = E.batch_bce(logits, y.cuda(), lens, 1e-8, want_grad=True)
+    assert abs(loss.item() - ref_loss.item()) < 2e-2 * max(1.0, abs(ref_loss.item()))
+    logits.backward(dl)
+    report = {}
+    for k, q in m.named_parameters():
+        st = err_stats(q.grad.cpu().numpy(), p[k].grad.numpy())
+        report[k] = round(st["rel_fro"], 4)
+        assert st["rel_fro"] < 3e-2, (k, st)
+    print("ibm-head grad rel errors:", report)
