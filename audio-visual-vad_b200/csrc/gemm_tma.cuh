@@ -435,16 +435,28 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             const int n0 = n_base + j * 32;
             if (m[mb] >= 0 && n0 < g.N) {
               const float4* bp = reinterpret_cast<const float4*>(bias_s + n0);
-              float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.C) + c_off + m[mb] * ep.ldc + n0);
+              float* crow = reinterpret_cast<float*>(ep.C) + c_off + m[mb] * ep.ldc + n0;
+              const bool wide32 = (reinterpret_cast<uintptr_t>(crow) & 31) == 0;  // 256-bit stores when aligned
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float4 b4 = bp[c];
-                float4 o = make_float4(__uint_as_float(v[4 * c + 0]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
-                                       __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
+              for (int c = 0; c < 4; ++c) {
+                const float4 ba = bp[2 * c], bb = bp[2 * c + 1];
+                float o[8] = {__uint_as_float(v[8 * c + 0]) + ba.x, __uint_as_float(v[8 * c + 1]) + ba.y,
+                              __uint_as_float(v[8 * c + 2]) + ba.z, __uint_as_float(v[8 * c + 3]) + ba.w,
+                              __uint_as_float(v[8 * c + 4]) + bb.x, __uint_as_float(v[8 * c + 5]) + bb.y,
+                              __uint_as_float(v[8 * c + 6]) + bb.z, __uint_as_float(v[8 * c + 7]) + bb.w};
                 if (ep.relu) {
-                  o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] = fmaxf(o[e], 0.f);
                 }
-                cp[c] = o;
+                if (wide32) {
+                  u32x8 w;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) w.v[e] = __float_as_uint(o[e]);
+                  st_global_256(crow + 8 * c, w);
+                } else {
+                  reinterpret_cast<float4*>(crow + 8 * c)[0] = make_float4(o[0], o[1], o[2], o[3]);
+                  reinterpret_cast<float4*>(crow + 8 * c)[1] = make_float4(o[4], o[5], o[6], o[7]);
+                }
               }
             }
           }
