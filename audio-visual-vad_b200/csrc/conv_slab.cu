@@ -82,7 +82,7 @@ static bool plan(int H, int Cin, int Cout, SlabPlan* out) {
   return true;
 }
 
-template <int BN, bool RES>
+template <int BN, bool RES, int MBC = 0>
 static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep, size_t smem, double flops,
                     cudaStream_t st) {
   static std::mutex mu;
@@ -90,7 +90,7 @@ static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep
   {
     std::lock_guard<std::mutex> lk(mu);
     if (smem > attr_set) {
-      AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES, MBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = smem;
     }
   }
@@ -102,7 +102,7 @@ static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep
   const unsigned grid = (unsigned)(g.total_tiles < num_sms ? g.total_tiles : num_sms);
   void* tok = nullptr;
   prof_begin(st, &tok);
-  tc_slab_kernel<BN, RES><<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
+  tc_slab_kernel<BN, RES, MBC><<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
   AVVAD_LAUNCHED();
   prof_end(st, tok, 0, flops);
   return AVVAD_OK;
@@ -135,6 +135,7 @@ int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiP
   rc = encode_weight_map(&maps.b, w, (uint64_t)9 * Cin, (uint64_t)Cout, (uint32_t)p.bn);
   if (rc) return rc;
   const double flops = 2.0 * (double)n * H * H * Cout * 9.0 * Cin;
+  if (p.resident && p.mb == 3) return launch_k<64, true, 3>(maps, g, ep, p.smem, flops, st);
   if (p.resident) return launch_k<64, true>(maps, g, ep, p.smem, flops, st);
   return launch_k<64, false>(maps, g, ep, p.smem, flops, st);
 }

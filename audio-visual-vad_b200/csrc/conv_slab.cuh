@@ -40,7 +40,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t saddr, int use_b
 }
 
 // dynamic smem: [slab 0][slab 1][weights: resident KB tiles or ring][barriers]
-template <int BN, bool RESIDENT_B>
+// MBC > 0: the number of accumulator blocks per tile is a compile-time constant (3 for the 17x17 maps of layer1), so the
+// 9 x MBC x 4 MMAs of a channel block are straight-line code with immediate descriptor offsets -- the issuing thread
+// was spending ~45 % of its slots on short-scoreboard stalls (constant-bank reloads, loop arithmetic) between
+// 48-cycle MMAs.  MBC = 0 keeps the generic loops.
+template <int BN, bool RESIDENT_B, int MBC = 0>
 __global__ void __launch_bounds__(kSlabThreads)
 tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,19 +154,39 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
         if (RESIDENT_B) {
           // every tap of this channel block in one elected region: 9 x mb x 4 MMAs issued back to back
           if (elect_one_sync()) {
+            const int Wp = g.Wp, cpb = g.cpb;
+            const uint32_t d0 = tmem_acc + acc * acc_cols;
+            if (MBC > 0) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t w_lo = desc_lo(w_base + (uint32_t)(tap * cpb + cb) * b_tile);
+                const int fr = tap / 3, fs = tap - fr * 3;
+                // descriptor low words count 16-byte units: one slab row = 8, one accumulator block (128 rows) = 1024
+                const uint32_t a0 = slab_lo + (uint32_t)(fr * Wp + fs) * 8u;
+                const uint32_t first = (cb | tap) != 0;
+#pragma unroll
+                for (int m = 0; m < MBC; ++m) {
+                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u, w_lo, idesc, first);
+                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 2, w_lo + 2, idesc, 1);
+                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 4, w_lo + 4, idesc, 1);
+                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 6, w_lo + 6, idesc, 1);
+                }
+              }
+            } else {
+              const int mb = g.mb;
 #pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t w_lo = desc_lo(w_base + (uint32_t)(tap * g.cpb + cb) * b_tile);
-              const int fr = tap / 3, fs = tap - fr * 3;
-              // descriptor low words count 16-byte units: one slab row = 8, one accumulator block (128 rows) = 1024
-              uint32_t a_lo = slab_lo + (uint32_t)(fr * g.Wp + fs) * 8u;
-              uint32_t d_tmem = tmem_acc + acc * acc_cols;
-              const uint32_t first = (cb | tap) != 0;
-              for (int m = 0; m < g.mb; ++m, a_lo += 1024u, d_tmem += BN) {
-                umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
-                umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
-                umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
-                umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t w_lo = desc_lo(w_base + (uint32_t)(tap * cpb + cb) * b_tile);
+                const int fr = tap / 3, fs = tap - fr * 3;
+                uint32_t a_lo = slab_lo + (uint32_t)(fr * Wp + fs) * 8u;
+                uint32_t d_tmem = d0;
+                const uint32_t first = (cb | tap) != 0;
+                for (int m = 0; m < mb; ++m, a_lo += 1024u, d_tmem += BN) {
+                  umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
+                  umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
+                  umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
+                  umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+                }
               }
             }
             umma_commit(BAR(2 + sb));
