@@ -308,14 +308,6 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
       return e ? atoi(e) : 0;
     }();
     g.variant = variant;
-    // AVVAD_LSTM_TRACE=<path>: clock64 stamps of CTA 0 (8 per step) dumped after the launch -- diagnosis only
-    static const char* trace_path = getenv("AVVAD_LSTM_TRACE");
-    long long* trace_dev = nullptr;
-    if (trace_path) {
-      AVVAD_CUDA(cudaMalloc(&trace_dev, sizeof(long long) * 8 * (size_t)T));
-      AVVAD_CUDA(cudaMemsetAsync(trace_dev, 0, sizeof(long long) * 8 * (size_t)T, st));
-    }
-    g.trace = trace_dev;
     g.gates_out = gates_out ? gates_out + g0 * T * 4 * H : nullptr;
     g.c_out = c_out ? c_out + g0 * T * H : nullptr;
     AVVAD_CUDA(cudaMemsetAsync(counters, 0, 4096, st));
@@ -369,18 +361,6 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     } else {
       AVVAD_CUDA(cudaLaunchCooperativeKernel((const void*)tc::lstm_persist_kernel, dim3(n_ctas),
                                              dim3(tc::kLstmThreads), args, smem, st));
-    }
-    if (trace_dev) {
-      std::vector<long long> hbuf(8 * (size_t)T);
-      cudaStreamSynchronize(st);
-      cudaMemcpy(hbuf.data(), trace_dev, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-      cudaFree(trace_dev);
-      if (FILE* f = fopen(trace_path, "w")) {
-        for (int64_t t = 0; t < T; ++t) {
-          for (int k = 0; k < 8; ++k) fprintf(f, "%lld%c", hbuf[t * 8 + k], k == 7 ? '\n' : ' ');
-        }
-        fclose(f);
-      }
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     tc::prof_end(st, tok, 2, 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1));
