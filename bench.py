@@ -344,9 +344,9 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
                      # dram__bytes_read+write per conv launch, averaged over the 16 launches of one 20,288-frame pass
-                     # (profiles/r01c_final_engine.md; ncu --set full, one capture); algorithmic operand bytes of the
+                     # (profiles/r01d_end_of_round.md; ncu --set full, one capture); algorithmic operand bytes of the
                      # same 16 launches: 17.3 GB = 1.08 GB per launch
-                     "traffic": 1.063e9, "traffic_unit": "bytes per launch (ncu dram bytes, avg of the 16 conv launches "
+                     "traffic": 1.037e9, "traffic_unit": "bytes per launch (ncu dram bytes, avg of the 16 conv launches "
                                                          "of one 64-utterance pass)",
                      "algorithmic_flops_per_frame": 2 * CONV_MAC_PER_FRAME,
                      "peak_source": peak_src,
