@@ -22,8 +22,9 @@
 // only; a batch of 2 frames is 5 such tiles + 1 edge tile.
 //
 //   warps 0-7  : builders  (global -> registers one frame ahead -> planes; double-buffered batches)
-//   warp  8    : TMEM alloc; lane 0 issues the MMAs
-//   warps 9-16 : epilogue  (TMEM -> horizontal pool -> ring; then vertical pool -> global)
+//   warp  8    : TMEM alloc; one elected lane issues the MMAs
+//   warps 9-16 : epilogue  (TMEM -> horizontal pool -> ring; then vertical pool -> global); two warps per TMEM lane
+//                quarter, 32 channels each (two 16-channel passes per tile)
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -32,8 +33,12 @@ namespace tc {
 
 constexpr int kS2Builders = 256;
 constexpr int kS2BuilderWarps = kS2Builders / 32;
+constexpr int kS2EpiWarps = 8;                         // two per TMEM lane quarter (16 warps measured slower: 3.1 vs 2.65 ms)
+constexpr int kS2EpiThreads = kS2EpiWarps * 32;
+constexpr int kS2ChPerWarp = 64 / (kS2EpiWarps / 4);   // channels of a row one epilogue warp owns (32)
+constexpr int kS2Passes = kS2ChPerWarp / 16;           // 16-channel passes per tile and warp
 constexpr int kS2Items = (67 * 37 + kS2Builders - 1) / kS2Builders;  // (row, pixel pair) items per builder thread and frame
-constexpr int kS2Threads = kS2Builders + 32 + 256;
+constexpr int kS2Threads = kS2Builders + 32 + kS2EpiThreads;
 constexpr int kS2FramesPerBatch = 2;
 constexpr int kS2RowsPerFrame = 37;                    // plane rows per frame: y = 0..36 (34 outputs + 3 filter-row halo)
 constexpr int kS2Pitch = 160;                          // bytes per plane row: 80 bf16 pixels (73 used)
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
       mbar_init(BAR(0 + i), kS2Builders);  // planes full: every builder thread arrives after its proxy fence
       mbar_init(BAR(2 + i), 1);            // planes empty: tcgen05.commit
       mbar_init(BAR(4 + i), 1);            // accumulator full: tcgen05.commit
-      mbar_init(BAR(6 + i), 8);            // accumulator empty: one arrival per epilogue warp
+      mbar_init(BAR(6 + i), kS2EpiWarps);  // accumulator empty: one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -315,19 +320,19 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
     }
   } else {
     // ======================= epilogue: the last 8 warps =======================
-    const int ew = warp - (kS2BuilderWarps + 1);  // 0..7
+    const int ew = warp - (kS2BuilderWarps + 1);  // 0..kS2EpiWarps-1
     const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = ew >> 2;          // channel half: [32*half, 32*half + 32)
-    const int etid = tid - (kS2Builders + 32);  // 0..255
+    const int half = ew >> 2;          // channel group: [kS2ChPerWarp*half, kS2ChPerWarp*(half+1))
+    const int etid = tid - (kS2Builders + 32);  // 0..kS2EpiThreads-1
     const int L = q * 32 + lane;       // accumulator row
     uint8_t* ring = smem + kS2OffRing;
     uint8_t* edge_hp = smem + kS2OffEdgeHp;
     uint32_t g = 0;
     if (STATS) {
       // per-thread running sums of this thread's 32 channels over all its rows and tiles; reduced once at the end
-      float sa[32], sq[32];
+      float sa[kS2ChPerWarp], sq[kS2ChPerWarp];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) sa[c] = sq[c] = 0.f;
+      for (int c = 0; c < kS2ChPerWarp; ++c) sa[c] = sq[c] = 0.f;
       for (int64_t bi = blockIdx.x; bi < n_batches; bi += gridDim.x) {
         const int nf = (int)((p.n_frames - bi * kS2FramesPerBatch) < kS2FramesPerBatch
                                  ? (p.n_frames - bi * kS2FramesPerBatch)
@@ -345,8 +350,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
           const bool live = (yy < n_rows) && (y < 34) && (t >= 0 || L < 80);
           const int s_first = (t < 0) ? 2 : 0;  // edge tile: conv columns 30,31 (s = 0,1) belong to the main tiles
 #pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            const int ch0 = half * 32 + pass * 16;
+          for (int pass = 0; pass < kS2Passes; ++pass) {
+            const int ch0 = half * kS2ChPerWarp + pass * 16;
 #pragma unroll
             for (int sft = 0; sft < 4; ++sft) {
               uint32_t v[16];
@@ -356,12 +361,12 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                   const float x = __uint_as_float(v[c]);
-                  if (pass == 0) {
+                  if (kS2Passes == 1 || pass == 0) {
                     sa[c] += x;
                     sq[c] = fmaf(x, x, sq[c]);
                   } else {
-                    sa[16 + c] += x;
-                    sq[16 + c] = fmaf(x, x, sq[16 + c]);
+                    sa[(16 + c) % kS2ChPerWarp] += x;
+                    sq[(16 + c) % kS2ChPerWarp] = fmaf(x, x, sq[(16 + c) % kS2ChPerWarp]);
                   }
                 }
               }
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
       }
       // warp reduction over the 32 rows of the quarter, then one fp64 atomic per channel and warp
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < kS2ChPerWarp; ++c) {
         float a = sa[c], b = sq[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -382,8 +387,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
           b += __shfl_xor_sync(0xffffffffu, b, o);
         }
         if (lane == 0) {
-          atomicAdd(p.stats + half * 32 + c, (double)a);
-          atomicAdd(p.stats + 64 + half * 32 + c, (double)b);
+          atomicAdd(p.stats + half * kS2ChPerWarp + c, (double)a);
+          atomicAdd(p.stats + 64 + half * kS2ChPerWarp + c, (double)b);
         }
       }
     } else
@@ -401,8 +406,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         if (t < 0) {
           // edge tile: row L = stream row yy; shifts s = 1,2,3 are conv columns 31,32,33 -> pooled column 16
 #pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            const int ch0 = half * 32 + pass * 16;
+          for (int pass = 0; pass < kS2Passes; ++pass) {
+            const int ch0 = half * kS2ChPerWarp + pass * 16;
             uint32_t v1[16], v2[16], v3[16];
             tmem_ld16(t_row + 64u + ch0, v1);
             tmem_ld16(t_row + 128u + ch0, v2);
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(6 + acc));
-          named_bar_sync(1, 256);  // edge_hp complete before any vertical pooling of this batch
+          named_bar_sync(1, kS2EpiThreads);  // edge_hp complete before any vertical pooling of this batch
           continue;
         }
         // main tile: row L = anchor (stream row yy = 16t + L/8, i = L%8): conv columns 4i+s, pooled 2i and 2i+1
@@ -434,8 +439,8 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         const int i = L & 7;
         uint8_t* rrow = ring + (uint32_t)(yy & (kS2RingRows - 1)) * kS2RingRowBytes;
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int ch0 = half * 32 + pass * 16;
+        for (int pass = 0; pass < kS2Passes; ++pass) {
+          const int ch0 = half * kS2ChPerWarp + pass * 16;
           uint32_t v0[16], v1[16], v2[16], v3[16];
           tmem_ld16(t_row + ch0, v0);
           tmem_ld16(t_row + 64u + ch0, v1);
@@ -471,12 +476,12 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(6 + acc));
-        named_bar_sync(1, 256);  // this tile's ring rows are visible to all epilogue warps
+        named_bar_sync(1, kS2EpiThreads);  // this tile's ring rows are visible to all epilogue warps
 
         // vertical pool: every odd conv row y = 2ph+1 inside this tile completes pooled row ph (rows y-2, y-1, y).
         // thread = (16-byte channel chunk ch, row pair rr of the tile, column group pg); columns pg, pg+4, ...
         {
-          const int ch = etid & 7, rr = (etid >> 3) & 7, pg = etid >> 6;
+          const int ch = etid & 7, rr = (etid >> 3) & 7, pg = etid >> 6;  // pg in [0, kS2EpiThreads / 64)
           // candidate stream rows 16t + 2rr + {0,1}: the one whose in-frame row y is odd is the trigger
           int ys = 16 * t + 2 * rr;
           int fi = (ys >= kS2RowsPerFrame) ? 1 : 0;
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
             const bool top = (y >= 2);  // pooled row 0 has no conv row -1
             __nv_bfloat16* orow = p.out + ((bi * kS2FramesPerBatch + fi) * 17 + ph) * (17 * 64) + ch * 8;
 #pragma unroll
-            for (int pw = pg; pw < 17; pw += 4) {
+            for (int pw = pg; pw < 17; pw += kS2EpiThreads / 64) {
               uint4 a, b, c;
               if (pw < 16) {
                 const uint32_t off = (uint32_t)pw * 128u + (uint32_t)((ch ^ (pw >> 1)) << 4);
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
             }
           }
         }
-        named_bar_sync(1, 256);  // ring rows of tile t-1 may be overwritten by tile t+1 from here on
+        named_bar_sync(1, kS2EpiThreads);  // ring rows of tile t-1 may be overwritten by tile t+1 from here on
       }
     }
   }
