@@ -350,9 +350,12 @@ def run_ours(args, rank, world, local_rank):
                                                          "of one 64-utterance pass)",
                      "algorithmic_flops_per_frame": 2 * CONV_MAC_PER_FRAME,
                      "peak_source": peak_src,
-                     "launches": int(conv_n), "kernel_ms_per_step": conv_ms / args.steps,
+                     # one CUDA-event record brackets the four convolution launches of a ResNet stage and trunk pass
+                     "launches": int(conv_n) * 4, "event_records": int(conv_n),
+                     "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
-                     "flops_per_launch_avg": conv_flops / conv_n if conv_n else None},
+                     "flops_per_launch_avg": conv_flops / (conv_n * 4) if conv_n else None,
+                     "ms_per_launch_avg": conv_ms / (conv_n * 4) if conv_n else None},
         "variants": {"dedup_video": {
             "value": frames_per_step * args.steps / (dedup_ms / 1e3), "unit": "frames/s",
             "ms_per_step": dedup_ms / args.steps,
