@@ -124,14 +124,15 @@ int avvad_resnet18_set_conv(avvad_resnet18* h, int layer, const float* w, const 
                             const float* beta, const float* mean, const float* var, float bn_eps,
                             void* stream);
 
+/* Workspace of one forward call: four rotating NHWC bf16 activation buffers of min(n_frames, chunk_frames) frames
+ * (36,992 bytes per frame each).  chunk_frames <= 0 selects 2048; large passes are faster (one launch per layer and
+ * pass), the Python engine uses 24,576. */
 size_t avvad_resnet18_workspace_bytes(int64_t n_frames, int64_t chunk_frames);
 
 /* frames : f32 [n_frames][67][67] device (already standardised, as the reference's forward gets)
  * feat   : f32 [n_frames][512] device (may be NULL)
  * feat_bf16 : optional bf16 [n_frames][ld_bf16] destination written at column col_off (the LSTM
- *          operand buffer of the concat fusion), may be NULL
- * debug_act : optional; when non-NULL must hold n_frames*17*17*64 bf16 and receives the
- *          activations after layer `debug_layer` (tests only), for the FIRST chunk. */
+ *          operand buffer of the concat fusion), may be NULL */
 int avvad_resnet18_forward(avvad_resnet18* h, const float* frames, int64_t n_frames,
                            int64_t chunk_frames, void* workspace, size_t workspace_bytes,
                            float* feat, void* feat_bf16, int64_t ld_bf16, int64_t col_off,
