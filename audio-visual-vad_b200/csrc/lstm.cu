@@ -5,10 +5,12 @@
 // -> nn.Linear), scripts/evaluate_AV_net.py:239-240.  nn.LSTM: gates i,f,g,o; c' = s(f)c + s(i)tanh(g);
 // h' = s(o)tanh(c'); zero initial state; outputs for t >= len_b are exactly zero so the head emits its bias there.
 //
-// B200 mapping: the input projection X*W_ih^T (+b_ih+b_hh) of ALL time steps is one tcgen05 GEMM; every time
-// step is one tcgen05 GEMM h_{t-1}*W_hh^T whose epilogue fuses the gate non-linearities, the cell update, the
-// length mask and the bf16 store of h_t (both as next-step operand and as layer output).  Weight rows are
-// re-ordered gate-interleaved (row 4u+g) so that one epilogue thread owns all four gates of a hidden unit.
+// B200 mapping: the input projection X*W_ih^T (+b_ih+b_hh) of ALL time steps is one tcgen05 GEMM; the recurrence
+// of a layer is ONE persistent cooperative kernel (lstm_persist.cuh: W_hh slice resident in shared memory, cell state
+// in registers, per-CTA step flags).  When that kernel cannot run (no cooperative launch, H > 1024) every time step
+// is one tcgen05 GEMM h_{t-1}*W_hh^T whose epilogue fuses the gate non-linearities, the cell update, the length mask
+// and the bf16 store of h_t.  Weight rows are re-ordered gate-interleaved (row 4u+g) so that one epilogue thread owns
+// all four gates of a hidden unit.
 #include <stdlib.h>
 
 #include <mutex>

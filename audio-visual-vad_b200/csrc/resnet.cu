@@ -3,11 +3,15 @@
 // Reference semantics: packages/models/AV_Net.py:78-94 (channel triple + torchvision resnet18 children[:-1]).
 // Data layout: activations NHWC bf16 [frame][h][w][c]; weights bf16 [Cout][R][S][Cin] (K order = tap-major,
 // channel-minor, the order the implicit-GEMM producer walks); folded bias fp32.
-//   conv1 7x7/2 + BN + ReLU + maxpool 3x3/2 : one fused kernel per frame (fp32 direct conv; the three identical
-//                                             input channels are folded into one by summing the weights)
-//   layer1..4 (19 convs)                     : tcgen05 implicit GEMM (gemm_tc.cuh) with fused bias/residual/ReLU
+//   conv1 7x7/2 + BN + ReLU + maxpool 3x3/2 : stem_s2d.cuh (the padded frame in shared memory is the UMMA A operand;
+//                                             the three identical input channels are folded into one by summing
+//                                             the weights); optionally fed from the u8 source frames
+//   layer1 (4 convs)                         : conv_slab.cuh (slab with halo, row-shifted descriptors)
+//   layer2..4 (12 launches)                  : gemm_tma.cuh (TMA-box im2col); the three downsample 1x1 branches are
+//                                             K-concatenated into the following conv_b
 //   global average pool                      : small bandwidth kernel, emits fp32 features and/or the bf16
 //                                              LSTM operand columns
+//   training mode (batch-statistics BN)      : raw convs + statistics / apply kernels, two-pass stem
 #include <stdlib.h>
 
 #include <mutex>
