@@ -9,7 +9,17 @@ namespace avvad {
 constexpr int kFftN = 1024;
 constexpr int kFftThreads = 256;
 
-// exp(-2*pi*i*k/1024), k in [0,512): filled once on the host in double precision.
+// Twiddle tables, filled once on the host in double precision.  Device layout (float2 entries):
+//   [0, 512)      exp(-2*pi*i*k/1024), k in [0,512)  (the front end derives the periodic Hann window from it)
+//   [512, 1536)   per-stage tables of the radix-4 Stockham FFT (kFftTwStage entries, 1020 used): stage s = 1..4 with
+//                 Ns = 4^s holds w^1[Ns], w^2[Ns], w^3[Ns] with w = exp(-2*pi*i*k/(4*Ns)), k in [0,Ns), at
+//                 fft_tw_off(s).  A thread of stage s reads entry k = tid & (Ns-1) of each: consecutive lanes read
+//                 consecutive entries (or the same one), so the loads are bank-conflict free.  Indexing one 512-entry
+//                 table with k*(256>>2s) instead put all lanes of a warp on 1-4 banks (ncu: 4.8-way conflicts on the
+//                 shared loads, 64 % of all load wavefronts of the MCB kernel).
+constexpr int kFftTwHann = 512;
+constexpr int kFftTwStage = 1024;
+__host__ __device__ __forceinline__ constexpr int fft_tw_off(int s) { return s == 1 ? 0 : s == 2 ? 12 : s == 3 ? 60 : 252; }
 const float2* fft_twiddles_device();  // returns device pointer, initialising on first use (nullptr on error)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -17,15 +27,11 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 
 // Transforms the 1024 complex values in `a` (shared memory); `b` is a 1024-entry scratch buffer and `tw` the
-// 512-entry twiddle table exp(-2*pi*i*k/1024) (shared memory).  All kFftThreads threads of the group must call it;
-// `tid` in [0,256).  Radix-4 Stockham autosort: five stages, one butterfly per thread and stage (half the
-// shared-memory passes and barriers of the radix-2 form).  The result lands in `b` (odd number of ping-pong
-// stages) and the function RETURNS the buffer holding it.  The caller must have synchronised after filling `a`;
-// the function ends with a __syncthreads().
-__device__ __forceinline__ float2 tw1024(const float2* __restrict__ tw, int i) {  // i in [0, 1024)
-  const float2 w = tw[i & 511];
-  return (i & 512) ? make_float2(-w.x, -w.y) : w;
-}
+// kFftTwStage-entry per-stage twiddle table (shared memory copy of fft_twiddles_device() + kFftTwHann).  All
+// kFftThreads threads of the group must call it; `tid` in [0,256).  Radix-4 Stockham autosort: five stages, one
+// butterfly per thread and stage (half the shared-memory passes and barriers of the radix-2 form).  The result lands
+// in `b` (odd number of ping-pong stages) and the function RETURNS the buffer holding it.  The caller must have
+// synchronised after filling `a` and `tw`; the function ends with a __syncthreads().
 __device__ __forceinline__ float2* fft1024_smem(float2* __restrict__ a, float2* __restrict__ b,
                                                 const float2* __restrict__ tw, int tid) {
   float2* in = a;
@@ -34,15 +40,15 @@ __device__ __forceinline__ float2* fft1024_smem(float2* __restrict__ a, float2* 
   for (int s = 0; s < 5; ++s) {
     const int Ns = 1 << (2 * s);        // 1, 4, 16, 64, 256
     const int k = tid & (Ns - 1);
-    const int tstep = k * (256 >> (2 * s));  // k * 1024 / (4 * Ns)
     float2 v0 = in[tid];
     float2 v1 = in[tid + 256];
     float2 v2 = in[tid + 512];
     float2 v3 = in[tid + 768];
     if (s > 0) {
-      v1 = cmul(v1, tw1024(tw, tstep));
-      v2 = cmul(v2, tw1024(tw, 2 * tstep));
-      v3 = cmul(v3, tw1024(tw, 3 * tstep));
+      const float2* ts = tw + fft_tw_off(s) + k;
+      v1 = cmul(v1, ts[0]);
+      v2 = cmul(v2, ts[Ns]);
+      v3 = cmul(v3, ts[2 * Ns]);
     }
     // 4-point DFT (forward, e^{-i...})
     const float2 b0 = make_float2(v0.x + v2.x, v0.y + v2.y);

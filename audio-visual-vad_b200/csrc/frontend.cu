@@ -18,11 +18,20 @@ static std::mutex g_tw_mu;
 const float2* fft_twiddles_device() {
   std::lock_guard<std::mutex> lk(g_tw_mu);
   if (g_tw_dev) return g_tw_dev;
-  float2 host[512];
+  static float2 host[kFftTwHann + kFftTwStage];
   const double two_pi = 6.283185307179586476925286766559;
+  for (int k = 0; k < kFftTwHann + kFftTwStage; ++k) host[k] = make_float2(1.f, 0.f);
   for (int k = 0; k < 512; ++k) {
     double a = -two_pi * (double)k / 1024.0;
     host[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  for (int s = 1; s <= 4; ++s) {
+    const int Ns = 1 << (2 * s);
+    for (int q = 1; q <= 3; ++q)
+      for (int k = 0; k < Ns; ++k) {
+        double a = -two_pi * (double)(q * k) / (4.0 * Ns);
+        host[kFftTwHann + fft_tw_off(s) + (q - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
+      }
   }
   float2* d = nullptr;
   if (cudaMalloc(&d, sizeof(host)) != cudaSuccess) return nullptr;
@@ -70,7 +79,7 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
                 const float2* __restrict__ tw_g, float* __restrict__ out) {
   __shared__ float2 sa[kFftN];
   __shared__ float2 sb[kFftN];
-  __shared__ float2 stw[512];
+  __shared__ float2 stw[kFftTwStage];
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -89,8 +98,9 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
     return;
   }
 
-  stw[tid] = tw_g[tid];
-  stw[tid + 256] = tw_g[tid + 256];
+#pragma unroll
+  for (int q = 0; q < kFftTwStage / kFftThreads; ++q)
+    stw[tid + q * kFftThreads] = tw_g[kFftTwHann + tid + q * kFftThreads];
 
   const int n = n_samples[b];
   const float* x = wave + (int64_t)b * wave_stride;
@@ -101,7 +111,7 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
   for (int q = 0; q < 4; ++q) {
     const int i = tid + q * kFftThreads;
     // periodic Hann: 0.5 - 0.5*cos(2*pi*i/1024); cos from the twiddle table
-    const float c = (i < 512) ? stw[i].x : -stw[i - 512].x;
+    const float c = (i < 512) ? __ldg(&tw_g[i].x) : -__ldg(&tw_g[i - 512].x);
     const float w = 0.5f - 0.5f * c;
     const int i0 = t * 256 + i;
     float v0 = (i0 < n) ? x[i0] : 0.f;  // samples past the end are the pad-at-end zeros

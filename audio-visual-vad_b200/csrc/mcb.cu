@@ -30,15 +30,16 @@ mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video,
                const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq) {
   __shared__ float2 sa[kFftN];
   __shared__ float2 sb[kFftN];
-  __shared__ float2 stw[512];
+  __shared__ float2 stw[kFftTwStage];
   __shared__ float xa[kNA];
   __shared__ float xv[kNV];
   __shared__ float red[8];
 
   const int tid = threadIdx.x;
   const int64_t row = blockIdx.x;
-  stw[tid] = tw_g[tid];
-  stw[tid + 256] = tw_g[tid + 256];
+#pragma unroll
+  for (int q = 0; q < kFftTwStage / kFftThreads; ++q)
+    stw[tid + q * kFftThreads] = tw_g[kFftTwHann + tid + q * kFftThreads];
   for (int i = tid; i < kNA; i += kFftThreads) xa[i] = audio[row * kNA + i];
   for (int i = tid; i < kNV; i += kFftThreads) xv[i] = video[row * kNV + i];
   __syncthreads();
