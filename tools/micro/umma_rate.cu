@@ -1,10 +1,10 @@
-// Micro-benchmark: cycles per tcgen05.mma (SS mode, bf16, M=128) as a function of N, operands resident in smem.
+// Micro-benchmark: cycles per tcgen05.mma (SS mode, bf16, M=128) as a function of N (and M = 64 / 128), operands resident in smem.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I audio-visual-vad_b200/csrc tools/micro/umma_rate.cu -o gpurun_out/umma_rate
 #include <cstdio>
 #include "gemm_tc.cuh"
 using namespace avvad::tc;
 
-template <int BN>
+template <int BN, int M = 128>
 __global__ void k(long long* out, int iters, int a_shift_rows) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -20,7 +20,7 @@ __global__ void k(long long* out, int iters, int a_shift_rows) {
   tc_fence_before(); __syncthreads(); tc_fence_after();
   const uint32_t tm = *slot;
   if (threadIdx.x == 0) {
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = (make_idesc(BN) & ~(0x1Fu << 24)) | ((uint32_t)(M >> 4) << 24);
     const uint32_t sa = base + a_shift_rows * 128, sb = base + 256 * 128;
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
@@ -37,22 +37,22 @@ __global__ void k(long long* out, int iters, int a_shift_rows) {
   if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
-template <int BN> void run(int grid, int shift) {
+template <int BN, int M = 128> void run(int grid, int shift) {
   long long* d; cudaMalloc(&d, sizeof(long long) * grid);
   size_t smem = (256 + BN) * 128 + 1024 + 64;
-  cudaFuncSetAttribute(k<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k<BN, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int iters = 2000;
-  k<BN><<<grid, 128, smem>>>(d, iters, shift);
-  k<BN><<<grid, 128, smem>>>(d, iters, shift);
+  k<BN, M><<<grid, 128, smem>>>(d, iters, shift);
+  k<BN, M><<<grid, 128, smem>>>(d, iters, shift);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[1024]; cudaMemcpy(h, d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
   double avg = 0; for (int i = 0; i < grid; ++i) avg += h[i]; avg /= grid;
-  printf("N=%3d grid=%3d shift=%2d: %.1f cycles per 128xNx16 MMA (floor %d)  err=%s\n", BN, grid, shift, avg / (iters * 4.0), BN / 2, cudaGetErrorString(e));
+  printf("M=%3d N=%3d grid=%3d shift=%2d: %.1f cycles per MxNx16 MMA (floor %d)  err=%s\n", M, BN, grid, shift, avg / (iters * 4.0), BN / 2, cudaGetErrorString(e));
   cudaFree(d);
 }
 int main() {
   for (int grid : {1, 148}) {
-    run<64>(grid, 0); run<64>(grid, 19); run<128>(grid, 0); run<256>(grid, 0);
+    run<64>(grid, 0); run<64>(grid, 19); run<64, 64>(grid, 0); run<64, 64>(grid, 18); run<128, 64>(grid, 0); run<128>(grid, 0); run<256>(grid, 0);
   }
   return 0;
 }
