@@ -5,6 +5,7 @@
 #include <mutex>
 
 #include "conv_slab.cuh"
+#include "conv_slab2.cuh"
 
 namespace avvad {
 namespace tc {
@@ -108,8 +109,71 @@ static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep
   return AVVAD_OK;
 }
 
+// Packed two-frame variant (conv_slab2.cuh) for the 64 -> 64 channel layers: opt-in with AVVAD_SLAB2=1.  It issues
+// one sixth fewer MMAs but has to stream the weights; measured on B200 (layer1, 81,152 frames): 9.6 ms against 9.1 ms
+// for the resident-weight kernel on the same box -- layer1 moves 2.2 GB per launch and sits at ~65 % of the HBM
+// peak as well as ~58 % tensor-pipe activity, so fewer MMAs alone do not shorten it.
+static int slab2_mode() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_SLAB2");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
+static int launch_slab2(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H,
+                        cudaStream_t st) {
+  Slab2Geom g{};
+  g.n_frames = n;
+  g.OH = H; g.OW = H; g.Wp = H + 1;
+  g.per_frame = (H + 1) * (H + 1);
+  g.total_tiles = (n + kSlab2Frames - 1) / kSlab2Frames;
+  g.box_bytes = (uint32_t)kSlab2Frames * g.per_frame * 128u;
+  const uint32_t rows = kSlab2Blocks * 128 + 2 * g.Wp + 2;
+  g.slab_bytes = (rows * 128u + 1023u) & ~1023u;
+  SlabMaps maps;
+  const uint32_t box[4] = {64, (uint32_t)g.Wp, (uint32_t)(H + 1), (uint32_t)kSlab2Frames};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  int rc = encode_act_map(&maps.a, in, 64, H, H, n, box, estr);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps.b, w, (uint64_t)9 * 64, 64, 64);
+  if (rc) return rc;
+  const size_t smem = 1024 + 2 * (size_t)g.slab_bytes + kSlab2WStages * kSlab2WTile + 8 * 24 + 16 + 64 * 4;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(tc_slab2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  AVVAD_CUDA(attr_err);
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  const unsigned grid = (unsigned)(g.total_tiles < num_sms ? g.total_tiles : num_sms);
+  const double flops = 2.0 * (double)n * H * H * 64 * 9.0 * 64;
+  void* tok = nullptr;
+  prof_begin(st, &tok);
+  tc_slab2_kernel<<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
+  AVVAD_LAUNCHED();
+  prof_end(st, tok, 0, flops);
+  return AVVAD_OK;
+}
+
+// two frames must fit five 128-row blocks and the slabs must fit shared memory: true for the 17x17 maps of layer1
+static bool slab2_fits(int H, int Cin, int Cout) {
+  if (slab2_mode() == 0 || Cin != 64 || Cout != 64) return false;
+  const int Wp = H + 1, per_frame = (H + 1) * (H + 1);
+  const int last = per_frame + (H - 1) * Wp + (H - 1);  // last valid GEMM row of the second frame
+  const size_t slab = ((size_t)(kSlab2Blocks * 128 + 2 * Wp + 2) * 128 + 1023) / 1024 * 1024;
+  return last < kSlab2Blocks * 128 && last >= (kSlab2Blocks - 1) * 128 &&
+         (size_t)kSlab2Frames * per_frame * 128 <= slab &&
+         1024 + 2 * slab + kSlab2WStages * kSlab2WTile + 512 <= 227 * 1024;
+}
+
 int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiParams& ep, int64_t n, int H, int Cin,
                      int Cout, cudaStream_t st) {
+  if (slab2_fits(H, Cin, Cout)) return launch_slab2(in, w, ep, n, H, st);
   SlabPlan p;
   if (!plan(H, Cin, Cout, &p)) {
     set_error("slab conv: no feasible plan");

@@ -44,6 +44,41 @@ def test_gemm_exact_on_small_integers():
     assert torch.equal(got, a.float() @ w.float().t())
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 301])
+def test_layer1_conv_exact_on_small_integers(n):
+    """17x17x64 -> 64 (the packed two-frame slab kernel): operands in {-1,0,1} keep every partial sum an integer
+    below 256, so the bf16 outputs must equal the fp32 reference exactly -- for odd frame counts (half-empty last
+    slab) as well."""
+    g = torch.Generator(device="cuda").manual_seed(100 + n)
+    x = torch.randint(-1, 2, (n, 17, 17, 64), device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randint(-1, 2, (64, 3, 3, 64), device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randint(-3, 4, (64,), device="cuda", generator=g).float()
+    res = torch.randint(-8, 9, (n, 17, 17, 64), device="cuda", generator=g).to(torch.bfloat16)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = torch.relu(ref.permute(0, 2, 3, 1) + res.float())
+    assert float(ref.abs().max()) <= 256
+    got = E.conv2d_nhwc_bf16(x, w, bias, 1, 1, residual=res, relu=True).float()
+    assert torch.equal(got, ref)
+    got2 = E.conv2d_nhwc_bf16(x, w, None, 1, 1, relu=False).float()
+    ref2 = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, padding=1)
+    assert torch.equal(got2, ref2.permute(0, 2, 3, 1))
+
+
+def test_packed_slab_variant_exact():
+    """The opt-in packed two-frame slab kernel (AVVAD_SLAB2=1) is read once per process: run the integer-exact layer1
+    check in a child process with the variant enabled."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, AVVAD_SLAB2="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_gemm.py"), "-q", "-m", "gpu",
+                        "-k", "layer1_conv_exact or (conv_matches and 17-64-64)", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
+
+
 CONVS = [  # (H, Cin, Cout, k, stride, pad) -- every distinct shape of the ResNet-18 trunk after conv1
     (17, 64, 64, 3, 1, 1), (17, 64, 128, 3, 2, 1), (9, 128, 128, 3, 1, 1), (17, 64, 128, 1, 2, 0),
     (9, 128, 256, 3, 2, 1), (5, 256, 256, 3, 1, 1), (9, 128, 256, 1, 2, 0),
