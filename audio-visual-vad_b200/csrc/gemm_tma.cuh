@@ -219,9 +219,13 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         if (elect_one_sync()) {
           const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
-          mbar_arrive_expect_tx(full, bytes);
+          // debug knobs (AVVAD_EPI_DEBUG): 4 = no A loads, 8 = no B loads (operands stay
+          // whatever shared memory held), 2 = no MMAs, 1 = no stores -- to time the pipeline stages in isolation
+          const bool no_a = (ep.debug & 4) != 0, no_b = (ep.debug & 8) != 0;
+          mbar_arrive_expect_tx(full, (no_a ? 0u : bytes - g.bytesB) + (no_b ? 0u : g.bytesB));
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
+            if (no_a) continue;
             if (g.mode == 0) {
               tma_load_4d(sa + mb * C::kABytes, &maps.a[0], kb * KE, (int)t[mb].n0, 0, 0, full);
             } else {
@@ -229,7 +233,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
                           t[mb].hstart * g.stride + fr - g.pad, (int)t[mb].n0, full);
             }
           }
-          tma_load_2d(sa + MB * C::kABytes, &maps.b, kb * KE, n_base, full);
+          if (!no_b) tma_load_2d(sa + MB * C::kABytes, &maps.b, kb * KE, n_base, full);
         }
         __syncwarp();
         if (++cb == g.cpb) {
@@ -279,6 +283,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           const uint32_t b_lo = a0 + ((MB * C::kABytes) >> 4);
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
+            if (ep.debug & 2) continue;  // debug: feed + epilogue only
             const uint32_t a_lo = a0 + ((mb * C::kABytes) >> 4);
             const uint32_t d = d_tmem + mb * BN;
             umma_f16_lo2(d, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
