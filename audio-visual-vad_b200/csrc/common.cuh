@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 #include <string>
 
 #include "../../include/avvad.h"
@@ -90,5 +91,26 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+
+// One-time initialisation PER DEVICE.  Kernel attributes (cudaFuncSetAttribute) and device-resident lookup tables belong
+// to one device's context, and nn.DataParallel -- what the reference's training scripts use -- drives several devices
+// from the threads of one process: a process-wide std::once_flag would leave every device but the first unconfigured.
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  std::mutex mu;
+  uint64_t done = 0;
+  cudaError_t err[kMaxDevices] = {};
+  template <class F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!((done >> dev) & 1ull)) {
+      err[dev] = f();
+      done |= 1ull << dev;
+    }
+    return err[dev];
+  }
+};
 
 }  // namespace avvad

@@ -87,12 +87,15 @@ template <int BN, bool RES, int MBC = 0>
 static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep, size_t smem, double flops,
                     cudaStream_t st) {
   static std::mutex mu;
-  static size_t attr_set = 0;
+  static size_t attr_set[kMaxDevices] = {};  // per device: function attributes live in the device's context
   {
+    int dev = 0;
+    AVVAD_CUDA(cudaGetDevice(&dev));
+    AVVAD_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "device index out of range");
     std::lock_guard<std::mutex> lk(mu);
-    if (smem > attr_set) {
+    if (smem > attr_set[dev]) {
       AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES, MBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = smem;
+      attr_set[dev] = smem;
     }
   }
   static int num_sms = [] {
@@ -139,12 +142,10 @@ static int launch_slab2(const __nv_bfloat16* in, const __nv_bfloat16* w, const E
   rc = encode_weight_map(&maps.b, w, (uint64_t)9 * 64, 64, 64);
   if (rc) return rc;
   const size_t smem = 1024 + 2 * (size_t)g.slab_bytes + kSlab2WStages * kSlab2WTile + 8 * 24 + 16 + 64 * 4;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_slab2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  AVVAD_CUDA(attr_err);
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    return cudaFuncSetAttribute(tc_slab2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }));
   static int num_sms = [] {
     int dev = 0, v = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);

@@ -20,23 +20,27 @@ constexpr size_t kDctSmem = 3 * kRoiHW * sizeof(double);
 
 // y[k] = x[0] + 2 sum_{j>=1} x[j] cos(pi (2k+1) j / 2n): scipy.fftpack.idct(x) (type 2, norm=None) as a matrix
 static const double* idct_matrix_device() {
-  static double* dev = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    double h[kRoiHW];
+  static double* table[kMaxDevices] = {};  // one copy per device (nn.DataParallel: several devices, one process)
+  static PerDeviceOnce once;
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) return nullptr;
+  const cudaError_t e = once.run([cur] {
+    static double h[kRoiHW];
     for (int k = 0; k < kRoi; ++k)
       for (int j = 0; j < kRoi; ++j)
         h[k * kRoi + j] = (j == 0) ? 1.0 : 2.0 * cos(M_PI * (2.0 * k + 1.0) * (double)j / (2.0 * kRoi));
-    if (cudaMalloc(&dev, sizeof(h)) != cudaSuccess) {
-      dev = nullptr;
-      return;
+    double* d = nullptr;
+    cudaError_t err = cudaMalloc(&d, sizeof(h));
+    if (err != cudaSuccess) return err;
+    err = cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+      cudaFree(d);
+      return err;
     }
-    if (cudaMemcpy(dev, h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaFree(dev);
-      dev = nullptr;
-    }
+    table[cur] = d;
+    return cudaSuccess;
   });
-  return dev;
+  return e == cudaSuccess ? table[cur] : nullptr;
 }
 
 // step2 = C @ (a @ C^T)   (== idct(idct(a).T).T of the reference), left in `s2` (shared)
@@ -201,14 +205,13 @@ extern "C" int avvad_dct_roi_decode(const float* dct, int64_t n_frames, int mode
     set_error("idct matrix allocation failed (no CUDA device?)");
     return AVVAD_ERR_CUDA;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(dct_roi_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDctSmem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(dct_roi_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDctSmem);
-  });
-  AVVAD_CUDA(attr_err);
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(dct_roi_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDctSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(dct_roi_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDctSmem);
+    return e;
+  }));
   if (mode == 0) {
     AVVAD_CHECK_ARG(out_u8 || out_f32, "mode 0 needs out_u8 (normalised, rotated) and/or out_f32 (raw decode)");
     dct_roi_u8_kernel<<<(unsigned)n_frames, kDctThreads, kDctSmem, st>>>(dct, C, out_u8, out_f32);

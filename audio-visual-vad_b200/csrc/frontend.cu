@@ -12,35 +12,40 @@
 
 namespace avvad {
 
-static float2* g_tw_dev = nullptr;
-static std::mutex g_tw_mu;
+static float2* g_tw_dev[kMaxDevices] = {};  // one table per device (nn.DataParallel: several devices, one process)
+static PerDeviceOnce g_tw_once;
 
 const float2* fft_twiddles_device() {
-  std::lock_guard<std::mutex> lk(g_tw_mu);
-  if (g_tw_dev) return g_tw_dev;
-  static float2 host[kFftTwHann + kFftTwStage];
-  const double two_pi = 6.283185307179586476925286766559;
-  for (int k = 0; k < kFftTwHann + kFftTwStage; ++k) host[k] = make_float2(1.f, 0.f);
-  for (int k = 0; k < 512; ++k) {
-    double a = -two_pi * (double)k / 1024.0;
-    host[k] = make_float2((float)cos(a), (float)sin(a));
-  }
-  for (int s = 1; s <= 4; ++s) {
-    const int Ns = 1 << (2 * s);
-    for (int q = 1; q <= 3; ++q)
-      for (int k = 0; k < Ns; ++k) {
-        double a = -two_pi * (double)(q * k) / (4.0 * Ns);
-        host[kFftTwHann + fft_tw_off(s) + (q - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
-      }
-  }
-  float2* d = nullptr;
-  if (cudaMalloc(&d, sizeof(host)) != cudaSuccess) return nullptr;
-  if (cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaFree(d);
-    return nullptr;
-  }
-  g_tw_dev = d;
-  return g_tw_dev;
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) return nullptr;
+  const cudaError_t e = g_tw_once.run([cur] {
+    static float2 host[kFftTwHann + kFftTwStage];
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < kFftTwHann + kFftTwStage; ++k) host[k] = make_float2(1.f, 0.f);
+    for (int k = 0; k < 512; ++k) {
+      double a = -two_pi * (double)k / 1024.0;
+      host[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int s = 1; s <= 4; ++s) {
+      const int Ns = 1 << (2 * s);
+      for (int q = 1; q <= 3; ++q)
+        for (int k = 0; k < Ns; ++k) {
+          double a = -two_pi * (double)(q * k) / (4.0 * Ns);
+          host[kFftTwHann + fft_tw_off(s) + (q - 1) * Ns + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    float2* d = nullptr;
+    cudaError_t err = cudaMalloc(&d, sizeof(host));
+    if (err != cudaSuccess) return err;
+    err = cudaMemcpy(d, host, sizeof(host), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) {
+      cudaFree(d);
+      return err;
+    }
+    g_tw_dev[cur] = d;
+    return cudaSuccess;
+  });
+  return e == cudaSuccess ? g_tw_dev[cur] : nullptr;
 }
 
 // ---- per-utterance max|x| ----------------------------------------------------------------------

@@ -122,11 +122,10 @@ static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int ep
   if (g.ksplit == 1) g.kb_split = g.KB;
   g.m_supers = (g.m_tiles + MB - 1) / MB;
   g.total_tiles = g.m_supers * g.n_tiles * g.ksplit;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc_tma_kernel<BN, KE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::kSmemBytes);
+  static PerDeviceOnce once;
+  const cudaError_t attr_err = once.run([] {
+    return cudaFuncSetAttribute(tc_tma_kernel<BN, KE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)C::kSmemBytes);
   });
   if (attr_err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(attr_err));

@@ -277,12 +277,10 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
   const int max_ms = num_sms / n_slices;
   if (!coop || max_ms < 1) return AVVAD_OK;
   const size_t smem = (size_t)(H / 64) * 8192 + tc::kLstmStages * 16384 + 256 + 1024;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [smem] {
-    attr_err = cudaFuncSetAttribute(tc::lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  AVVAD_CUDA(attr_err);
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    return cudaFuncSetAttribute(tc::lstm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }));
   const int64_t Bg = (int64_t)max_ms * 128;
   for (int64_t g0 = 0; g0 < B; g0 += Bg) {
     const int64_t Bc = (B - g0 < Bg) ? (B - g0) : Bg;

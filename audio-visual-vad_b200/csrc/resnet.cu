@@ -436,17 +436,15 @@ struct StemInput {
 // statistics-only first pass of the training stem (fp32 frames)
 static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __nv_bfloat16* out, cudaStream_t st,
                            const __nv_bfloat16* w = nullptr, const float* bias = nullptr, double* stats = nullptr) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(tc::stem_s2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)tc::kS2Smem);
-  });
-  AVVAD_CUDA(attr_err);
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(tc::stem_s2d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::stem_s2d_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::stem_s2d_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kS2Smem);
+    return e;
+  }));
   static int num_sms = [] {
     int dev = 0, v = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);

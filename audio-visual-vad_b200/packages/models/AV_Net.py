@@ -6,7 +6,8 @@ import torchvision.models as models
 
 from .compact_bilinear_pooling import CompactBilinearPooling
 from .utils import weights_init_normal
-from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, device_of, lstm_params, trunk_bn_modules)
+from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, all_parameters, device_of, full_state_dict,
+                      lstm_params, trunk_bn_modules)
 
 
 class DeepVAD_AV(nn.Module):
@@ -55,7 +56,7 @@ class DeepVAD_AV(nn.Module):
             eng = old or {"trunk": E.ResNet18Trunk(),
                           "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim),
                           "mcb": E.Mcb() if self.use_mcb else None}
-            sd = self.state_dict()
+            sd = full_state_dict(self)
             eng["trunk"].load(sd, device)
             eng["trunk"].load_train(sd, device)
             eng["lstm"].load(sd, device, "lstm_merged", "vad_merged")
@@ -75,8 +76,8 @@ class DeepVAD_AV(nn.Module):
         vid = video.detach().to(torch.float32).reshape(M, height, width)
         aud = audio.detach().to(torch.float32).reshape(M, self.num_audio_ftrs).contiguous()
         # eval() forward is inference only (detached logits, folded BN); the autograd path is the train() step
-        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if need_grad and any(p.requires_grad for p in self.features.parameters()):
+        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self))
+        if need_grad and any(p.requires_grad for p in all_parameters(self.features)):
             raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze "
                                       "'features' as scripts/train_AV_net.py:241-245 does")
 

@@ -3,7 +3,7 @@ import torch
 import torch.nn as nn
 
 from .utils import weights_init_normal
-from ._engine import E, EngineCache, LstmHeadFunction, device_of, lstm_params
+from ._engine import E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params
 
 
 class DeepVAD_audio(nn.Module):
@@ -35,7 +35,7 @@ class DeepVAD_audio(nn.Module):
     def _build(self, device):
         def builder(old):
             eng = old or {"lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
-            eng["lstm"].load(self.state_dict(), device, "lstm_audio", "vad_audio")
+            eng["lstm"].load(full_state_dict(self), device, "lstm_audio", "vad_audio")
             return eng
         return self._engines.get(self, device, builder)
 
@@ -46,7 +46,7 @@ class DeepVAD_audio(nn.Module):
         B, T, F = x.shape
         xb = eng["lstm"].new_input(B, T, device)
         E.pack_rows_bf16(x.detach().to(torch.float32).reshape(B * T, F).contiguous(), xb.view(B * T, -1), 0, False)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self)):
             # training step: forward keeps a tape, loss.backward() runs BPTT on the device
             return LstmHeadFunction.apply(eng["lstm"], xb, lengths, x if x.requires_grad else None,
                                           *lstm_params(self.lstm_audio, self.vad_audio))

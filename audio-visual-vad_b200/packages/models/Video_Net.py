@@ -4,7 +4,7 @@ import torch.nn as nn
 import torchvision.models as models
 
 from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
-from ._engine import E, EngineCache, check_inference_only, device_of
+from ._engine import E, EngineCache, check_inference_only, device_of, full_state_dict
 
 
 class DeepVAD_video(nn.Module):
@@ -41,7 +41,7 @@ class DeepVAD_video(nn.Module):
         def builder(old):
             eng = old or {"trunk": E.ResNet18Trunk(),
                           "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
-            sd = self.state_dict()
+            sd = full_state_dict(self)
             eng["trunk"].load(sd, device)
             eng["lstm"].load(sd, device, "lstm_video", "vad_video")
             return eng

@@ -21,6 +21,33 @@ from avvad import engine as E  # noqa: E402
 from avvad import lib as L  # noqa: E402
 
 
+def _replica_parameters(module: torch.nn.Module):
+    """(qualified name, tensor) of the parameter copies of an nn.DataParallel replica.  torch.nn.parallel.replicate
+    empties ``_parameters`` of every replica module and re-attaches the broadcast copies as plain tensor attributes
+    (listed in ``_former_parameters``), so ``parameters()`` / ``state_dict()`` of a replica see buffers only."""
+    for prefix, mod in module.named_modules():
+        former = getattr(mod, "_former_parameters", None)
+        if former:
+            for k, v in former.items():
+                if v is not None:
+                    yield (prefix + "." if prefix else "") + k, v
+
+
+def all_parameters(module: torch.nn.Module):
+    """``module.parameters()`` plus, inside an nn.DataParallel replica, the broadcast parameter copies."""
+    return list(module.parameters()) + [v for _, v in _replica_parameters(module)]
+
+
+def full_state_dict(module: torch.nn.Module):
+    """``module.state_dict()`` that is also complete inside an nn.DataParallel replica (reference:
+    scripts/train_AV_net.py:193 wraps the model in nn.parallel.DataParallel)."""
+    sd = module.state_dict()
+    for k, v in _replica_parameters(module):
+        if k not in sd:
+            sd[k] = v.detach()
+    return sd
+
+
 class EngineCache:
     def __init__(self):
         self.by_device = {}
@@ -28,7 +55,8 @@ class EngineCache:
     @staticmethod
     def _signature(module: torch.nn.Module):
         sig = []
-        for t in list(module.parameters()) + list(module.buffers()):
+        tensors = list(module.parameters()) + list(module.buffers()) + [v for _, v in _replica_parameters(module)]
+        for t in tensors:
             sig.append((t.data_ptr(), t._version, getattr(t, "_avvad_gen", 0)))
         return tuple(sig)
 

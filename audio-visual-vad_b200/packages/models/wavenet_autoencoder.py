@@ -3,7 +3,7 @@
 import torch
 import torch.nn as nn
 
-from ._engine import E, EngineCache, device_of
+from ._engine import E, EngineCache, device_of, full_state_dict
 
 
 class wavenet_autoencoder(nn.Module):
@@ -44,7 +44,7 @@ class wavenet_autoencoder(nn.Module):
             eng = old or E.WaveNetEncoder(self.filter_width, self.quantization_channel, list(self.dilations),
                                           self.en_residual_channel, self.en_dilation_channel,
                                           self.en_bottleneck_width, self.en_pool_kernel_size)
-            eng.load(self.state_dict(), device)
+            eng.load(full_state_dict(self), device)
             return eng
         return self._engines.get(self, device, builder)
 

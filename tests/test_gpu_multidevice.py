@@ -1,0 +1,104 @@
+"""Several devices driven from ONE process -- what nn.DataParallel does in the reference's training scripts
+(scripts/train_AV_net.py:193 `nn.parallel.DataParallel(model, device_ids=[0,1,2,3])`): kernel attributes and lookup
+tables are per device, engines are cached per device, replicas run in threads.  Needs two GPUs
+(gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_multidevice.py -m gpu'); skipped on a one-GPU box."""
+import numpy as np
+import pytest
+import torch
+
+from avvad import engine as E
+from avvad import synth
+
+pytestmark = pytest.mark.gpu
+
+needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+
+
+def _inputs(B, T, seed, lens):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, T, 513, generator=g)
+    v = torch.randn(B, T, 67, 67, generator=g)
+    return a, v, torch.tensor(lens)
+
+
+@needs2
+@pytest.mark.parametrize("use_mcb", [False, True])
+def test_second_device_first_touch_and_parity(use_mcb):
+    """cuda:1 is used BEFORE cuda:0 in this test module's process where possible, and both devices must give the same
+    logits: every per-device initialisation (dynamic shared memory attributes, FFT twiddles) has to happen on each."""
+    from packages.models.AV_Net import DeepVAD_AV
+    B, T = 4, 24
+    lens = [24, 17, 24, 9]
+    a, v, l = _inputs(B, T, 5, lens)
+    outs = []
+    for dev in ("cuda:1", "cuda:0"):
+        m = synth.fill_module_(DeepVAD_AV(2, 1024, 1, use_mcb=use_mcb, eps=1e-8), seed=77).to(dev).eval()
+        with torch.no_grad(), torch.cuda.device(dev):
+            outs.append(m(a.to(dev), v.to(dev), l.to(dev)).float().cpu())
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+
+
+@needs2
+def test_raw_ops_on_second_device():
+    with torch.cuda.device(1):
+        n = 81920
+        w = torch.randn(2, n, device="cuda:1") * 0.1
+        T = E.stft_num_frames(n)
+        f1 = E.frontend_logpower(w, [n, n], [T, T], T, None, None, 1e-8, True)
+        x = torch.randint(-1, 2, (3, 17, 17, 64), device="cuda:1").to(torch.bfloat16)
+        k = torch.randint(-1, 2, (64, 3, 3, 64), device="cuda:1").to(torch.bfloat16)
+        y1 = E.conv2d_nhwc_bf16(x, k, None, 1, 1)
+        k2 = torch.randint(-1, 2, (256, 3, 3, 64), device="cuda:1").to(torch.bfloat16)
+        z1 = E.conv2d_nhwc_bf16(x, k2, None, 2, 1)
+    with torch.cuda.device(0):
+        f0 = E.frontend_logpower(w.to("cuda:0"), [n, n], [T, T], T, None, None, 1e-8, True)
+        y0 = E.conv2d_nhwc_bf16(x.to("cuda:0"), k.to("cuda:0"), None, 1, 1)
+        z0 = E.conv2d_nhwc_bf16(x.to("cuda:0"), k2.to("cuda:0"), None, 2, 1)
+    assert torch.equal(f0.cpu(), f1.cpu())
+    assert torch.equal(y0.cpu(), y1.cpu()) and torch.equal(z0.cpu(), z1.cpu())
+    ref = torch.nn.functional.conv2d(x.float().cpu().permute(0, 3, 1, 2), k.float().cpu().permute(0, 3, 1, 2), padding=1)
+    assert torch.equal(y1.float().cpu(), ref.permute(0, 2, 3, 1))
+
+
+@needs2
+@pytest.mark.parametrize("use_mcb", [False, True])
+def test_dataparallel_forward_matches_per_replica_forward(use_mcb):
+    """nn.DataParallel splits the batch over two replicas; BN running statistics (eval) are shared, the MCB whole-tensor
+    L2 norm is per replica -- so the reference result is the concatenation of the two half-batch forwards."""
+    from packages.models.AV_Net import DeepVAD_AV
+    B, T = 4, 20
+    lens = [20, 13, 20, 7]
+    a, v, l = _inputs(B, T, 9, lens)
+    m = synth.fill_module_(DeepVAD_AV(2, 1024, 1, use_mcb=use_mcb, eps=1e-8), seed=78).to("cuda:0").eval()
+    with torch.no_grad():
+        halves = [m(a[i:i + 2].cuda(), v[i:i + 2].cuda(), l[i:i + 2].cuda()).float().cpu() for i in (0, 2)]
+        dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+        out = dp(a.cuda(), v.cuda(), l.cuda()).float().cpu()
+    assert out.shape == (B, T, 1)
+    assert torch.equal(out, torch.cat(halves, 0))
+
+
+@needs2
+def test_dataparallel_training_step_runs():
+    """train_AV_net.py's step under DataParallel: frozen trunk in train() mode, loss.backward() through the device
+    BPTT of both replicas, gradients reduced onto the source module by DataParallel."""
+    from packages.models.AV_Net import DeepVAD_AV
+    from packages.models.utils import binary_cross_entropy
+    B, T = 4, 12
+    lens = [12, 9, 12, 5]
+    a, v, l = _inputs(B, T, 11, lens)
+    m = synth.fill_module_(DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8), seed=79).to("cuda:0")
+    for name, child in m.named_children():
+        if name == "features":
+            for p in child.parameters():
+                p.requires_grad = False
+    m.train()
+    dp = torch.nn.DataParallel(m, device_ids=[0, 1])
+    y = (torch.rand(B, T, 1) > 0.5).float().cuda()
+    out = dp(a.cuda(), v.cuda(), l.cuda())
+    loss = sum(binary_cross_entropy(out[b, :lens[b]], y[b, :lens[b]], 1e-8) for b in range(B))
+    loss.backward()
+    g = m.lstm_merged.weight_hh_l1.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    assert m.mcb_bn.weight.grad is not None and torch.isfinite(m.mcb_bn.weight.grad).all()

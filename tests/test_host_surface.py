@@ -87,3 +87,29 @@ def test_metrics_helpers():
     assert sdr > 15 and sir > 15
     m, h = mean_confidence_interval([1.0, 2.0, 3.0, 4.0])
     assert m == 2.5 and h > 0
+
+
+def test_full_state_dict_inside_dataparallel_replica():
+    """torch.nn.parallel.replicate strips nn.Parameters from replicas (plain tensor attributes + `_former_parameters`);
+    the engines must still find every weight (scripts/train_AV_net.py:193 wraps the model in nn.DataParallel).  The
+    replication is emulated here on the CPU exactly as torch/nn/parallel/replicate.py does it."""
+    from collections import OrderedDict
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models._engine import all_parameters, full_state_dict
+    m = DeepVAD_audio(2, 1024, 1)
+    reps = {mod: mod._replicate_for_data_parallel() for mod in m.modules()}
+    for mod, rep in reps.items():
+        rep._former_parameters = OrderedDict()
+        for k, child in mod._modules.items():
+            setattr(rep, k, reps[child])
+        for k, p in mod._parameters.items():
+            c = p.detach().clone().requires_grad_(p.requires_grad)
+            setattr(rep, k, c)
+            rep._former_parameters[k] = c
+    r = reps[m]
+    ref = m.state_dict()
+    assert len(r.state_dict()) < len(ref)            # what broke the engines: parameters are gone
+    sd = full_state_dict(r)
+    assert set(sd.keys()) == set(ref.keys())
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)
+    assert len(all_parameters(r)) == len(list(m.parameters())) and any(p.requires_grad for p in all_parameters(r))
