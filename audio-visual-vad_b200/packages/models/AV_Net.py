@@ -7,7 +7,7 @@ import torchvision.models as models
 from .compact_bilinear_pooling import CompactBilinearPooling
 from .utils import weights_init_normal
 from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, all_parameters, device_of, full_state_dict,
-                      lstm_params, trunk_bn_modules)
+                      lstm_params, on_input_device, trunk_bn_modules)
 
 
 class DeepVAD_AV(nn.Module):
@@ -65,6 +65,7 @@ class DeepVAD_AV(nn.Module):
             return eng
         return self._engines.get(self, device, builder)
 
+    @on_input_device
     def forward(self, audio, video, lengths, return_posteriors=False):
         """audio (B,T,513), video (B,T,67,67), lengths list / CPU / CUDA tensor -> logits (B,T,y_dim)."""
         device = device_of(audio, video)

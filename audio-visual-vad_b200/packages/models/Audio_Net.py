@@ -3,7 +3,8 @@ import torch
 import torch.nn as nn
 
 from .utils import weights_init_normal
-from ._engine import E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params
+from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params,
+                      on_input_device)
 
 
 class DeepVAD_audio(nn.Module):
@@ -39,6 +40,7 @@ class DeepVAD_audio(nn.Module):
             return eng
         return self._engines.get(self, device, builder)
 
+    @on_input_device
     def forward(self, x, lengths, return_posteriors=False):
         """x (B,T,513) standardised log-power, lengths -> logits (B,T,y_dim)."""
         device = device_of(x)

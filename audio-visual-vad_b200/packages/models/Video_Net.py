@@ -4,7 +4,7 @@ import torch.nn as nn
 import torchvision.models as models
 
 from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
-from ._engine import E, EngineCache, check_inference_only, device_of, full_state_dict
+from ._engine import E, EngineCache, check_inference_only, device_of, full_state_dict, on_input_device
 
 
 class DeepVAD_video(nn.Module):
@@ -47,6 +47,7 @@ class DeepVAD_video(nn.Module):
             return eng
         return self._engines.get(self, device, builder)
 
+    @on_input_device
     def forward(self, x, lengths, return_last=False):
         """x (B,T,67,67), lengths -> logits (B,T,y_dim), or (B,y_dim) at the last valid step."""
         device = device_of(x)

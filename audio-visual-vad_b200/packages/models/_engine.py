@@ -161,6 +161,23 @@ def check_inference_only(module: torch.nn.Module):
             "call .eval() first.  The training step (batch-statistics BN, backward, Adam) is not built yet.")
 
 
+def on_input_device(forward):
+    """Runs a module's forward with the CUDA device of its first tensor argument made current.  libavvad launches on
+    the calling thread's current device and stream, whereas the reference's evaluation workers only ever call
+    ``classifier.to(device)`` with an integer index (scripts/evaluate_AV_net.py:253, device = 4 + i % nb_devices) and
+    never ``torch.cuda.set_device`` -- PyTorch's own ops switch devices per call, so these modules must too."""
+    import functools
+
+    @functools.wraps(forward)
+    def wrapper(self, *args, **kwargs):
+        for t in args:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return forward(self, *args, **kwargs)
+        return forward(self, *args, **kwargs)
+    return wrapper
+
+
 def device_of(*tensors) -> torch.device:
     L.require_cuda(*tensors)
     return tensors[0].device

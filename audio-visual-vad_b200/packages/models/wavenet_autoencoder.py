@@ -3,7 +3,7 @@
 import torch
 import torch.nn as nn
 
-from ._engine import E, EngineCache, device_of, full_state_dict
+from ._engine import E, EngineCache, device_of, full_state_dict, on_input_device
 
 
 class wavenet_autoencoder(nn.Module):
@@ -52,5 +52,6 @@ class wavenet_autoencoder(nn.Module):
         device = device_of(sample)
         return self._build(device).forward(sample)
 
+    @on_input_device
     def forward(self, wave_sample):
         return self._encode(wave_sample)

@@ -31,9 +31,12 @@ def test_second_device_first_touch_and_parity(use_mcb):
     lens = [24, 17, 24, 9]
     a, v, l = _inputs(B, T, 5, lens)
     outs = []
-    for dev in ("cuda:1", "cuda:0"):
+    # as scripts/evaluate_AV_net.py:253 does: an integer device index, no torch.cuda.set_device -- the current device
+    # stays 0 while the module and its inputs live on device 1
+    for dev in (1, 0):
         m = synth.fill_module_(DeepVAD_AV(2, 1024, 1, use_mcb=use_mcb, eps=1e-8), seed=77).to(dev).eval()
-        with torch.no_grad(), torch.cuda.device(dev):
+        with torch.no_grad():
+            assert torch.cuda.current_device() == 0
             outs.append(m(a.to(dev), v.to(dev), l.to(dev)).float().cpu())
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
