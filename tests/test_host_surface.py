@@ -113,3 +113,20 @@ def test_full_state_dict_inside_dataparallel_replica():
     assert set(sd.keys()) == set(ref.keys())
     assert all(torch.equal(sd[k], ref[k]) for k in ref)
     assert len(all_parameters(r)) == len(list(m.parameters())) and any(p.requires_grad for p in all_parameters(r))
+
+
+def test_modules_survive_pickle_and_deepcopy():
+    """scripts/evaluate_AV_net.py:332-339 hands the classifier to a spawn-context process pool (pickle); the engine
+    cache (ctypes handles) must not travel and must be re-created empty on the other side."""
+    import copy
+    import pickle
+    from packages.models.AV_Net import DeepVAD_AV
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models.Video_Net import DeepVAD_video
+    for m in (DeepVAD_AV(2, 1024, 1, use_mcb=True), DeepVAD_audio(2, 1024, 1), DeepVAD_video(2, 1024, 1)):
+        ref = m.state_dict()
+        for clone in (pickle.loads(pickle.dumps(m)), copy.deepcopy(m)):
+            sd = clone.state_dict()
+            assert list(sd.keys()) == list(ref.keys())
+            assert all(torch.equal(sd[k], ref[k]) for k in ref)
+            assert clone._engines is not m._engines and clone._engines.by_device == {}
