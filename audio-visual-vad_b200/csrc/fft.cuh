@@ -17,6 +17,9 @@ constexpr int kFftThreads = 256;
 //                 consecutive entries (or the same one), so the loads are bank-conflict free.  Indexing one 512-entry
 //                 table with k*(256>>2s) instead put all lanes of a warp on 1-4 banks (ncu: 4.8-way conflicts on the
 //                 shared loads, 64 % of all load wavefronts of the MCB kernel).
+#ifndef AVVAD_FFT_ROT
+#define AVVAD_FFT_ROT 1
+#endif
 constexpr int kFftTwHann = 512;
 constexpr int kFftTwStage = 1024;
 __host__ __device__ __forceinline__ constexpr int fft_tw_off(int s) { return s == 1 ? 0 : s == 2 ? 12 : s == 3 ? 60 : 252; }
@@ -56,10 +59,28 @@ __device__ __forceinline__ float2* fft1024_smem(float2* __restrict__ a, float2* 
     const float2 b2 = make_float2(v1.x + v3.x, v1.y + v3.y);
     const float2 b3 = make_float2(v1.y - v3.y, v3.x - v1.x);  // (v1 - v3) * (-i)
     const int o = ((tid - k) << 2) + k;
-    out[o] = make_float2(b0.x + b2.x, b0.y + b2.y);
-    out[o + Ns] = make_float2(b1.x + b3.x, b1.y + b3.y);
-    out[o + 2 * Ns] = make_float2(b0.x - b2.x, b0.y - b2.y);
-    out[o + 3 * Ns] = make_float2(b1.x - b3.x, b1.y - b3.y);
+    const float2 r0 = make_float2(b0.x + b2.x, b0.y + b2.y);
+    const float2 r1 = make_float2(b1.x + b3.x, b1.y + b3.y);
+    const float2 r2 = make_float2(b0.x - b2.x, b0.y - b2.y);
+    const float2 r3 = make_float2(b1.x - b3.x, b1.y - b3.y);
+    if (AVVAD_FFT_ROT && s < 2) {
+      // Stages 0 and 1 scatter with a stride of 4 / 16 elements: for a fixed q all lanes of a warp fall on 4 bank
+      // pairs (8-way conflict, 45 % of the store wavefronts of the MCB kernel).  Rotating the order in which a lane
+      // writes its four outputs (q = i + lane for stage 0, i + lane/4 for stage 1) spreads every store instruction
+      // over 16 bank pairs x 2 lanes = the conflict-free two wavefronts.
+      const int rot = (s == 0) ? tid : (tid >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = (i + rot) & 3;
+        const float2 lo = (q & 1) ? r1 : r0, hi = (q & 1) ? r3 : r2;
+        out[o + q * Ns] = (q & 2) ? hi : lo;
+      }
+    } else {
+      out[o] = r0;
+      out[o + Ns] = r1;
+      out[o + 2 * Ns] = r2;
+      out[o + 3 * Ns] = r3;
+    }
     __syncthreads();
     float2* t = in;
     in = out;
