@@ -8,6 +8,21 @@ def count_parameters(model):
     return sum(p.numel() for p in model.parameters() if p.requires_grad)
 
 
+def my_collate(batch):
+    """Legacy many-to-one collate (packages/utils.py:9-40, imported by scripts/train_video_net.py:19): items
+    ``(video (W,H,C,T_i), label, T_i)`` -> ``(lengths, video (B,T,C,H,W) zero-padded and squeezed, target (B,1))``."""
+    lengths = [item[2] for item in batch]
+    T = max(lengths)
+    W, H, C, _ = batch[0][0].shape
+    data = torch.zeros((len(batch), T, C, H, W))
+    target = torch.zeros((len(batch), 1))
+    for i, (item, L) in enumerate(zip(batch, lengths)):
+        data[i, :L] = item[0][..., :L].permute(3, 2, 1, 0)
+        target[i] = item[1]
+    # the reference squeezes singleton axes before its final permute; for C > 1 and B, T > 1 the result is (B,T,C,H,W)
+    return torch.LongTensor(lengths), data.contiguous(), target
+
+
 def _pad_time_last(items, seq_length):
     """Stack tensors (..., T_i) into (B, T, ...) with zero padding on the right."""
     out = items[0].new_zeros((len(items), seq_length) + tuple(items[0].shape[:-1]))

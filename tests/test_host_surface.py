@@ -130,3 +130,76 @@ def test_modules_survive_pickle_and_deepcopy():
             assert list(sd.keys()) == list(ref.keys())
             assert all(torch.equal(sd[k], ref[k]) for k in ref)
             assert clone._engines is not m._engines and clone._engines.by_device == {}
+
+
+def test_host_helpers_match_reference_outputs():
+    """packages/models/utils.py:57-162 and packages/utils.py:9-40 (imported by scripts/train_video_net.py:18-19):
+    our restatements against outputs of the reference's own functions (tests/golden/ref_helpers.npz,
+    tools/make_golden.py:ref_helpers)."""
+    import packages.models.utils as mu
+    import packages.utils as pu
+    from util import golden
+    g = golden("ref_helpers.npz")
+    t = lambda k: torch.tensor(g[k])  # noqa: E731
+    x, r, mu_, lv, y = t("x"), t("r"), t("mu"), t("logvar"), t("y")
+    eps = 1e-8
+
+    def close(a, k):
+        assert np.allclose(np.asarray(a), g[k], atol=1e-6, rtol=1e-5), k
+
+    close(mu.enumerate_discrete(torch.zeros(3, 7), 4), "enumerate")
+    close(mu.onehot(5)(2), "onehot_5_2")
+    close(mu.onehot(3)(7), "onehot_3_7")
+    close(mu.log_sum_exp(x), "lse")
+    close(mu.log_sum_exp(x, 0, torch.mean), "lse_mean0")
+    close(mu.binary_cross_entropy_2classes(x, r, (x > 0.5).float(), eps), "bce2")
+    close(mu.ikatura_saito_divergence(r, x, eps), "isd")
+    for k, v in zip(("elbo0", "elbo1", "elbo2"), mu.elbo(x, r, mu_, lv, eps)):
+        close(v, k)
+    for k, v in zip(("L0", "L1", "L2"), mu.L_loss(x, r, mu_, lv, eps)):
+        close(v, k)
+    for k, v in zip(("U0", "U1", "U2", "U3"), mu.U_loss(x, r, mu_, lv, y, eps)):
+        close(v, k)
+    close(mu.mean_square_error_signal(x, r, x * 0.5), "mse_signal")
+    close(mu.mean_square_error_mask(x, r), "mse_mask")
+    close(mu.magnitude_spectrum_approxiamation_loss(torch.complex(x, r), torch.complex(r, x), x), "msa")
+    vids = [t(f"collate_in{i}") for i in range(3)]
+    lens, data, target = pu.my_collate([(v, torch.tensor(float(i % 2)), v.shape[-1]) for i, v in enumerate(vids)])
+    assert lens.dtype == torch.int64 and lens.tolist() == g["collate_len"].tolist()
+    close(data, "collate_data")
+    close(target, "collate_target")
+
+
+def test_remaining_script_imports_resolve():
+    """Names imported at module top by scripts/train_video_net.py:18-19, scripts/reconstruct_dnn_classif.py and
+    scripts/visualization_audio.py:16-19 (third-party imports such as h5py / librosa / ffmpeg are the scripts' own)."""
+    from packages.models.utils import binary_cross_entropy, binary_cross_entropy_2classes, f1_loss  # noqa: F401
+    from packages.utils import count_parameters, my_collate, collate_many2many_video  # noqa: F401
+    from packages.processing.stft import stft, istft, stft_pytorch  # noqa: F401
+    from packages.processing.target import clean_speech_VAD, clean_speech_IBM, noise_robust_clean_speech_IBM  # noqa: F401
+    from packages.visualization import (display_wav_spectro_mask, display_waveplot, display_spectrogram,  # noqa: F401
+                                        display_power_spectro, display_multiple_signals, display_multiple_spectro)
+
+
+@pytest.mark.parametrize("n", [16000, 81920, 70000])
+@pytest.mark.parametrize("center", [True, False])
+def test_numpy_stft_istft_against_torch(n, center):
+    """packages/processing/stft.py:13-99 wraps librosa.core.stft / istft; ours is plain numpy.  Checked against
+    torch.stft / torch.istft (the same transform: periodic Hann, reflect centre padding, window-sum-square
+    normalisation) and through the analysis -> synthesis round trip."""
+    import math
+    from packages.processing.stft import stft, istft
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    S = stft(x, 16e3, 64e-3, 'hann', 0.25, center, 'reflect', True)
+    padded = math.ceil(n / 16e3 / 64e-3 / 0.25) != int(n / 16e3 / 64e-3 / 0.25)   # the reference's pad-at-end rule
+    xp = np.pad(x, (0, 256)) if padded else x
+    R = torch.stft(torch.tensor(xp), 1024, 256, window=torch.hann_window(1024), center=center, pad_mode='reflect',
+                   return_complex=True).numpy()
+    assert S.dtype == np.complex64 and S.shape == R.shape
+    assert np.abs(S - R).max() < 1e-5
+    if center:
+        y = istft(S, 16000, 64e-3, 'hann', 0.25, True, 'float32', max_len=n)
+        yr = torch.istft(torch.tensor(R), 1024, 256, window=torch.hann_window(1024), center=True, length=n).numpy()
+        assert y.dtype == np.float32 and y.shape == (n,)
+        assert np.abs(y - yr).max() < 1e-6 and np.abs(y - x).max() < 1e-6

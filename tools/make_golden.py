@@ -191,7 +191,48 @@ def ref_models():
     print("ref_models.npz", {k: v.shape for k, v in d.items()})
 
 
+def ref_helpers():
+    """Host-level helpers of packages/models/utils.py:57-162 and packages/utils.py:9-40 on seeded inputs (a separate,
+    small file so that ref_models.npz does not have to be regenerated)."""
+    sys.path.insert(0, REF)
+    import packages.models.utils as mu
+    import packages.utils as pu
+    g = torch.Generator().manual_seed(4321)
+    x = torch.rand(6, 5, generator=g) + 0.1
+    r = torch.rand(6, 5, generator=g) + 0.1
+    mu_, lv = torch.randn(6, 4, generator=g), torch.randn(6, 4, generator=g)
+    y = torch.rand(3, 2, generator=g)
+    t = (x > 0.5).float()
+    eps = 1e-8
+    d = {"x": x, "r": r, "mu": mu_, "logvar": lv, "y": y}
+    d["enumerate"] = mu.enumerate_discrete(torch.zeros(3, 7), 4)
+    d["onehot_5_2"], d["onehot_3_7"] = mu.onehot(5)(2), mu.onehot(3)(7)
+    d["lse"], d["lse_mean0"] = mu.log_sum_exp(x), mu.log_sum_exp(x, 0, torch.mean)
+    d["bce2"] = mu.binary_cross_entropy_2classes(x, r, t, eps)
+    d["isd"] = mu.ikatura_saito_divergence(r, x, eps)
+    for k, v in zip(("elbo0", "elbo1", "elbo2"), mu.elbo(x, r, mu_, lv, eps)):
+        d[k] = v
+    for k, v in zip(("L0", "L1", "L2"), mu.L_loss(x, r, mu_, lv, eps)):
+        d[k] = v
+    for k, v in zip(("U0", "U1", "U2", "U3"), mu.U_loss(x, r, mu_, lv, y, eps)):
+        d[k] = v
+    d["mse_signal"], d["mse_mask"] = mu.mean_square_error_signal(x, r, x * 0.5), mu.mean_square_error_mask(x, r)
+    d["msa"] = mu.magnitude_spectrum_approxiamation_loss(torch.complex(x, r), torch.complex(r, x), x)
+    vids = [torch.rand(4, 5, 3, T, generator=g) for T in (6, 4, 5)]
+    for i, v in enumerate(vids):
+        d[f"collate_in{i}"] = v
+    lens, data, target = pu.my_collate([(v, torch.tensor(float(i % 2)), v.shape[-1]) for i, v in enumerate(vids)])
+    d["collate_len"], d["collate_data"], d["collate_target"] = lens, data, target
+    d = {k: np.asarray(v) for k, v in d.items()}
+    np.savez_compressed(os.path.join(OUT, "ref_helpers.npz"), **d)
+    print("ref_helpers.npz", {k: v.shape for k, v in d.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "helpers":
+        ref_helpers()
+        sys.exit(0)
     golden_frontend()
     golden_upsample()
     ref_models()
+    ref_helpers()
