@@ -203,3 +203,36 @@ def test_numpy_stft_istft_against_torch(n, center):
         yr = torch.istft(torch.tensor(R), 1024, 256, window=torch.hann_window(1024), center=True, length=n).numpy()
         assert y.dtype == np.float32 and y.shape == (n,)
         assert np.abs(y - yr).max() < 1e-6 and np.abs(y - x).max() < 1e-6
+
+
+def test_raw_corpus_listers(tmp_path):
+    """packages/dataset/ntcd_timit.py:57-96,193-381 (imported by scripts/create_audio_train_files.py:27 and
+    scripts/create_video_train_files_upsampled.py:27).  Expected mappings were checked against the reference's own
+    functions on the same synthetic tree in the build container."""
+    from packages.dataset.ntcd_timit import kaldi_list, noisy_clean_pair_dict, noisy_speech_dict
+    root = str(tmp_path) + '/'
+    for split in ('train', 'dev', 'test'):
+        for spk in ('01M', '08F'):
+            for utt in ('sa1', 'si494'):
+                for sub, exts in (('matlab_raw', ('.mat',)), ('kaldi_fMLLR', ('.ark', '.scp'))):
+                    d = os.path.join(root, 'ntcd_timit', sub, split, spk)
+                    os.makedirs(d, exist_ok=True)
+                    for e in exts:
+                        open(os.path.join(d, utt + e), 'w').close()
+    noisy = 'ntcd_timit/u/drspeech/data/TCDTIMIT/Noisy_TCDTIMIT/'
+    sub = noisy_clean_pair_dict(root, 'test', 'subset')
+    assert list(sub.items()) == [
+        (noisy + 'Babble/-5/volunteers/01M/straightcam/sa1.wav', 'ntcd_timit/Clean/test/01M/sa1.wav'),
+        (noisy + 'Babble/-5/volunteers/01M/straightcam/si494.wav', 'ntcd_timit/Clean/test/01M/si494.wav'),
+        (noisy + 'Babble/-5/volunteers/08F/straightcam/sa1.wav', 'ntcd_timit/Clean/test/08F/sa1.wav'),
+        (noisy + 'Babble/-5/volunteers/08F/straightcam/si494.wav', 'ntcd_timit/Clean/test/08F/si494.wav')]
+    full = noisy_clean_pair_dict(root, 'validation')
+    assert len(full) == 6 * 3 * 4 and full[noisy + 'White/5/volunteers/08F/straightcam/si494.wav'] == \
+        'ntcd_timit/Clean/dev/08F/si494.wav'
+    out = noisy_speech_dict(root, 'train', 'subset')
+    assert out[noisy + 'Babble/-5/volunteers/01M/straightcam/sa1.wav'] == 'ntcd_timit/Noisy/Babble/-5/train/01M/sa1.wav'
+    assert len(noisy_speech_dict(root, 'train')) == 72
+    ark, scp = kaldi_list(root, 'test')
+    assert ark == ['ntcd_timit/kaldi_fMLLR/test/01M/sa1.ark', 'ntcd_timit/kaldi_fMLLR/test/01M/si494.ark',
+                   'ntcd_timit/kaldi_fMLLR/test/08F/sa1.ark', 'ntcd_timit/kaldi_fMLLR/test/08F/si494.ark']
+    assert [p[:-4] for p in scp] == [p[:-4] for p in ark]
