@@ -236,3 +236,14 @@ def test_raw_corpus_listers(tmp_path):
     assert ark == ['ntcd_timit/kaldi_fMLLR/test/01M/sa1.ark', 'ntcd_timit/kaldi_fMLLR/test/01M/si494.ark',
                    'ntcd_timit/kaldi_fMLLR/test/08F/sa1.ark', 'ntcd_timit/kaldi_fMLLR/test/08F/si494.ark']
     assert [p[:-4] for p in scp] == [p[:-4] for p in ark]
+
+
+def test_csr1_pickle_round_trip(tmp_path, capsys):
+    from packages.dataset.csr1_wjs0 import read_dataset, write_dataset
+    root = str(tmp_path) + '/'
+    data = {"x": np.arange(6).reshape(2, 3), "names": ["a", "b"]}
+    write_dataset(data, root, 'validation', suffix='frames')
+    assert os.path.exists(root + 'CSR-1-WSJ-0/si_dt_05_frames.p')
+    back = read_dataset(root, 'validation', suffix='frames')
+    assert back["names"] == data["names"] and np.array_equal(back["x"], data["x"])
+    assert "data is stored in" in capsys.readouterr().out
