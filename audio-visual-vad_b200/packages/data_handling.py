@@ -2,7 +2,9 @@
 packages/data_handling.py:192-495).  The per-utterance front end (peak-normalise -> STFT -> |.|^2 -> log) runs through
 packages.processing.stft.stft_pytorch, i.e. on the GPU: use num_workers=0 (or a 'spawn' worker context) with the
 spectrogram datasets, or the *Wav* variants + avvad.pipeline / collate_many2many_*_waveform to keep the workers CPU-only
-and do the whole front end batched on the device.  The legacy HDF5*/VideoFrames datasets are not provided."""
+and do the whole front end batched on the device.  The legacy HDF5*/VideoFrames datasets (data_handling.py:19-189, unused
+by the VAD scripts) are kept as thin host-side classes at the end of the file."""
+import math
 import os
 
 import numpy as np
@@ -118,3 +120,107 @@ class NoisyWavWholeSequenceWavLabeledFrames(_NoisyBase):
         wave = wave / torch.max(torch.abs(wave))
         label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
         return wave, label, wave.shape[-1], label.shape[-1]
+
+
+# ---- legacy datasets (data_handling.py:19-189): frame / sequence views of one big "X_<split>" / "Y_<split>" pair ---------
+
+class _H5Pair(Dataset):
+    """Shared part of the three HDF5* datasets: the file is opened lazily in the worker (first __getitem__), the two
+    arrays are (features, N) and (labels, N) with the frame index last."""
+
+    def __init__(self, output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots):
+        self.output_h5_dir, self.dataset_type = output_h5_dir, dataset_type
+        self.rdcc_nbytes, self.rdcc_nslots = rdcc_nbytes, rdcc_nslots  # chunk-cache hints of h5py; unused by read_h5
+        self.n_frames = read_h5(output_h5_dir, "X_" + dataset_type).shape[-1]
+
+    def open_hdf5(self):
+        self.data = read_h5(self.output_h5_dir, "X_" + self.dataset_type)
+        self.labels = read_h5(self.output_h5_dir, "Y_" + self.dataset_type)
+        self.f = True
+
+    def _ensure_open(self):
+        if not hasattr(self, "f"):
+            self.open_hdf5()
+
+
+class HDF5SpectrogramLabeledFrames(_H5Pair):
+    """Item i = (spectrogram column i, label column i) (data_handling.py:51-80)."""
+
+    def __init__(self, output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots):
+        super().__init__(output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots)
+        self.dataset_len = self.n_frames
+
+    def __getitem__(self, i):
+        self._ensure_open()
+        return self.data[:, i], self.labels[:, i]
+
+    def __len__(self):
+        return self.dataset_len
+
+
+class HDF5SequenceSpectrogramLabeledFrames(_H5Pair):
+    """Item i = (the up-to-seq_length frames ending at i, the label of frame i, length) (data_handling.py:82-138)."""
+
+    def __init__(self, output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots, seq_length):
+        super().__init__(output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots)
+        self.seq_length, self.dataset_len = seq_length, self.n_frames
+
+    def __getitem__(self, i):
+        self._ensure_open()
+        first = 0 if i < self.seq_length else i + 1 - self.seq_length
+        data = np.array(self.data[..., first:i + 1])
+        labels = np.array(self.labels[..., i:i + 1])
+        return torch.Tensor(data), torch.Tensor(labels), data.shape[-1]
+
+    def __len__(self):
+        return self.dataset_len
+
+
+class HDF5WholeSequenceSpectrogramLabeledFrames(_H5Pair):
+    """Item i = the i-th non-overlapping block of seq_length frames with all its labels (data_handling.py:140-189)."""
+
+    def __init__(self, output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots, seq_length):
+        super().__init__(output_h5_dir, dataset_type, rdcc_nbytes, rdcc_nslots)
+        self.seq_length, self.dataset_len = seq_length, math.ceil(self.n_frames / seq_length)
+
+    def __getitem__(self, i):
+        self._ensure_open()
+        lo = i * self.seq_length
+        data = np.array(self.data[..., lo:lo + self.seq_length])
+        labels = np.array(self.labels[..., lo:lo + self.seq_length])
+        return torch.Tensor(data), torch.Tensor(labels), data.shape[-1]
+
+    def __len__(self):
+        return self.dataset_len
+
+
+class VideoFrames(Dataset):
+    """Random seq_length-frame window of one speaker's DCT frames, decoded to 3x67x67, with the label of the frame
+    after the window (data_handling.py:19-49; paths relative to the working directory as in the reference)."""
+
+    def __init__(self, data, seq_length):
+        self.data, self.seq_length = data, seq_length
+        self.index = np.arange(len(self.data))
+
+    def __getitem__(self, i):
+        from packages.processing.video import _idct_unnormalised
+        from avvad.h5min import H5File
+        mat_file_path = os.path.join("data/complete/matlab_raw", self.data[i]) + ".mat"
+        try:
+            import h5py
+            with h5py.File(mat_file_path, "r") as f:
+                frames = [np.array(v) for v in f.values()][-1]
+        except ImportError:
+            f = H5File(mat_file_path)
+            frames = f[list(f.keys())[-1]]
+        peak = frames.flatten().max() + 1e-8
+        video = torch.empty(frames.shape[0], 3, 67, 67)
+        for k in range(frames.shape[0]):
+            img = _idct_unnormalised(_idct_unnormalised(frames[k].reshape(67, 67)).T).T
+            video[k] = torch.from_numpy(np.ascontiguousarray(np.rot90(img / peak * 255.0, 3))).float().expand(3, 67, 67)
+        start = np.random.randint(frames.shape[0] - self.seq_length)
+        labels = np.load("{}{}.npy".format("data/complete/labels/", self.data[i]))[start + self.seq_length]
+        return video[start:start + self.seq_length], labels
+
+    def __len__(self):
+        return len(self.data)

@@ -247,3 +247,23 @@ def test_csr1_pickle_round_trip(tmp_path, capsys):
     back = read_dataset(root, 'validation', suffix='frames')
     assert back["names"] == data["names"] and np.array_equal(back["x"], data["x"])
     assert "data is stored in" in capsys.readouterr().out
+
+
+def test_legacy_hdf5_datasets(monkeypatch):
+    """data_handling.py:51-189: frame, trailing-sequence and block views over one (F, N) / (y, N) array pair."""
+    import packages.data_handling as dh
+    X = np.arange(3 * 10, dtype=np.float32).reshape(3, 10)
+    Y = (np.arange(10, dtype=np.float32) % 2)[None]
+    monkeypatch.setattr(dh, "read_h5", lambda path, key: {"X_train": X, "Y_train": Y}[key])
+    a = dh.HDF5SpectrogramLabeledFrames("f.h5", "train", 1, 1)
+    assert len(a) == 10 and np.array_equal(a[4][0], X[:, 4]) and np.array_equal(a[4][1], Y[:, 4])
+    b = dh.HDF5SequenceSpectrogramLabeledFrames("f.h5", "train", 1, 1, seq_length=4)
+    d, l, n = b[2]
+    assert n == 3 and torch.equal(d, torch.tensor(X[:, :3])) and torch.equal(l, torch.tensor(Y[:, 2:3]))
+    d, l, n = b[7]
+    assert n == 4 and torch.equal(d, torch.tensor(X[:, 4:8])) and torch.equal(l, torch.tensor(Y[:, 7:8]))
+    c = dh.HDF5WholeSequenceSpectrogramLabeledFrames("f.h5", "train", 1, 1, seq_length=4)
+    assert len(c) == 3
+    d, l, n = c[2]
+    assert n == 2 and torch.equal(d, torch.tensor(X[:, 8:])) and torch.equal(l, torch.tensor(Y[:, 8:]))
+    assert len(dh.VideoFrames(["01M/sa1", "01M/sa2"], 5)) == 2
