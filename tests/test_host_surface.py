@@ -267,3 +267,17 @@ def test_legacy_hdf5_datasets(monkeypatch):
     d, l, n = c[2]
     assert n == 2 and torch.equal(d, torch.tensor(X[:, 8:])) and torch.equal(l, torch.tensor(Y[:, 8:]))
     assert len(dh.VideoFrames(["01M/sa1", "01M/sa2"], 5)) == 2
+
+
+def test_threshold_masks_match_reference_outputs():
+    """packages/processing/target.py:110-251 against outputs of the reference's own functions
+    (tests/golden/ref_target_masks.npz, tools/make_golden.py:ref_target_masks): tables and masks bit-exact."""
+    from packages.processing.target import _voiced_unvoiced_split_characteristic, noise_aware_IBM, threshold_IBM
+    from util import golden
+    g = golden("ref_target_masks.npz")
+    voiced, unvoiced = _voiced_unvoiced_split_characteristic(513)
+    assert np.array_equal(voiced, g["voiced"]) and np.array_equal(unvoiced, g["unvoiced"])
+    speech, noise = noise_aware_IBM(g["X"], g["N"])
+    assert np.array_equal(speech, g["speech"]) and np.array_equal(noise, g["noise"])
+    assert np.array_equal(threshold_IBM(g["X"]), g["thresh"])
+    assert 0.2 < speech.mean() < 0.6  # the fixture is not degenerate

@@ -228,11 +228,34 @@ def ref_helpers():
     print("ref_helpers.npz", {k: v.shape for k, v in d.items()})
 
 
+def ref_target_masks():
+    """Threshold-based masks of packages/processing/target.py:110-251 on a seeded complex spectrogram pair.  The module
+    imports librosa at its top (absent here; only clean_speech_VAD uses it), so an empty stand-in is registered."""
+    import importlib.util
+    import types
+    for name in ("librosa", "librosa.util"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["librosa"].util = sys.modules["librosa.util"]
+    spec = importlib.util.spec_from_file_location("ref_target", os.path.join(REF, "packages/processing/target.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(3)
+    X = (rng.standard_normal((7, 513)) + 1j * rng.standard_normal((7, 513))) * rng.uniform(0.01, 5, (7, 513))
+    N = (rng.standard_normal((7, 513)) + 1j * rng.standard_normal((7, 513))) * rng.uniform(0.01, 5, (7, 513))
+    voiced, unvoiced = ref._voiced_unvoiced_split_characteristic(513)
+    speech, noise = ref.noise_aware_IBM(X, N)
+    np.savez_compressed(os.path.join(OUT, "ref_target_masks.npz"), X=X, N=N, voiced=voiced, unvoiced=unvoiced,
+                        speech=speech, noise=noise, thresh=ref.threshold_IBM(X))
+    print("ref_target_masks.npz", speech.mean(), noise.mean())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[2] == "helpers":
         ref_helpers()
+        ref_target_masks()
         sys.exit(0)
     golden_frontend()
     golden_upsample()
     ref_models()
     ref_helpers()
+    ref_target_masks()
