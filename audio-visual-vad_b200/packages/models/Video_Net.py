@@ -4,7 +4,8 @@ import torch.nn as nn
 import torchvision.models as models
 
 from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
-from ._engine import E, EngineCache, check_inference_only, device_of, full_state_dict, on_input_device
+from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params,
+                      on_input_device, trunk_bn_modules)
 
 
 class DeepVAD_video(nn.Module):
@@ -43,6 +44,7 @@ class DeepVAD_video(nn.Module):
                           "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
             sd = full_state_dict(self)
             eng["trunk"].load(sd, device)
+            eng["trunk"].load_train(sd, device)
             eng["lstm"].load(sd, device, "lstm_video", "vad_video")
             return eng
         return self._engines.get(self, device, builder)
@@ -51,12 +53,29 @@ class DeepVAD_video(nn.Module):
     def forward(self, x, lengths, return_last=False):
         """x (B,T,67,67), lengths -> logits (B,T,y_dim), or (B,y_dim) at the last valid step."""
         device = device_of(x)
-        check_inference_only(self)
         eng = self._build(device)
         batch, frames, height, width = x.size()
         M = batch * frames
         xb = eng["lstm"].new_input(batch, frames, device)
-        eng["trunk"].forward(x.detach().to(torch.float32).reshape(M, height, width), feat_bf16=xb.view(M, -1),
-                             col_off=0, want_f32=False)
+        vid = x.detach().to(torch.float32).reshape(M, height, width)
+        # eval() forward is inference only (detached logits, folded BN).  train(): the LSTM + head train through the
+        # device BPTT with the trunk FROZEN in batch-statistics mode -- what scripts/train_AV_net.py:241-253 does to the
+        # same trunk; scripts/train_video_net.py leaves it trainable, which needs the ResNet backward (not implemented).
+        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self))
+        if need_grad and any(p.requires_grad for p in all_parameters(self.features)):
+            raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze 'features' "
+                                      "(as scripts/train_AV_net.py:241-245 does) to train the LSTM and the head")
+        if self.training:
+            bns = trunk_bn_modules(self.features)
+            eng["trunk"].forward_train(vid, [(b.running_mean, b.running_var) for b in bns], feat_bf16=xb.view(M, -1),
+                                       col_off=0, want_f32=False)
+            for b in bns:
+                b.num_batches_tracked += 1
+        else:
+            eng["trunk"].forward(vid, feat_bf16=xb.view(M, -1), col_off=0, want_f32=False)
+        if need_grad:
+            if return_last:
+                raise NotImplementedError("return_last=True has no training path (unused by the scripts)")
+            return LstmHeadFunction.apply(eng["lstm"], xb, lengths, None, *lstm_params(self.lstm_video, self.vad_video))
         logits, _, _, last = eng["lstm"].forward(xb, lengths, want_last=return_last)
         return last if return_last else logits

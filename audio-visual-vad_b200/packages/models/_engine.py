@@ -154,13 +154,6 @@ class FusedAdam(torch.optim.Optimizer):
                 p._avvad_gen = getattr(p, "_avvad_gen", 0) + 1
 
 
-def check_inference_only(module: torch.nn.Module):
-    if module.training:
-        raise NotImplementedError(
-            "libavvad implements the eval-mode forward (BatchNorm running statistics) of this module; "
-            "call .eval() first.  The training step (batch-statistics BN, backward, Adam) is not built yet.")
-
-
 def on_input_device(forward):
     """Runs a module's forward with the CUDA device of its first tensor argument made current.  libavvad launches on
     the calling thread's current device and stream, whereas the reference's evaluation workers only ever call

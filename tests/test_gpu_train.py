@@ -188,3 +188,43 @@ def test_ibm_head_training_gradients_match_autograd():
         report[k] = round(st["rel_fro"], 4)
         assert st["rel_fro"] < 3e-2, (k, st)
     print("ibm-head grad rel errors:", report)
+
+
+def test_video_training_step_with_frozen_trunk_matches_autograd():
+    """DeepVAD_video in train() with `features` frozen (train_AV_net.py:241-245 applied to the video-only model):
+    batch-statistics trunk + device BPTT vs fp32 autograd of the oracle; an un-frozen trunk must raise."""
+    from packages.models.Video_Net import DeepVAD_video
+    B, T = 3, 10
+    lens = [10, 7, 4]
+    g = torch.Generator().manual_seed(18)
+    v = torch.randn(B, T, 67, 67, generator=g)
+    y = (torch.rand(B, T, 1, generator=g) > 0.5).float()
+    sd = synth.seeded_state_dict(synth.model_spec("video"), seed=56)
+    p = {k: (t.clone().requires_grad_(True) if (t.is_floating_point() and not k.startswith("features.")) else t.clone())
+         for k, t in sd.items()}
+    logits_ref = om.deepvad_video_forward(v, lens, p, training=True)
+    loss_ref = om.batch_loss(logits_ref, y, lens, 1e-8)
+    loss_ref.backward()
+    m = DeepVAD_video(2, 1024, 1)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    with pytest.raises(NotImplementedError):
+        m(v.cuda(), torch.tensor(lens).cuda())
+    for q in m.features.parameters():
+        q.requires_grad = False
+    logits = m(v.cuda(), torch.tensor(lens).cuda())
+    loss, _, dl = E.batch_bce(logits, y.cuda(), lens, 1e-8, want_grad=True)
+    assert abs(loss.item() - loss_ref.item()) < 3e-2 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    logits.backward(dl)
+    params = dict(m.named_parameters())
+    report = {}
+    for k in ("lstm_video.weight_ih_l0", "lstm_video.weight_hh_l0", "lstm_video.bias_ih_l0", "lstm_video.weight_ih_l1",
+              "lstm_video.weight_hh_l1", "vad_video.weight", "vad_video.bias"):
+        report[k] = round(err_stats(params[k].grad.cpu().numpy(), p[k].grad.numpy())["rel_fro"], 4)
+    print("video grad rel errors:", report)
+    assert all(e < 6e-2 for e in report.values()), report
+    assert int(m.features[1].num_batches_tracked) == 1
+    m.eval()
+    with torch.no_grad():
+        out = m(v.cuda(), lens)
+    assert out.shape == (B, T, 1) and not out.requires_grad
