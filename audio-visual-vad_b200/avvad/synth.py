@@ -97,10 +97,40 @@ def _gen(seed: int, key: str) -> torch.Generator:
     return g
 
 
-def seeded_tensor(key: str, shape, dtype, seed: int) -> torch.Tensor:
-    """One tensor of a synthetic state_dict, a pure function of (seed, key, shape)."""
+# Weight families.  "default" = PyTorch's own init scale: with H = 1024 the LSTM / head weights are U(+-1/32) and the
+# resulting logits stay within a few 1e-2 of the head bias, so posterior tolerances alone cannot tell a working recurrence
+# from a broken one.  "strong" scales the LSTM weights x2 and the head weights x16: logits span several units, so
+# relative errors on the LOGITS are meaningful.  For the >= 99.9 % decision-agreement gate of BASELINE.json the head bias
+# is additionally placed with `decision_bias` below.
+FAMILIES = {"default": (1.0, 1.0), "strong": (2.0, 16.0)}
+
+
+def decision_bias(logits, lengths, bias, z=2.5):
+    """Head bias that puts the valid-frame logit distribution of every output unit j at mean s_j * z * sigma
+    (s_j = +1 for even j, -1 for odd j; sigma = pooled std), given `logits` (B,T,Y) computed with head bias `bias` (Y,).
+
+    Why: a zero-centred random logit flips sign with probability ~0.8 x (relative logit error) under ANY bf16
+    implementation (~0.3 % here), whereas the logits of a trained VAD are confident; moving the bulk z sigma away from
+    the threshold leaves both classes present (the lower tail for y_dim = 1, alternating units for y_dim = 513) and the
+    expected flip rate of a correct bf16 path well under 0.1 %.  Logits are affine in the bias, so the calibration is
+    exact: new_logits = logits - bias + new_bias."""
+    import numpy as _np
+    lg = _np.asarray(logits, dtype=_np.float64)
+    mask = _np.zeros(lg.shape[:2], dtype=bool)
+    for b, n in enumerate(lengths):
+        mask[b, : int(n)] = True
+    v = lg[mask]                                   # (frames, Y)
+    mu = v.mean(0)
+    sigma = float((v - mu).std())
+    sign = _np.where(_np.arange(v.shape[1]) % 2 == 0, 1.0, -1.0)
+    return torch.tensor(_np.asarray(bias, dtype=_np.float64) - mu + sign * z * sigma, dtype=torch.float32)
+
+
+def seeded_tensor(key: str, shape, dtype, seed: int, family: str = "default") -> torch.Tensor:
+    """One tensor of a synthetic state_dict, a pure function of (seed, key, shape, family)."""
     g = _gen(seed, key)
     leaf = key.rsplit(".", 1)[-1]
+    lstm_gain, head_gain = FAMILIES[family]
     if leaf == "num_batches_tracked":
         return torch.zeros((), dtype=torch.int64)
     if leaf == "h":
@@ -125,18 +155,32 @@ def seeded_tensor(key: str, shape, dtype, seed: int) -> torch.Tensor:
         return torch.randn(shape, generator=g) * (1.0 / fan_in) ** 0.5
     if "lstm" in key or key.startswith("vad_"):
         k = 1.0 / 32.0  # PyTorch default U(-1/sqrt(H), 1/sqrt(H)) with H=1024
-        return (torch.rand(shape, generator=g) * 2 - 1) * k
+        t = (torch.rand(shape, generator=g) * 2 - 1) * k
+        if "lstm" in key and leaf.startswith("weight"):
+            t = t * lstm_gain
+        elif key.startswith("vad_") and leaf == "weight":
+            t = t * head_gain
+        return t
     return torch.randn(shape, generator=g) * 0.05
 
 
-def seeded_state_dict(spec, seed=0) -> "OrderedDict[str, torch.Tensor]":
-    return OrderedDict((k, seeded_tensor(k, shp, dt, seed)) for k, (shp, dt) in spec.items())
+def seeded_state_dict(spec, seed=0, family="default") -> "OrderedDict[str, torch.Tensor]":
+    return OrderedDict((k, seeded_tensor(k, shp, dt, seed, family)) for k, (shp, dt) in spec.items())
 
 
-def fill_module_(module: torch.nn.Module, seed=0):
+def calibrate_mcb_bn_(sd, rows: int):
+    """Set mcb_bn's running statistics to the scale the whole-tensor L2 normalisation produces for a call of `rows`
+    frames (AV_Net.py:117 divides by the norm of all rows x 1024 values, so each element is ~1/sqrt(rows*1024)); without
+    this the eval-mode BatchNorm1d output is ~1e-3 and the LSTM sees no signal."""
+    sd["mcb_bn.running_mean"] = torch.zeros(1024)
+    sd["mcb_bn.running_var"] = torch.full((1024,), 1.0 / (rows * 1024.0))
+    return sd
+
+
+def fill_module_(module: torch.nn.Module, seed=0, family="default"):
     """Overwrite every tensor in module.state_dict() with its seeded value (in place)."""
     sd = module.state_dict()
-    new = OrderedDict((k, seeded_tensor(k, tuple(v.shape), v.dtype, seed)) for k, v in sd.items())
+    new = OrderedDict((k, seeded_tensor(k, tuple(v.shape), v.dtype, seed, family)) for k, v in sd.items())
     module.load_state_dict(new)
     return module
 
@@ -163,6 +207,25 @@ def synth_video_u8(n_frames: int, seed: int, h=67, w=67) -> np.ndarray:
     sm = np.apply_along_axis(lambda v: np.convolve(v, k, mode="valid"), 2, sm)
     sm = (sm - sm.min()) / (sm.max() - sm.min()) * 255.0
     return np.clip(np.rint(sm), 0, 255).astype(np.uint8)
+
+
+def batch_inputs(B: int, seed: int, n_samples=81920, n_src=152):
+    """A whole synthetic batch at once (torch RNG; the per-utterance numpy generators above are too slow for B=256):
+    waveforms (B,n_samples) f32 = 0.1*N(0,1) under a 0.5-4 Hz envelope, clipped; video (B,n_src,67,67) u8 = 5x5 box-filtered
+    uniform noise stretched to [0,255]; plus the synthetic per-bin audio statistics.  Shared by bench.py and the
+    benchmark-shape parity test."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n_samples, dtype=torch.float32) / 16000.0
+    f_env = 0.5 + 3.5 * torch.rand(B, 1, generator=g)
+    ph = 6.2831853 * torch.rand(B, 1, generator=g)
+    env = 0.55 + 0.45 * torch.sin(6.2831853 * f_env * t[None, :] + ph)
+    wave = (0.1 * torch.randn(B, n_samples, generator=g) * env).clamp_(-1, 1)
+    vid = torch.rand(B * n_src, 1, 71, 71, generator=g) * 255.0
+    vid = torch.nn.functional.avg_pool2d(vid, 5, stride=1)  # low-pass -> (.,1,67,67)
+    lo, hi = vid.amin(), vid.amax()
+    vid = ((vid - lo) / (hi - lo) * 255.0).round_().clamp_(0, 255).to(torch.uint8).view(B, n_src, 67, 67)
+    mean, std = synth_audio_stats(0)
+    return wave.contiguous(), vid.contiguous(), mean, std
 
 
 def synth_audio_stats(seed=0):

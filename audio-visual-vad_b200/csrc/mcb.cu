@@ -217,6 +217,117 @@ __global__ void __launch_bounds__(256) mcb_bn_grad_kernel(const float* __restric
   }
 }
 
+// ---- stand-alone count sketch / compact bilinear pooling (compact_bilinear_pooling.py:59-113,140-263) ----
+// Generic sizes: out[row][j] = sum_{i: h_i = j} s_i x[row][i], collisions summed in ascending i (CSR built by the host).
+__global__ void count_sketch_fwd_kernel(const float* __restrict__ x, int64_t rows, int in_size, int out_size,
+                                        const int32_t* __restrict__ off, const int32_t* __restrict__ idx,
+                                        const float* __restrict__ s, float* __restrict__ out) {
+  const int64_t row = blockIdx.x;
+  const float* xr = x + row * in_size;
+  for (int j = threadIdx.x; j < out_size; j += blockDim.x) {
+    float acc = 0.f;
+    for (int e = off[j]; e < off[j + 1]; ++e) {
+      const int i = idx[e];
+      acc += xr[i] * s[i];
+    }
+    out[row * out_size + j] = acc;
+  }
+}
+// grad_x[row][i] = s_i * grad_out[row][h_i]   (CountSketchFn_backward, compact_bilinear_pooling.py:29-41)
+__global__ void count_sketch_bwd_kernel(const float* __restrict__ go, int64_t rows, int in_size, int out_size,
+                                        const int32_t* __restrict__ h, const float* __restrict__ s,
+                                        float* __restrict__ gx) {
+  const int64_t row = blockIdx.x;
+  for (int i = threadIdx.x; i < in_size; i += blockDim.x) gx[row * in_size + i] = s[i] * go[row * out_size + h[i]];
+}
+
+// One row of irfft(rfft(u) * rfft(v)) (MODE 0: circular convolution) or irfft(rfft(u) * conj(rfft(v))) (MODE 1:
+// circular correlation, the adjoint the reference's backward applies: compact_bilinear_pooling.py:186-215), u and v real
+// length-1024 sequences already in `z` as (u, v) pairs.  Returns the buffer whose .x holds 1024 * result.
+template <int MODE>
+__device__ __forceinline__ const float2* circ_product_1024(float2* z, float2* scratch, const float2* stw, int tid) {
+  float2* z1 = fft1024_smem(z, scratch, stw, tid);
+  float2* z2 = (z1 == z) ? scratch : z;
+  for (int k = tid; k <= 512; k += kFftThreads) {
+    if (k == 0 || k == 512) {
+      const float2 q = z1[k];
+      z1[k] = make_float2(q.x * q.y, 0.f);
+    } else {
+      const float2 zk = z1[k];
+      const float2 zn = z1[kFftN - k];
+      const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      float2 Y = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      if (MODE == 1) Y.y = -Y.y;
+      const float2 P = cmul(X, Y);
+      z1[k] = make_float2(P.x, -P.y);
+      z1[kFftN - k] = make_float2(P.x, P.y);
+    }
+  }
+  __syncthreads();
+  return fft1024_smem(z1, z2, stw, tid);
+}
+
+// MODE 0: out[1024] = sketch1(x) (*) sketch2(y)                       (forward)
+// MODE 1: gx[513]  = sketch1^T( go (corr) sketch2(y) )                 (gradient w.r.t. x)
+// MODE 2: gy[512]  = sketch2^T( go (corr) sketch1(x) )                 (gradient w.r.t. y)
+template <int MODE>
+__global__ void __launch_bounds__(kFftThreads)
+mcb_raw_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ go, McbTables tb,
+               const int32_t* __restrict__ hsel, const float2* __restrict__ tw_g, float* __restrict__ out) {
+  __shared__ float2 sa[kFftN];
+  __shared__ float2 sb[kFftN];
+  __shared__ float2 stw[kFftTwStage];
+  __shared__ float xin[kNA];
+  const int tid = threadIdx.x;
+  const int64_t row = blockIdx.x;
+#pragma unroll
+  for (int q = 0; q < kFftTwStage / kFftThreads; ++q)
+    stw[tid + q * kFftThreads] = tw_g[kFftTwHann + tid + q * kFftThreads];
+  if (MODE == 0) {
+    __shared__ float yin[kNV];
+    for (int i = tid; i < kNA; i += kFftThreads) xin[i] = x[row * kNA + i];
+    for (int i = tid; i < kNV; i += kFftThreads) yin[i] = y[row * kNV + i];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = tid + q * kFftThreads;
+      float px = 0.f, py = 0.f;
+      for (int e = tb.off1[j]; e < tb.off1[j + 1]; ++e) px += xin[tb.idx1[e]] * tb.s1[tb.idx1[e]];
+      for (int e = tb.off2[j]; e < tb.off2[j + 1]; ++e) py += yin[tb.idx2[e]] * tb.s2[tb.idx2[e]];
+      sa[j] = make_float2(px, py);
+    }
+  } else {
+    // the sketch of the OTHER input is the correlation kernel
+    const int n_other = (MODE == 1) ? kNV : kNA;
+    const float* other = (MODE == 1) ? y : x;
+    const int32_t* off = (MODE == 1) ? tb.off2 : tb.off1;
+    const int32_t* idx = (MODE == 1) ? tb.idx2 : tb.idx1;
+    const float* sg = (MODE == 1) ? tb.s2 : tb.s1;
+    for (int i = tid; i < n_other; i += kFftThreads) xin[i] = other[row * n_other + i];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = tid + q * kFftThreads;
+      float p = 0.f;
+      for (int e = off[j]; e < off[j + 1]; ++e) p += xin[idx[e]] * sg[idx[e]];
+      sa[j] = make_float2(go[row * kMcbOut + j], p);
+    }
+  }
+  __syncthreads();
+  const float2* res = circ_product_1024<(MODE == 0) ? 0 : 1>(sa, sb, stw, tid);
+  if (MODE == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = tid + q * kFftThreads;
+      out[row * kMcbOut + j] = res[j].x * (1.0f / kFftN);
+    }
+  } else {
+    const int n_self = (MODE == 1) ? kNA : kNV;
+    const float* ss = (MODE == 1) ? tb.s1 : tb.s2;
+    for (int i = tid; i < n_self; i += kFftThreads) out[row * n_self + i] = ss[i] * res[hsel[i]].x * (1.0f / kFftN);
+  }
+}
+
 __global__ void bn_invstd_kernel(const float* __restrict__ var, float eps, float* __restrict__ invstd, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) invstd[i] = 1.0f / sqrtf(var[i] + eps);
@@ -391,5 +502,55 @@ extern "C" int avvad_mcb_backward_bn(avvad_mcb* h, void* workspace, const float*
   float* mean_invstd = norm + 64;
   mcb_bn_grad_kernel<<<kMcbOut, 256, 0, (cudaStream_t)stream>>>(y, norm, mean_invstd, dx, ld_dx, rows, dgamma, dbeta);
   AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+
+// ---- stand-alone modules (CountSketch / CompactBilinearPooling used outside DeepVAD_AV) ----
+extern "C" int avvad_count_sketch_forward(const float* x, int64_t rows, int in_size, int out_size, const int32_t* off,
+                                          const int32_t* idx, const float* s, float* out, void* stream) {
+  AVVAD_CHECK_ARG(x && off && idx && s && out && rows > 0 && in_size > 0 && out_size > 0, "bad argument");
+  AVVAD_CHECK_ARG(rows < (1ll << 31), "too many rows");
+  count_sketch_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(x, rows, in_size, out_size, off, idx, s, out);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+extern "C" int avvad_count_sketch_backward(const float* grad_out, int64_t rows, int in_size, int out_size,
+                                           const int32_t* h, const float* s, float* grad_x, void* stream) {
+  AVVAD_CHECK_ARG(grad_out && h && s && grad_x && rows > 0 && in_size > 0 && out_size > 0, "bad argument");
+  AVVAD_CHECK_ARG(rows < (1ll << 31), "too many rows");
+  count_sketch_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(grad_out, rows, in_size, out_size, h, s,
+                                                                            grad_x);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+extern "C" int avvad_mcb_raw_forward(const int32_t* off1, const int32_t* idx1, const float* s1, const int32_t* off2,
+                                     const int32_t* idx2, const float* s2, const float* x, const float* y, int64_t rows,
+                                     float* out, void* stream) {
+  AVVAD_CHECK_ARG(off1 && idx1 && s1 && off2 && idx2 && s2 && x && y && out && rows > 0, "bad argument");
+  AVVAD_CHECK_ARG(rows < (1ll << 31), "too many rows");
+  const float2* tw = fft_twiddles_device();
+  if (!tw) { set_error("twiddle table allocation failed"); return AVVAD_ERR_CUDA; }
+  McbTables tb{off1, idx1, s1, off2, idx2, s2};
+  mcb_raw_kernel<0><<<(unsigned)rows, kFftThreads, 0, (cudaStream_t)stream>>>(x, y, nullptr, tb, nullptr, tw, out);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
+}
+extern "C" int avvad_mcb_raw_backward(const int32_t* off1, const int32_t* idx1, const float* s1, const int32_t* h1,
+                                      const int32_t* off2, const int32_t* idx2, const float* s2, const int32_t* h2,
+                                      const float* x, const float* y, const float* grad_out, int64_t rows, float* grad_x,
+                                      float* grad_y, void* stream) {
+  AVVAD_CHECK_ARG(off1 && idx1 && s1 && h1 && off2 && idx2 && s2 && h2 && x && y && grad_out && rows > 0, "bad argument");
+  AVVAD_CHECK_ARG(rows < (1ll << 31), "too many rows");
+  const float2* tw = fft_twiddles_device();
+  if (!tw) { set_error("twiddle table allocation failed"); return AVVAD_ERR_CUDA; }
+  McbTables tb{off1, idx1, s1, off2, idx2, s2};
+  if (grad_x) {
+    mcb_raw_kernel<1><<<(unsigned)rows, kFftThreads, 0, (cudaStream_t)stream>>>(x, y, grad_out, tb, h1, tw, grad_x);
+    AVVAD_LAUNCHED();
+  }
+  if (grad_y) {
+    mcb_raw_kernel<2><<<(unsigned)rows, kFftThreads, 0, (cudaStream_t)stream>>>(x, y, grad_out, tb, h2, tw, grad_y);
+    AVVAD_LAUNCHED();
+  }
   return AVVAD_OK;
 }

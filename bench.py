@@ -51,18 +51,7 @@ def synth_batch(B: int, seed: int):
     """Synthetic raw inputs of the reference's shapes."""
     from avvad import synth
 
-    g = torch.Generator().manual_seed(seed)
-    t = torch.arange(N_SAMPLES, dtype=torch.float32) / 16000.0
-    f_env = 0.5 + 3.5 * torch.rand(B, 1, generator=g)
-    ph = 6.2831853 * torch.rand(B, 1, generator=g)
-    env = 0.55 + 0.45 * torch.sin(6.2831853 * f_env * t[None, :] + ph)
-    wave = (0.1 * torch.randn(B, N_SAMPLES, generator=g) * env).clamp_(-1, 1)
-    vid = torch.rand(B * N_SRC, 1, 71, 71, generator=g) * 255.0
-    vid = torch.nn.functional.avg_pool2d(vid, 5, stride=1)  # low-pass -> (.,1,67,67)
-    lo, hi = vid.amin(), vid.amax()
-    vid = ((vid - lo) / (hi - lo) * 255.0).round_().clamp_(0, 255).to(torch.uint8).view(B, N_SRC, 67, 67)
-    mean, std = synth.synth_audio_stats(0)
-    return wave.contiguous(), vid.contiguous(), mean, std
+    return synth.batch_inputs(B, seed, N_SAMPLES, N_SRC)
 
 
 def synth_weights(B: int, seed=0):

@@ -256,6 +256,24 @@ int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const float* video
 int avvad_mcb_backward_bn(avvad_mcb* h, void* workspace, const float* dx, int64_t ld_dx, int64_t rows, float* dgamma,
                           float* dbeta, void* stream);
 
+/* Stand-alone CountSketch / CompactBilinearPooling modules
+ * replaces: packages/models/compact_bilinear_pooling.py:7-57 (CountSketchFn forward/backward) and :140-220
+ *           (CompactBilinearPoolingFn forward and hand-written backward).
+ * off/idx: CSR of the inverse map j -> {i : h_i = j} (ascending i; off has out_size+1 entries), h: int32 copy of the
+ * sketch indices, s: +-1.  The raw MCB entry points are fixed to the model's sizes (513, 512 -> 1024). */
+int avvad_count_sketch_forward(const float* x, int64_t rows, int in_size, int out_size, const int32_t* off,
+                               const int32_t* idx, const float* s, float* out, void* stream);
+int avvad_count_sketch_backward(const float* grad_out, int64_t rows, int in_size, int out_size, const int32_t* h,
+                                const float* s, float* grad_x, void* stream);
+int avvad_mcb_raw_forward(const int32_t* off1, const int32_t* idx1, const float* s1, const int32_t* off2,
+                          const int32_t* idx2, const float* s2, const float* x, const float* y, int64_t rows,
+                          float* out, void* stream);
+/* grad_x [rows][513] and/or grad_y [rows][512] (NULL = skip) from grad_out [rows][1024]. */
+int avvad_mcb_raw_backward(const int32_t* off1, const int32_t* idx1, const float* s1, const int32_t* h1,
+                           const int32_t* off2, const int32_t* idx2, const float* s2, const int32_t* h2,
+                           const float* x, const float* y, const float* grad_out, int64_t rows, float* grad_x,
+                           float* grad_y, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 2-layer (generic L) unidirectional LSTM over padded batches + Linear head (SURVEY R1,R2,H1,H2)
  * replaces: AV_Net.py:127-140, Audio_Net.py:50-59, Video_Net.py:101-116

@@ -65,10 +65,9 @@ class RefDeepVADAV(nn.Module):
         return self.vad_merged(out)
 
 
-def cpu_av_step(model: RefDeepVADAV, waves, videos_u8, audio_mean, audio_std, video_mean, video_std, eps=1e-8):
-    """One reference-style pass over a list of utterances on the CPU: per-utterance torch.stft front
-    end and frame-rate conversion, collate (zero-pad, then standardise), batched forward, sigmoid,
-    threshold.  Returns (posteriors (B,T), decisions (B,T), lengths)."""
+def cpu_av_inputs(waves, videos_u8, audio_mean, audio_std, video_mean, video_std, eps=1e-8):
+    """Per-utterance torch.stft front end and frame-rate conversion, collate (zero-pad, THEN standardise:
+    packages/utils.py:157-166 -> scripts/train_AV_net.py:287-291).  Returns (audio (B,T,513), video (B,T,67,67), lengths)."""
     feats, vids, lens = [], [], []
     for w, v in zip(waves, videos_u8):
         x = ofe.peak_normalise(w)
@@ -87,6 +86,13 @@ def cpu_av_step(model: RefDeepVADAV, waves, videos_u8, audio_mean, audio_std, vi
         vv[i, : lens[i]] = vids[i]
     a = (a - torch.as_tensor(audio_mean).reshape(1, 1, -1)) / (torch.as_tensor(audio_std).reshape(1, 1, -1) + eps)
     vv = (vv - video_mean) / (video_std + eps)
+    return a, vv, lens
+
+
+def cpu_av_step(model: RefDeepVADAV, waves, videos_u8, audio_mean, audio_std, video_mean, video_std, eps=1e-8):
+    """One reference-style pass over a list of utterances on the CPU: cpu_av_inputs, batched forward, sigmoid,
+    threshold.  Returns (posteriors (B,T), decisions (B,T), lengths)."""
+    a, vv, lens = cpu_av_inputs(waves, videos_u8, audio_mean, audio_std, video_mean, video_std, eps)
     with torch.no_grad():
         logits = model(a, vv, lens)[..., 0]
     post = torch.sigmoid(logits)

@@ -191,6 +191,152 @@ def ref_models():
     print("ref_models.npz", {k: v.shape for k, v in d.items()})
 
 
+def install_legacy_fft_shim():
+    """torch.rfft / torch.irfft were removed in torch 1.8; the reference's MCB (compact_bilinear_pooling.py:152-171,
+    186-215) still calls them.  Two pure re-spellings through torch.fft restore the legacy signatures
+    (rfft(x, 1) -> (..., N/2+1, 2) real view, un-normalised; irfft(X, 1, signal_sizes=(N,)) -> 1/N-normalised inverse),
+    so the UNMODIFIED reference module executes here."""
+    if not hasattr(torch, "rfft"):
+        torch.rfft = lambda x, signal_ndim=1, normalized=False, onesided=True: torch.view_as_real(torch.fft.rfft(x))
+    _new_irfft = torch.fft.irfft
+
+    def _irfft(x, signal_ndim=1, normalized=False, onesided=True, signal_sizes=None):
+        return _new_irfft(torch.view_as_complex(x.contiguous()), n=signal_sizes[0])
+    if not hasattr(torch, "irfft"):
+        torch.irfft = _irfft
+
+
+def grad_digest(d, tag, named_params):
+    """Compact, discriminating fingerprint of a gradient set: Frobenius norm and a strided sample of <= 2048 elements of
+    every tensor (full gradients of the 11-28 M-parameter models are too large to commit)."""
+    for k, p in named_params:
+        if p.grad is None:
+            continue
+        g = p.grad.detach().reshape(-1)
+        step = max(1, g.numel() // 2048)
+        d[f"{tag}/{k}/norm"] = np.asarray(g.double().norm().item())
+        d[f"{tag}/{k}/sample"] = g[::step][:2048].numpy().copy()
+
+
+def ref_strong():
+    """Second fixture file, all from the reference's own modules:
+      * the assembled use_mcb=True forward (AV_Net.py:111-121) and the stand-alone CompactBilinearPooling forward /
+        hand-written backward (compact_bilinear_pooling.py:140-220), executed through install_legacy_fft_shim();
+      * every module on the "strong" weight family (avvad.synth.FAMILIES) whose logits span several units;
+      * one training step (train() mode, loss as scripts/train_AV_net.py:298-301) of DeepVAD_AV(use_mcb=True) with the
+        trunk frozen (train_AV_net.py:241-245) and of DeepVAD_video with the trunk trainable
+        (train_video_net.py:145-173): loss + gradient digests, running-statistics of all 20 BatchNorm2d layers."""
+    sys.path.insert(0, REF)
+    install_legacy_fft_shim()
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models.Video_Net import DeepVAD_video
+    from packages.models.AV_Net import DeepVAD_AV
+    from packages.models.compact_bilinear_pooling import CompactBilinearPooling
+    from packages.models.utils import binary_cross_entropy
+
+    base = np.load(os.path.join(OUT, "ref_models.npz"))
+    d = {}
+    g = torch.Generator().manual_seed(4242)
+
+    # ---- stand-alone MCB: forward + backward of the reference Function ----
+    h1 = synth.seeded_tensor("mcb.sketch1.h", (513,), torch.int64, 15)
+    s1 = synth.seeded_tensor("mcb.sketch1.s", (513,), torch.float32, 15)
+    h2 = synth.seeded_tensor("mcb.sketch2.h", (512,), torch.int64, 15)
+    s2 = synth.seeded_tensor("mcb.sketch2.s", (512,), torch.float32, 15)
+    cbp = CompactBilinearPooling(513, 512, 1024, h1=h1, s1=s1, h2=h2, s2=s2)
+    x = torch.randn(2, 5, 513, generator=g, requires_grad=True)
+    y = torch.randn(2, 5, 512, generator=g).abs().requires_grad_(True)
+    go = torch.randn(2, 5, 1024, generator=g)
+    out = cbp(x, y)
+    out.backward(go)
+    d["cbp_x"], d["cbp_y"], d["cbp_go"] = x.detach().numpy(), y.detach().numpy(), go.numpy()
+    d["cbp_out"], d["cbp_gx"], d["cbp_gy"] = out.detach().numpy(), x.grad.numpy(), y.grad.numpy()
+
+    a6, v6, l6 = torch.tensor(base["av_audio"]), torch.tensor(base["av_video"]), base["av_len"].tolist()
+
+    def strong_forward(m, head, key, *inputs, lengths):
+        """Forward with the strong family, head bias placed by synth.decision_bias (stored as <key>_bias)."""
+        m.eval()
+        with torch.no_grad():
+            out0 = m(*inputs, lengths).numpy()
+            nb = synth.decision_bias(out0, lengths, head.bias.detach().numpy())
+            head.bias.copy_(nb)
+            d[key + "_bias"] = nb.numpy()
+            d[key] = m(*inputs, lengths).numpy()
+        return m
+
+    # ---- assembled AV + MCB forward (seed 22 default family as in the GPU test; seed 42 strong family) ----
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8)
+    m.load_state_dict(synth.calibrate_mcb_bn_(synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 22), 12))
+    m.eval()
+    with torch.no_grad():
+        d["av_mcb_out_default"] = m(a6, v6, l6).numpy()
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8)
+    m.load_state_dict(synth.calibrate_mcb_bn_(synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 42, "strong"), 12))
+    strong_forward(m, m.vad_merged, "av_mcb_out_strong", a6, v6, lengths=l6)
+
+    # ---- strong family, all modules ----
+    # long ragged batch: exercises error growth over many recurrence steps
+    # (input = numpy PCG64 stream, regenerated by the tests instead of being stored: 2.6 MB)
+    xl = torch.tensor(np.random.default_rng(77).standard_normal((4, 317, 513)).astype(np.float32))
+    ll = [317, 301, 158, 317]
+    m = synth.fill_module_(DeepVAD_audio(2, 1024, 1), seed=41, family="strong")
+    strong_forward(m, m.vad_audio, "audio_long_out_strong", xl, lengths=ll)
+    d["audio_long_len"] = np.asarray(ll)
+    xa, la = torch.tensor(base["audio_x"]), base["audio_len"].tolist()
+    with torch.no_grad():   # same weights and (calibrated) bias on the short batch of ref_models.npz
+        d["audio_out_strong"] = m(xa, la).numpy()
+    # video / AV: 40 frames per utterance so that the bias placement has a distribution to work with
+    vl = torch.tensor(np.random.default_rng(78).standard_normal((2, 40, 67, 67)).astype(np.float32))
+    al = torch.tensor(np.random.default_rng(79).standard_normal((2, 40, 513)).astype(np.float32))
+    lv = [40, 29]
+    d["av_long_len"] = np.asarray(lv)
+    m = synth.fill_module_(DeepVAD_video(2, 1024, 1), seed=43, family="strong")
+    strong_forward(m, m.vad_video, "video_out_strong", vl, lengths=lv)
+    for y_dim, seed, key in ((1, 44, "av_out_strong"), (513, 45, "av513_out_strong")):
+        m = synth.fill_module_(DeepVAD_AV(2, 1024, y_dim, use_mcb=False, eps=1e-8), seed=seed, family="strong")
+        strong_forward(m, m.vad_merged, key, al, vl, lengths=lv)
+
+    # ---- training step, AV + MCB, trunk frozen (reference loop: train_AV_net.py:241-245,253,293-305) ----
+    tgt = (torch.rand(2, 6, 1, generator=g) > 0.5).float()
+    d["train_target"] = tgt.numpy()
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8)
+    m.load_state_dict(synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 46, "strong"))
+    for name, child in m.named_children():
+        if name == "features":
+            for p in child.parameters():
+                p.requires_grad = False
+    m.train()
+    out = m(a6, v6, torch.tensor(l6))
+    loss = 0.
+    for length, pred, target in zip(l6, out, tgt.long()):
+        loss = loss + binary_cross_entropy(pred[:length], target[:length], 1e-8)
+    loss.backward()
+    d["train_av_mcb_logits"], d["train_av_mcb_loss"] = out.detach().numpy(), np.asarray(loss.item())
+    grad_digest(d, "train_av_mcb", m.named_parameters())
+    d["train_av_mcb/mcb_bn.running_mean"] = m.mcb_bn.running_mean.numpy().copy()
+    d["train_av_mcb/mcb_bn.running_var"] = m.mcb_bn.running_var.numpy().copy()
+
+    # ---- training step, video-only, trunk TRAINABLE (train_video_net.py:145-173) ----
+    m = synth.fill_module_(DeepVAD_video(2, 1024, 1), seed=47, family="strong")
+    m.train()
+    out = m(v6, torch.tensor(l6))
+    loss = 0.
+    for length, pred, target in zip(l6, out, tgt.long()):
+        loss = loss + binary_cross_entropy(pred[:length], target[:length], 1e-8)
+    loss.backward()
+    d["train_video_logits"], d["train_video_loss"] = out.detach().numpy(), np.asarray(loss.item())
+    grad_digest(d, "train_video", m.named_parameters())
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            d["train_video/" + k] = v.numpy().copy()
+
+    np.savez_compressed(os.path.join(OUT, "ref_strong.npz"), **d)
+    print("ref_strong.npz", len(d), "arrays;",
+          {k: (round(float(np.min(d[k])), 2), round(float(np.max(d[k])), 2), round(float((d[k] > 0).mean()), 3))
+           for k in d if k.endswith("_strong") or k.startswith("av_mcb_out")})
+
+
 def ref_helpers():
     """Host-level helpers of packages/models/utils.py:57-162 and packages/utils.py:9-40 on seeded inputs (a separate,
     small file so that ref_models.npz does not have to be regenerated)."""
@@ -250,6 +396,9 @@ def ref_target_masks():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "strong":
+        ref_strong()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "helpers":
         ref_helpers()
         ref_target_masks()
@@ -257,5 +406,6 @@ if __name__ == "__main__":
     golden_frontend()
     golden_upsample()
     ref_models()
+    ref_strong()
     ref_helpers()
     ref_target_masks()
