@@ -74,6 +74,8 @@ PROTOTYPES = {
     "avvad_count_sketch_backward": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP]),
     "avvad_mcb_raw_forward": (C.c_int, [VP] * 8 + [C.c_int64, VP, VP]),
     "avvad_mcb_raw_backward": (C.c_int, [VP] * 11 + [C.c_int64, VP, VP, VP]),
+    "avvad_lzf_compress": (C.c_int64, [VP, C.c_int64, VP, C.c_int64, C.c_int, VP]),
+    "avvad_lzf_decompress": (C.c_int64, [VP, C.c_int64, VP, C.c_int64]),
     "avvad_lstm_tape_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64, C.c_int64]),
     "avvad_lstm_forward_train": (C.c_int, [VP, VP, VP, C.c_int64, C.c_int64, VP, C.c_size_t, VP, C.c_size_t, VP, VP]),
     "avvad_lstm_backward_workspace_bytes": (C.c_size_t, [VP, C.c_int64, C.c_int64]),

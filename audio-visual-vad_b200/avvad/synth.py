@@ -237,3 +237,42 @@ def synth_audio_stats(seed=0):
 
 
 VIDEO_MEAN, VIDEO_STD = 153.435, 48.071  # data/subset/.../matlab_raw/ntcd_timit_statistics.h5
+
+
+def write_synthetic_corpus(root: str, utterances=(("train", "01M", "sa1", 20000, 38), ("train", "01M", "sa2", 26500, 51),
+                                                   ("train", "02F", "si1", 17000, 33), ("dev", "08F", "sa1", 22000, 44)),
+                           labels="vad_labels", seed=0):
+    """A miniature processed NTCD-TIMIT tree in the reference's layout and file formats, written
+    with avvad.h5min (HDF5 + LZF) -- what scripts/create_{audio,video}_train_files*.py leave on disk:
+        <root>/ntcd_timit/Noisy/Babble/-5/<split>/<spk>/<utt>.wav               16 kHz mono PCM16
+        <root>/ntcd_timit/Clean/<split>/<spk>/<utt>_<labels>_upsampled.h5       /Y (y_dim, T) f32 lzf
+        <root>/ntcd_timit/matlab_raw/<split>/<spk>/<utt>_upsampled.h5           /X (67, 67, T_video) f32 lzf
+    utterances: (split, speaker, utt, n_samples, n_src_frames).  Returns {(split, spk, utt): (wave int16, video, label)}."""
+    import os
+
+    from . import h5min
+    from .engine import FPS_DEN, FPS_NUM
+
+    y_dim = 1 if labels == "vad_labels" else 513
+    made = {}
+    for k, (split, spk, utt, n, f) in enumerate(utterances):
+        wav = np.clip(np.rint(synth_wave(n, seed + k) * 20000.0), -32768, 32767).astype(np.int16)
+        t_video = int(f * FPS_NUM / FPS_DEN + 0.5)
+        src = synth_video_u8(f, seed + k).astype(np.float32)
+        idx = np.minimum((np.arange(t_video) * FPS_DEN + FPS_DEN // 2) // FPS_NUM, f - 1)   # any monotone map will do here
+        video = np.ascontiguousarray(np.moveaxis(src[idx], 0, -1))                        # (67,67,T)
+        t_audio = 1 + (n + (256 if n % 256 else 0) - 1024) // 256
+        t_lab = min(t_video, t_audio) + (k % 2)                                           # lengths disagree, as in the corpus
+        lab = (np.random.default_rng(seed + 100 + k).random((y_dim, t_lab)) > 0.4).astype(np.float32)
+        d_noisy = os.path.join(root, "ntcd_timit", "Noisy", "Babble", "-5", split, spk)
+        d_clean = os.path.join(root, "ntcd_timit", "Clean", split, spk)
+        d_video = os.path.join(root, "ntcd_timit", "matlab_raw", split, spk)
+        for d in (d_noisy, d_clean, d_video):
+            os.makedirs(d, exist_ok=True)
+        h5min.write_wav_int16(os.path.join(d_noisy, utt + ".wav"), wav)
+        h5min.write_h5(os.path.join(d_clean, f"{utt}_{labels}_upsampled.h5"),
+                       {"Y": (lab, dict(maxshape=(y_dim, None), creation_shape=(y_dim, 0)))})
+        h5min.write_h5(os.path.join(d_video, f"{utt}_upsampled.h5"),
+                       {"X": (video, dict(maxshape=(67, 67, None), creation_shape=(67, 67, 0)))})
+        made[(split, spk, utt)] = (wav, video, lab)
+    return made

@@ -1,9 +1,12 @@
 """Dataset classes the three train scripts build (same names, constructor keywords and item tuples as
-packages/data_handling.py:192-495).  The per-utterance front end (peak-normalise -> STFT -> |.|^2 -> log) runs through
-packages.processing.stft.stft_pytorch, i.e. on the GPU: use num_workers=0 (or a 'spawn' worker context) with the
-spectrogram datasets, or the *Wav* variants + avvad.pipeline / collate_many2many_*_waveform to keep the workers CPU-only
-and do the whole front end batched on the device.  The legacy HDF5*/VideoFrames datasets (data_handling.py:19-189, unused
-by the VAD scripts) are kept as thin host-side classes at the end of the file."""
+packages/data_handling.py:192-566).
+
+The per-utterance front end (peak-normalise -> STFT -> |.|^2 -> log, data_handling.py:441-457) is a CUDA kernel here.
+In the main process ``__getitem__`` returns the computed (513, T) tensor like the reference.  Inside a DataLoader worker
+-- the unchanged scripts fork 16 of them after CUDA is initialised (train_AV_net.py:50,141-146), where CUDA cannot be
+used -- it returns a packages.processing.deferred.DeferredLogPower instead; collate_many2many_{AV,audio} turn those into
+one batched device call that runs in the parent when the batch arrives (see deferred.py).  The legacy HDF5*/VideoFrames
+datasets (data_handling.py:19-189, unused by the VAD scripts) are kept as thin host-side classes at the end."""
 import math
 import os
 
@@ -13,15 +16,19 @@ from torch.utils.data import Dataset
 
 from packages._io import load_wav, read_h5
 from packages.dataset.ntcd_timit import proc_noisy_clean_pair_dict, proc_video_audio_pair_dict
-from packages.processing.stft import stft_pytorch
+from packages.processing.deferred import DeferredLogPower, in_worker
+from packages.processing.stft import stft_pytorch, stft_frame_count
 
 
 def _log_power(wave, ds):
-    """data_handling.py:441-457: x / max|x| -> STFT -> re^2 + im^2 -> log(. + eps), (513, T)."""
-    wave = wave / torch.max(torch.abs(wave))
-    tf = stft_pytorch(wave, fs=ds.fs, wlen_sec=ds.wlen_sec, win=ds.win, hop_percent=ds.hop_percent, center=ds.center,
-                      pad_mode=ds.pad_mode, pad_at_end=ds.pad_at_end)
-    return torch.log(tf[..., 0] ** 2 + tf[..., 1] ** 2 + ds.eps)
+    """data_handling.py:441-457: x / max|x| -> STFT -> re^2 + im^2 -> log(. + eps), (513, T); deferred inside a
+    DataLoader worker."""
+    nfft, hop = int(ds.wlen_sec * ds.fs), int(ds.hop_percent * int(ds.wlen_sec * ds.fs))
+    if nfft != 1024 or hop != 256 or ds.center or ds.win != 'hann':
+        raise NotImplementedError("libavvad front end supports nfft=1024, hop=256, win='hann', center=False")
+    T = stft_frame_count(wave.shape[-1], ds.fs, ds.wlen_sec, ds.hop_percent, ds.pad_at_end)
+    item = DeferredLogPower(wave.to(torch.float32).contiguous(), T, ds.eps)
+    return item if in_worker() else item.materialise()
 
 
 class _StftConfig:
@@ -100,16 +107,17 @@ class AudioVisualSequenceLabeledFrames(_NoisyBase):
 
 
 class AudioVisualSequenceWavLabeledFrames(_NoisyBase):
-    """Waveform variant (data_handling.py:497-566): (peak-normalised wave (N,), video, label, length, time_length);
-    pair with collate_many2many_AV_waveform and the on-device front end."""
+    """Waveform variant (data_handling.py:497-566): (peak-normalised wave (N,), video (67,67,T), label (y_dim,T),
+    time_length, tf_length) -- untrimmed, video always from '<utt>_upsampled.h5', tf_length = video frames; pair with
+    collate_many2many_AV_waveform (which reads lengths = item[-1], time_lengths = item[-2])."""
 
     def __getitem__(self, i):
         wave, clean = self._wave(i)
-        wave = wave / torch.max(torch.abs(wave))
-        video = torch.Tensor(read_h5(self._video_path(clean), "X"))
+        data = wave / torch.max(torch.abs(wave))
+        p = clean.replace('Clean', 'matlab_raw').replace('_' + self.labels, '')
+        video = torch.Tensor(read_h5(self.input_video_dir + os.path.splitext(p)[0] + '_upsampled.h5', "X"))
         label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
-        n = min(video.shape[-1], label.shape[-1])
-        return wave, video[..., :n], label[..., :n], n, wave.shape[-1]
+        return data, video, label, data.shape[-1], video.shape[-1]
 
 
 class NoisyWavWholeSequenceWavLabeledFrames(_NoisyBase):
@@ -117,9 +125,9 @@ class NoisyWavWholeSequenceWavLabeledFrames(_NoisyBase):
 
     def __getitem__(self, i):
         wave, clean = self._wave(i)
-        wave = wave / torch.max(torch.abs(wave))
+        data = wave / torch.max(torch.abs(wave))
         label = torch.Tensor(read_h5(self.input_video_dir + clean, "Y"))
-        return wave, label, wave.shape[-1], label.shape[-1]
+        return data, label, data.shape[-1], label.shape[-1]
 
 
 # ---- legacy datasets (data_handling.py:19-189): frame / sequence views of one big "X_<split>" / "Y_<split>" pair ---------

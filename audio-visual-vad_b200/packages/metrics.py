@@ -32,26 +32,36 @@ def energy_ratios(s_hat, s, n):
     return si_sdr, si_sir, si_sar
 
 
-def compute_stats(metrics_keys, all_metrics, all_snr_db=None, all_noise_types=None, model_data_dir=None,
-                  confidence=0.95, all_speaker_ids=None, **_):
-    """Prints mean +- confidence interval per metric (overall, then per SNR / noise type / speaker when given)."""
-    arr = np.asarray(all_metrics, dtype=float)
-    lines = []
-    for i, key in enumerate(metrics_keys):
-        m, h = mean_confidence_interval(arr[:, i], confidence=confidence)
-        lines.append("{}: {} +- {}".format(key, m, h))
-    for name, groups in (("SNR", all_snr_db), ("noise", all_noise_types), ("speaker", all_speaker_ids)):
-        if groups is None:
-            continue
-        groups = np.asarray(groups)
-        for gval in np.unique(groups):
-            sel = arr[groups == gval]
-            for i, key in enumerate(metrics_keys):
-                m, h = mean_confidence_interval(sel[:, i], confidence=confidence)
-                lines.append("{} {} | {}: {} +- {}".format(name, gval, key, m, h))
-    text = "\n".join(lines)
-    print(text)
-    if model_data_dir:
-        with open(str(model_data_dir) + "stats.txt", "w") as f:
-            f.write(text + "\n")
-    return text
+def compute_stats(metrics_keys, all_metrics, model_data_dir, confidence, all_snr_db=None, all_noise_types=None,
+                  all_speakers=None):
+    """Prints mean and confidence half-width per metric -- overall, then per input SNR / noise type / speaker when those
+    lists are given (packages/metrics.py:62-131: same parameter names and order, same tables; nothing is written to
+    disk).  Returns the overall {metric: {'avg', '+/-'}} dictionary for convenience (the reference returns None)."""
+    columns = {key: [row[i] for row in all_metrics] for i, key in enumerate(metrics_keys)}
+    header = "{:<10} {:<10} {:<10}".format('METRIC', 'AVERAGE', 'CONF. INT.')
+
+    def table(select):
+        stats = {}
+        print(header)
+        for key, col in columns.items():
+            m, h = mean_confidence_interval(select(col), confidence=confidence)
+            stats[key] = {'avg': m, '+/-': h}
+            print("{:<10} {:<10} {:<10}".format(key, m, h))
+        print('\n')
+        return stats
+
+    overall = table(lambda col: col)
+    if all_snr_db is not None:
+        snr = np.asarray(all_snr_db)
+        for value in np.unique(snr):
+            print('Input SNR = {:.2f}'.format(value))
+            table(lambda col, v=value: np.asarray(col)[np.where(snr == v)])
+    if all_noise_types is not None:
+        for value in set(all_noise_types):
+            print('Noise type = {}'.format(value))
+            table(lambda col, v=value: [x for x, g in zip(col, all_noise_types) if g == v])
+    if all_speakers is not None:
+        for value in set(all_speakers):
+            print('Speaker = {}'.format(value))
+            table(lambda col, v=value: [x for x, g in zip(col, all_speakers) if g == v])
+    return overall

@@ -29,9 +29,18 @@ def stft_pytorch(x, fs=16e3, wlen_sec=50e-3, win='hann', hop_percent=0.25, cente
         raise ValueError("stft_pytorch expects a 1-D signal")
     n = x.shape[0]
     T = _E.stft_num_frames(n, fs, wlen_sec, hop_percent, pad_at_end)
-    xd = x.detach().to(device='cuda', dtype=torch.float32)
-    out = _E.stft(xd[None], [n], [T], T)[0]  # (513, T, 2)
+    # the input's own device when it is a CUDA tensor, otherwise the calling thread's current CUDA device
+    dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        xd = x.detach().to(device=dev, dtype=torch.float32)
+        out = _E.stft(xd[None], [n], [T], T)[0]  # (513, T, 2)
     return out.to(x.device)
+
+
+def stft_frame_count(n_samples, fs=16e3, wlen_sec=64e-3, hop_percent=0.25, pad_at_end=True):
+    """Number of frames stft_pytorch(center=False) returns for a signal of n_samples (host arithmetic only: safe in
+    forked DataLoader workers)."""
+    return _E.stft_num_frames(int(n_samples), fs, wlen_sec, hop_percent, pad_at_end)
 
 
 # ---- host-side numpy STFT / inverse STFT (packages/processing/stft.py:13-99) --------------------------------------

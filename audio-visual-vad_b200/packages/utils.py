@@ -32,6 +32,17 @@ def _pad_time_last(items, seq_length):
     return out.contiguous()
 
 
+def _audio_batch(items, seq_length):
+    """(B,T,513) from per-utterance (513,T_i) spectrograms.  Items are tensors in the main process and
+    DeferredLogPower objects inside DataLoader workers (packages/processing/deferred.py): those become one batched
+    device front-end call, executed here (num_workers=0) or by the parent process when it receives the batch."""
+    from packages.processing.deferred import DeferredLogPower, DeferredLogPowerBatch, in_worker
+    if not isinstance(items[0], DeferredLogPower):
+        return _pad_time_last([it.float() for it in items], seq_length)
+    batch = DeferredLogPowerBatch(items)
+    return batch if in_worker() else batch.materialise(seq_length)
+
+
 def collate_many2many_video(batch):
     lengths = [item[-1] for item in batch]
     T = max(lengths)
@@ -43,7 +54,7 @@ def collate_many2many_video(batch):
 def collate_many2many_audio(batch):
     lengths = [item[-1] for item in batch]
     T = max(lengths)
-    data = _pad_time_last([item[0].float() for item in batch], T)      # (B,T,x_dim)
+    data = _audio_batch([item[0] for item in batch], T)                # (B,T,x_dim)
     target = _pad_time_last([item[1].float() for item in batch], T)
     return torch.LongTensor(lengths), data, target
 
@@ -51,7 +62,7 @@ def collate_many2many_audio(batch):
 def collate_many2many_AV(batch):
     lengths = [item[-1] for item in batch]
     T = max(lengths)
-    audio = _pad_time_last([item[0].float() for item in batch], T)     # (B,T,x_dim)
+    audio = _audio_batch([item[0] for item in batch], T)               # (B,T,x_dim)
     video = _pad_time_last([item[1].float() for item in batch], T)     # (B,T,H,W)
     target = _pad_time_last([item[2].float() for item in batch], T)    # (B,T,y_dim)
     return torch.LongTensor(lengths), audio, video, target
@@ -65,7 +76,7 @@ def _pad_wave(waves, n):
 
 
 def collate_many2many_audio_waveform(batch):
-    """Items (wave (N,), label (y_dim,T), time_length, length): waveform batches for the on-device
+    """Items (wave (N,), label (y_dim,T), time_length, tf_length): waveform batches for the on-device
     front end (packages/utils.py:110-146)."""
     lengths = [item[-1] for item in batch]
     time_lengths = [item[-2] for item in batch]
@@ -75,7 +86,7 @@ def collate_many2many_audio_waveform(batch):
 
 
 def collate_many2many_AV_waveform(batch):
-    """Items (wave, video (H,W,T), label, time_length, length) (packages/utils.py:187-227)."""
+    """Items (wave, video (H,W,T), label, time_length, tf_length) (packages/utils.py:187-227)."""
     lengths = [item[-1] for item in batch]
     time_lengths = [item[-2] for item in batch]
     T = max(lengths)

@@ -256,6 +256,18 @@ int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const float* video
 int avvad_mcb_backward_bn(avvad_mcb* h, void* workspace, const float* dx, int64_t ld_dx, int64_t rows, float* dgamma,
                           float* dbeta, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-side codec of the reference's on-disk format: LZF, the chunk filter (HDF5 filter id 32000)
+ * the reference writes every *.h5 with (scripts/create_video_train_files_upsampled.py:99,261; create_audio_train_files.py:86).
+ * replaces: the h5py/liblzf dependency of packages/data_handling.py:6 for reading and of the create_*_train_files
+ *           scripts for writing; the HDF5 container itself is handled by avvad/h5min.py.  Host pointers, no CUDA.
+ * compress: returns the compressed size, 0 if it does not fit in `cap`; hlog = log2 of the hash-table size (h5py: 17);
+ *           table = NULL or a caller-owned uint32[2^hlog] carried from chunk to chunk (reproduces h5py byte for byte).
+ * decompress: returns the number of bytes produced, -1 on a malformed stream.
+ * ---------------------------------------------------------------------------------------- */
+int64_t avvad_lzf_compress(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t cap, int hlog, uint32_t* table);
+int64_t avvad_lzf_decompress(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t cap);
+
 /* Stand-alone CountSketch / CompactBilinearPooling modules
  * replaces: packages/models/compact_bilinear_pooling.py:7-57 (CountSketchFn forward/backward) and :140-220
  *           (CompactBilinearPoolingFn forward and hand-written backward).

@@ -89,6 +89,23 @@ def test_metrics_helpers():
     assert m == 2.5 and h > 0
 
 
+def test_compute_stats_has_the_reference_signature(capsys):
+    """packages/metrics.py:62-68: (metrics_keys, all_metrics, model_data_dir, confidence, all_snr_db, all_noise_types,
+    all_speakers) -- the scripts pass all_speakers=... by keyword; unknown keywords must raise, nothing is written."""
+    import inspect
+    from packages.metrics import compute_stats
+    assert list(inspect.signature(compute_stats).parameters) == [
+        "metrics_keys", "all_metrics", "model_data_dir", "confidence", "all_snr_db", "all_noise_types", "all_speakers"]
+    rows = [(0.9, 0.8), (0.7, 0.6), (0.5, 0.4), (0.3, 0.2)]
+    compute_stats(["acc", "f1"], rows, "/nonexistent/dir/", 0.95, all_snr_db=np.array([-5, -5, 0, 0]),
+                  all_noise_types=["Babble", "Cafe", "Babble", "Cafe"], all_speakers=["34M", "34M", "08F", "08F"])
+    out = capsys.readouterr().out
+    assert "Input SNR = -5.00" in out and "Noise type = Cafe" in out and "Speaker = 08F" in out
+    assert out.count("METRIC") == 1 + 2 + 2 + 2
+    with pytest.raises(TypeError):
+        compute_stats(["acc"], [(1.0,)], "", 0.95, all_speaker_ids=["x"])
+
+
 def test_full_state_dict_inside_dataparallel_replica():
     """torch.nn.parallel.replicate strips nn.Parameters from replicas (plain tensor attributes + `_former_parameters`);
     the engines must still find every weight (scripts/train_AV_net.py:193 wraps the model in nn.DataParallel).  The

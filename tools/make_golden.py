@@ -26,7 +26,7 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.join(REPO, "audio-visual-vad_b200"))
 sys.path.insert(0, REPO)
 
-from h5min import H5File, read_wav_int16  # noqa: E402
+from avvad.h5min import H5File, read_wav_int16  # noqa: E402
 from avvad import synth  # noqa: E402
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
@@ -337,6 +337,43 @@ def ref_strong():
            for k in d if k.endswith("_strong") or k.startswith("av_mcb_out")})
 
 
+def golden_h5():
+    """Two small files of the reference copied verbatim (data, 4 KB + 9 KB) and the first LZF chunks of a video file:
+    they pin the HDF5 writer (message bytes, chunk shapes) and the LZF encoder (stored bytes) of avvad/h5min.py."""
+    import shutil
+    import struct
+    os.makedirs(os.path.join(OUT, "h5"), exist_ok=True)
+    base = os.path.join(SUB, "processed/ntcd_timit")
+    shutil.copyfile(os.path.join(base, "Clean/test/34M/sa1_vad_labels.h5"), os.path.join(OUT, "h5", "sa1_vad_labels.h5"))
+    shutil.copyfile(os.path.join(base, "matlab_raw/ntcd_timit_statistics.h5"), os.path.join(OUT, "h5", "ntcd_timit_statistics.h5"))
+    h = H5File(os.path.join(base, "matlab_raw/test/34M/sa1_upsampled.h5"))
+    layout = [d for t, d in h._messages(h.datasets["/X"]) if t == 0x08][0]
+    ndim = layout[2]
+    btree = struct.unpack_from("<Q", layout, 3)[0]
+    found = []
+
+    def walk(addr):
+        b = h.buf
+        _, level, used = struct.unpack_from("<BBH", b, addr + 4)
+        p, ks = addr + 24, 8 + 8 * ndim
+        for _ in range(used):
+            nbytes, fmask = struct.unpack_from("<II", b, p)
+            child = struct.unpack_from("<Q", b, p + ks)[0]
+            p += ks + 8
+            if level > 0:
+                walk(child)
+            else:
+                found.append((child, nbytes, fmask))
+    walk(btree)
+    found.sort()
+    d = {"chunk_dims": np.asarray(struct.unpack_from("<" + "I" * ndim, layout, 11)), "n_chunks_in_file": np.asarray(len(found))}
+    for i, (a, n, m) in enumerate(found[:12]):   # in file (= write) order, from the start of the file
+        assert m == 0
+        d[f"chunk{i}"] = np.frombuffer(h.buf[a:a + n], dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "golden_lzf_chunks.npz"), **d)
+    print("golden_lzf_chunks.npz", len(found), "chunks in file, stored", min(12, len(found)))
+
+
 def ref_helpers():
     """Host-level helpers of packages/models/utils.py:57-162 and packages/utils.py:9-40 on seeded inputs (a separate,
     small file so that ref_models.npz does not have to be regenerated)."""
@@ -396,6 +433,9 @@ def ref_target_masks():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[2] == "h5":
+        golden_h5()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "strong":
         ref_strong()
         sys.exit(0)
@@ -407,5 +447,6 @@ if __name__ == "__main__":
     golden_upsample()
     ref_models()
     ref_strong()
+    golden_h5()
     ref_helpers()
     ref_target_masks()
