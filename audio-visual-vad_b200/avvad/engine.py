@@ -512,7 +512,16 @@ def lstm_train_forward(lstm: "Lstm", x_bf16: torch.Tensor, lengths):
     nbytes = L.lib().avvad_lstm_workspace_bytes(lstm.h, B, T)
     ws = lstm.ws.get(nbytes, dev)
     tb = L.lib().avvad_lstm_tape_bytes(lstm.layers, lstm.hidden, B, T)
-    tape = torch.empty(tb, dtype=torch.uint8, device=dev)
+    # The tape lives with the engine and is reused step after step: its address is baked into the cached CUDA graph of
+    # the backward recurrence (csrc/lstm_train.cu), so a stable buffer means graph replays instead of re-captures.  A
+    # second forward before the first one's backward (gradient accumulation over micro-batches) gets its own tape.
+    tape = getattr(lstm, "_tape", None)
+    if tape is None or tape.numel() != tb or tape.device != dev or getattr(lstm, "_tape_busy", False):
+        tape = torch.empty(tb, dtype=torch.uint8, device=dev)
+        if not getattr(lstm, "_tape_busy", False):
+            lstm._tape = tape
+    if tape is getattr(lstm, "_tape", None):
+        lstm._tape_busy = True
     logits = torch.empty(B, T, lstm.y_dim, dtype=torch.float32, device=dev)
     L.check(L.lib().avvad_lstm_forward_train(lstm.h, L.ptr(x_bf16), L.ptr(lens), B, T, L.ptr(ws), ws.numel(),
                                              L.ptr(tape), tape.numel(), L.ptr(logits), L.stream_ptr()))
@@ -539,6 +548,8 @@ def lstm_train_backward(lstm: "Lstm", tape_pack, dlogits: torch.Tensor, want_dx=
     L.check(L.lib().avvad_lstm_backward(lstm.h, L.ptr(x_bf16), L.ptr(lens), B, T, L.ptr(tape), L.ptr(dl), L.ptr(ws),
                                         ws.numel(), _ptr_array(dwi), _ptr_array(dwh), _ptr_array(dbs), L.ptr(dhw),
                                         L.ptr(dhb), L.ptr(dx), L.stream_ptr()))
+    if tape is getattr(lstm, "_tape", None):
+        lstm._tape_busy = False
     return {"weight_ih": dwi, "weight_hh": dwh, "bias": dbs, "head_w": dhw, "head_b": dhb, "dx": dx}
 
 

@@ -20,6 +20,11 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_prof_pool;
 
+bool profiling_on() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  return g_prof_on;
+}
+
 static cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) {
     cudaEvent_t e = g_prof_pool.back();

@@ -265,6 +265,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int mode, co
 }
 
 // ---- host-side launcher -----------------------------------------------------------------------------
+bool profiling_on();
 int prof_begin(cudaStream_t st, void** tok);
 void prof_end(cudaStream_t st, void* tok, int cat, double flops);
 int prof_group_begin(cudaStream_t st, void** tok);

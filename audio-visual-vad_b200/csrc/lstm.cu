@@ -97,6 +97,12 @@ __global__ void gather_last_kernel(const __nv_bfloat16* __restrict__ hseq, const
 
 }  // namespace avvad
 
+namespace avvad {
+struct BpttGraphCache;
+BpttGraphCache* bptt_cache_create();
+void bptt_cache_destroy(BpttGraphCache* c);
+}  // namespace avvad
+
 using namespace avvad;
 
 struct avvad_lstm {
@@ -110,6 +116,7 @@ struct avvad_lstm {
   float* head_b;             // [y_dim]
   bool set[8];
   bool head_set;
+  BpttGraphCache* bptt;      // cached CUDA graphs of the backward recurrence (lstm_train.cu)
 };
 
 extern "C" int avvad_lstm_create(avvad_lstm** out, int layers, int input_size, int hidden, int y_dim) {
@@ -124,6 +131,7 @@ extern "C" int avvad_lstm_create(avvad_lstm** out, int layers, int input_size, i
   h->y_dim = y_dim;
   h->ld0 = (input_size + 63) / 64 * 64;
   h->head_set = false;
+  h->bptt = bptt_cache_create();
   for (int l = 0; l < 8; ++l) {
     h->w_ih[l] = h->w_hh[l] = nullptr;
     h->bias[l] = nullptr;
@@ -152,6 +160,7 @@ extern "C" void avvad_lstm_destroy(avvad_lstm* h) {
   cudaFree(h->head_w32);
   cudaFree(h->head_w16);
   cudaFree(h->head_b);
+  bptt_cache_destroy(h->bptt);
   delete h;
 }
 
@@ -205,7 +214,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
-                       float* dx, cudaStream_t st);
+                       float* dx, cudaStream_t st, BpttGraphCache* cache);
 size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T);
 }  // namespace avvad
 
@@ -512,5 +521,5 @@ extern "C" int avvad_lstm_backward(avvad_lstm* h, const void* x_bf16, const int3
   return lstm_backward_impl(h->layers, h->input_size, h->ld0, h->H, h->y_dim, h->w_ih, h->w_hh, h->head_w32,
                             h->head_w16, x_bf16,
                             lengths, B, T, tape, dlogits, workspace, workspace_bytes, dW_ih, dW_hh, db, dW_head, db_head,
-                            dx, (cudaStream_t)stream);
+                            dx, (cudaStream_t)stream, h->bptt);
 }

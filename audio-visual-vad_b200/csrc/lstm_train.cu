@@ -220,14 +220,44 @@ extern "C" int avvad_adam_step(float* param, const float* grad, float* exp_avg, 
 }
 
 namespace avvad {
+// The backward recurrence is 2 launches per time step and layer (1,268 for T = 317, two layers), each a few
+// microseconds of work: issued one by one the step is bound by launch latency.  The T-step loop of a layer is therefore
+// captured once into a CUDA graph and replayed while every pointer baked into its kernel parameters is unchanged (the
+// key below); the per-call inputs that PyTorch re-allocates (lengths, dlogits) are first copied into the caller's
+// workspace so that a steady-state training loop always hits the cache.  AVVAD_BPTT_GRAPH=0 disables it.
+struct BpttGraphCache {
+  cudaGraphExec_t exec[8] = {};
+  std::vector<uintptr_t> key[8];
+  size_t nodes[8] = {};
+  // Capture happens on a private stream: PyTorch's default current stream is the legacy NULL stream, which cannot be
+  // captured; the instantiated graph is then launched into the caller's stream (any stream, the NULL stream included).
+  cudaStream_t cap_stream = nullptr;
+  int cap_device = -1;
+  ~BpttGraphCache() {
+    for (auto e : exec)
+      if (e) cudaGraphExecDestroy(e);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
+};
+BpttGraphCache* bptt_cache_create() { return new BpttGraphCache(); }
+void bptt_cache_destroy(BpttGraphCache* c) { delete c; }
+
 // exposed to lstm.cu
 int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
                        __nv_bfloat16* const* w_hh, const float* head_w32, const __nv_bfloat16* head_w16,
                        const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
-                       float* dx, cudaStream_t st);
+                       float* dx, cudaStream_t st, BpttGraphCache* cache);
 constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
+
+static bool bptt_graph_enabled() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_BPTT_GRAPH");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0;
+}
 
 size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T);
 
@@ -262,6 +292,7 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)4 * H * maxI * 4, 256);        // dW' (interleaved)
   s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
+  s += align_up((size_t)B * 4, 256) + align_up((size_t)BT * 4, 256);  // stable copies of lengths / dlogits (y_dim == 1)
   if (y_dim > 1) {
     const int64_t yp = head_pad(y_dim);
     s += align_up((size_t)BT * yp * 2, 256);           // dlogits bf16, padded columns
@@ -276,7 +307,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        const void* x_bf16, const int32_t* lengths,
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
-                       float* dx, cudaStream_t st) {
+                       float* dx, cudaStream_t st, BpttGraphCache* cache) {
   AVVAD_CHECK_ARG(y_dim >= 1, "bad y_dim");
   AVVAD_CHECK_ARG(workspace_bytes >= lstm_backward_workspace(layers, input_size, ld0, H, y_dim, B, T),
                   "workspace too small");
@@ -295,6 +326,13 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   float* dWp = (float*)take((size_t)H4 * maxI * 4);
   __nv_bfloat16* WT = (__nv_bfloat16*)take((size_t)maxI * H4 * 2);
   float* partial = (float*)take((size_t)1024 * (H + 1) * 4);
+  int32_t* len_st = (int32_t*)take((size_t)B * 4);
+  float* dl_st = (float*)take((size_t)BT * 4);
+  // stable-address copies of the per-call inputs the step kernels read (see BpttGraphCache)
+  AVVAD_CUDA(cudaMemcpyAsync(len_st, lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  if (y_dim == 1) AVVAD_CUDA(cudaMemcpyAsync(dl_st, dlogits, (size_t)BT * 4, cudaMemcpyDeviceToDevice, st));
+  const float* dl_step = (y_dim == 1) ? dl_st : dlogits;
+  const bool use_graph = cache && bptt_graph_enabled() && !tc::profiling_on();
 
   const float* dY_head = nullptr;  // y_dim > 1: gradient of the top layer's output through the head (GEMM)
   if (y_dim == 1) {
@@ -359,20 +397,80 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_hh[l], H4, H, H, WT);
     AVVAD_LAUNCHED();
     AVVAD_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
-    for (int t = (int)T - 1; t >= 0; --t) {
-      const int has_rec = (t < (int)T - 1) ? kBpttSplit : 0;  // number of partial products to sum
-      lstm_bwd_cell_kernel<<<(unsigned)ceil_div(B * H, 256), 256, 0, st>>>(tv.gates, tv.c, dY, dlogits, head_w32, dh_rec,
-                                                                          dc, lengths, (int)B, (int)T, H, t, has_rec, dG);
-      AVVAD_LAUNCHED();
-      if (t > 0) {
-        tc::EpiParams ep{};
-        ep.C = dh_rec;
-        ep.ldc = H;
-        // M = B is tiny: split K = 4H over kBpttSplit CTAs per output tile so the step fills the GPU
-        int rc = tc::launch_tma_gemm(dG + (int64_t)t * H4, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st,
-                                     kBpttSplit, (int64_t)B * H);
-        if (rc) return rc;
+    auto run_steps = [&](cudaStream_t st) -> int {   // `st`: the caller's stream, or the capture stream
+      for (int t = (int)T - 1; t >= 0; --t) {
+        const int has_rec = (t < (int)T - 1) ? kBpttSplit : 0;  // number of partial products to sum
+        lstm_bwd_cell_kernel<<<(unsigned)ceil_div(B * H, 256), 256, 0, st>>>(tv.gates, tv.c, dY, dl_step, head_w32, dh_rec,
+                                                                            dc, len_st, (int)B, (int)T, H, t, has_rec, dG);
+        AVVAD_LAUNCHED();
+        if (t > 0) {
+          tc::EpiParams ep{};
+          ep.C = dh_rec;
+          ep.ldc = H;
+          // M = B is tiny: split K = 4H over kBpttSplit CTAs per output tile so the step fills the GPU
+          int rc = tc::launch_tma_gemm(dG + (int64_t)t * H4, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st,
+                                       kBpttSplit, (int64_t)B * H);
+          if (rc) return rc;
+        }
       }
+      return AVVAD_OK;
+    };
+    if (!use_graph) {
+      int rc = run_steps(st);
+      if (rc) return rc;
+    } else {
+      int dev = 0;
+      AVVAD_CUDA(cudaGetDevice(&dev));
+      if (!cache->cap_stream || cache->cap_device != dev) {
+        if (cache->cap_stream) cudaStreamDestroy(cache->cap_stream);
+        cache->cap_stream = nullptr;
+        AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream, cudaStreamNonBlocking));
+        cache->cap_device = dev;
+      }
+      const std::vector<uintptr_t> key = {(uintptr_t)tv.gates, (uintptr_t)tv.c, (uintptr_t)dY, (uintptr_t)dl_step,
+                                          (uintptr_t)head_w32, (uintptr_t)dh_rec, (uintptr_t)dc, (uintptr_t)len_st,
+                                          (uintptr_t)dG, (uintptr_t)WT, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H,
+                                          (uintptr_t)dev};
+      if (!cache->exec[l] || cache->key[l] != key) {
+        if (cache->exec[l]) {
+          cudaGraphExecDestroy(cache->exec[l]);
+          cache->exec[l] = nullptr;
+        }
+        const uint64_t before = g_launches.load();
+        // make sure the kernels' one-time attribute setup (not capturable) has happened: one real split-K launch
+        {
+          tc::EpiParams ep{};
+          ep.C = dh_rec;
+          ep.ldc = H;
+          int rc0 = tc::launch_tma_gemm(dG, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st, kBpttSplit,
+                                        (int64_t)B * H);
+          if (rc0) return rc0;
+        }
+        AVVAD_CUDA(cudaStreamBeginCapture(cache->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_steps(cache->cap_stream);
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(cache->cap_stream, &graph);
+        if (rc) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess) {
+          set_error(std::string("BPTT graph capture failed: ") + cudaGetErrorString(ce));
+          return AVVAD_ERR_CUDA;
+        }
+        ce = cudaGraphInstantiate(&cache->exec[l], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+          cache->exec[l] = nullptr;
+          set_error(std::string("BPTT graph instantiation failed: ") + cudaGetErrorString(ce));
+          return AVVAD_ERR_CUDA;
+        }
+        cache->key[l] = key;
+        cache->nodes[l] = (size_t)(g_launches.load() - before);  // launches counted while capturing = kernel nodes
+      } else {
+        g_launches.fetch_add(cache->nodes[l], std::memory_order_relaxed);  // a replay launches every captured kernel
+      }
+      AVVAD_CUDA(cudaGraphLaunch(cache->exec[l], st));
     }
     // db (= db_ih = db_hh)
     bias_grad_partial_kernel<<<dim3(H4 / 256, kBiasChunks), 256, 0, st>>>(dG, BT, H4, dWp);  // dWp is free here

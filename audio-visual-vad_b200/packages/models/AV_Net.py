@@ -6,8 +6,8 @@ import torchvision.models as models
 
 from .compact_bilinear_pooling import CompactBilinearPooling
 from .utils import weights_init_normal
-from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, all_parameters, device_of, full_state_dict,
-                      lstm_params, on_input_device, trunk_bn_modules)
+from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, all_parameters, bump_generation, device_of,
+                      full_state_dict, lstm_params, on_input_device, select_state, trunk_bn_modules, trunk_engine)
 
 
 class DeepVAD_AV(nn.Module):
@@ -52,18 +52,20 @@ class DeepVAD_AV(nn.Module):
             weights_init_normal(m, mean=mean, std=std)
 
     def _build(self, device):
-        def builder(old):
-            eng = old or {"trunk": E.ResNet18Trunk(),
-                          "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim),
-                          "mcb": E.Mcb() if self.use_mcb else None}
-            sd = full_state_dict(self)
-            eng["trunk"].load(sd, device)
-            eng["trunk"].load_train(sd, device)
-            eng["lstm"].load(sd, device, "lstm_merged", "vad_merged")
-            if self.use_mcb:
-                eng["mcb"].load(sd, device, self.eps)
-            return eng
-        return self._engines.get(self, device, builder)
+        """Sub-engines for `device`, each re-packed only when one of ITS tensors changed (see EngineCache)."""
+        sd = full_state_dict(self)
+        c = self._engines
+        eng = {"trunk": trunk_engine(c, sd, device, self.training)}
+        eng["lstm"] = c.get(device, "lstm", select_state(sd, ("lstm_merged.", "vad_merged.")),
+                            lambda: E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim),
+                            lambda e: e.load(sd, device, "lstm_merged", "vad_merged"))
+        eng["mcb"] = None
+        if self.use_mcb:
+            # train(): gamma / beta / running statistics are passed per call, only the sketches are packed
+            keys = ("mcb.",) if self.training else ("mcb.", "mcb_bn.")
+            eng["mcb"] = c.get(device, "mcb_train" if self.training else "mcb_eval", select_state(sd, keys),
+                               lambda: c.shared(device, "_mcb_handle", E.Mcb), lambda e: e.load(sd, device, self.eps))
+        return eng
 
     @on_input_device
     def forward(self, audio, video, lengths, return_posteriors=False):
@@ -90,6 +92,7 @@ class DeepVAD_AV(nn.Module):
                                                  feat_bf16=feat_bf16, col_off=col_off, want_f32=want_f32)
                 for b in bns:
                     b.num_batches_tracked += 1
+                    bump_generation(b.running_mean, b.running_var)
                 return out
             return eng["trunk"].forward(vid, feat_bf16=feat_bf16, col_off=col_off, want_f32=want_f32)
 
@@ -99,6 +102,7 @@ class DeepVAD_AV(nn.Module):
             if self.training:
                 proxy = McbBnFunction.apply(eng["mcb"], aud, feat, x, self.mcb_bn, self.mcb_bn.weight, self.mcb_bn.bias)
                 self.mcb_bn.num_batches_tracked += 1
+                bump_generation(self.mcb_bn.running_mean, self.mcb_bn.running_var)
             else:
                 eng["mcb"].forward(aud, feat, out_bf16=xv)
         else:

@@ -4,7 +4,7 @@ import torch.nn as nn
 
 from .utils import weights_init_normal
 from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params,
-                      on_input_device)
+                      on_input_device, select_state)
 
 
 class DeepVAD_audio(nn.Module):
@@ -34,11 +34,11 @@ class DeepVAD_audio(nn.Module):
             weights_init_normal(m, mean=mean, std=std)
 
     def _build(self, device):
-        def builder(old):
-            eng = old or {"lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
-            eng["lstm"].load(full_state_dict(self), device, "lstm_audio", "vad_audio")
-            return eng
-        return self._engines.get(self, device, builder)
+        sd = full_state_dict(self)
+        return {"lstm": self._engines.get(device, "lstm", select_state(sd, ("lstm_audio.", "vad_audio.")),
+                                          lambda: E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size,
+                                                         self.y_dim),
+                                          lambda e: e.load(sd, device, "lstm_audio", "vad_audio"))}
 
     @on_input_device
     def forward(self, x, lengths, return_posteriors=False):

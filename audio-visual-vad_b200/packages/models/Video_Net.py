@@ -4,8 +4,8 @@ import torch.nn as nn
 import torchvision.models as models
 
 from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
-from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, device_of, full_state_dict, lstm_params,
-                      on_input_device, trunk_bn_modules)
+from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, bump_generation, device_of, full_state_dict,
+                      lstm_params, on_input_device, select_state, trunk_bn_modules, trunk_engine)
 
 
 class DeepVAD_video(nn.Module):
@@ -39,15 +39,12 @@ class DeepVAD_video(nn.Module):
             weights_init_normal(m, mean=mean, std=std)
 
     def _build(self, device):
-        def builder(old):
-            eng = old or {"trunk": E.ResNet18Trunk(),
-                          "lstm": E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim)}
-            sd = full_state_dict(self)
-            eng["trunk"].load(sd, device)
-            eng["trunk"].load_train(sd, device)
-            eng["lstm"].load(sd, device, "lstm_video", "vad_video")
-            return eng
-        return self._engines.get(self, device, builder)
+        sd = full_state_dict(self)
+        c = self._engines
+        return {"trunk": trunk_engine(c, sd, device, self.training),
+                "lstm": c.get(device, "lstm", select_state(sd, ("lstm_video.", "vad_video.")),
+                              lambda: E.Lstm(self.lstm_layers, self.lstm_input_size, self.lstm_hidden_size, self.y_dim),
+                              lambda e: e.load(sd, device, "lstm_video", "vad_video"))}
 
     @on_input_device
     def forward(self, x, lengths, return_last=False):
@@ -71,6 +68,7 @@ class DeepVAD_video(nn.Module):
                                        col_off=0, want_f32=False)
             for b in bns:
                 b.num_batches_tracked += 1
+                bump_generation(b.running_mean, b.running_var)
         else:
             eng["trunk"].forward(vid, feat_bf16=xb.view(M, -1), col_off=0, want_f32=False)
         if need_grad:

@@ -39,36 +39,80 @@ def all_parameters(module: torch.nn.Module):
 
 
 def full_state_dict(module: torch.nn.Module):
-    """``module.state_dict()`` that is also complete inside an nn.DataParallel replica (reference:
-    scripts/train_AV_net.py:193 wraps the model in nn.parallel.DataParallel)."""
-    sd = module.state_dict()
+    """name -> LIVE tensor object (Parameter / buffer, not the detached copies ``state_dict()`` hands out) for every
+    entry of ``module.state_dict()``; also complete inside an nn.DataParallel replica (reference:
+    scripts/train_AV_net.py:193 wraps the model in nn.parallel.DataParallel).  The engine caches key on these objects'
+    (data_ptr, version, generation): the generation tag that marks raw-pointer updates (fused Adam, in-kernel running
+    statistics) lives on the tensor OBJECT, so detached copies would never see it."""
+    sd = dict(module.named_parameters(remove_duplicate=False))
+    sd.update(dict(module.named_buffers(remove_duplicate=False)))
     for k, v in _replica_parameters(module):
         if k not in sd:
-            sd[k] = v.detach()
+            sd[k] = v
     return sd
 
 
+def bump_generation(*tensors):
+    """Mark tensors whose storage was updated in place by a libavvad kernel (autograd's version counter does not see
+    raw-pointer writes): BatchNorm running statistics after a training-mode forward, parameters after the fused Adam."""
+    for t in tensors:
+        t._avvad_gen = getattr(t, "_avvad_gen", 0) + 1
+
+
 class EngineCache:
+    """Per-device, per-sub-engine cache of the packed device weights (trunk folded for eval, trunk un-folded for
+    train(), LSTM + head, MCB).  Every sub-engine has its OWN signature -- (data_ptr, version, generation) of exactly the
+    tensors it packs -- so an optimiser step that changes the LSTM does not re-pack the frozen trunk (40 conv uploads and
+    two stream synchronisations per step before), and `num_batches_tracked` (bumped every training forward) is in no
+    signature at all."""
+
     def __init__(self):
         self.by_device = {}
 
     @staticmethod
-    def _signature(module: torch.nn.Module):
-        sig = []
-        tensors = list(module.parameters()) + list(module.buffers()) + [v for _, v in _replica_parameters(module)]
-        for t in tensors:
-            sig.append((t.data_ptr(), t._version, getattr(t, "_avvad_gen", 0)))
-        return tuple(sig)
+    def signature(tensors):
+        return tuple((t.data_ptr(), t._version, getattr(t, "_avvad_gen", 0)) for t in tensors)
 
-    def get(self, module: torch.nn.Module, device: torch.device, builder):
-        sig = self._signature(module)
-        key = (device.type, device.index)
-        hit = self.by_device.get(key)
+    def get(self, device: torch.device, name: str, tensors, build, load):
+        slot = self.by_device.setdefault((device.type, device.index), {})
+        sig = self.signature(tensors)
+        hit = slot.get(name)
         if hit is not None and hit[0] == sig:
             return hit[1]
-        eng = builder(hit[1] if hit is not None else None)
-        self.by_device[key] = (sig, eng)
+        eng = hit[1] if hit is not None else build()
+        load(eng)
+        slot[name] = (sig, eng)
         return eng
+
+    def shared(self, device: torch.device, name: str, build):
+        """An object several sub-engines share (one ResNet18Trunk handle holds the eval AND the train weights)."""
+        slot = self.by_device.setdefault((device.type, device.index), {})
+        if name not in slot:
+            slot[name] = build()
+        return slot[name]
+
+
+def select_state(sd, prefixes, running=True):
+    """Tensors of a (full) state_dict under the given key prefixes, without num_batches_tracked (and without the
+    BatchNorm running statistics when running=False: the train()-mode engines do not read them)."""
+    out = []
+    for k, v in sd.items():
+        if not k.startswith(prefixes) or k.endswith("num_batches_tracked"):
+            continue
+        if not running and (k.endswith("running_mean") or k.endswith("running_var")):
+            continue
+        out.append(v)
+    return out
+
+
+def trunk_engine(cache: EngineCache, sd, device, training: bool):
+    """The ResNet-18 engine with the weights the current mode needs: BN folded from the running statistics in eval(),
+    raw convolution weights + BN affine parameters in train() (batch statistics)."""
+    obj = cache.shared(device, "_trunk_handle", E.ResNet18Trunk)
+    if training:
+        return cache.get(device, "trunk_train", select_state(sd, ("features.",), running=False), lambda: obj,
+                         lambda e: e.load_train(sd, device))
+    return cache.get(device, "trunk_eval", select_state(sd, ("features.",)), lambda: obj, lambda e: e.load(sd, device))
 
 
 class LstmHeadFunction(torch.autograd.Function):
@@ -151,7 +195,7 @@ class FusedAdam(torch.optim.Optimizer):
                             group["betas"], group["eps"])
                 # the in-place kernel bypasses autograd's version counter: bump a generation tag so that the packed
                 # (bf16, gate-interleaved) weight caches of the engines are refreshed on the next forward
-                p._avvad_gen = getattr(p, "_avvad_gen", 0) + 1
+                bump_generation(p)
 
 
 def on_input_device(forward):

@@ -40,13 +40,13 @@ class wavenet_autoencoder(nn.Module):
         object.__setattr__(self, "_engines", EngineCache())
 
     def _build(self, device):
-        def builder(old):
-            eng = old or E.WaveNetEncoder(self.filter_width, self.quantization_channel, list(self.dilations),
-                                          self.en_residual_channel, self.en_dilation_channel,
-                                          self.en_bottleneck_width, self.en_pool_kernel_size)
-            eng.load(full_state_dict(self), device)
-            return eng
-        return self._engines.get(self, device, builder)
+        sd = full_state_dict(self)
+        return self._engines.get(device, "encoder", list(sd.values()),
+                                 lambda: E.WaveNetEncoder(self.filter_width, self.quantization_channel,
+                                                          list(self.dilations), self.en_residual_channel,
+                                                          self.en_dilation_channel, self.en_bottleneck_width,
+                                                          self.en_pool_kernel_size),
+                                 lambda e: e.load(sd, device))
 
     def _encode(self, sample):
         device = device_of(sample)

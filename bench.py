@@ -14,7 +14,11 @@ one pass of the whole hot path over one batch: peak-normalise -> STFT/log-power/
           D2H of posteriors+decisions inside the timed region)
   roofline : the tcgen05 implicit-GEMM convolution kernel (ResNet trunk), algorithmic FLOPs / device
           time of those launches measured with CUDA events inside the timed region
-  cpu_baseline : the reference forward as a CPU port (oracle/reference_port.py) on a bounded sample
+  cpu_baseline : the reference forward as a CPU port (oracle/reference_port.py) on a bounded sample; the GPU path is
+          run on the SAME utterances and compared with it (`parity`, asserted: logits 2e-2 relative, posteriors 1e-2)
+  train    : BASELINE config 5, the AV+MCB training step (frozen ResNet in train() mode, device BPTT, ONE NCCL all-reduce
+          of the 16.8 M trainable gradients, fused Adam), GLOBAL batch 256 split over the ranks (strong scaling)
+  variants.ragged : config 4's variable-length utterances (N ~ U{64,000..102,400}) through the same call
 
 `--impl reference` times that CPU port alone (the reference's own CPU implementation of the path:
 the reference cannot be pip-installed -- it has no setup.py -- and its MCB branch does not run on
@@ -57,11 +61,10 @@ def synth_batch(B: int, seed: int):
 def synth_weights(B: int, seed=0):
     from avvad import synth
 
-    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), seed)
+    # "strong" family: logits span several units, so the parity check below can fail (avvad/synth.py FAMILIES);
     # running statistics of mcb_bn at the scale the whole-tensor L2 norm produces for this batch size
-    sd["mcb_bn.running_mean"] = torch.zeros(1024)
-    sd["mcb_bn.running_var"] = torch.full((1024,), 1.0 / (B * T_FRAMES * 1024.0))
-    return sd
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), seed, "strong")
+    return synth.calibrate_mcb_bn_(sd, B * T_FRAMES)
 
 
 class ClockSampler:
@@ -146,7 +149,164 @@ def cpu_baseline(sd, wave, vid, mean, std, n_utt: int, reps: int):
         frames = int(sum(lens))
         if r > 0:
             best = dt if best is None else min(best, dt)
-    return frames / best, cores, frames, torch.get_num_threads()
+    return frames / best, cores, frames, torch.get_num_threads(), post
+
+
+def parity_vs_cpu(sd, wave, vid, mean, std, n_utt, cpu_post, dev):
+    """The GPU path on the utterances the CPU leg just ran (its own call: the MCB norm is per call), against the CPU
+    port's posteriors.  Outside every timed region.  Raises when the north_star tolerances are exceeded."""
+    from avvad import synth
+    from avvad.pipeline import AVVADPipeline
+
+    sd8 = dict(sd)
+    pipe = AVVADPipeline(sd8, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD, use_mcb=True, device=dev)
+    ns, nf = [wave.shape[1]] * n_utt, [vid.shape[1]] * n_utt
+    logits, post, dec = pipe.infer_device(wave[:n_utt].to(dev), ns, vid[:n_utt].to(dev), nf)
+    got = post[..., 0].float().cpu()
+    ref = cpu_post.float()
+    lg, lr = torch.logit(got.double().clamp(1e-12, 1 - 1e-12)), torch.logit(ref.double().clamp(1e-12, 1 - 1e-12))
+    out = {"utterances": n_utt, "frames": int(ref.numel()),
+           "max_abs_posterior_err": float((got - ref).abs().max()),
+           "logit_rel_fro": float((lg - lr).norm() / lr.norm()),
+           "logit_std": float(lr.std()),
+           "decisions_agree": float(((got > 0.5) == (ref > 0.5)).double().mean()),
+           "tolerance": {"posterior": 1e-2, "logit_rel_fro": 2e-2}}
+    out["ok"] = out["max_abs_posterior_err"] <= 1e-2 and out["logit_rel_fro"] <= 2e-2
+    return out
+
+
+
+def train_block(args, rank, world, dev):
+    """BASELINE config 5: AV+MCB training step, GLOBAL batch 256 utterances x 317 frames split over the ranks (strong
+    scaling), trunk frozen but in train() mode (batch-statistics BN, scripts/train_AV_net.py:241-253), device BPTT, one
+    in-place NCCL all-reduce of the flat gradient arena, fused Adam.  Inputs are the standardised features the reference
+    loop feeds the model (train_AV_net.py:287-296), resident on the device.  Also: gradient equivalence of the sharded +
+    all-reduced step against the full batch on the audio-only model (no BatchNorm: exact up to summation order)."""
+    import torch.distributed as dist
+
+    from avvad import engine as E
+    from avvad import synth
+    from avvad.train import GradientArena, Trainer
+    from packages.models.Audio_Net import DeepVAD_audio
+    from packages.models.AV_Net import DeepVAD_AV
+
+    out = {"workload": "AV-VAD (DeepVAD_AV, MCB) training step, global batch 256 x 317 frames, frozen ResNet-18 in train() "
+                       "mode, BPTT through 2x LSTM-1024, Adam", "global_batch": args.train_batch, "scaling": "strong"}
+    Bg, Tt = args.train_batch, T_FRAMES
+    if Bg % world:
+        out["skipped"] = f"global batch {Bg} not divisible by {world} ranks"
+        return out
+    Bl = Bg // world
+    g = torch.Generator().manual_seed(77 + rank)
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), seed=1)
+    av = DeepVAD_AV(2, 1024, 1, use_mcb=True)
+    av.load_state_dict(sd)
+    for name, child in av.named_children():      # train_AV_net.py:241-245
+        if name == "features":
+            for q in child.parameters():
+                q.requires_grad = False
+    av = av.to(dev)
+    tr = Trainer(av, lr=1e-4)
+    a = torch.randn(Bl, Tt, 513, generator=g).to(dev)
+    v = torch.randn(Bl, Tt, 67, 67, generator=g).to(dev)
+    tgt = (torch.rand(Bl, Tt, 1, generator=g) > 0.5).float().to(dev)
+    ln = torch.full((Bl,), Tt, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        loss = tr.step((a, v), tgt, ln)
+    barrier()
+    steps = max(3, min(args.steps, 10))
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step((a, v), tgt, ln)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (E.launch_count() - l0) / steps
+    # the collective alone (same arena, in place)
+    ar_ms = 0.0
+    if world > 1:
+        for _ in range(2):
+            tr.arena.all_reduce()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(5):
+            tr.arena.all_reduce()
+        r1.record()
+        barrier()
+        ar_ms = r0.elapsed_time(r1) / 5
+        tr.arena.zero()
+    t = torch.tensor([ms, ar_ms, float(loss)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms, ar_ms, loss_sum = float(tmax[0]), float(tmax[1]), float(t[2])
+    else:
+        loss_sum = float(t[2])
+    out.update({"ms_per_step": ms, "frames_per_s": Bg * Tt / (ms / 1e3), "batch_per_gpu": Bl, "timed_steps": steps,
+                "gpu_launches_per_step": launches, "allreduce_ms": ar_ms, "allreduce_bytes": int(tr.arena.flat.numel() * 4),
+                "trainable_parameters": int(tr.arena.flat.numel()), "loss_sum_over_ranks": loss_sum,
+                "collective": "one in-place NCCL all-reduce (sum) of the flat fp32 gradient arena per step"
+                              if world > 1 else "none (single rank)"})
+    del tr, av, a, v
+
+    # ---- sharded + all-reduced gradients == full-batch gradients (audio-only model)
+    B, T = 8 * world, 40
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, T, 513, generator=g)
+    y = (torch.rand(B, T, 1, generator=g) > 0.5).float()
+    lens = [T - (i * 3) % 17 for i in range(B)]
+    m = DeepVAD_audio(2, 1024, 1)
+    m.load_state_dict(synth.seeded_state_dict(synth.model_spec("audio"), seed=5, family="strong"))
+    m = m.to(dev).train()
+    arena = GradientArena(list(m.parameters()))
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    logits = m(x[sl].to(dev), lens[sl])
+    _, _, dl = E.batch_bce(logits, y[sl].to(dev), lens[sl], 1e-8, want_grad=True)
+    logits.backward(dl)
+    sharded = arena.all_reduce().clone()
+    arena.zero()
+    logits = m(x.to(dev), lens)
+    _, _, dl = E.batch_bce(logits, y.to(dev), lens, 1e-8, want_grad=True)
+    logits.backward(dl)
+    err = ((sharded - arena.flat).norm() / arena.flat.norm()).item()
+    e = torch.tensor([err], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e, op=dist.ReduceOp.MAX)
+    out["grad_check"] = {"model": "DeepVAD_audio, B = 8 per rank, T = 40, ragged", "rel_fro_sharded_vs_full_batch": float(e[0]),
+                         "ok": float(e[0]) < 1e-4}
+    return out
+
+
+def ragged_lengths(B: int, seed: int):
+    """Config 4's variable-length utterances: N ~ U{64,000 .. 102,400} samples, 30 fps video of the same duration."""
+    rng = np.random.default_rng(seed)
+    ns = rng.integers(64000, 102401, size=B)
+    nf = np.maximum(1, np.rint(ns / 16000.0 * 30.0).astype(np.int64))
+    return ns.tolist(), nf.tolist()
+
+
+def traffic_from_profiles():
+    """dram bytes per launch of the dominant kernel from the newest committed ncu summary (profiles/*traffic*.json)."""
+    import glob
+
+    best = None
+    for f in sorted(glob.glob(os.path.join(REPO, "profiles", "*traffic*.json"))):
+        try:
+            d = json.load(open(f))
+            best = (d, os.path.relpath(f, REPO))
+        except Exception:
+            continue
+    return best
 
 
 def run_reference(args, rank, world):
@@ -298,18 +458,62 @@ def run_ours(args, rank, world, local_rank):
     dedup_ms = d0.elapsed_time(d1)
     pipe.dedup_video = False
 
+    # ---- variant (reported separately): BASELINE config 4's ragged utterances through the same device call ----
+    rg_ns, rg_nf = ragged_lengths(B, 4321 + rank)
+    rg_wave_h, rg_vid_h, _, _ = synth.batch_inputs(B, 99 + rank, max(rg_ns), max(rg_nf))
+    rg_wave_d, rg_vid_d = rg_wave_h.to(dev), rg_vid_h.to(dev)
+    del rg_wave_h, rg_vid_h
+    rg_lens = AVVADPipeline.frame_counts(rg_ns, rg_nf)
+    rg_ns_d = torch.tensor(rg_ns, dtype=torch.int32, device=dev)
+    rg_nf_d = torch.tensor(rg_nf, dtype=torch.int32, device=dev)
+    rg_lens_d = torch.tensor(rg_lens, dtype=torch.int32, device=dev)
+    rg_tmax = max(rg_lens)
+
+    def step_ragged():
+        return pipe.infer_device(rg_wave_d, rg_ns_d, rg_vid_d, rg_nf_d, lengths=rg_lens_d, t_max=rg_tmax)
+
+    for _ in range(2):
+        step_ragged()
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(args.steps):
+        step_ragged()
+    q1.record()
+    barrier()
+    ragged_ms = q0.elapsed_time(q1)
+    del rg_wave_d, rg_vid_d
+    pipe._bufs.clear()
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE config 5: the training step (the only path with a collective) ----
+    train = None
+    if not args.no_train:
+        try:
+            train = train_block(args, rank, world, dev)
+        except Exception as ex:  # reported, never hidden: a failing training leg must not erase the inference numbers
+            train = {"failed": f"{type(ex).__name__}: {ex}"}
+            if world > 1:
+                raise
+
     if world > 1:
         import torch.distributed as dist
 
-        t = torch.tensor([ms, e2e_ms, dedup_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_ms, dedup_ms, ragged_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, dedup_ms = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_ms, dedup_ms, ragged_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        rv = torch.tensor([float(sum(rg_lens)), float(B * rg_tmax)], dtype=torch.float64, device=dev)
+        dist.all_reduce(rv, op=dist.ReduceOp.SUM)
+        rg_valid, rg_padded = float(rv[0]), float(rv[1])
+    else:
+        rg_valid, rg_padded = float(sum(rg_lens)), float(B * rg_tmax)
 
     frames_per_step = B * T_FRAMES * world
     value = frames_per_step * args.steps / (ms / 1e3)
     e2e_val = frames_per_step * args.steps / (e2e_ms / 1e3)
     peak_tf, peak_hbm, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
+    traffic = traffic_from_profiles()
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -320,7 +524,8 @@ def run_ours(args, rank, world, local_rank):
                                "raw audio/video in, posteriors + decisions out",
                    "batch_per_gpu": B, "frames_per_utterance": T_FRAMES, "frames_per_step": frames_per_step,
                    "parallelism": f"utterance-sharded x{world}, no collective",
-                   "l2": "inputs (259 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush"},
+                   "l2": "inputs (259 MB) and activations (>1 GB) per step exceed the 126 MB L2; no explicit flush",
+                   "weights": "seeded random init, 'strong' family (logits span several units; avvad/synth.py)"},
         "e2e": {"value": e2e_val, "unit": "frames/s", "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(wave_p.numel() * 4 + vid_p.numel()) * world,
                 "d2h_bytes_per_step": int(B * T_FRAMES * (4 + 4)) * world},
@@ -332,11 +537,13 @@ def run_ours(args, rank, world, local_rank):
                                "with the downsample 1x1 branches K-concatenated into conv_b)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
-                     # dram__bytes_read+write per conv launch, averaged over the 16 launches of one 20,288-frame pass
-                     # (profiles/r01d_end_of_round.md; ncu --set full, one capture); algorithmic operand bytes of the
-                     # same 16 launches: 17.3 GB = 1.08 GB per launch
-                     "traffic": 1.037e9, "traffic_unit": "bytes per launch (ncu dram bytes, avg of the 16 conv launches "
-                                                         "of one 64-utterance pass)",
+                     # dram__bytes_read.sum + dram__bytes_write.sum per conv launch from the newest committed ncu
+                     # capture (profiles/*traffic*.json, written by tools/profile_summary.py from an `ncu --set full`
+                     # report of `bench.py --ncu`); null when no capture is committed
+                     "traffic": traffic[0].get("conv_dram_bytes_per_launch") if traffic else None,
+                     "traffic_source": ({"file": traffic[1], "commit": traffic[0].get("commit"),
+                                         "algorithmic_bytes_per_launch": traffic[0].get("conv_algorithmic_bytes_per_launch"),
+                                         "unit": traffic[0].get("unit")} if traffic else None),
                      "algorithmic_flops_per_frame": 2 * CONV_MAC_PER_FRAME,
                      "peak_source": peak_src,
                      # one CUDA-event record brackets the four convolution launches of a ResNet stage and trunk pass
@@ -350,7 +557,17 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": dedup_ms / args.steps,
             "note": "NOT the headline: ResNet on the 152 source frames per utterance + index-exact gather of the 512-d "
                     "features to 317 frames; bit-identical posteriors (tests/test_gpu_pipeline.py), 2.09x less "
-                    "convolution work than the reference's order (every upsampled frame through the ResNet)"}},
+                    "convolution work than the reference's order (every upsampled frame through the ResNet)"},
+            "ragged": {
+                "value": rg_valid * args.steps / (ragged_ms / 1e3), "unit": "valid frames/s",
+                "padded_frames_per_s": rg_padded * args.steps / (ragged_ms / 1e3), "ms_per_step": ragged_ms / args.steps,
+                "valid_frames_per_step": rg_valid, "padded_frames_per_step": rg_padded,
+                "padding_overhead": rg_padded / rg_valid - 1.0,
+                "note": "BASELINE config 4 input statistics: utterance lengths N ~ U{64,000..102,400} samples "
+                        "(T 247..397), zero-padded to the longest of the batch as the reference's collate does; the padded "
+                        "frames run through the ResNet and MCB exactly as in the reference (SURVEY 8g), so the gap to the "
+                        "headline is the padding + imbalance cost"}},
+        "train": train,
         "breakdown_ms_per_step": {"conv_tc": conv_ms / args.steps, "gemm_tc": gemm_ms / args.steps,
                                   "lstm_step_tc": lstm_ms / args.steps, "stem_tc": stem_ms / args.steps, "lstm_step_launches": int(lstm_n / args.steps),
                                   "lstm_step_tflops": (lstm_flops / (lstm_ms / 1e3) / 1e12) if lstm_ms > 0 else None,
@@ -358,15 +575,23 @@ def run_ours(args, rank, world, local_rank):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
+            cpu_post = None
+            sd_ref = synth_weights(args.ref_batch)  # mcb_bn statistics at the scale of a ref_batch-utterance call
             try:
-                v, cores, fr, thr = cpu_baseline(sd, wave_h, vid_h, mean, std, args.ref_batch, 1)
+                v, cores, fr, thr, cpu_post = cpu_baseline(sd_ref, wave_h, vid_h, mean, std, args.ref_batch, 1)
                 line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                                         "sample": f"{args.ref_batch} utterances ({fr} frames) of the same synthetic "
                                                   f"batch, best of 1 after a warm-up, {thr} torch threads"}
             except Exception as ex:  # the CPU leg must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": f"failed: {type(ex).__name__}: {ex}"}
+            if cpu_post is not None:
+                line["parity"] = parity_vs_cpu(sd_ref, wave_h, vid_h, mean, std, args.ref_batch, cpu_post, dev)
         print(json.dumps(line), flush=True)
+        if line.get("parity") and not line["parity"]["ok"]:
+            raise SystemExit(f"bench.py: the timed GPU path disagrees with the CPU port: {line['parity']}")
+        if train and train.get("grad_check") and not train["grad_check"]["ok"]:
+            raise SystemExit(f"bench.py: sharded gradients disagree with the full batch: {train['grad_check']}")
     if world > 1:
         import torch.distributed as dist
 
@@ -382,6 +607,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="utterances per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=8, help="utterances per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block (config 5)")
+    ap.add_argument("--train-batch", type=int, default=256, help="GLOBAL utterances per training step")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: warm-up + one pass, prints nothing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
