@@ -372,6 +372,67 @@ class ResNet18Trunk:
                                                      L.stream_ptr()))
         return feat
 
+    def forward_tape(self, frames: torch.Tensor, running: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
+                     bn_eps=1e-5, momentum=0.1):
+        """Training-mode forward of a TRAINABLE trunk: returns (feat f32 (n,512), tape) -- the tape (a caller-owned
+        byte tensor) carries every activation `backward` needs."""
+        L.require_cuda(frames)
+        frames = frames.contiguous()
+        n = frames.numel() // (67 * 67)
+        if not hasattr(self, "tws"):
+            self.tws = _Workspace()
+        ws = self.tws.get(L.lib().avvad_resnet18_tape_workspace_bytes(n), frames.device)
+        tape = torch.empty(L.lib().avvad_resnet18_tape_bytes(n), dtype=torch.uint8, device=frames.device)
+        feat = torch.empty(n, 512, dtype=torch.float32, device=frames.device)
+        rm = _ptr_array([r[0] for r in running]) if running is not None else None
+        rv = _ptr_array([r[1] for r in running]) if running is not None else None
+        L.check(L.lib().avvad_resnet18_forward_tape(self.h, L.ptr(frames), n, L.ptr(ws), ws.numel(), L.ptr(tape),
+                                                    tape.numel(), bn_eps, momentum, rm, rv, L.ptr(feat), None, 0, 0,
+                                                    L.stream_ptr()))
+        return feat, tape
+
+    @staticmethod
+    def tape_tensors(tape: torch.Tensor, n: int):
+        """Views into a tape (inspection hook for the parity tests): dict with 'raw' (20 NHWC bf16 tensors), 'act0',
+        'pool', 'y1' / 'out' (8 each) and 'stats' (float (20, 1024): per layer mean[:C] | invstd[C:2C])."""
+        off = (C.c_int64 * 39)()
+        L.check(L.lib().avvad_resnet18_tape_layout(n, off, 39))
+        shapes = [(34, 34, 64), (34, 34, 64), (17, 17, 64)]
+        specs = [(64, 17), (64, 17), (64, 17), (64, 17), (128, 9), (128, 9), (128, 9), (128, 9), (128, 9), (256, 5),
+                 (256, 5), (256, 5), (256, 5), (256, 5), (512, 3), (512, 3), (512, 3), (512, 3), (512, 3)]
+        shapes += [(h, h, c) for c, h in specs]
+        for c, h in ((64, 17), (64, 17), (128, 9), (128, 9), (256, 5), (256, 5), (512, 3), (512, 3)):
+            shapes += [(h, h, c), (h, h, c)]
+
+        def view(i):
+            numel = n * shapes[i][0] * shapes[i][1] * shapes[i][2]
+            return tape[off[i]:off[i] + 2 * numel].view(torch.bfloat16).view((n,) + shapes[i])
+        stats = tape[off[38]:off[38] + 20 * 1024 * 4].view(torch.float32).view(20, 1024)
+        return {"raw": [view(0)] + [view(3 + l - 1) for l in range(1, 20)], "act0": view(1), "pool": view(2),
+                "y1": [view(22 + 2 * b) for b in range(8)], "out": [view(23 + 2 * b) for b in range(8)], "stats": stats}
+
+    def backward(self, frames: torch.Tensor, tape: torch.Tensor, dfeat: torch.Tensor, bn_eps=1e-5):
+        """Gradients of the 20 conv weights (PyTorch layout) and BatchNorm (weight, bias) pairs from dfeat (n,512)."""
+        frames = frames.contiguous()
+        n = frames.numel() // (67 * 67)
+        dev = frames.device
+        dfeat = dfeat.detach().to(torch.float32).reshape(n, 512).contiguous()
+        if not hasattr(self, "bws"):
+            self.bws = _Workspace()
+        ws = self.bws.get(L.lib().avvad_resnet18_backward_workspace_bytes(n), dev)
+        shapes = [(64, 3, 7, 7)]
+        for stage, cin, cout in ((4, 64, 64), (5, 64, 128), (6, 128, 256), (7, 256, 512)):
+            shapes += [(cout, cin, 3, 3), (cout, cout, 3, 3)]
+            if stage != 4:
+                shapes += [(cout, cin, 1, 1)]
+            shapes += [(cout, cout, 3, 3), (cout, cout, 3, 3)]
+        dw = [torch.empty(s, dtype=torch.float32, device=dev) for s in shapes]
+        dg = [torch.empty(s[0], dtype=torch.float32, device=dev) for s in shapes]
+        db = [torch.empty(s[0], dtype=torch.float32, device=dev) for s in shapes]
+        L.check(L.lib().avvad_resnet18_backward(self.h, L.ptr(frames), n, L.ptr(tape), L.ptr(dfeat), L.ptr(ws), ws.numel(),
+                                                bn_eps, _ptr_array(dw), _ptr_array(dg), _ptr_array(db), L.stream_ptr()))
+        return dw, dg, db
+
     def forward_upto(self, frames: torch.Tensor, upto: int, shape: Tuple[int, int, int]) -> torch.Tensor:
         """Test hook: NHWC bf16 activation after conv layer `upto` (shape = (h, w, c))."""
         frames = frames.contiguous()

@@ -50,6 +50,13 @@ PROTOTYPES = {
     "avvad_resnet18_train_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "avvad_resnet18_forward_train": (C.c_int, [VP, VP, C.c_int64, VP, C.c_size_t, C.c_float, C.c_float, VP, VP, VP, VP,
                                                C.c_int64, C.c_int64, VP]),
+    "avvad_resnet18_tape_bytes": (C.c_size_t, [C.c_int64]),
+    "avvad_resnet18_tape_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "avvad_resnet18_tape_layout": (C.c_int, [C.c_int64, c_i64p, C.c_int]),
+    "avvad_resnet18_forward_tape": (C.c_int, [VP, VP, C.c_int64, VP, C.c_size_t, VP, C.c_size_t, C.c_float, C.c_float, VP,
+                                              VP, VP, VP, C.c_int64, C.c_int64, VP]),
+    "avvad_resnet18_backward_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "avvad_resnet18_backward": (C.c_int, [VP, VP, C.c_int64, VP, VP, VP, C.c_size_t, C.c_float, VP, VP, VP, VP]),
     "avvad_gemm_bf16": (C.c_int, [VP, C.c_int64, VP, C.c_int64, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int64,
                                   C.c_int64, C.c_int64, VP]),
     "avvad_conv2d_nhwc_bf16": (C.c_int, [VP, VP, VP, VP, VP, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -35,11 +35,15 @@ extern std::atomic<uint64_t> g_launches;
     }                                                                                         \
   } while (0)
 
-// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.  With AVVAD_SYNC_DEBUG=1 in the
+// environment every launch is followed by a device synchronisation, so an asynchronous fault (illegal address, ...) is
+// reported with the file:line of the kernel that caused it (debugging aid; never set in production or benchmarks).
+bool sync_debug();
 #define AVVAD_LAUNCHED()                                                                      \
   do {                                                                                        \
     ::avvad::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
     cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ == cudaSuccess && ::avvad::sync_debug()) e__ = cudaDeviceSynchronize();           \
     if (e__ != cudaSuccess) {                                                                 \
       ::avvad::set_error(std::string("kernel launch failed: ") + cudaGetErrorString(e__) +    \
                          " at " + __FILE__ + ":" + std::to_string(__LINE__));                 \

@@ -332,7 +332,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   AVVAD_CUDA(cudaMemcpyAsync(len_st, lengths, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
   if (y_dim == 1) AVVAD_CUDA(cudaMemcpyAsync(dl_st, dlogits, (size_t)BT * 4, cudaMemcpyDeviceToDevice, st));
   const float* dl_step = (y_dim == 1) ? dl_st : dlogits;
-  const bool use_graph = cache && bptt_graph_enabled() && !tc::profiling_on();
+  const bool use_graph = cache && bptt_graph_enabled() && !tc::profiling_on() && !sync_debug();
 
   const float* dY_head = nullptr;  // y_dim > 1: gradient of the top layer's output through the head (GEMM)
   if (y_dim == 1) {

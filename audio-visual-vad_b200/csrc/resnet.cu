@@ -167,12 +167,16 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, int64_t M, int C, float eps, float momentum,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale_shift, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
+                                   float* __restrict__ running_var, float* __restrict__ mean_invstd_out = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = stats[c] / (double)M;
   double var = stats[C + c] / (double)M - mean * mean;
   if (var < 0) var = 0;
+  if (mean_invstd_out) {  // kept on the tape for the BatchNorm backward (resnet_bwd.cuh)
+    mean_invstd_out[c] = (float)mean;
+    mean_invstd_out[C + c] = (float)(1.0 / sqrt(var + (double)eps));
+  }
   // same fp32 operation order as before the scale/shift refactoring is not required: (x-mean)*invstd*gamma+beta is
   // evaluated as x*a + b in fp32 from fp64-derived a, b
   const double a = (1.0 / sqrt(var + (double)eps)) * (double)gamma[c];
@@ -717,7 +721,7 @@ struct TrainCtx {
 
 // raw [M][C] -> out = act(bn(raw) (+res)); updates the running statistics of `layer`
 int bn_train(const TrainCtx& c, int layer, const __nv_bfloat16* raw, int64_t M, int C, const __nv_bfloat16* residual,
-             int relu, __nv_bfloat16* out) {
+             int relu, __nv_bfloat16* out, float* mean_invstd_out = nullptr) {
   AVVAD_CUDA(cudaMemsetAsync(c.stats, 0, sizeof(double) * 2 * C, c.st));
   const int lanes = 256 / (C / 8);
   bn_stats_kernel<<<(unsigned)ceil_div(M, kStatRows), 256, (size_t)lanes * 2 * C * sizeof(float), c.st>>>(raw, M, C,
@@ -725,7 +729,7 @@ int bn_train(const TrainCtx& c, int layer, const __nv_bfloat16* raw, int64_t M, 
   AVVAD_LAUNCHED();
   bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, c.st>>>(
       c.stats, M, C, c.bn_eps, c.momentum, c.h->gamma[layer], c.h->beta[layer], c.mean_invstd,
-      c.running_mean ? c.running_mean[layer] : nullptr, c.running_var ? c.running_var[layer] : nullptr);
+      c.running_mean ? c.running_mean[layer] : nullptr, c.running_var ? c.running_var[layer] : nullptr, mean_invstd_out);
   AVVAD_LAUNCHED();
   const int rows_per_block = lanes * kApplyRows;
   bn_apply_kernel<<<(unsigned)ceil_div(M, rows_per_block), 256, 2 * C * sizeof(float), c.st>>>(
@@ -822,3 +826,5 @@ extern "C" int avvad_resnet18_forward_train(avvad_resnet18* h, const float* fram
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }
+
+#include "resnet_bwd.cuh"

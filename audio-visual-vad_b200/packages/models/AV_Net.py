@@ -6,8 +6,9 @@ import torchvision.models as models
 
 from .compact_bilinear_pooling import CompactBilinearPooling
 from .utils import weights_init_normal
-from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, all_parameters, bump_generation, device_of,
-                      full_state_dict, lstm_params, on_input_device, select_state, trunk_bn_modules, trunk_engine)
+from ._engine import (E, EngineCache, LstmHeadFunction, McbBnFunction, TrunkFunction, all_parameters, bump_generation,
+                      device_of, full_state_dict, lstm_params, on_input_device, select_state, trunk_bn_modules,
+                      trunk_engine, trunk_params)
 
 
 class DeepVAD_AV(nn.Module):
@@ -80,16 +81,22 @@ class DeepVAD_AV(nn.Module):
         aud = audio.detach().to(torch.float32).reshape(M, self.num_audio_ftrs).contiguous()
         # eval() forward is inference only (detached logits, folded BN); the autograd path is the train() step
         need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self))
-        if need_grad and any(p.requires_grad for p in all_parameters(self.features)):
-            raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze "
-                                      "'features' as scripts/train_AV_net.py:241-245 does")
+        trunk_trainable = need_grad and any(p.requires_grad for p in all_parameters(self.features))
+        if trunk_trainable and self.use_mcb:
+            raise NotImplementedError("MCB fusion with a trainable ResNet trunk: the gradient of the fusion w.r.t. the "
+                                      "video features is not wired into this module (scripts/train_AV_net.py:241-245 "
+                                      "freezes 'features'; the concat fusion and DeepVAD_video train the trunk)")
 
         # ---- video branch: batch-statistics BN while the module is in train() (train_AV_net.py:253), folded BN in eval()
         def trunk(feat_bf16=None, col_off=0, want_f32=True):
             if self.training:
                 bns = trunk_bn_modules(self.features)
-                out = eng["trunk"].forward_train(vid, [(b.running_mean, b.running_var) for b in bns],
-                                                 feat_bf16=feat_bf16, col_off=col_off, want_f32=want_f32)
+                running = [(b.running_mean, b.running_var) for b in bns]
+                if trunk_trainable:   # concat fusion only: features with a tape, packed into the operand below
+                    out = TrunkFunction.apply(eng["trunk"], vid, running, *trunk_params(self.features))
+                else:
+                    out = eng["trunk"].forward_train(vid, running, feat_bf16=feat_bf16, col_off=col_off,
+                                                     want_f32=want_f32)
                 for b in bns:
                     b.num_batches_tracked += 1
                     bump_generation(b.running_mean, b.running_var)
@@ -107,7 +114,11 @@ class DeepVAD_AV(nn.Module):
                 eng["mcb"].forward(aud, feat, out_bf16=xv)
         else:
             E.pack_rows_bf16(aud, xv, 0, False)
-            trunk(feat_bf16=xv, col_off=self.num_audio_ftrs, want_f32=False)
+            feat = trunk(feat_bf16=xv, col_off=self.num_audio_ftrs, want_f32=False)
+            if trunk_trainable:
+                E.pack_rows_bf16(feat.detach(), xv, self.num_audio_ftrs, False)
+                # the LSTM's input gradient (B,T,1025) reaches the trunk through this concatenation (AV_Net.py:124)
+                proxy = torch.cat([aud.view(batch, frames, -1), feat.view(batch, frames, -1)], dim=2)
         if need_grad:
             return LstmHeadFunction.apply(eng["lstm"], x, lengths, proxy,
                                           *lstm_params(self.lstm_merged, self.vad_merged))

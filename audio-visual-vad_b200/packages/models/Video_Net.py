@@ -4,8 +4,9 @@ import torch.nn as nn
 import torchvision.models as models
 
 from .utils import weights_init_normal, method1, method3  # noqa: F401  (re-exported like the reference)
-from ._engine import (E, EngineCache, LstmHeadFunction, all_parameters, bump_generation, device_of, full_state_dict,
-                      lstm_params, on_input_device, select_state, trunk_bn_modules, trunk_engine)
+from ._engine import (E, EngineCache, LstmHeadFunction, TrunkFunction, all_parameters, bump_generation, device_of,
+                      full_state_dict, lstm_params, on_input_device, select_state, trunk_bn_modules, trunk_engine,
+                      trunk_params)
 
 
 class DeepVAD_video(nn.Module):
@@ -55,25 +56,30 @@ class DeepVAD_video(nn.Module):
         M = batch * frames
         xb = eng["lstm"].new_input(batch, frames, device)
         vid = x.detach().to(torch.float32).reshape(M, height, width)
-        # eval() forward is inference only (detached logits, folded BN).  train(): the LSTM + head train through the
-        # device BPTT with the trunk FROZEN in batch-statistics mode -- what scripts/train_AV_net.py:241-253 does to the
-        # same trunk; scripts/train_video_net.py leaves it trainable, which needs the ResNet backward (not implemented).
+        # eval() forward is inference only (detached logits, folded BN).  train(): batch-statistics BatchNorm; the LSTM +
+        # head train through the device BPTT, and a trainable trunk -- scripts/train_video_net.py:145-173 hands every
+        # parameter to Adam -- through the device dgrad / wgrad / BatchNorm backward (TrunkFunction); a frozen trunk
+        # (scripts/train_AV_net.py:241-245 style) takes the cheaper forward without a tape.
         need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self))
-        if need_grad and any(p.requires_grad for p in all_parameters(self.features)):
-            raise NotImplementedError("back-propagation through the ResNet trunk is not implemented: freeze 'features' "
-                                      "(as scripts/train_AV_net.py:241-245 does) to train the LSTM and the head")
+        trunk_trainable = need_grad and any(p.requires_grad for p in all_parameters(self.features))
+        if need_grad and return_last:
+            raise NotImplementedError("return_last=True has no training path (unused by the scripts)")
+        x_src = None
         if self.training:
             bns = trunk_bn_modules(self.features)
-            eng["trunk"].forward_train(vid, [(b.running_mean, b.running_var) for b in bns], feat_bf16=xb.view(M, -1),
-                                       col_off=0, want_f32=False)
+            running = [(b.running_mean, b.running_var) for b in bns]
+            if trunk_trainable:
+                feat = TrunkFunction.apply(eng["trunk"], vid, running, *trunk_params(self.features))
+                E.pack_rows_bf16(feat.detach(), xb.view(M, -1), 0, False)
+                x_src = feat.view(batch, frames, self.lstm_input_size)
+            else:
+                eng["trunk"].forward_train(vid, running, feat_bf16=xb.view(M, -1), col_off=0, want_f32=False)
             for b in bns:
                 b.num_batches_tracked += 1
                 bump_generation(b.running_mean, b.running_var)
         else:
             eng["trunk"].forward(vid, feat_bf16=xb.view(M, -1), col_off=0, want_f32=False)
         if need_grad:
-            if return_last:
-                raise NotImplementedError("return_last=True has no training path (unused by the scripts)")
-            return LstmHeadFunction.apply(eng["lstm"], xb, lengths, None, *lstm_params(self.lstm_video, self.vad_video))
+            return LstmHeadFunction.apply(eng["lstm"], xb, lengths, x_src, *lstm_params(self.lstm_video, self.vad_video))
         logits, _, _, last = eng["lstm"].forward(xb, lengths, want_last=return_last)
         return last if return_last else logits

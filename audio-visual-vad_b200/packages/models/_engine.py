@@ -160,6 +160,37 @@ class McbBnFunction(torch.autograd.Function):
         return None, None, None, None, None, dg, db
 
 
+class TrunkFunction(torch.autograd.Function):
+    """Differentiable training-mode ResNet-18 trunk on libavvad: forward keeps a tape, backward runs the device
+    dgrad / wgrad / BatchNorm / pooling gradients (csrc/resnet_bwd.cuh) and returns the gradients of the 20 convolution
+    weights and 40 BatchNorm affine parameters in the order `trunk_params` lists them.  This is what makes
+    scripts/train_video_net.py -- which leaves the trunk trainable -- run unchanged."""
+
+    @staticmethod
+    def forward(ctx, trunk_engine, frames, running, *params):
+        feat, tape = trunk_engine.forward_tape(frames, running)
+        ctx.trunk_engine, ctx.tape, ctx.frames = trunk_engine, tape, frames
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        dw, dg, db = ctx.trunk_engine.backward(ctx.frames, ctx.tape, dfeat)
+        ctx.tape = None
+        grads = []
+        for i in range(20):  # parameter order of trunk_params: conv weight, bn weight, bn bias per layer
+            grads += [dw[i], dg[i], db[i]]
+        return (None, None, None) + tuple(grads)
+
+
+def trunk_params(features: torch.nn.Module):
+    """(conv.weight, bn.weight, bn.bias) of the 20 conv layers in libavvad's layer order."""
+    ps = []
+    for ck, bk in E.RESNET_LAYER_KEYS:
+        bn = features.get_submodule(bk)
+        ps += [features.get_submodule(ck).weight, bn.weight, bn.bias]
+    return ps
+
+
 def trunk_bn_modules(features: torch.nn.Module):
     """The 20 BatchNorm2d modules of the trunk in libavvad's conv-layer order."""
     return [features.get_submodule(bk) for _, bk in E.RESNET_LAYER_KEYS]

@@ -167,6 +167,29 @@ int avvad_resnet18_forward_train(avvad_resnet18* h, const float* frames, int64_t
                                  float* const* running_var, float* feat, void* feat_bf16, int64_t ld_bf16,
                                  int64_t col_off, void* stream);
 
+/* Trainable trunk (scripts/train_video_net.py:145-173 hands ALL parameters to Adam, the ResNet included).
+ * replaces: autograd of packages/models/Video_Net.py:60-99 (torchvision resnet18 children[:-1] in train() mode).
+ * avvad_resnet18_forward_tape = avvad_resnet18_forward_train that also keeps, in the caller-owned `tape`
+ * (avvad_resnet18_tape_bytes), every tensor the backward needs (raw conv outputs, post-activation tensors, batch mean /
+ * inverse std per BatchNorm layer).  avvad_resnet18_backward turns dfeat (f32 [n][512], the gradient w.r.t. the trunk's
+ * features) into the gradients of the 20 convolution weights (PyTorch layout [O][I][k][k] fp32; layer 0: [64][3][7][7])
+ * and of the 20 BatchNorm affine parameter pairs (dgamma, dbeta fp32 [C]); dW / dgamma / dbeta are arrays of 20 device
+ * pointers in the conv layer order above.  `frames` must be the tensor the matching forward saw. */
+size_t avvad_resnet18_tape_bytes(int64_t n_frames);
+size_t avvad_resnet18_tape_workspace_bytes(int64_t n_frames);
+/* Byte offsets of the tape's tensors (inspection hook used by the parity tests): offsets[0..37] = raw conv1 output
+ * (n,34,34,64), its BN+ReLU (n,34,34,64), the pooled map (n,17,17,64), the raw outputs of conv layers 1..19, then
+ * (first activation, block output) of the 8 BasicBlocks -- NHWC bf16 --, offsets[38] = float [20][1024] (mean | invstd). */
+int avvad_resnet18_tape_layout(int64_t n_frames, int64_t* offsets, int count);
+int avvad_resnet18_forward_tape(avvad_resnet18* h, const float* frames, int64_t n_frames, void* workspace,
+                                size_t workspace_bytes, void* tape, size_t tape_bytes, float bn_eps, float momentum,
+                                float* const* running_mean, float* const* running_var, float* feat, void* feat_bf16,
+                                int64_t ld_bf16, int64_t col_off, void* stream);
+size_t avvad_resnet18_backward_workspace_bytes(int64_t n_frames);
+int avvad_resnet18_backward(avvad_resnet18* h, const float* frames, int64_t n_frames, void* tape, const float* dfeat,
+                            void* workspace, size_t workspace_bytes, float bn_eps, float* const* dW,
+                            float* const* dgamma, float* const* dbeta, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Data preparation on the device
  *
