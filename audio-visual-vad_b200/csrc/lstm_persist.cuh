@@ -280,6 +280,7 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       }
       if (row_ok) {
         float hv[8];
+        __nv_bfloat16* gsave = g.gates_out ? g.gates_out + ((int64_t)b * g.T + t) * H4 + ns * 64 + half * 32 : nullptr;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int o = u * 4;
@@ -300,11 +301,17 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
             tc = tanh_hw(c[u]);
           }
           hv[u] = go * tc;
-          // training tape: keep the activated gates packed in the (now dead) accumulator registers; they are written
-          // AFTER h_t has been published -- the release of the step flag orders every earlier store of the CTA, so tape
-          // stores issued before it would sit on the recurrence's critical path
-          v[o + 0] = pack_bf16x2(gi, gf);
-          v[o + 1] = pack_bf16x2(gg, go);
+          if (gsave) {
+            uint2 pk;
+            pk.x = pack_bf16x2(gi, gf);
+            pk.y = pack_bf16x2(gg, go);
+            *reinterpret_cast<uint2*>(gsave + 4 * u) = pk;
+          }
+        }
+        if (g.c_out) {
+          float4* cp = reinterpret_cast<float4*>(g.c_out + ((int64_t)b * g.T + t) * g.H + ns * 16 + half * 8);
+          cp[0] = make_float4(c[0], c[1], c[2], c[3]);
+          cp[1] = make_float4(c[4], c[5], c[6], c[7]);
         }
         const bool live = t < len;
         uint4 h0;
@@ -329,20 +336,6 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
         // (variant bit 4: hold the other warps until the flag is out, so that MEMBAR.GPU does not wait behind the next
         // step's input-projection reads.  Measured without instrumentation: 7.6 ms with, 7.4-7.5 ms without -> off.)
         if (g.variant & 16) asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      if (row_ok && g.gates_out) {  // tape stores, off the critical path (see above)
-        __nv_bfloat16* gsave = g.gates_out + ((int64_t)b * g.T + t) * H4 + ns * 64 + half * 32;
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          uint4 pk;
-          pk.x = v[u * 4 + 0]; pk.y = v[u * 4 + 1]; pk.z = v[u * 4 + 4]; pk.w = v[u * 4 + 5];
-          *reinterpret_cast<uint4*>(gsave + 4 * u) = pk;
-        }
-        if (g.c_out) {
-          float4* cp = reinterpret_cast<float4*>(g.c_out + ((int64_t)b * g.T + t) * g.H + ns * 16 + half * 8);
-          cp[0] = make_float4(c[0], c[1], c[2], c[3]);
-          cp[1] = make_float4(c[4], c[5], c[6], c[7]);
-        }
       }
     }
   }
