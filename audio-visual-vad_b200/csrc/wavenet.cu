@@ -8,7 +8,9 @@
 // in the GEMM epilogue; the residual stream stays fp32.
 #include <vector>
 
-#include "gemm_tc.cuh"
+#include <stdlib.h>
+
+#include "wavenet_fused.cuh"
 
 namespace avvad {
 
@@ -65,6 +67,14 @@ __global__ void wn_add_slice_kernel(const float* __restrict__ dense, const float
   const int t = (int)(row % Lout), b = (int)(row / Lout);
   out[idx] = dense[idx] + cur[((int64_t)b * Lin + t + (Lin - Lout)) * Cp + c];
 }
+// fused path: all weight matrices as one stack of SW128-loadable [64][64] tiles (tap j of a layer = columns j*64.. of its
+// packed [64][k*64] matrix), in the order causal taps | per layer: dilated taps, dense | bottleneck
+__global__ void wn_stack_tile_kernel(const __nv_bfloat16* __restrict__ w, int k_cols, int tap, __nv_bfloat16* __restrict__ tile) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * 64) return;
+  const int o = idx >> 6, i = idx & 63;
+  tile[idx] = w[(int64_t)o * k_cols + tap * 64 + i];
+}
 // AdaptiveAvgPool1d: out[b][c][p] = mean_{t in [floor(p L / P), ceil((p+1) L / P))} s[b][t][c]
 __global__ void wn_pool_kernel(const float* __restrict__ s, int B, int L, int Cp, int C, int P, float* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,7 +102,38 @@ struct avvad_wavenet {
   std::vector<int> dil;
   WnLayer causal, bottleneck;
   std::vector<WnLayer> dilated, dense;
+  // fused kernel (wavenet_fused.cuh): stacked weight tiles / biases, rebuilt after any set_layer
+  __nv_bfloat16* wstack = nullptr;
+  float* bstack = nullptr;
+  bool stack_ready = false;
 };
+
+namespace avvad {
+namespace tc {
+int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, uint32_t bn);
+bool tma_available();
+}  // namespace tc
+}  // namespace avvad
+
+static bool wn_fused_enabled() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_WAVENET_FUSED");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0;
+}
+// The fused kernel holds one 64-channel block per tensor and 256 working rows of history per tile.
+static bool wn_fused_supported(const avvad_wavenet* h) {
+  if (!wn_fused_enabled() || !tc::tma_available()) return false;
+  if (h->qp != 64 || h->Rp != 64 || h->Dp != 64 || h->bp != 64) return false;
+  if (h->k < 1 || h->k > tc::kWnMaxK || (int)h->dil.size() > tc::kWnMaxLayers) return false;
+  int64_t sum = 0;
+  for (int d : h->dil) {
+    if ((int64_t)(h->k - 1) * d > 128) return false;
+    sum += (int64_t)(h->k - 1) * d;
+  }
+  return sum + h->k <= tc::kWnWork - 1;
+}
 
 static int alloc_layer(WnLayer& l, int Op, int K) {
   AVVAD_CUDA(cudaMalloc(&l.w, sizeof(__nv_bfloat16) * (size_t)Op * K));
@@ -130,6 +171,8 @@ extern "C" int avvad_wavenet_create(avvad_wavenet** out, int filter_width, int q
 extern "C" void avvad_wavenet_destroy(avvad_wavenet* h) {
   if (!h) return;
   auto fr = [](WnLayer& l) { cudaFree(l.w); cudaFree(l.b); };
+  cudaFree(h->wstack);
+  cudaFree(h->bstack);
   fr(h->causal); fr(h->bottleneck);
   for (auto& l : h->dilated) fr(l);
   for (auto& l : h->dense) fr(l);
@@ -157,6 +200,7 @@ extern "C" int avvad_wavenet_set_layer(avvad_wavenet* h, int kind, int index, co
   wn_pack_b_kernel<<<(unsigned)ceil_div(Op, 256), 256, 0, st>>>(bias, O, Op, l->b);
   AVVAD_LAUNCHED();
   l->set = true;
+  h->stack_ready = false;
   return AVVAD_OK;
 }
 
@@ -195,6 +239,74 @@ extern "C" int avvad_wavenet_encode(avvad_wavenet* h, const float* x, int64_t B,
     if (!h->dilated[i].set || !h->dense[i].set) { set_error("wavenet: layers not loaded"); return AVVAD_ERR_STATE; }
   if (workspace_bytes < avvad_wavenet_workspace_bytes(h, B, N)) { set_error("wavenet: workspace too small"); return AVVAD_ERR_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (wn_fused_supported(h)) {
+    // ---- fused path: one kernel for the whole stack, history in shared memory (wavenet_fused.cuh) ----
+    const int n = (int)h->dil.size(), k = h->k;
+    const int n_tiles = k + n * (k + 1) + 1;
+    if (!h->stack_ready) {
+      if (!h->wstack) {
+        AVVAD_CUDA(cudaMalloc(&h->wstack, (size_t)n_tiles * 64 * 64 * sizeof(__nv_bfloat16)));
+        AVVAD_CUDA(cudaMalloc(&h->bstack, (size_t)(2 + 2 * n) * 64 * sizeof(float)));
+      }
+      int t = 0;
+      auto put = [&](const WnLayer& l, int taps) -> int {
+        for (int j = 0; j < taps; ++j, ++t) {
+          wn_stack_tile_kernel<<<16, 256, 0, st>>>(l.w, taps * 64, j, h->wstack + (size_t)t * 4096);
+          AVVAD_LAUNCHED();
+        }
+        return AVVAD_OK;
+      };
+      int rc = put(h->causal, k);
+      if (rc) return rc;
+      AVVAD_CUDA(cudaMemcpyAsync(h->bstack, h->causal.b, 64 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      for (int i = 0; i < n; ++i) {
+        rc = put(h->dilated[i], k);
+        if (rc) return rc;
+        rc = put(h->dense[i], 1);
+        if (rc) return rc;
+        AVVAD_CUDA(cudaMemcpyAsync(h->bstack + (1 + 2 * i) * 64, h->dilated[i].b, 64 * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+        AVVAD_CUDA(cudaMemcpyAsync(h->bstack + (2 + 2 * i) * 64, h->dense[i].b, 64 * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+      }
+      rc = put(h->bottleneck, 1);
+      if (rc) return rc;
+      AVVAD_CUDA(cudaMemcpyAsync(h->bstack + (1 + 2 * n) * 64, h->bottleneck.b, 64 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st));
+      h->stack_ready = true;
+    }
+    tc::WnFusedGeom g{};
+    g.B = (int)B; g.q = h->q; g.N = (int)N; g.k = k; g.n_layers = n;
+    int sum = 0;
+    for (int i = 0; i < n; ++i) {
+      g.dil[i] = h->dil[i];
+      sum += (k - 1) * h->dil[i];
+    }
+    g.sum_shift = sum;
+    g.lt = tc::kWnWork - sum - (k - 1);
+    g.L_final = (int)Lfinal;
+    g.tiles_per_item = (int)ceil_div(Lfinal, g.lt);
+    g.x = x;
+    g.bias = h->bstack;
+    float* act = reinterpret_cast<float*>(workspace);   // [B][L_final][64] fp32 (fits: the workspace holds 3 fp32 streams)
+    g.out = act;
+    CUtensorMap wmap;
+    int rc = tc::encode_weight_map(&wmap, h->wstack, 64, (uint64_t)n_tiles * 64, 64);
+    if (rc) return rc;
+    const size_t smem = tc::wavenet_fused_smem_bytes(k);
+    static PerDeviceOnce once;
+    const cudaError_t ae = once.run([] {
+      return cudaFuncSetAttribute(tc::wavenet_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)tc::wavenet_fused_smem_bytes(tc::kWnMaxK));
+    });
+    if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute(wavenet): ") + cudaGetErrorString(ae)); return AVVAD_ERR_CUDA; }
+    tc::wavenet_fused_kernel<<<(unsigned)(B * g.tiles_per_item), tc::kWnThreads, smem, st>>>(wmap, g);
+    AVVAD_LAUNCHED();
+    const int np = (int)(B * h->bott * h->pool);
+    wn_pool_kernel<<<(unsigned)ceil_div(np, 128), 128, 0, st>>>(act, (int)B, (int)Lfinal, 64, h->bott, h->pool, out);
+    AVVAD_LAUNCHED();
+    return AVVAD_OK;
+  }
   const int64_t L0 = N - (h->k - 1);
   const int maxC = std::max(std::max(h->qp, h->Rp), std::max(h->Dp, h->bp));
   const size_t rows0 = (size_t)B * L0;

@@ -86,6 +86,22 @@ def main():
     print(lt)
     print("\n## `ncu --set full --clock-control none --import-source on`, one pass of 20,288 frames (`--batch 64`)\n")
     print(nt)
+    # machine-readable copy for bench.py's roofline.traffic (profiles/*traffic*.json, newest file wins)
+    if len(sys.argv) > 1:
+        commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        frames = 64 * 317
+        # algorithmic operand bytes of the same launches: bf16 activations in + out per conv layer (NHWC), weights once
+        layers = [(17, 64, 64, 17)] * 4 + [(17, 64, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9),
+                  (9, 128, 256, 5), (5, 256, 256, 5), (5, 256, 256, 5), (5, 256, 256, 5),
+                  (5, 256, 512, 3), (3, 512, 512, 3), (3, 512, 512, 3), (3, 512, 512, 3)]
+        alg = sum(frames * 2 * (hi * hi * ci + ho * ho * co) for hi, ci, co, ho in layers)
+        alg += frames * 2 * (17 * 17 * 64 * 2 + 9 * 9 * 128 * 2 + 5 * 5 * 256 * 2 + 3 * 3 * 512 * 2)  # residual reads + ds inputs
+        json.dump({"commit": commit, "source": "ncu --set full --clock-control none, bench.py --ncu --warmup 0 --batch 64 "
+                                               "(one 20,288-frame trunk pass), dram__bytes_read.sum + dram__bytes_write.sum",
+                   "conv_launches": n, "conv_dram_bytes_per_launch": (rd + wr) * 1e6 / max(n, 1),
+                   "conv_dram_read_bytes": rd * 1e6, "conv_dram_write_bytes": wr * 1e6,
+                   "conv_algorithmic_bytes_per_launch": alg / max(n, 1), "unit": "bytes per launch (average over the "
+                   "convolution launches of one 64-utterance pass)"}, open(sys.argv[1], "w"), indent=1)
     print(f"\nDRAM bytes of the {n} convolution launches (slab + TMA launches that read > 100 MB, i.e. without the two xproj GEMMs): {rd / 1000:.2f} GB read + {wr / 1000:.2f} GB written = "
           f"{(rd + wr) / max(n, 1) / 1000:.3f} GB per launch.")
 
