@@ -279,6 +279,9 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
   TmaGeom g{};
   g.ksplit = ksplit;
   g.kb_split = (K / 64 + ksplit - 1) / ksplit;
+  // every split must own at least one K block: a CTA with an empty K range would wait for an accumulator that no MMA
+  // ever commits (the bounded barrier wait then traps)
+  AVVAD_CHECK_ARG((int64_t)(ksplit - 1) * g.kb_split < K / 64, "split-K: empty split (choose ksplit = ceil(KB / ceil(KB / ksplit)))");
   g.split_stride = split_stride;
   g.mode = 0;
   g.KB = K / 64;

@@ -141,10 +141,46 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ in, int64_t
   *reinterpret_cast<uint4*>(out + pix * C + gq * 8) = o;
 }
 
-// Gradient of the max-pool: an input pixel receives the gradient of every window whose FIRST maximum (scan order rows,
-// then columns, strict '>' as in PyTorch's kernels) it is.  One thread per input pixel and 8 channels: no atomics.
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ gpool,
-                                   int64_t n, int Hin, int Hout, int C, __nv_bfloat16* __restrict__ gact) {
+// Gradient of the max-pool, two small kernels (no atomics, no recomputation per input pixel):
+//   1. per pooled output and channel: which of the 9 window positions holds the FIRST maximum (scan order rows, then
+//      columns, strict '>' as in PyTorch's kernels) -> one byte (0..8);
+//   2. per input pixel and 8 channels: sum the gradients of the (at most four) windows that selected it.
+__global__ void maxpool_argmax_kernel(const __nv_bfloat16* __restrict__ act, int64_t n, int Hin, int Hout, int C,
+                                      uint8_t* __restrict__ which) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = C / 8;
+  if (idx >= n * Hout * Hout * groups) return;
+  const int gq = (int)(idx % groups);
+  const int64_t pix = idx / groups;
+  const int ow = (int)(pix % Hout), oh = (int)((pix / Hout) % Hout);
+  const int64_t f = pix / ((int64_t)Hout * Hout);
+  float best[8];
+  uint32_t sel[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; sel[e] = 0; }
+  for (int r = 0; r < 3; ++r) {
+    const int y = 2 * oh - 1 + r;
+    if (y < 0 || y >= Hin) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int x = 2 * ow - 1 + s;
+      if (x < 0 || x >= Hin) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(act + ((f * Hin + y) * Hin + x) * C + gq * 8);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
+        if (a > best[2 * e]) { best[2 * e] = a; sel[2 * e] = r * 3 + s; }
+        if (b > best[2 * e + 1]) { best[2 * e + 1] = b; sel[2 * e + 1] = r * 3 + s; }
+      }
+    }
+  }
+  uint2 o;
+  o.x = sel[0] | (sel[1] << 8) | (sel[2] << 16) | (sel[3] << 24);
+  o.y = sel[4] | (sel[5] << 8) | (sel[6] << 16) | (sel[7] << 24);
+  *reinterpret_cast<uint2*>(which + pix * C + gq * 8) = o;
+}
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ which, const __nv_bfloat16* __restrict__ gpool, int64_t n,
+                                   int Hin, int Hout, int C, __nv_bfloat16* __restrict__ gact) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int groups = C / 8;
   if (idx >= n * Hin * Hin * groups) return;
@@ -155,41 +191,21 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ act, const 
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  // windows covering (ih, iw): oh with 2*oh-1 <= ih <= 2*oh+1
-  const int oh_lo = ih / 2, oh_hi = (ih + 1) / 2;   // ih even: {ih/2}; ih odd: {(ih-1)/2, (ih+1)/2}
-  const int ow_lo = iw / 2, ow_hi = (iw + 1) / 2;
-  for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+  // windows covering (ih, iw): oh with 2*oh-1 <= ih <= 2*oh+1, i.e. ih even: {ih/2}; ih odd: {(ih-1)/2, (ih+1)/2}
+  for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {
     if (oh >= Hout) continue;
-    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+    for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
       if (ow >= Hout) continue;
-      // first-maximum position of this window, per channel
-      float best[8];
-      int where[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; where[e] = -1; }
-      for (int r = 0; r < 3; ++r) {
-        const int y = 2 * oh - 1 + r;
-        if (y < 0 || y >= Hin) continue;
-        for (int s = 0; s < 3; ++s) {
-          const int x = 2 * ow - 1 + s;
-          if (x < 0 || x >= Hin) continue;
-          const uint4 v = *reinterpret_cast<const uint4*>(act + ((f * Hin + y) * Hin + x) * C + gq * 8);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xFFFF0000u);
-            if (a > best[2 * e]) { best[2 * e] = a; where[2 * e] = y * Hin + x; }
-            if (b > best[2 * e + 1]) { best[2 * e + 1] = b; where[2 * e + 1] = y * Hin + x; }
-          }
-        }
-      }
-      const uint4 gv = *reinterpret_cast<const uint4*>(gpool + ((f * Hout + oh) * Hout + ow) * C + gq * 8);
+      const uint32_t me = (uint32_t)((ih - (2 * oh - 1)) * 3 + (iw - (2 * ow - 1)));   // my position inside that window
+      const int64_t o = ((f * Hout + oh) * Hout + ow) * C + gq * 8;
+      const uint2 w = *reinterpret_cast<const uint2*>(which + o);
+      const uint4 gv = *reinterpret_cast<const uint4*>(gpool + o);
       const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
-      const int me = ih * Hin + iw;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        if (where[2 * e] == me) acc[2 * e] += __uint_as_float(gw[e] << 16);
-        if (where[2 * e + 1] == me) acc[2 * e + 1] += __uint_as_float(gw[e] & 0xFFFF0000u);
+        const uint32_t s0 = ((e < 2 ? w.x : w.y) >> (16 * (e & 1))) & 0xFFu, s1 = ((e < 2 ? w.x : w.y) >> (16 * (e & 1) + 8)) & 0xFFu;
+        if (s0 == me) acc[2 * e] += __uint_as_float(gw[e] << 16);
+        if (s1 == me) acc[2 * e + 1] += __uint_as_float(gw[e] & 0xFFFF0000u);
       }
     }
   }
@@ -355,29 +371,48 @@ __global__ void transpose_pc_kernel(const __nv_bfloat16* __restrict__ in, int64_
   }
 }
 // transposed im2col: col[(tap*Cin + c)][p] = X[f][oh*stride + r - pad][ow*stride + s - pad][c] (0 outside the frame or for
-// p >= P), p = (f*OH + oh)*OW + ow over the frames of the chunk
-__global__ void im2col_t_kernel(const __nv_bfloat16* __restrict__ x, int H, int Cin, int OH, int k, int stride, int pad,
-                                int64_t P, int64_t Pp, __nv_bfloat16* __restrict__ col) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int64_t p0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
+// p >= P), p = (f*OH + oh)*OW + ow over the frames of the chunk.  One block moves a 64-pixel x 64-channel tile of one tap
+// through shared memory: 16-byte loads along the channels of a pixel (whole 128-byte pixel rows per 8 lanes), 16-byte
+// stores along the pixels of a channel (whole 128-byte rows of the K-major GEMM operand per 8 lanes).  Tile rows are
+// pitched 33 words so both phases are (nearly) bank-conflict free.  (The first version moved 32x32 tiles element by
+// element: 33.6 ms of an 82 ms video-net training step, 8x off the HBM time of the 12 GB it writes.)
+__global__ void __launch_bounds__(256) im2col_t_kernel(const __nv_bfloat16* __restrict__ x, int H, int Cin, int OH, int k,
+                                                       int stride, int pad, int64_t P, int64_t Pp,
+                                                       __nv_bfloat16* __restrict__ col) {
+  __shared__ uint32_t tile[64 * 33];
+  const int64_t p0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
   const int tap = blockIdx.z;
   const int r = tap / k, s = tap % k;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t p = p0 + i;
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = threadIdx.x + q * 256;
+    const int pix = i >> 3, ch = i & 7;
+    const int64_t p = p0 + pix;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (p < P) {
       const int ow = (int)(p % OH), oh = (int)((p / OH) % OH);
       const int64_t f = p / ((int64_t)OH * OH);
       const int ih = oh * stride + r - pad, iw = ow * stride + s - pad;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < H) v = x[((f * H + ih) * H + iw) * Cin + c0 + threadIdx.x];
+      if (ih >= 0 && ih < H && iw >= 0 && iw < H)
+        v = *reinterpret_cast<const uint4*>(x + ((f * H + ih) * H + iw) * Cin + c0 + ch * 8);
     }
-    tile[i][threadIdx.x] = v;
+    uint32_t* dst = tile + pix * 33 + ch * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int64_t p = p0 + threadIdx.x;
-    if (p < Pp) col[((int64_t)tap * Cin + c0 + i) * Pp + p] = tile[threadIdx.x][i];
+  const uint16_t* t16 = reinterpret_cast<const uint16_t*>(tile);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int i = threadIdx.x + q * 256;
+    const int c = i >> 3, pc = i & 7;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = t16[(pc * 8 + 2 * j) * 66 + c], hi = t16[(pc * 8 + 2 * j + 1) * 66 + c];
+      w[j] = lo | (hi << 16);
+    }
+    *reinterpret_cast<uint4*>(col + ((int64_t)tap * Cin + c0 + c) * Pp + p0 + pc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 // acc[j] (+)= sum_s part[s][j]
@@ -405,8 +440,13 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
   __shared__ float img[73 * 73];
   const int o = threadIdx.x & 63, q = threadIdx.x >> 6;  // taps q, q+4, q+8, ...
   float acc[13];
+  int off[13];   // image offset of tap q + 4j relative to the window origin (hoisted: q is a run-time value)
 #pragma unroll
-  for (int j = 0; j < 13; ++j) acc[j] = 0.f;
+  for (int j = 0; j < 13; ++j) {
+    acc[j] = 0.f;
+    const int tap = q + 4 * j;
+    off[j] = tap < 49 ? (tap / 7) * 73 + tap % 7 : 0;
+  }
   for (int64_t f = blockIdx.x; f < n; f += gridDim.x) {
     __syncthreads();
     for (int i = threadIdx.x; i < 73 * 73; i += 256) {
@@ -420,10 +460,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
       const int oh = p / 34, ow = p % 34;
       const float* base = img + (2 * oh) * 73 + 2 * ow;
 #pragma unroll
-      for (int j = 0; j < 13; ++j) {
-        const int tap = q + 4 * j;
-        if (tap < 49) acc[j] = fmaf(dv, base[(tap / 7) * 73 + tap % 7], acc[j]);
-      }
+      for (int j = 0; j < 13; ++j) acc[j] = fmaf(dv, base[off[j]], acc[j]);   // tap >= 49: accumulates garbage, never stored
     }
   }
 #pragma unroll
@@ -456,7 +493,16 @@ struct BwdCtx {
 };
 
 // workspace sizing shared by the query and the implementation
-constexpr int64_t kWgradPixels = 1 << 19;  // pixels per weight-gradient chunk (K of the GEMM)
+constexpr int64_t kWgradPixels = 1 << 19;  // pixels per weight-gradient chunk (K of the GEMM): sizes the workspace
+// AVVAD_WGRAD_PIXELS (<= 2^19) shrinks the chunk: the tests use it to drive the multi-chunk accumulation on small inputs
+static int64_t wgrad_pixels() {
+  static int64_t v = [] {
+    const char* e = getenv("AVVAD_WGRAD_PIXELS");
+    const int64_t x = e ? atoll(e) : kWgradPixels;
+    return (x >= 64 && x <= kWgradPixels) ? x / 64 * 64 : kWgradPixels;
+  }();
+  return v;
+}
 static size_t wgrad_part_bytes() { return (size_t)64 * 1024 * 1024; }
 
 static int bn_backward(const BwdCtx& c, int layer, const __nv_bfloat16* raw, const __nv_bfloat16* g,
@@ -513,8 +559,8 @@ static int conv_wgrad(const BwdCtx& c, int layer, const __nv_bfloat16* x, const 
     dim3 g1((unsigned)ceil_div(Pp, 32), (unsigned)(s.cout / 32));
     transpose_pc_kernel<<<g1, dim3(32, 8), 0, c.st>>>(dr, P, s.cout, Pp, c.drawT);
     AVVAD_LAUNCHED();
-    dim3 g2((unsigned)ceil_div(Pp, 32), (unsigned)(s.cin / 32), (unsigned)taps);
-    im2col_t_kernel<<<g2, dim3(32, 8), 0, c.st>>>(xi, s.hin, s.cin, s.hout, s.k, s.stride, s.pad, P, Pp, c.colT);
+    dim3 g2((unsigned)(Pp / 64), (unsigned)(s.cin / 64), (unsigned)taps);
+    im2col_t_kernel<<<g2, 256, 0, c.st>>>(xi, s.hin, s.cin, s.hout, s.k, s.stride, s.pad, P, Pp, c.colT);
     AVVAD_LAUNCHED();
     // split K = pixels over the SMs
     const int64_t kblocks = Pp / 64;
@@ -697,7 +743,7 @@ extern "C" int avvad_resnet18_backward(avvad_resnet18* h, const float* frames, i
     // pixels per wgrad chunk such that taps*Cin*pixels stays within the im2col^T buffer (9*64*kWgradPixels elements)
     auto chunk_for = [&](const ConvSpec& s) {
       const int64_t cap = (int64_t)9 * 64 * bwd::kWgradPixels / ((int64_t)s.k * s.k * s.cin);
-      return std::min<int64_t>(bwd::kWgradPixels, cap / 64 * 64);
+      return std::min<int64_t>(bwd::wgrad_pixels(), cap / 64 * 64);
     };
     __nv_bfloat16* gx = G[cur ^ 1];
     // out = relu(bn_b(conv_b(y1)) + shortcut): mask with out, BatchNorm backward of layer lb
@@ -737,8 +783,12 @@ extern "C" int avvad_resnet18_backward(avvad_resnet18* h, const float* frames, i
   }
   // stem: max-pool backward -> ReLU mask + BatchNorm backward -> conv1 weight gradient
   {
+    uint8_t* which = reinterpret_cast<uint8_t*>(gbig1);   // (n,17,17,64) bytes; gbig1 is free until the BatchNorm backward
+    const int64_t total_o = n * 17 * 17 * (64 / 8);
+    bwd::maxpool_argmax_kernel<<<(unsigned)ceil_div(total_o, 256), 256, 0, st>>>(tp.t(1), n, 34, 17, 64, which);
+    AVVAD_LAUNCHED();
     const int64_t total = n * 34 * 34 * (64 / 8);
-    bwd::maxpool_bwd_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(tp.t(1), g_out, n, 34, 17, 64, gbig0);
+    bwd::maxpool_bwd_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(which, g_out, n, 34, 17, 64, gbig0);
     AVVAD_LAUNCHED();
     int rc = bwd::bn_backward(c, 0, tp.raw(0), gbig0, tp.t(1), tp.stats(0), n * 1156, 64, gbig1, nullptr, dgamma[0],
                               dbeta[0]);

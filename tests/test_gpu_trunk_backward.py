@@ -204,3 +204,34 @@ def test_video_net_optimiser_steps_with_torch_adam_reduce_the_loss():
         losses.append(loss.item())
     assert losses[-1] < losses[0], losses
     assert not torch.equal(w0, m.features[0].weight.detach())      # conv1 really is being trained
+
+
+def test_weight_gradient_chunking_is_invisible():
+    """The weight-gradient GEMMs run over chunks of <= 2^19 pixels and accumulate; with AVVAD_WGRAD_PIXELS=2048 the
+    44-frame test input is split into up to 7 chunks per layer (and the last one is ragged).  Both settings must give the
+    same gradients (fp32 accumulation order differs only across the split-K partials)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import torch\n"
+        "from avvad import engine as E, synth\n"
+        "g = torch.Generator().manual_seed(5)\n"
+        "frames = torch.randn(44, 67, 67, generator=g).cuda()\n"
+        "dfeat = (torch.randn(44, 512, generator=g) * 1e-2).cuda()\n"
+        "sd = synth.seeded_state_dict(synth.model_spec('video'), 61, 'strong')\n"
+        "t = E.ResNet18Trunk(); t.load_train(sd, 'cuda')\n"
+        "feat, tape = t.forward_tape(frames, None)\n"
+        "dw, dg, db = t.backward(frames, tape, dfeat)\n"
+        "torch.save([x.cpu() for x in dw], sys.argv[1])\n"
+    ) % (os.path.join(root, "audio-visual-vad_b200"), root)
+    outs = []
+    for px in ("524288", "2048"):
+        path = f"/tmp/avvad_wgrad_{px}.pt"
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=dict(os.environ, AVVAD_WGRAD_PIXELS=px))
+        outs.append(torch.load(path))
+    for i, (a, b) in enumerate(zip(*outs)):
+        rel = float((a - b).norm() / b.norm())
+        assert rel < 1e-5, (i, rel)
