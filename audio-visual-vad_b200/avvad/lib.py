@@ -28,6 +28,7 @@ PROTOTYPES = {
     "avvad_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "avvad_profile_clear": (C.c_int, []),
     "avvad_profile_dump": (C.c_int64, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int64]),
+    "avvad_debug_lstm_trace": (None, [VP]),
     "avvad_stft_num_frames": (C.c_int64, [C.c_int64, C.c_double, C.c_double, C.c_double, C.c_int]),
     "avvad_frontend_logpower": (C.c_int, [VP, C.c_int64, VP, VP, C.c_int32, C.c_int32, C.c_int, VP, VP, C.c_float,
                                           VP, VP, VP]),

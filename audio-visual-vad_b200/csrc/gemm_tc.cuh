@@ -10,7 +10,8 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per K block = 128 bytes = one swizzle row
-enum EpiMode { EPI_BF16 = 0, EPI_F32 = 1, EPI_LSTM = 2 };
+// EPI_XT: fp32 output of the LSTM input projection in the recurrence's layout xT[t][u][b][4] (see launch_tma_gemm_xt)
+enum EpiMode { EPI_BF16 = 0, EPI_F32 = 1, EPI_LSTM = 2, EPI_XT = 3 };
 
 struct EpiParams {
   const float* bias;              // [N] or null

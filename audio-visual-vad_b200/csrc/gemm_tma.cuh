@@ -55,6 +55,9 @@ struct TmaGeom {
   int64_t split_stride, m_supers;
   int64_t n_frames;     // conv: frames in this launch; gemm: M
   int N;
+  // time-major GEMM over a [B][T][K] operand (launch_tma_gemm_xt): row index m = t * tm_bp + b, tm_bp = B rounded up to
+  // 128, so that a 128-row tile is 128 consecutive batch items of ONE time step (0 = plain row order)
+  int tm_bp, tm_b;
   uint32_t bytesA[2];   // TMA box bytes per phase
   uint32_t bytesB;
 };
@@ -227,7 +230,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           for (int mb = 0; mb < MB; ++mb) {
             if (no_a) continue;
             if (g.mode == 0) {
-              tma_load_4d(sa + mb * C::kABytes, &maps.a[0], kb * KE, (int)t[mb].n0, 0, 0, full);
+              if (g.tm_bp)
+                tma_load_4d(sa + mb * C::kABytes, &maps.a[0], kb * KE, (int)(t[mb].n0 % g.tm_bp),
+                            (int)(t[mb].n0 / g.tm_bp), 0, full);
+              else
+                tma_load_4d(sa + mb * C::kABytes, &maps.a[0], kb * KE, (int)t[mb].n0, 0, 0, full);
             } else {
               tma_load_4d(sa + mb * C::kABytes, &maps.a[t[mb].phase], cb * KE, fs - g.pad,
                           t[mb].hstart * g.stride + fr - g.pad, (int)t[mb].n0, full);
@@ -426,6 +433,36 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
               }
             }
           }
+      } else if (epi_mode == EPI_XT) {
+        // LSTM input projection in the recurrence's layout: xT[t][u][b][4] (u = hidden unit, the four floats are its
+        // gates): lane = batch item, so every 16-byte store of a warp lands in one contiguous 512-byte run, and the
+        // recurrence reads it back the same way
+        mbar_wait(bar0 + 8 * (2 * S + acc), aph);
+        tc_fence_after();
+        const int U = g.N >> 2;
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const int tt = (m[mb] >= 0) ? (int)(m[mb] / g.tm_bp) : 0;
+          const int bb = (m[mb] >= 0) ? (int)(m[mb] - (int64_t)tt * g.tm_bp) : g.tm_b;
+#pragma unroll 1
+          for (int j = half; j < kJ; j += 2) {
+            uint32_t v[32];
+            tmem_ld32(t_row + mb * BN + j * 32, v);
+            tmem_ld_wait();
+            const int n0 = n_base + j * 32;
+            if (bb < g.tm_b && n0 < g.N) {
+              float4* dst = reinterpret_cast<float4*>(ep.C) + ((int64_t)tt * U + (n0 >> 2)) * g.tm_bp + bb;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                float4 b4;
+                if (bias_in_smem) b4 = reinterpret_cast<const float4*>(bias_s + n0)[c];
+                else b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                dst[(int64_t)c * g.tm_bp] = make_float4(__uint_as_float(v[4 * c + 0]) + b4.x, __uint_as_float(v[4 * c + 1]) + b4.y,
+                                                        __uint_as_float(v[4 * c + 2]) + b4.z, __uint_as_float(v[4 * c + 3]) + b4.w);
+              }
+            }
+          }
+        }
       } else if (fast32) {
         // fp32 output (LSTM input projection): smem bias, 8 x 16-byte stores per 32-column chunk
         mbar_wait(bar0 + 8 * (2 * S + acc), aph);
@@ -513,6 +550,10 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
 int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t M, int N, int K,
                     const EpiParams& ep, int epi_mode, int bn_hint, cudaStream_t st, int ksplit = 1,
                     int64_t split_stride = 0);
+// xT[t][u][b][4] (fp32, b < Bp = B rounded up to 128) = X[b][t][:] * Wt[4u+g][:]^T + bias[4u+g] for an operand X laid out
+// [B][T][lda]: the LSTM input projection in the layout the persistent recurrences read (N = 4H, N % 32 == 0)
+int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
+                       int N, int K, const float* bias, float* xT, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace avvad

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "lstm_persist.cuh"
+#include "lstm_pair.cuh"
 
 namespace avvad {
 
@@ -219,6 +220,8 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
 }  // namespace avvad
 
 namespace {
+// flag area: [16 batch slices][64] shared lines (lstm_persist.cuh, lstm_pair.cuh) + [2][32][32] private lines (pairs)
+constexpr size_t kCounterBytes = 16384;
 struct LstmWs {
   float* xproj;
   __nv_bfloat16* hseq[2];
@@ -237,14 +240,14 @@ LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
     return p;
   };
   const int64_t H = h->H;
-  w.xproj = (float*)take((size_t)B * T * 4 * H * sizeof(float));
+  w.xproj = (float*)take((size_t)((B + 127) / 128 * 128) * T * 4 * H * sizeof(float));  // xT layout pads B to 128
   w.hseq[0] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
   w.hseq[1] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
   w.hbuf[0] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.hbuf[1] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.c = (float*)take((size_t)B * H * sizeof(float));
   w.hlast = (__nv_bfloat16*)take((size_t)B * H * 2);
-  w.counters = (unsigned int*)take(4096);  // per-CTA step flags of the persistent recurrence
+  w.counters = (unsigned int*)take(kCounterBytes);  // per-CTA step flags of the persistent recurrences
   w.total = off;
   return w;
 }
@@ -265,26 +268,120 @@ static int persist_mode() {
   return v;
 }
 
+// CTA-pair recurrence (lstm_pair.cuh) for 129..256 batch rows; AVVAD_LSTM_PAIR=0 selects the one-CTA-per-block kernel.
+static int pair_mode() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_LSTM_PAIR");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v;
+}
+// debug aid (tools/micro/lstm_ab.py): when set, the next pair launches run the tracing instantiation and write
+// [CTA][T][8] globaltimer stamps here
+static unsigned long long* g_pair_trace = nullptr;
+extern "C" void avvad_debug_lstm_trace(void* buf) { g_pair_trace = (unsigned long long*)buf; }
+
+template <int kEW>
+static int run_pair_ew(const tc::LstmMaps& maps, const tc::PairGeom& g, size_t smem, unsigned int* counters,
+                       cudaStream_t st, double flops) {
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_pair_kernel<false, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc::lstm_pair_kernel<true, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                227 * 1024);
+  }));
+  const void* fn = g.trace ? (const void*)tc::lstm_pair_kernel<true, kEW> : (const void*)tc::lstm_pair_kernel<false, kEW>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * g.n_pairs);
+  cfg.blockDim = dim3(tc::kPairThreadsOf(kEW));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute la[2];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  la[1].id = cudaLaunchAttributeCooperative;
+  la[1].val.cooperative = 1;
+  cfg.attrs = la;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess || max_clusters < g.n_pairs) {
+    cudaGetLastError();
+    return AVVAD_ERR_STATE;
+  }
+  cfg.numAttrs = 2;
+  AVVAD_CUDA(cudaMemsetAsync(counters, 0, kCounterBytes, st));
+  void* args[2] = {(void*)&maps, (void*)&g};
+  void* tok = nullptr;
+  tc::prof_begin(st, &tok);
+  AVVAD_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  tc::prof_end(st, tok, 2, flops);
+  return AVVAD_OK;
+}
+
+static int run_pair(const tc::LstmMaps& maps, const float4* xT, int64_t Bp, __nv_bfloat16* hseq, const int32_t* lengths,
+                    int64_t Bc, int64_t T, int H, unsigned int* counters, cudaStream_t st, __nv_bfloat16* gates_out,
+                    float* c_out) {
+  const size_t smem = (size_t)(H / 64) * 8192 + tc::kPairStages * 16384 + 256 + 1024;
+  tc::PairGeom g{};
+  g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64; g.n_pairs = 4 * H / 128;
+  g.xT = xT;
+  g.Bp = (int)Bp;
+  g.hseq = hseq;
+  g.lengths = lengths;
+  g.counters = counters;
+  g.gates_out = gates_out;
+  g.c_out = c_out;
+  g.trace = g_pair_trace;
+  static int variant = [] {
+    const char* e = getenv("AVVAD_LSTM_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  g.variant = variant;
+  static int epi_warps = [] {
+    const char* e = getenv("AVVAD_LSTM_EPI_WARPS");
+    return (e && atoi(e) == 16) ? 16 : 8;
+  }();
+  const double flops = 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1);
+  return epi_warps == 16 ? run_pair_ew<16>(maps, g, smem, counters, st, flops)
+                         : run_pair_ew<8>(maps, g, smem, counters, st, flops);
+}
+
+static int lstm_num_sms() {
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return num_sms;
+}
+// Can the persistent recurrence (one cooperative launch per layer and batch group) run this shape on this device?
+static bool persistent_ok(const avvad_lstm* h, int64_t T) {
+  const int H = h->H;
+  if (!persist_mode() || H % 64 != 0 || H > 1024 || 4 * H / 64 > tc::kLstmMaxSlices || T < 1) return false;
+  static int coop = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+    return v;
+  }();
+  return coop && lstm_num_sms() / (4 * H / 64) >= 1;
+}
+
+// xproj: the input projection in the xT layout (tc::launch_tma_gemm_xt) over the whole batch, Bp = B rounded up to 128
 static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, __nv_bfloat16* hseq,
                                      const int32_t* lengths, int64_t B, int64_t T, unsigned int* counters,
                                      cudaStream_t st, bool* done, __nv_bfloat16* gates_out = nullptr,
                                      float* c_out = nullptr) {
   *done = false;
   const int H = h->H;
-  if (!persist_mode() || H % 64 != 0 || H > 1024 || 4 * H / 64 > tc::kLstmMaxSlices || T < 1) return AVVAD_OK;
-  static int num_sms = [] {
-    int dev = 0, v = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  static int coop = [] {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
-    return v;
-  }();
+  if (!persistent_ok(h, T)) return AVVAD_OK;
+  const int64_t Bp = (B + 127) / 128 * 128;
+  const int num_sms = lstm_num_sms();
   const int n_slices = 4 * H / 64;
-  const int max_ms = num_sms / n_slices;
-  if (!coop || max_ms < 1) return AVVAD_OK;
+  int max_ms = num_sms / n_slices;
+  if (max_ms > 16) max_ms = 16;  // flag lines per launch (kCounterBytes)
   const size_t smem = (size_t)(H / 64) * 8192 + tc::kLstmStages * 16384 + 256 + 1024;
   static PerDeviceOnce once;
   AVVAD_CUDA(once.run([] {
@@ -306,9 +403,16 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     const uint32_t wbox[2] = {64, 64};
     rc = tc::encode_tiled_bf16(&maps.w, h->w_hh[l], 2, wd, wstr, wbox);
     if (rc) return rc;
+    if (pair_mode() && max_ms <= 2 && Bc > 128 && n_slices % 2 == 0 && n_slices / 2 <= 32) {
+      rc = run_pair(maps, reinterpret_cast<const float4*>(xproj) + g0, Bp, hs, lengths + g0, Bc, T, H, counters, st,
+                    gates_out ? gates_out + g0 * T * 4 * H : nullptr, c_out ? c_out + g0 * T * H : nullptr);
+      if (rc == AVVAD_OK) continue;
+      if (rc != AVVAD_ERR_STATE) return rc;  // AVVAD_ERR_STATE: the pairs do not fit this device -> one CTA per block
+    }
     tc::LstmGeom g{};
     g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64; g.n_slices = n_slices;
-    g.xproj = xproj + g0 * T * 4 * H;
+    g.xT = reinterpret_cast<const float4*>(xproj) + g0;
+    g.Bp = (int)Bp;
     g.hseq = hs;
     g.lengths = lengths + g0;
     g.counters = counters;
@@ -432,13 +536,22 @@ static int lstm_forward_impl(avvad_lstm* h, const void* x_bf16, const int32_t* l
       tv = tape_layer(tape, l, H, B, T);
       layer_out = tv.hseq;
     }
-    // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'
-    int rc = avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4, ld_in, st);
+    // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'.  The persistent recurrences read it
+    // time-major and unit-major (xT[t][u][b][4]: lane = batch row -> coalesced), the per-step fallback row-major.
+    const bool persistent = persistent_ok(h, T);
+    int rc = persistent ? tc::launch_tma_gemm_xt(layer_in, ld_in, h->w_ih[l], ld_in, B, T, H4, (int)ld_in, h->bias[l],
+                                                 ws.xproj, st)
+                        : avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4,
+                                          ld_in, st);
     if (rc) return rc;
     // (2) recurrence: one persistent cooperative kernel per layer, or (fallback) one GEMM launch per time step
     bool done = false;
     rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done, tv.gates, tv.c);
     if (rc) return rc;
+    if (persistent && !done) {
+      set_error("lstm: persistent recurrence unavailable after the xT input projection");
+      return AVVAD_ERR_STATE;
+    }
     if (tape && !done) {
       set_error("lstm: the training forward needs the persistent recurrence (TMA + cooperative launch, H <= 1024)");
       return AVVAD_ERR_STATE;

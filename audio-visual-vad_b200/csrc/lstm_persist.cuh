@@ -32,7 +32,9 @@ constexpr int kLstmMaxSlices = 64;  // flags per batch slice: two per polling la
 struct LstmGeom {
   int B, T, H, KB;      // KB = H / 64
   int n_slices;         // 4H / 64
-  const float* xproj;   // [B][T][4H] fp32, gate-interleaved, both biases folded in
+  const float4* xT;     // input projection xT[t][u][b][4] (b < Bp), both biases folded in; already offset to this
+                        // launch's first batch row
+  int Bp;
   __nv_bfloat16* hseq;  // [B][T][H] bf16 layer output
   const int32_t* lengths;
   unsigned int* counters;  // flags [m_slices][kLstmMaxSlices], zeroed before the launch
@@ -105,10 +107,12 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
   const uint32_t sW = base;
   const uint32_t sA = base + w_bytes;
   const uint32_t bar0 = sA + kLstmStages * 16384u;
-  // barriers: full[S] | empty[S] | wfull | tfull
-  constexpr int kBarW = 2 * kLstmStages, kBarT = 2 * kLstmStages + 1;
+  // barriers: full[S] | empty[S] | wfull | tfull[2] | tempty[2]
+  // The accumulator is double buffered: K block 0 of step t+1 only depends on four OTHER CTAs, so without `tempty` the
+  // MMAs of step t+1 could overwrite an accumulator that this CTA's cell update (step t) has not read yet.
+  constexpr int kBarW = 2 * kLstmStages, kBarT = 2 * kLstmStages + 1, kBarTE = 2 * kLstmStages + 3;
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - base) + 8 * (2 * kLstmStages + 4));
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + (bar0 - base) + 8 * (2 * kLstmStages + 6));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ns = blockIdx.x % g.n_slices;
@@ -121,13 +125,16 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       mbar_init(BAR(kLstmStages + s), (uint32_t)g.cluster);  // every cluster member's MMA releases the slot
     }
     mbar_init(BAR(kBarW), 1);
-    mbar_init(BAR(kBarT), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(BAR(kBarT + a), 1);
+      mbar_init(BAR(kBarTE + a), 8);  // one arrival per cell-update warp
+    }
     fence_barrier_init();
     tma_prefetch_desc(&maps.h);
     tma_prefetch_desc(&maps.w);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 64);
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 128);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -225,6 +232,10 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     tc_fence_after();
     uint32_t it = 0;
     for (int t = 1; t < g.T; ++t) {
+      const uint32_t acc = (uint32_t)t & 1u;
+      if (t >= 3) mbar_wait(BAR(kBarTE + acc), (uint32_t)((t - 3) >> 1) & 1u);  // step t-2 has left this accumulator
+      tc_fence_after();
+      const uint32_t d = tmem_acc + acc * 64u;
       for (int kb = 0; kb < g.KB; ++kb, ++it) {
         const int s = it % kLstmStages;
         mbar_wait(BAR(s), (it / kLstmStages) & 1u);
@@ -232,15 +243,15 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
         if (elect_one_sync()) {
           const uint32_t a_lo = desc_lo(sA + s * 16384u);
           const uint32_t b_lo = desc_lo(sW + kb * 8192u);
-          umma_f16_lo(tmem_acc, a_lo, b_lo, idesc, kb != 0);
-          umma_f16_lo(tmem_acc, a_lo + 2, b_lo + 2, idesc, 1);
-          umma_f16_lo(tmem_acc, a_lo + 4, b_lo + 4, idesc, 1);
-          umma_f16_lo(tmem_acc, a_lo + 6, b_lo + 6, idesc, 1);
+          umma_f16_lo(d, a_lo, b_lo, idesc, kb != 0);
+          umma_f16_lo(d, a_lo + 2, b_lo + 2, idesc, 1);
+          umma_f16_lo(d, a_lo + 4, b_lo + 4, idesc, 1);
+          umma_f16_lo(d, a_lo + 6, b_lo + 6, idesc, 1);
           if (CL > 1)
             umma_commit_mc(BAR(kLstmStages + s), cmask);
           else
             umma_commit(BAR(kLstmStages + s));
-          if (kb == g.KB - 1) umma_commit(BAR(kBarT));
+          if (kb == g.KB - 1) umma_commit(BAR(kBarT + acc));
         }
         __syncwarp();
       }
@@ -257,23 +268,27 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     float c[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) c[u] = 0.f;
-    const float* xrow = g.xproj + ((int64_t)(row_ok ? b : 0) * g.T) * H4 + ns * 64 + half * 32;
+    // lane = batch row: a warp's load of one unit's gates is one contiguous 512-byte run
+    const float4* xcol = g.xT + (int64_t)(ns * 16 + half * 8) * g.Bp + (row_ok ? b : 0);
     __nv_bfloat16* hrow = g.hseq + ((int64_t)(row_ok ? b : 0) * g.T) * g.H + ns * 16 + half * 8;
     for (int t = 0; t < g.T; ++t) {
       // input projection of this step: independent of h, requested before the wait on the accumulator
       float4 x[8];
       if (row_ok) {
-        const float4* xp = reinterpret_cast<const float4*>(xrow + (int64_t)t * H4);
+        const float4* xp = xcol + (int64_t)t * g.H * g.Bp;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = __ldg(xp + u);
+        for (int u = 0; u < 8; ++u) x[u] = __ldg(xp + (int64_t)u * g.Bp);
       }
       uint32_t v[32];
       if (t > 0) {
-        mbar_wait(BAR(kBarT), (uint32_t)(t - 1) & 1u);
+        const uint32_t acc = (uint32_t)t & 1u;
+        mbar_wait(BAR(kBarT + acc), (uint32_t)((t - 1) >> 1) & 1u);
         tc_fence_after();
-        tmem_ld32(tmem_acc + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld32(tmem_acc + acc * 64u + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
         tmem_ld_wait();
         tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(kBarTE + acc));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -345,7 +360,7 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
   if (CL > 1) cluster_sync_all();  // no member exits while peers may still arrive on its barriers
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_acc, 64);
+    tmem_dealloc(tmem_acc, 128);
   }
 }
 

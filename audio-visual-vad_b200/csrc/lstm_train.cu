@@ -56,6 +56,87 @@ __global__ void lstm_bwd_cell_kernel(const __nv_bfloat16* __restrict__ gates, co
   *out = o;
 }
 
+// ---- two-layer wavefront (small per-rank batches): layer 1 at step t1 = T-1-s and layer 0 at step t0 = T-s run in the
+// SAME launches, so the dependent chain is T+1 (cell, GEMM) pairs instead of 2T.  One GEMM per iteration does all three
+// products on a block-structured operand:
+//   A [2B][2*4H]:  rows 0..B-1   = [ dG1_t1 | 0 ],   rows B..2B-1 = [ 0 | dG0_t0 ]
+//   W [2H][2*4H]:  rows 0..H-1   = [ W_hh1^T | W_hh0^T ],   rows H..2H-1 = [ W_ih1^T | 0 ]
+//   C [2B][2H]  :  rows 0..B-1   = [ dh_rec1 | dY0_t1 ],    rows B..2B-1 = [ dh_rec0 | 0 ]
+// which the next iteration's cell launch consumes (layer 0 then sits at the step layer 1 just left).
+__global__ void lstm_bwd_cell_wf_kernel(const __nv_bfloat16* __restrict__ gates1, const float* __restrict__ cst1,
+                                        const __nv_bfloat16* __restrict__ gates0, const float* __restrict__ cst0,
+                                        const float* __restrict__ dY1, const float* __restrict__ dl,
+                                        const float* __restrict__ w_head, const float* __restrict__ Cpart, int nsplit,
+                                        float* __restrict__ dc2, const int32_t* __restrict__ lengths, int B, int T, int H,
+                                        int s, __nv_bfloat16* __restrict__ dG1, __nv_bfloat16* __restrict__ dG0,
+                                        __nv_bfloat16* __restrict__ Abuf) {
+  const int layer = 1 - (int)blockIdx.y;   // blockIdx.y 0 -> layer 1, 1 -> layer 0
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * H) return;
+  const int b = idx / H, u = idx - b * H;
+  const int t = (layer == 1) ? (T - 1 - s) : (T - s);
+  const int64_t K2 = 8ll * H;              // row length of Abuf
+  uint2* aout = reinterpret_cast<uint2*>(Abuf + (int64_t)(layer == 1 ? b : B + b) * K2 + (layer == 1 ? 0 : 4 * H) + 4 * u);
+  if (t < 0 || t > T - 1) {                // this layer is idle in iteration s: contribute nothing to the GEMM
+    *aout = make_uint2(0u, 0u);
+    return;
+  }
+  const int64_t row = (int64_t)b * T + t;
+  __nv_bfloat16* dG = layer == 1 ? dG1 : dG0;
+  uint2* gout = reinterpret_cast<uint2*>(dG + row * 4 * H + 4 * u);
+  float* dc = dc2 + (int64_t)layer * B * H;
+  if (t >= lengths[b]) {
+    *gout = make_uint2(0u, 0u);
+    *aout = make_uint2(0u, 0u);
+    dc[idx] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* gates = layer == 1 ? gates1 : gates0;
+  const float* cst = layer == 1 ? cst1 : cst0;
+  const uint2 gp = *reinterpret_cast<const uint2*>(gates + row * 4 * H + 4 * u);
+  const float gi = bf16lo(gp.x), gf = bf16hi(gp.x), gg = bf16lo(gp.y), go = bf16hi(gp.y);
+  const float c = cst[row * H + u];
+  const float cp = t > 0 ? cst[(row - 1) * H + u] : 0.f;
+  const int64_t cstride = 2ll * B * 2 * H;  // one split-K partial of C
+  float dh;
+  if (layer == 1) {
+    dh = dY1 ? dY1[row * H + u] : dl[row] * w_head[u];
+    if (s > 0)
+      for (int sp = 0; sp < nsplit; ++sp) dh += Cpart[sp * cstride + (int64_t)b * 2 * H + u];
+  } else {
+    dh = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      dh += Cpart[sp * cstride + (int64_t)b * 2 * H + H + u];                      // dY0_t = dG1_t * W_ih1
+      if (t < T - 1) dh += Cpart[sp * cstride + (int64_t)(B + b) * 2 * H + u];      // recurrent term from step t+1
+    }
+  }
+  const float tc = tanhf(c);
+  const float d_o = dh * tc * go * (1.f - go);
+  const float dcc = dh * go * (1.f - tc * tc) + dc[idx];
+  const float d_i = dcc * gg * gi * (1.f - gi);
+  const float d_g = dcc * gi * (1.f - gg * gg);
+  const float d_f = dcc * cp * gf * (1.f - gf);
+  dc[idx] = dcc * gf;
+  uint2 o;
+  o.x = pack_bf16x2(d_i, d_f);
+  o.y = pack_bf16x2(d_g, d_o);
+  *gout = o;
+  *aout = o;
+}
+// Wcat [2H][8H] from the gate-interleaved packed weights W' [4H][ld] (see the layout above)
+__global__ void lstm_wf_pack_w_kernel(const __nv_bfloat16* __restrict__ whh1, const __nv_bfloat16* __restrict__ wih1,
+                                      const __nv_bfloat16* __restrict__ whh0, int H, __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t K2 = 8ll * H;
+  if (idx >= 2ll * H * K2) return;
+  const int n = (int)(idx / K2);
+  const int k = (int)(idx - (int64_t)n * K2);
+  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+  if (n < H) v = (k < 4 * H) ? whh1[(int64_t)k * H + n] : whh0[(int64_t)(k - 4 * H) * H + n];
+  else if (k < 4 * H) v = wih1[(int64_t)k * H + (n - H)];
+  out[idx] = v;
+}
+
 // bf16 [R][ld] (first C columns) -> [C][Rp] with zero fill for r >= R; `shift` > 0 reads row r - shift*? (see below)
 // mode 0: plain transpose.  mode 1: H_prev transpose: out[c][b*T + t] = in[b*T + t - 1][c] for t > 0, else 0.
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t R, int C, int64_t ld, int64_t Rp,
@@ -251,6 +332,15 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        float* dx, cudaStream_t st, BpttGraphCache* cache);
 constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
 
+// The wavefront needs both layers' gate gradients at once and fits one 128-row MMA block: 2 layers, 2B <= 128.
+static bool bptt_wavefront(int layers, int64_t B) {
+  static int v = [] {
+    const char* e = getenv("AVVAD_BPTT_WAVEFRONT");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0 && layers == 2 && 2 * B <= 128;
+}
+
 static bool bptt_graph_enabled() {
   static int v = [] {
     const char* e = getenv("AVVAD_BPTT_GRAPH");
@@ -280,7 +370,7 @@ TapeView tape_layer(void* tape, int l, int H, int64_t B, int64_t T) {
 static int64_t head_pad(int y_dim) { return ((int64_t)y_dim + 63) / 64 * 64; }
 
 size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, int y_dim, int64_t B, int64_t T) {
-  (void)layers; (void)input_size;
+  (void)input_size;
   const int64_t BT = B * T, BTp = (BT + 63) / 64 * 64;
   const int64_t maxI = ld0 > H ? ld0 : H;
   size_t s = 0;
@@ -293,6 +383,13 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
   s += align_up((size_t)B * 4, 256) + align_up((size_t)BT * 4, 256);  // stable copies of lengths / dlogits (y_dim == 1)
+  if (bptt_wavefront(layers, B)) {
+    s += align_up((size_t)BT * 4 * H * 2, 256);                        // second dG (both layers are live at once)
+    s += align_up((size_t)128 * 8 * H * 2, 256);                       // A [2B <= 128][8H]
+    s += align_up((size_t)2 * H * 8 * H * 2, 256);                     // Wcat [2H][8H]
+    s += align_up((size_t)kBpttSplit * 128 * 2 * H * 4, 256);          // C partials [split][2B][2H]
+    s += align_up((size_t)2 * B * H * 4, 256);                         // dc of both layers
+  }
   if (y_dim > 1) {
     const int64_t yp = head_pad(y_dim);
     s += align_up((size_t)BT * yp * 2, 256);           // dlogits bf16, padded columns
@@ -300,6 +397,58 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
     s += align_up((size_t)H * yp * 2, 256);            // W_head^T bf16 [H][yp]
   }
   return s + 1024;
+}
+
+// Runs `steps(stream)` -- a long chain of tiny dependent launches -- either directly (cache == nullptr) or as a CUDA graph
+// captured once on the cache's private stream and replayed while `key` (every pointer / size baked into the kernel
+// parameters) is unchanged.
+template <class Warm, class Steps>
+static int run_captured(BpttGraphCache* cache, int slot, std::vector<uintptr_t> key, Warm&& warm, Steps&& steps,
+                        cudaStream_t st) {
+  if (!cache) return steps(st);
+  int dev = 0;
+  AVVAD_CUDA(cudaGetDevice(&dev));
+  key.push_back((uintptr_t)dev);
+  if (!cache->cap_stream || cache->cap_device != dev) {
+    if (cache->cap_stream) cudaStreamDestroy(cache->cap_stream);
+    cache->cap_stream = nullptr;
+    AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream, cudaStreamNonBlocking));
+    cache->cap_device = dev;
+  }
+  if (!cache->exec[slot] || cache->key[slot] != key) {
+    if (cache->exec[slot]) {
+      cudaGraphExecDestroy(cache->exec[slot]);
+      cache->exec[slot] = nullptr;
+    }
+    int rc0 = warm();
+    if (rc0) return rc0;
+    const uint64_t before = g_launches.load();
+    AVVAD_CUDA(cudaStreamBeginCapture(cache->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = steps(cache->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cache->cap_stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) {
+      set_error(std::string("BPTT graph capture failed: ") + cudaGetErrorString(ce));
+      return AVVAD_ERR_CUDA;
+    }
+    ce = cudaGraphInstantiate(&cache->exec[slot], graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      cache->exec[slot] = nullptr;
+      set_error(std::string("BPTT graph instantiation failed: ") + cudaGetErrorString(ce));
+      return AVVAD_ERR_CUDA;
+    }
+    cache->key[slot] = key;
+    cache->nodes[slot] = (size_t)(g_launches.load() - before);  // launches counted while capturing = kernel nodes
+  } else {
+    g_launches.fetch_add(cache->nodes[slot], std::memory_order_relaxed);  // a replay launches every captured kernel
+  }
+  AVVAD_CUDA(cudaGraphLaunch(cache->exec[slot], st));
+  return AVVAD_OK;
 }
 
 int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim, __nv_bfloat16* const* w_ih,
@@ -415,62 +564,19 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
       }
       return AVVAD_OK;
     };
-    if (!use_graph) {
-      int rc = run_steps(st);
-      if (rc) return rc;
-    } else {
-      int dev = 0;
-      AVVAD_CUDA(cudaGetDevice(&dev));
-      if (!cache->cap_stream || cache->cap_device != dev) {
-        if (cache->cap_stream) cudaStreamDestroy(cache->cap_stream);
-        cache->cap_stream = nullptr;
-        AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream, cudaStreamNonBlocking));
-        cache->cap_device = dev;
-      }
+    {
       const std::vector<uintptr_t> key = {(uintptr_t)tv.gates, (uintptr_t)tv.c, (uintptr_t)dY, (uintptr_t)dl_step,
                                           (uintptr_t)head_w32, (uintptr_t)dh_rec, (uintptr_t)dc, (uintptr_t)len_st,
-                                          (uintptr_t)dG, (uintptr_t)WT, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H,
-                                          (uintptr_t)dev};
-      if (!cache->exec[l] || cache->key[l] != key) {
-        if (cache->exec[l]) {
-          cudaGraphExecDestroy(cache->exec[l]);
-          cache->exec[l] = nullptr;
-        }
-        const uint64_t before = g_launches.load();
-        // make sure the kernels' one-time attribute setup (not capturable) has happened: one real split-K launch
-        {
-          tc::EpiParams ep{};
-          ep.C = dh_rec;
-          ep.ldc = H;
-          int rc0 = tc::launch_tma_gemm(dG, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st, kBpttSplit,
-                                        (int64_t)B * H);
-          if (rc0) return rc0;
-        }
-        AVVAD_CUDA(cudaStreamBeginCapture(cache->cap_stream, cudaStreamCaptureModeThreadLocal));
-        int rc = run_steps(cache->cap_stream);
-        cudaGraph_t graph = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(cache->cap_stream, &graph);
-        if (rc) {
-          if (graph) cudaGraphDestroy(graph);
-          return rc;
-        }
-        if (ce != cudaSuccess) {
-          set_error(std::string("BPTT graph capture failed: ") + cudaGetErrorString(ce));
-          return AVVAD_ERR_CUDA;
-        }
-        ce = cudaGraphInstantiate(&cache->exec[l], graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) {
-          cache->exec[l] = nullptr;
-          set_error(std::string("BPTT graph instantiation failed: ") + cudaGetErrorString(ce));
-          return AVVAD_ERR_CUDA;
-        }
-        cache->key[l] = key;
-        cache->nodes[l] = (size_t)(g_launches.load() - before);  // launches counted while capturing = kernel nodes
-      } else {
-        g_launches.fetch_add(cache->nodes[l], std::memory_order_relaxed);  // a replay launches every captured kernel
-      }
-      AVVAD_CUDA(cudaGraphLaunch(cache->exec[l], st));
+                                          (uintptr_t)dG, (uintptr_t)WT, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H};
+      auto warm = [&]() -> int {   // the kernels' one-time attribute setup is not capturable: one real split-K launch
+        tc::EpiParams ep{};
+        ep.C = dh_rec;
+        ep.ldc = H;
+        return tc::launch_tma_gemm(dG, (int64_t)T * H4, WT, H4, B, H, H4, ep, tc::EPI_F32, 64, st, kBpttSplit,
+                                   (int64_t)B * H);
+      };
+      int rc = run_captured(use_graph ? cache : nullptr, l, key, warm, run_steps, st);
+      if (rc) return rc;
     }
     // db (= db_ih = db_hh)
     bias_grad_partial_kernel<<<dim3(H4 / 256, kBiasChunks), 256, 0, st>>>(dG, BT, H4, dWp);  // dWp is free here

@@ -43,6 +43,10 @@ int avvad_profile_read(int cat, double* ms, double* flops, uint64_t* launches);
 int avvad_profile_clear(void);
 /* Per-launch records (launch order) of one category; returns how many were written (<= max_n). */
 int64_t avvad_profile_dump(int cat, double* ms, double* flops, int64_t max_n);
+/* Debug aid (tools/micro/lstm_ab.py): while `buf` is non-null, the CTA-pair LSTM recurrence runs its tracing
+ * instantiation and writes u64 [CTA][T][8] %globaltimer stamps (first K block ready, last TMA issued, first MMA, last
+ * commit, accumulator observed, h stored, CTA barrier passed, flag published) into this device buffer. */
+void avvad_debug_lstm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------
  * Audio front end
