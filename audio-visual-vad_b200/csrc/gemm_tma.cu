@@ -114,17 +114,31 @@ int encode_weight_map(CUtensorMap* m, const void* ptr, uint64_t K, uint64_t N, u
   return encode2(m, ptr, K, N, K * 2, 64, bn);
 }
 
-template <int BN, int KE = 64, int MB = 1>
+// N = 256 tiles run on CTA pairs (tcgen05 cta_group::2) unless AVVAD_CG2=0; split-K launches and the per-step LSTM
+// epilogue keep the one-CTA kernel.  The weight map of a pair launch has a BN/2-row box (each CTA loads its half).
+static bool pair_enabled() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_CG2");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0;
+}
+static bool use_pair(int bn, int ksplit, int epi_mode) {
+  return pair_enabled() && bn == 256 && ksplit <= 1 && epi_mode != EPI_LSTM;
+}
+
+template <int BN, int KE = 64, int MB = 1, int CG = 1>
 static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {
-  using C = TmaCfg<BN, KE, MB>;
+  using C = TmaCfg<BN, KE, MB, CG>;
+  constexpr int MBT = (CG == 2) ? 2 : MB;
   if (g.ksplit < 1) g.ksplit = 1;
   if (g.ksplit == 1) g.kb_split = g.KB;
-  g.m_supers = (g.m_tiles + MB - 1) / MB;
+  g.m_supers = (g.m_tiles + MBT - 1) / MBT;
   g.total_tiles = g.m_supers * g.n_tiles * g.ksplit;
   static PerDeviceOnce once;
   const cudaError_t attr_err = once.run([] {
-    return cudaFuncSetAttribute(tc_tma_kernel<BN, KE, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(tc_tma_kernel<BN, KE, MB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)C::kSmemBytes);
   });
   if (attr_err != cudaSuccess) {
@@ -143,11 +157,33 @@ static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int ep
   }();
   EpiParams epd = ep;
   epd.debug = epi_debug;
+  void* tok = nullptr;
+  if (CG == 2) {
+    const int64_t pairs = num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)(g.total_tiles < pairs ? g.total_tiles : pairs));
+    cfg.blockDim = dim3(kTmaThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la;
+    cfg.numAttrs = 1;
+    prof_begin(st, &tok);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_tma_kernel<BN, KE, MB, CG>, maps, g, epd, epi_mode);
+    if (le != cudaSuccess) {
+      set_error(std::string("pair launch failed: ") + cudaGetErrorString(le));
+      return AVVAD_ERR_CUDA;
+    }
+    AVVAD_LAUNCHED();
+    prof_end(st, tok, cat, flops);
+    return AVVAD_OK;
+  }
   const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
   const unsigned grid = (unsigned)(g.total_tiles < resident ? g.total_tiles : resident);
-  void* tok = nullptr;
   prof_begin(st, &tok);
-  tc_tma_kernel<BN, KE, MB><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, epd, epi_mode);
+  tc_tma_kernel<BN, KE, MB, CG><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, epd, epi_mode);
   AVVAD_LAUNCHED();
   prof_end(st, tok, cat, flops);
   return AVVAD_OK;
@@ -166,7 +202,9 @@ static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiPara
       if (mb2 && epi_mode != EPI_LSTM) return launch_bn<128, 64, 2>(maps, g, ep, epi_mode, cat, flops, st);
       return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
     }
-    case 256: return launch_bn<256>(maps, g, ep, epi_mode, cat, flops, st);
+    case 256:
+      if (use_pair(256, g.ksplit, epi_mode)) return launch_bn<256, 64, 1, 2>(maps, g, ep, epi_mode, cat, flops, st);
+      return launch_bn<256>(maps, g, ep, epi_mode, cat, flops, st);
   }
   set_error("bad BN");
   return AVVAD_ERR_ARG;
@@ -263,7 +301,9 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
     }
   }
   const int K = R * S * Cin + (dual ? second->Cin2 : 0);
-  int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)KE, (uint32_t)bn, KE == 16);
+  const bool pair = KE == 64 && use_pair(bn, 1, EPI_BF16);
+  int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)KE, (uint32_t)(pair ? bn / 2 : bn),
+                   KE == 16);
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * (uint32_t)(KE * 2);
   const double flops = flops_override > 0 ? flops_override : 2.0 * (double)n * OH * OW * Cout * K;
@@ -305,7 +345,8 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
   maps.a[1] = maps.a[0];
   maps.a2[0] = maps.a2[1] = maps.a[0];
   g.bytesA[0] = g.bytesA[1] = 128u * 128u;
-  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)bn);
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64,
+               (uint32_t)(use_pair(bn, ksplit, epi_mode) ? bn / 2 : bn));
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * 128u;
   const double flops = 2.0 * (double)M * N * K;
@@ -345,7 +386,8 @@ int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16*
   maps.a[1] = maps.a[0];
   maps.a2[0] = maps.a2[1] = maps.a[0];
   g.bytesA[0] = g.bytesA[1] = 128u * 128u;
-  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)bn);
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64,
+               (uint32_t)(use_pair(bn, 1, EPI_XT) ? bn / 2 : bn));
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * 128u;
   EpiParams ep{};

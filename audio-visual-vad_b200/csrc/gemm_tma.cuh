@@ -95,6 +95,61 @@ __device__ __forceinline__ void umma_f16_lo2(uint32_t tmem_d, uint32_t a_lo, uin
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(hi)
       : "memory");
 }
+// ---- CTA-pair (tcgen05 cta_group::2) primitives: both CTAs of a cluster of two execute the loads, the transaction bytes
+// complete on the LEADER's barrier (cluster address `bar_leader`); rank 0 issues the M = 256 MMAs; commits are multicast
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_leader)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_leader) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar_leader)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_f16_lo2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                              uint32_t accum, uint32_t hi) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accum), "r"(hi)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pair_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t pair_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void pair_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void pair_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// kind::f16 instruction descriptor, M = 256 over the pair
+__host__ __device__ constexpr uint32_t make_idesc_m256(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -105,15 +160,20 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 // 32 KB through L2 -> SMEM per 256 MMA cycles (128 B/clk/SM, more than L2 delivers to 148 SMs at once: the N = 128
 // layers sat at 51-57 % tensor activity with L2 at 62-65 %); MB = 2 makes it 48 KB per 512 cycles (96 B/clk), the
 // ratio of the 128x256 tiles.  TMEM: 2 (double buffer) x MB x BN columns <= 512.
-template <int BN, int KE = 64, int MB = 1>
+// CG = 2: the tile is two accumulator blocks x BN columns computed by a CTA PAIR (tcgen05 cta_group::2, M = 256): each CTA
+// stages its own block of A and HALF of the weight box (the tensor cores of both SMs read both halves), so a K block
+// costs 32 KB of L2 -> SMEM traffic per SM instead of 48 KB and the same shared memory holds six stages instead of four.
+template <int BN, int KE = 64, int MB = 1, int CG = 1>
 struct TmaCfg {
   static constexpr uint32_t kRowBytes = KE * 2;
   static constexpr uint32_t kABytes = BM * kRowBytes;
-  static constexpr uint32_t kBBytes = BN * kRowBytes;
+  static constexpr uint32_t kBBytes = (BN / CG) * kRowBytes;  // per CTA
   static constexpr uint32_t kStageBytes = MB * kABytes + kBBytes;
   static constexpr int kCtasPerSm = (BN == 256 || MB > 1) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
-  static constexpr int kStages = (KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? (MB > 1 ? 4 : 3) : 4));
+  static constexpr int kStages =
+      (CG == 2) ? 6 : ((KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? (MB > 1 ? 4 : 3) : 4)));
+  static_assert(CG == 1 || (MB == 1 && BN == 256 && KE == 64), "pair mode: one block per CTA, BN = 256");
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + TmaBias<BN>::kEntries * 4;
   // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
   static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
@@ -147,12 +207,17 @@ __device__ __forceinline__ TileCoord decode_block(const TmaGeom& g, int64_t mt) 
   return t;
 }
 
-template <int BN, int KE, int MB>
-__global__ void __launch_bounds__(kTmaThreads, TmaCfg<BN, KE, MB>::kCtasPerSm)
+template <int BN, int KE, int MB, int CG = 1>
+__global__ void __launch_bounds__(kTmaThreads, TmaCfg<BN, KE, MB, CG>::kCtasPerSm)
 tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaGeom g, const EpiParams ep,
               const int epi_mode) {
-  using C = TmaCfg<BN, KE, MB>;
+  using C = TmaCfg<BN, KE, MB, CG>;
   constexpr int S = C::kStages;
+  constexpr int MBT = (CG == 2) ? 2 : MB;  // accumulator blocks per tile (over the pair when CG == 2)
+  // pair mode: CTA `rank` owns block `rank` of every tile; tiles are distributed over clusters
+  const uint32_t rank = (CG == 2) ? pair_rank() : 0u;
+  const int64_t tile0 = (CG == 2) ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tile_step = (CG == 2) ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
   constexpr uint32_t kAccCols = MB * BN;       // columns of one accumulator stage
   constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +237,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar0 + 8 * (2 * S + a), 1);      // tmem full
-      mbar_init(bar0 + 8 * (2 * S + 2 + a), kTmaEpiWarps);  // tmem empty: one arrival per epilogue warp
+      mbar_init(bar0 + 8 * (2 * S + 2 + a), CG * kTmaEpiWarps);  // tmem empty: one arrival per epilogue warp (of the pair)
     }
     fence_barrier_init();
     tma_prefetch_desc(&maps.a[0]);
@@ -189,39 +254,64 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
   if (bias_in_smem)
     for (int i = threadIdx.x; i < g.N; i += kTmaThreads) bias_s[i] = ep.bias ? ep.bias[i] : 0.f;
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) pair_sync();  // the peer's barriers are initialised and its TMEM allocated before anything targets them
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t bar0_leader = (CG == 2) ? pair_mapa(bar0, 0) : bar0;
 
-  // tile = (n-tile fastest, super m-tile); super m-tile sm covers m-tiles sm*MB .. sm*MB + MB-1
+  // tile = (n-tile fastest, super m-tile); super m-tile sm covers m-tiles sm*MBT .. sm*MBT + MBT-1
   if (warp == 0) {
     // ================= TMA producer (warp-converged; one elected lane issues) =================
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const int n_base = (int)(tile % g.n_tiles) * BN;
+    for (int64_t tile = tile0; tile < g.total_tiles; tile += tile_step) {
+      const int n_base = (int)(tile % g.n_tiles) * BN + (int)rank * (BN / CG);  // pair mode: this CTA's half of the box
       const int64_t sm = (tile / g.n_tiles) % g.m_supers;
       const int split = (int)(tile / (g.n_tiles * g.m_supers));
       const int kb0 = split * g.kb_split;
       const int kb1 = (kb0 + g.kb_split < g.KB) ? kb0 + g.kb_split : g.KB;
       TileCoord t[MB];
-      uint32_t bytes = g.bytesB;
+      uint32_t bytes = g.bytesB;  // pair mode: the leader expects both halves of the weight box and both A blocks
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        t[mb] = decode_block(g, sm * MB + mb);
+        t[mb] = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank : 0));
         bytes += g.bytesA[t[mb].phase];
       }
+      if (CG == 2) bytes += g.bytesA[decode_block(g, sm * MBT + 1 - (int)rank).phase];
       int cb = 0, fr = 0, fs = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {  // conv mode: kb0 = 0, kb1 = KB
         const int s = it % S;
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
         if (elect_one_sync()) {
-          const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
+          if (CG == 2) {
+            const uint32_t full = bar0_leader + 8 * s;
+            if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
+            if (g.mode == 0) {
+              if (g.tm_bp)
+                tma_load_4d_2sm(sa, &maps.a[0], kb * KE, (int)(t[0].n0 % g.tm_bp), (int)(t[0].n0 / g.tm_bp), 0, full);
+              else
+                tma_load_4d_2sm(sa, &maps.a[0], kb * KE, (int)t[0].n0, 0, 0, full);
+            } else {
+              tma_load_4d_2sm(sa, &maps.a[t[0].phase], cb * KE, fs - g.pad, t[0].hstart * g.stride + fr - g.pad,
+                              (int)t[0].n0, full);
+            }
+            tma_load_2d_2sm(sa + C::kABytes, &maps.b, kb * KE, n_base, full);
+          } else {
+          const uint32_t full = bar0 + 8 * s;
           // debug knobs (AVVAD_EPI_DEBUG): 4 = no A loads, 8 = no B loads (operands stay
           // whatever shared memory held), 2 = no MMAs, 1 = no stores -- to time the pipeline stages in isolation
           const bool no_a = (ep.debug & 4) != 0, no_b = (ep.debug & 8) != 0;
@@ -241,6 +331,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             }
           }
           if (!no_b) tma_load_2d(sa + MB * C::kABytes, &maps.b, kb * KE, n_base, full);
+          }
         }
         __syncwarp();
         if (++cb == g.cpb) {
@@ -256,23 +347,31 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         const uint32_t ph = (it / S) & 1u;
         mbar_wait(bar0 + 8 * (S + s), ph ^ 1u);
         if (elect_one_sync()) {
-          const uint32_t full = bar0 + 8 * s;
           const uint32_t sa = base + s * C::kStageBytes;
+          if (CG == 2) {
+            const uint32_t full = bar0_leader + 8 * s;
+            if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
+            tma_load_4d_2sm(sa, &maps.a2[t[0].phase], kb2 * KE, 0, t[0].hstart * g.stride2, (int)t[0].n0, full);
+            tma_load_2d_2sm(sa + C::kABytes, &maps.b, (g.KB + kb2) * KE, n_base, full);
+          } else {
+          const uint32_t full = bar0 + 8 * s;
           mbar_arrive_expect_tx(full, bytes);
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb)
             tma_load_4d(sa + mb * C::kABytes, &maps.a2[t[mb].phase], kb2 * KE, 0, t[mb].hstart * g.stride2,
                         (int)t[mb].n0, full);
           tma_load_2d(sa + MB * C::kABytes, &maps.b, (g.KB + kb2) * KE, n_base, full);
+          }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (warp-converged; one elected lane issues MMAs and commits) =================
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = (CG == 2) ? make_idesc_m256(BN) : make_idesc(BN);
     uint32_t it = 0, tl = 0;
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+    if (CG == 1 || rank == 0)  // pair mode: the leader issues for both CTAs
+    for (int64_t tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       const int split = (int)(tile / (g.n_tiles * g.m_supers));
       const int kbs = split * g.kb_split;
@@ -293,6 +392,13 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
             if (ep.debug & 2) continue;  // debug: feed + epilogue only
             const uint32_t a_lo = a0 + ((mb * C::kABytes) >> 4);
             const uint32_t d = d_tmem + mb * BN;
+            if (CG == 2) {
+              umma2_f16_lo2(d, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
+              umma2_f16_lo2(d, a_lo + 2, b_lo + 2, idesc, 1, C::kDescHiWord);
+              umma2_f16_lo2(d, a_lo + 4, b_lo + 4, idesc, 1, C::kDescHiWord);
+              umma2_f16_lo2(d, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
+              continue;
+            }
             umma_f16_lo2(d, a_lo, b_lo, idesc, kb != 0, C::kDescHiWord);
             if (KE == 64) {
               umma_f16_lo2(d, a_lo + 2, b_lo + 2, idesc, 1, C::kDescHiWord);
@@ -300,8 +406,13 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
               umma_f16_lo2(d, a_lo + 6, b_lo + 6, idesc, 1, C::kDescHiWord);
             }
           }
-          umma_commit(bar0 + 8 * (S + s));
-          if (kb == kb_total - 1) umma_commit(bar0 + 8 * (2 * S + acc));
+          if (CG == 2) {
+            umma2_commit_mc2(bar0 + 8 * (S + s));
+            if (kb == kb_total - 1) umma2_commit_mc2(bar0 + 8 * (2 * S + acc));
+          } else {
+            umma_commit(bar0 + 8 * (S + s));
+            if (kb == kb_total - 1) umma_commit(bar0 + 8 * (2 * S + acc));
+          }
         }
         __syncwarp();
       }
@@ -316,7 +427,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
     const bool fast32 = (epi_mode == EPI_F32) && bias_in_smem && (g.N % 32 == 0) && (ep.ldc % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0);
     uint32_t tl = 0;
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+    for (int64_t tile = tile0; tile < g.total_tiles; tile += tile_step, ++tl) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
       const int64_t sm = (tile / g.n_tiles) % g.m_supers;
       const int64_t c_off = (tile / (g.n_tiles * g.m_supers)) * g.split_stride;  // split-K partial (fp32 paths)
@@ -326,7 +437,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       int64_t m[MB];
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        const TileCoord t = decode_block(g, sm * MB + mb);
+        const TileCoord t = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank : 0));
         m[mb] = -1;
         if (!t.valid) continue;
         if (g.mode == 0) {
@@ -524,15 +635,20 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar0 + 8 * (2 * S + 2 + acc));
+      if (lane == 0) {
+        if (CG == 2) pair_arrive(bar0_leader + 8 * (2 * S + 2 + acc));  // the leader's MMAs overwrite both CTAs' TMEM
+        else mbar_arrive(bar0 + 8 * (2 * S + 2 + acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) pair_sync();  // no CTA exits (or frees TMEM) while the peer may still signal it or read its operands
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_acc, kTmemCols);
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
+    else tmem_dealloc(tmem_acc, kTmemCols);
   }
 }
 

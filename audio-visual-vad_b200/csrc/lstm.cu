@@ -281,18 +281,28 @@ static int pair_mode() {
 static unsigned long long* g_pair_trace = nullptr;
 extern "C" void avvad_debug_lstm_trace(void* buf) { g_pair_trace = (unsigned long long*)buf; }
 
-template <int kEW>
-static int run_pair_ew(const tc::LstmMaps& maps, const tc::PairGeom& g, size_t smem, unsigned int* counters,
-                       cudaStream_t st, double flops) {
+template <int kEW, int NP>
+static int run_pair_cfg(tc::LstmMaps maps, tc::PairGeom g, const __nv_bfloat16* w_hh, unsigned int* counters,
+                        cudaStream_t st, double flops) {
+  const int H = g.H;
+  const size_t smem = (size_t)(H / 64) * (NP / 2) * 128 + tc::kPairStagesOf(NP) * 16384 + 256 + 1024;
   static PerDeviceOnce once;
   AVVAD_CUDA(once.run([] {
-    cudaError_t e = cudaFuncSetAttribute(tc::lstm_pair_kernel<false, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(tc::lstm_pair_kernel<false, kEW, NP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc::lstm_pair_kernel<true, kEW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(tc::lstm_pair_kernel<true, kEW, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 227 * 1024);
   }));
-  const void* fn = g.trace ? (const void*)tc::lstm_pair_kernel<true, kEW> : (const void*)tc::lstm_pair_kernel<false, kEW>;
+  g.n_pairs = 4 * H / NP;
+  // this CTA's half of a pair's weight slice: NP/2 gate columns per box
+  const uint64_t wd[2] = {(uint64_t)H, (uint64_t)4 * H};
+  const uint64_t wstr[1] = {(uint64_t)H * 2};
+  const uint32_t wbox[2] = {64, NP / 2};
+  int rc = tc::encode_tiled_bf16(&maps.w, w_hh, 2, wd, wstr, wbox);
+  if (rc) return rc;
+  const void* fn = g.trace ? (const void*)tc::lstm_pair_kernel<true, kEW, NP>
+                           : (const void*)tc::lstm_pair_kernel<false, kEW, NP>;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * g.n_pairs);
   cfg.blockDim = dim3(tc::kPairThreadsOf(kEW));
@@ -321,12 +331,11 @@ static int run_pair_ew(const tc::LstmMaps& maps, const tc::PairGeom& g, size_t s
   return AVVAD_OK;
 }
 
-static int run_pair(const tc::LstmMaps& maps, const float4* xT, int64_t Bp, __nv_bfloat16* hseq, const int32_t* lengths,
-                    int64_t Bc, int64_t T, int H, unsigned int* counters, cudaStream_t st, __nv_bfloat16* gates_out,
-                    float* c_out) {
-  const size_t smem = (size_t)(H / 64) * 8192 + tc::kPairStages * 16384 + 256 + 1024;
+static int run_pair(const tc::LstmMaps& maps, const __nv_bfloat16* w_hh, const float4* xT, int64_t Bp,
+                    __nv_bfloat16* hseq, const int32_t* lengths, int64_t Bc, int64_t T, int H, unsigned int* counters,
+                    cudaStream_t st, __nv_bfloat16* gates_out, float* c_out) {
   tc::PairGeom g{};
-  g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64; g.n_pairs = 4 * H / 128;
+  g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64;
   g.xT = xT;
   g.Bp = (int)Bp;
   g.hseq = hseq;
@@ -340,13 +349,22 @@ static int run_pair(const tc::LstmMaps& maps, const float4* xT, int64_t Bp, __nv
     return e ? atoi(e) : 0;
   }();
   g.variant = variant;
+  // AVVAD_LSTM_NP = gate columns per pair (128 | 64), AVVAD_LSTM_EPI_WARPS = cell-update warps per CTA
+  static int np = [] {
+    const char* e = getenv("AVVAD_LSTM_NP");
+    return (e && atoi(e) == 128) ? 128 : (e && atoi(e) == 64) ? 64 : 128;
+  }();
   static int epi_warps = [] {
     const char* e = getenv("AVVAD_LSTM_EPI_WARPS");
-    return (e && atoi(e) == 16) ? 16 : 8;
+    return e ? atoi(e) : 8;
   }();
   const double flops = 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1);
-  return epi_warps == 16 ? run_pair_ew<16>(maps, g, smem, counters, st, flops)
-                         : run_pair_ew<8>(maps, g, smem, counters, st, flops);
+  if (np == 64 && 4 * H / 64 <= 64) {
+    if (epi_warps == 4) return run_pair_cfg<4, 64>(maps, g, w_hh, counters, st, flops);
+    return run_pair_cfg<8, 64>(maps, g, w_hh, counters, st, flops);
+  }
+  if (epi_warps == 16) return run_pair_cfg<16, 128>(maps, g, w_hh, counters, st, flops);
+  return run_pair_cfg<8, 128>(maps, g, w_hh, counters, st, flops);
 }
 
 static int lstm_num_sms() {
@@ -404,7 +422,7 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     rc = tc::encode_tiled_bf16(&maps.w, h->w_hh[l], 2, wd, wstr, wbox);
     if (rc) return rc;
     if (pair_mode() && max_ms <= 2 && Bc > 128 && n_slices % 2 == 0 && n_slices / 2 <= 32) {
-      rc = run_pair(maps, reinterpret_cast<const float4*>(xproj) + g0, Bp, hs, lengths + g0, Bc, T, H, counters, st,
+      rc = run_pair(maps, h->w_hh[l], reinterpret_cast<const float4*>(xproj) + g0, Bp, hs, lengths + g0, Bc, T, H, counters, st,
                     gates_out ? gates_out + g0 * T * 4 * H : nullptr, c_out ? c_out + g0 * T * H : nullptr);
       if (rc == AVVAD_OK) continue;
       if (rc != AVVAD_ERR_STATE) return rc;  // AVVAD_ERR_STATE: the pairs do not fit this device -> one CTA per block

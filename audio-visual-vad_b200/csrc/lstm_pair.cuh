@@ -29,13 +29,14 @@ namespace tc {
 
 // cell-update warps per CTA: 16 (32 rows x 32 columns each, 16-byte h stores) or 8 (32 rows x 64 columns: every thread
 // owns 16 hidden units = one full 32-byte sector of h_t)
-constexpr int kPairThreadsOf(int epi_warps) { return 64 + 32 * epi_warps; }
-constexpr int kPairStages = 6;
+__host__ __device__ constexpr int kPairThreadsOf(int epi_warps) { return 64 + 32 * epi_warps; }
+// operand ring: whatever the resident weight slice leaves of the 227 KB (NP = 128: 6 x 16 KB, NP = 64: 9 x 16 KB)
+__host__ __device__ constexpr int kPairStagesOf(int np) { return np == 128 ? 6 : 9; }
 constexpr int kPairTraceSlots = 12;
 
 struct PairGeom {
   int B, T, H, KB;      // KB = H / 64
-  int n_pairs;          // 4H / 128 (<= 32)
+  int n_pairs;          // 4H / NP (<= 64)
   const float4* xT;     // input projection xT[t][u][b][4] (b < Bp), both biases folded in; already offset to this
                         // launch's first batch row
   int Bp;
@@ -45,9 +46,9 @@ struct PairGeom {
   __nv_bfloat16* gates_out;  // training tape (may be null)
   float* c_out;
   unsigned long long* trace;  // kTrace only: [CTA][T][kPairTraceSlots] globaltimer stamps
-  // tuning knobs (AVVAD_LSTM_VARIANT): 1 = private flag lines (every CTA pushes its flag into a line per consumer, so a
-  // line has one poller), 2 = no acquire fence behind the poll, 4 = no proxy fence behind the poll, 8 = no proxy fence
-  // before the publish, 16 = back-off between polls
+  // diagnostics (AVVAD_LSTM_VARIANT): 2 = acquire fence behind the poll, 4 = generic->async proxy fence behind the poll
+  // (neither is needed: the producers release h_t at gpu scope before their flag and TMA reads L2; measured +0.6 us
+  // per step because both wait for the SM's outstanding input-projection loads), 256 = no input-projection loads
   int variant;
 };
 
@@ -105,15 +106,20 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-template <bool kTrace, int kEW>
+// NP = gate columns per pair (128: 32 pairs = 64 CTAs; 64: 64 pairs = 128 CTAs, half the cell-update work per SM and a
+// deeper operand ring, twice the h traffic through L2); kEW = cell-update warps per CTA.
+template <bool kTrace, int kEW, int NP>
 __global__ void __launch_bounds__(kPairThreadsOf(kEW), 1)
 lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  constexpr int S = kPairStages;
-  const uint32_t w_bytes = (uint32_t)g.KB * 8192u;  // KB tiles of [64 gate columns][64 k]
+  constexpr int S = kPairStagesOf(NP);
+  constexpr uint32_t kWTile = (NP / 2) * 128u;  // one K block of this CTA's weight half: [NP/2 gate columns][64 k]
+  constexpr int kUnitsPair = NP / 4;            // hidden units per pair
+  constexpr int kPerKb = 64 / kUnitsPair;       // pairs that produce one K block of h (2 or 4)
+  const uint32_t w_bytes = (uint32_t)g.KB * kWTile;
   const uint32_t sW = base;
   const uint32_t sA = base + w_bytes;
   const uint32_t bar0 = sA + S * 16384u;
@@ -125,12 +131,7 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // = batch slice of this CTA; rank 0 issues the MMAs
   const int pair = blockIdx.x >> 1;
-  // flags[p] = steps published by CTA `rank` of pair p.  Shared mode: one line per batch slice, polled by every CTA of
-  // the slice.  Private mode: line (rank, pair) belongs to this CTA alone; producers push their flag into every line.
-  const bool priv = (g.variant & 1) != 0;
-  unsigned int* flags = priv ? g.counters + 2 * kLstmMaxSlices + ((int)rank * 32 + pair) * 32
-                             : g.counters + rank * kLstmMaxSlices;
-  unsigned int* push = g.counters + 2 * kLstmMaxSlices + ((int)rank * 32 + lane) * 32 + pair;  // lane = consumer pair
+  unsigned int* flags = g.counters + rank * kLstmMaxSlices;  // flags[p] = steps published by CTA `rank` of pair p
   unsigned long long* trace = nullptr;
   if (kTrace) trace = g.trace + (size_t)blockIdx.x * g.T * kPairTraceSlots;
 
@@ -150,10 +151,10 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     // this CTA's half of the pair's weight slice, resident for the whole sequence
     mbar_arrive_expect_tx(BAR(kBarW), w_bytes);
     for (int kb = 0; kb < g.KB; ++kb)
-      tma_load_2d(sW + kb * 8192u, &maps.w, kb * 64, pair * 128 + (int)rank * 64, BAR(kBarW));
+      tma_load_2d(sW + kb * kWTile, &maps.w, kb * 64, pair * NP + (int)rank * (NP / 2), BAR(kBarW));
   }
   if (warp == 1) {
-    tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), 256);
+    tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), 2 * NP);
     tmem_relinquish2();
   }
   if (warp == 0) mbar_wait(BAR(kBarW), 0);
@@ -167,6 +168,8 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
 
   if (warp == 0) {
     // ================= producer: flags -> TMA ring =================
+    // lane l watches kPerKb / 2 ... flags such that K block kb is covered by ballot bits 2kb, 2kb+1:
+    //   NP = 128: one flag per lane (pairs 2kb, 2kb+1);  NP = 64: two flags per lane in one 8-byte load (pairs 4kb..4kb+3)
     uint32_t it = 0;
     for (int t = 1; t < g.T; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
       const unsigned int target = (unsigned int)t;
@@ -175,25 +178,31 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
       uint32_t spins = 0;
       while (kb < g.KB) {
         if (!ok) {
-          if (lane >= g.n_pairs) {
-            ok = true;
+          // relaxed poll: the data is only ever read by TMA (L2)
+          if (kPerKb == 2) {
+            if (lane >= g.n_pairs) {
+              ok = true;
+            } else {
+              unsigned int fv;
+              asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(fv) : "l"(flags + lane) : "memory");
+              ok = fv >= target;
+            }
           } else {
-            // relaxed poll: the data is only ever read by TMA (L2); the acquire + proxy fences below order the TMA
-            // reads after the observation
-            unsigned int fv;
-            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(fv) : "l"(flags + lane) : "memory");
-            ok = fv >= target;
+            if (2 * lane >= g.n_pairs) {
+              ok = true;
+            } else {
+              unsigned long long fv;
+              asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(fv) : "l"(flags + 2 * lane) : "memory");
+              ok = ((unsigned int)fv >= target) && ((unsigned int)(fv >> 32) >= target);
+            }
           }
           if (++spins > (1u << 26)) __trap();
-          if (!ok && (g.variant & 16)) __nanosleep(32);
         }
         const unsigned int m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0 && ((m >> (2 * kb)) & 3u) == 3u) {
           if (kTrace && kb == 0) trace[t * kPairTraceSlots + 0] = globaltimer_ns();
-          // The producers released h_t before their flag (membar + store), and TMA reads L2: the acquire fence only
-          // restates the control dependency between the flag observation and the TMA issue
-          if (!(g.variant & 2)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          if (!(g.variant & 4)) fence_proxy_async_global();
+          if (g.variant & 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          if (g.variant & 4) fence_proxy_async_global();
         }
         while (kb < g.KB && ((m >> (2 * kb)) & 3u) == 3u) {
           if (lane == 0) {
@@ -212,13 +221,13 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
   } else if (warp == 1) {
     // ================= MMA issuer: leader CTA only =================
     if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_pair(128);
+      constexpr uint32_t idesc = make_idesc_pair(NP);
       uint32_t it = 0;
       for (int t = 1; t < g.T; ++t) {
         const uint32_t a = (uint32_t)t & 1u;
         if (t >= 3) mbar_wait(BAR(kBarTE + a), (uint32_t)((t - 3) >> 1) & 1u);  // step t-2 has left this accumulator
         tc_fence_after();
-        const uint32_t d = tmem_acc + a * 128u;
+        const uint32_t d = tmem_acc + a * (uint32_t)NP;
         for (int kb = 0; kb < g.KB; ++kb, ++it) {
           const int s = it % S;
           mbar_wait(BAR(s), (it / S) & 1u);
@@ -226,7 +235,7 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
           if (elect_one_sync()) {
             if (kTrace && kb == 0) trace[t * kPairTraceSlots + 3] = globaltimer_ns();
             const uint32_t a_lo = desc_lo(sA + s * 16384u);
-            const uint32_t b_lo = desc_lo(sW + kb * 8192u);
+            const uint32_t b_lo = desc_lo(sW + kb * kWTile);
             umma2_f16_lo(d, a_lo, b_lo, idesc, kb != 0);
             umma2_f16_lo(d, a_lo + 2, b_lo + 2, idesc, 1);
             umma2_f16_lo(d, a_lo + 4, b_lo + 4, idesc, 1);
@@ -243,10 +252,11 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     }
   } else {
     // ================= cell update: warps 2.. =================
-    constexpr int kCols = 512 / kEW;   // accumulator columns per warp (32 or 64)
-    constexpr int kU = kCols / 4;      // hidden units per thread (8 or 16)
-    constexpr int kG = kU / 8;         // 32-column TMEM loads per thread
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    constexpr int kCols = 4 * NP / kEW;  // accumulator columns per warp (32 or 64)
+    constexpr int kU = kCols / 4;        // hidden units per thread (8 or 16)
+    constexpr int kG = kU / 8;           // 32-column TMEM loads per thread
+    static_assert(kCols == 32 || kCols == 64, "cell-update warps cover 32 or 64 accumulator columns");
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int chunk = (warp - 2) >> 2;
     const int b = (int)rank * 128 + q * 32 + lane;
     const bool row_ok = b < g.B;
@@ -256,9 +266,10 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     float c[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) c[u] = 0.f;
+    const int unit0 = pair * kUnitsPair + chunk * kU;  // first hidden unit of this thread
     // lane = batch row: a warp's load of one unit's gates is one contiguous 512-byte run
-    const float4* xcol = g.xT + (int64_t)(pair * 32 + chunk * kU) * g.Bp + (row_ok ? b : 0);
-    __nv_bfloat16* hrow = g.hseq + ((int64_t)(row_ok ? b : 0) * g.T) * g.H + pair * 32 + chunk * kU;
+    const float4* xcol = g.xT + (int64_t)unit0 * g.Bp + (row_ok ? b : 0);
+    __nv_bfloat16* hrow = g.hseq + ((int64_t)(row_ok ? b : 0) * g.T) * g.H + unit0;
     const uint32_t t_row = tmem_acc + (uint32_t)(chunk * kCols) + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < g.T; ++t) {
       // input projection of this step: independent of h, requested before the wait on the accumulator
@@ -266,71 +277,70 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
       if (g.variant & 256) {  // diagnostic: no input-projection loads (wrong results; what do these loads cost?)
 #pragma unroll
         for (int u = 0; u < kU; ++u) x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else if (row_ok) {
+      } else {  // rows past B read row 0 and store nothing
         const float4* xp = xcol + (int64_t)t * g.H * g.Bp;
 #pragma unroll
-        for (int u = 0; u < kU; ++u) x[u] = __ldg(xp + (int64_t)u * g.Bp);
+        for (int u = 0; u < kU; ++u, xp += g.Bp) x[u] = __ldg(xp);
       }
-      uint32_t v[kG][32];
+      const uint32_t a = (uint32_t)t & 1u;
       if (t > 0) {
-        const uint32_t a = (uint32_t)t & 1u;
         mbar_wait(BAR(kBarTF + a), (uint32_t)((t - 1) >> 1) & 1u);
         tc_fence_after();
         if (tr) trace[t * kPairTraceSlots + 5] = globaltimer_ns();
+      }
+      const bool live = t < len;
+      uint32_t hp[kU / 2];
+      __nv_bfloat16* gsave = (g.gates_out && row_ok) ? g.gates_out + ((int64_t)b * g.T + t) * H4 + 4 * unit0 : nullptr;
 #pragma unroll
-        for (int gi = 0; gi < kG; ++gi) tmem_ld32(t_row + a * 128u + gi * 32, v[gi]);
-        tmem_ld_wait();
-        if (tr) trace[t * kPairTraceSlots + 6] = globaltimer_ns();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(LBAR(kBarTE + a));
-      } else {
+      for (int gi = 0; gi < kG; ++gi) {  // 32 accumulator columns = 8 hidden units at a time (bounds the live registers)
+        uint32_t v[32];
+        if (t > 0) {
+          tmem_ld32(t_row + a * (uint32_t)NP + gi * 32, v);
+          tmem_ld_wait();
+          if (gi == kG - 1) {
+            if (tr) trace[t * kPairTraceSlots + 6] = globaltimer_ns();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(LBAR(kBarTE + a));
+          }
+        } else {
 #pragma unroll
-        for (int gi = 0; gi < kG; ++gi)
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[gi][i] = 0u;
+        for (int k = 0; k < 2; ++k) {  // groups of four units = one 32-byte sector of the gate tape
+          u32x8 gp;
+          float hv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int u = 8 * gi + 4 * k + j;
+            const int o = (4 * k + j) * 4;
+            const float gi_ = sigmoid_hw(__uint_as_float(v[o + 0]) + x[u].x);
+            const float gf = sigmoid_hw(__uint_as_float(v[o + 1]) + x[u].y);
+            const float gg = tanh_hw(__uint_as_float(v[o + 2]) + x[u].z);
+            const float go = sigmoid_hw(__uint_as_float(v[o + 3]) + x[u].w);
+            c[u] = gf * c[u] + gi_ * gg;
+            hv[j] = go * tanh_hw(c[u]);
+            gp.v[2 * j] = pack_bf16x2(gi_, gf);
+            gp.v[2 * j + 1] = pack_bf16x2(gg, go);
+          }
+          hp[4 * gi + 2 * k] = live ? pack_bf16x2(hv[0], hv[1]) : 0u;
+          hp[4 * gi + 2 * k + 1] = live ? pack_bf16x2(hv[2], hv[3]) : 0u;
+          if (gsave) st_global_256(gsave + 32 * gi + 16 * k, gp);  // training tape: post-activation gates, bf16
+        }
       }
       if (row_ok) {
-        float hv[kU];
-        uint32_t gpk[2 * kU];
-#pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          const int o = (u & 7) * 4;
-          const float gi = sigmoid_hw(__uint_as_float(v[u >> 3][o + 0]) + x[u].x);
-          const float gf = sigmoid_hw(__uint_as_float(v[u >> 3][o + 1]) + x[u].y);
-          const float gg = tanh_hw(__uint_as_float(v[u >> 3][o + 2]) + x[u].z);
-          const float go = sigmoid_hw(__uint_as_float(v[u >> 3][o + 3]) + x[u].w);
-          c[u] = gf * c[u] + gi * gg;
-          hv[u] = go * tanh_hw(c[u]);
-          gpk[2 * u] = pack_bf16x2(gi, gf);
-          gpk[2 * u + 1] = pack_bf16x2(gg, go);
-        }
-        const bool live = t < len;
-        uint32_t hp[kU / 2];
-#pragma unroll
-        for (int u = 0; u < kU / 2; ++u) hp[u] = live ? pack_bf16x2(hv[2 * u], hv[2 * u + 1]) : 0u;
-        // h_t first: it is what the other CTAs wait for.  16 units per thread = one full 32-byte sector.
-        if (g.variant & 32) {  // diagnostic: no h store at all (wrong results; what do the outstanding stores cost?)
-        } else if (kU == 16) {
+        // h_t: what the other CTAs wait for (16 units per thread = one full 32-byte sector)
+        if (kU == 16) {
           u32x8 o;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] = hp[e];
+          for (int e = 0; e < 8; ++e) o.v[e] = hp[e & (kU / 2 - 1)];
           st_global_256(hrow + (int64_t)t * g.H, o);
         } else {
           *reinterpret_cast<uint4*>(hrow + (int64_t)t * g.H) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         }
-        if (g.gates_out) {  // training tape: full-sector stores (post-activation gates bf16, cell state f32)
-          __nv_bfloat16* gsave = g.gates_out + ((int64_t)b * g.T + t) * H4 + pair * 128 + chunk * kCols;
-#pragma unroll
-          for (int k = 0; k < kU / 4; ++k) {
-            u32x8 o;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) o.v[e] = gpk[8 * k + e];
-            st_global_256(gsave + 16 * k, o);
-          }
-        }
-        if (g.c_out) {
-          float* cp = g.c_out + ((int64_t)b * g.T + t) * g.H + pair * 32 + chunk * kU;
+        if (g.c_out) {  // training tape: cell state, f32
+          float* cp = g.c_out + ((int64_t)b * g.T + t) * g.H + unit0;
 #pragma unroll
           for (int k = 0; k < kU / 8; ++k) {
             u32x8 o;
@@ -342,28 +352,12 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
       }
       // publish: all cell-update warps have stored their part of h_t; one thread makes it visible and raises the flag
       if (tr) trace[t * kPairTraceSlots + 7] = globaltimer_ns();
-      if (!(g.variant & 8)) fence_proxy_async_global();
-      if (tr) trace[t * kPairTraceSlots + 8] = globaltimer_ns();
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
-      if (warp == 2) {
-        if (tr) trace[t * kPairTraceSlots + 9] = globaltimer_ns();
-        if (priv) {
-          if (lane < g.n_pairs)
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(push), "r"((unsigned int)(t + 1)) : "memory");
-        } else if (g.variant & 64) {  // diagnostic: flag without release ordering (what does the membar cost?)
-          if (lane == 0)
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(g.counters + rank * kLstmMaxSlices + pair),
-                         "r"((unsigned int)(t + 1))
-                         : "memory");
-        } else if (lane == 0) {
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.counters + rank * kLstmMaxSlices + pair),
-                       "r"((unsigned int)(t + 1))
-                       : "memory");
-        }
-        if (tr) trace[t * kPairTraceSlots + 10] = globaltimer_ns();
+      if (warp == 2 && lane == 0) {
+        if (kTrace) trace[t * kPairTraceSlots + 9] = globaltimer_ns();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + pair), "r"((unsigned int)(t + 1)) : "memory");
+        if (kTrace) trace[t * kPairTraceSlots + 10] = globaltimer_ns();
       }
-      // diagnostic: the other warps' next input-projection loads wait until the flag is out
-      if (g.variant & 128) asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
     }
   }
 
@@ -372,7 +366,7 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
   cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer may still arrive on its barriers / use its operands
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc2(tmem_acc, 256);
+    tmem_dealloc2(tmem_acc, 2 * NP);
   }
 }
 

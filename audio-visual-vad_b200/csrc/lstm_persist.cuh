@@ -42,7 +42,8 @@ struct LstmGeom {
   __nv_bfloat16* gates_out;
   float* c_out;
   int cluster;  // CTAs per cluster sharing h through TMA multicast (1 = none)
-  int variant;  // tuning knob (AVVAD_LSTM_VARIANT): bit 0 = every thread fences before the barrier, bit 1 = back-off between polls
+  int variant;  // tuning knobs (AVVAD_LSTM_VARIANT): 1 = every thread fences before the barrier, 2 = back-off between
+                // polls, 32 / 64 = acquire / proxy fence behind the poll
 };
 
 struct LstmMaps {
@@ -207,10 +208,11 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
         }
         const unsigned int m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0 && kb < g.KB && ((m >> (2 * kb)) & 3u) == 3u) {
-          // one fence pair per batch of newly ready K blocks: peers wrote h through the generic proxy (released with
-          // their flag), TMA reads it through the async proxy
-          asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          fence_proxy_async_global();
+          // Peers released h_t at gpu scope before their flag and TMA reads L2, so the fences behind the poll only
+          // restate the control dependency -- and both wait for every outstanding load of the SM (the cell-update warps'
+          // input-projection prefetch): off unless AVVAD_LSTM_VARIANT bits 32 / 64 ask for them.
+          if (g.variant & 32) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          if (g.variant & 64) fence_proxy_async_global();
         }
         while (kb < g.KB && ((m >> (2 * kb)) & 3u) == 3u) {
           if (lane == 0) {
