@@ -123,15 +123,24 @@ static bool pair_enabled() {
   }();
   return v != 0;
 }
+// AVVAD_CG2_128 = 0: N = 128 tiles stay on single CTAs; 1 / 2 (default): pairs with one / two blocks per CTA
+static int pair128_mode() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_CG2_128");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
 static bool use_pair(int bn, int ksplit, int epi_mode) {
-  return pair_enabled() && bn == 256 && ksplit <= 1 && epi_mode != EPI_LSTM;
+  if (!pair_enabled() || ksplit > 1 || epi_mode == EPI_LSTM) return false;
+  return bn == 256 || (bn == 128 && pair128_mode() != 0);
 }
 
 template <int BN, int KE = 64, int MB = 1, int CG = 1>
 static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int epi_mode, int cat, double flops,
                      cudaStream_t st) {
   using C = TmaCfg<BN, KE, MB, CG>;
-  constexpr int MBT = (CG == 2) ? 2 : MB;
+  constexpr int MBT = CG * MB;
   if (g.ksplit < 1) g.ksplit = 1;
   if (g.ksplit == 1) g.kb_split = g.KB;
   g.m_supers = (g.m_tiles + MBT - 1) / MBT;
@@ -199,6 +208,10 @@ static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiPara
         const char* e = getenv("AVVAD_MB");
         return (e && atoi(e) == 1) ? 0 : 1;
       }();
+      if (use_pair(128, g.ksplit, epi_mode)) {
+        if (pair128_mode() == 1) return launch_bn<128, 64, 1, 2>(maps, g, ep, epi_mode, cat, flops, st);
+        return launch_bn<128, 64, 2, 2>(maps, g, ep, epi_mode, cat, flops, st);
+      }
       if (mb2 && epi_mode != EPI_LSTM) return launch_bn<128, 64, 2>(maps, g, ep, epi_mode, cat, flops, st);
       return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
     }

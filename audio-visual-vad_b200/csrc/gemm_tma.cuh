@@ -169,11 +169,12 @@ struct TmaCfg {
   static constexpr uint32_t kABytes = BM * kRowBytes;
   static constexpr uint32_t kBBytes = (BN / CG) * kRowBytes;  // per CTA
   static constexpr uint32_t kStageBytes = MB * kABytes + kBBytes;
-  static constexpr int kCtasPerSm = (BN == 256 || MB > 1) ? 1 : 2;
+  static constexpr int kCtasPerSm = (BN == 256 || MB > 1 || CG == 2) ? 1 : 2;
   // ring depth: fill ~200 KB per SM
   static constexpr int kStages =
-      (CG == 2) ? 6 : ((KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? (MB > 1 ? 4 : 3) : 4)));
-  static_assert(CG == 1 || (MB == 1 && BN == 256 && KE == 64), "pair mode: one block per CTA, BN = 256");
+      (CG == 2) ? (int)((200u * 1024u) / kStageBytes)
+                : ((KE == 16) ? 8 : ((BN == 256) ? 4 : ((BN == 128) ? (MB > 1 ? 4 : 3) : 4)));
+  static_assert(CG == 1 || (KE == 64 && (BN == 256 || BN == 128)), "pair mode: BN = 256 or 128");
   static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + TmaBias<BN>::kEntries * 4;
   // descriptor high word: SBO (8 rows) >> 4 | version 1 << 14 | layout (2 = SW128, 6 = SW32) << 29
   static constexpr uint32_t kDescHiWord = ((8 * kRowBytes) >> 4) | (1u << 14) | ((KE == 64 ? 2u : 6u) << 29);
@@ -213,8 +214,9 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
               const int epi_mode) {
   using C = TmaCfg<BN, KE, MB, CG>;
   constexpr int S = C::kStages;
-  constexpr int MBT = (CG == 2) ? 2 : MB;  // accumulator blocks per tile (over the pair when CG == 2)
-  // pair mode: CTA `rank` owns block `rank` of every tile; tiles are distributed over clusters
+  constexpr int MBT = CG * MB;  // accumulator blocks per tile (over the pair when CG == 2)
+  // pair mode: CTA `rank` owns blocks rank*MB .. rank*MB + MB-1 of every tile (MMA mb pairs block mb of both CTAs into
+  // one M = 256 instruction); tiles are distributed over clusters
   const uint32_t rank = (CG == 2) ? pair_rank() : 0u;
   const int64_t tile0 = (CG == 2) ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t tile_step = (CG == 2) ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
@@ -286,10 +288,13 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       uint32_t bytes = g.bytesB;  // pair mode: the leader expects both halves of the weight box and both A blocks
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        t[mb] = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank : 0));
+        t[mb] = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank * MB : 0));
         bytes += g.bytesA[t[mb].phase];
       }
-      if (CG == 2) bytes += g.bytesA[decode_block(g, sm * MBT + 1 - (int)rank).phase];
+      if (CG == 2) {
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) bytes += g.bytesA[decode_block(g, sm * MBT + mb + (1 - (int)rank) * MB).phase];
+      }
       int cb = 0, fr = 0, fs = 0;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {  // conv mode: kb0 = 0, kb1 = KB
         const int s = it % S;
@@ -300,16 +305,20 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           if (CG == 2) {
             const uint32_t full = bar0_leader + 8 * s;
             if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
-            if (g.mode == 0) {
-              if (g.tm_bp)
-                tma_load_4d_2sm(sa, &maps.a[0], kb * KE, (int)(t[0].n0 % g.tm_bp), (int)(t[0].n0 / g.tm_bp), 0, full);
-              else
-                tma_load_4d_2sm(sa, &maps.a[0], kb * KE, (int)t[0].n0, 0, 0, full);
-            } else {
-              tma_load_4d_2sm(sa, &maps.a[t[0].phase], cb * KE, fs - g.pad, t[0].hstart * g.stride + fr - g.pad,
-                              (int)t[0].n0, full);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint32_t da = sa + mb * C::kABytes;
+              if (g.mode == 0) {
+                if (g.tm_bp)
+                  tma_load_4d_2sm(da, &maps.a[0], kb * KE, (int)(t[mb].n0 % g.tm_bp), (int)(t[mb].n0 / g.tm_bp), 0, full);
+                else
+                  tma_load_4d_2sm(da, &maps.a[0], kb * KE, (int)t[mb].n0, 0, 0, full);
+              } else {
+                tma_load_4d_2sm(da, &maps.a[t[mb].phase], cb * KE, fs - g.pad, t[mb].hstart * g.stride + fr - g.pad,
+                                (int)t[mb].n0, full);
+              }
             }
-            tma_load_2d_2sm(sa + C::kABytes, &maps.b, kb * KE, n_base, full);
+            tma_load_2d_2sm(sa + MB * C::kABytes, &maps.b, kb * KE, n_base, full);
           } else {
           const uint32_t full = bar0 + 8 * s;
           // debug knobs (AVVAD_EPI_DEBUG): 4 = no A loads, 8 = no B loads (operands stay
@@ -351,8 +360,11 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
           if (CG == 2) {
             const uint32_t full = bar0_leader + 8 * s;
             if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
-            tma_load_4d_2sm(sa, &maps.a2[t[0].phase], kb2 * KE, 0, t[0].hstart * g.stride2, (int)t[0].n0, full);
-            tma_load_2d_2sm(sa + C::kABytes, &maps.b, (g.KB + kb2) * KE, n_base, full);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb)
+              tma_load_4d_2sm(sa + mb * C::kABytes, &maps.a2[t[mb].phase], kb2 * KE, 0, t[mb].hstart * g.stride2,
+                              (int)t[mb].n0, full);
+            tma_load_2d_2sm(sa + MB * C::kABytes, &maps.b, (g.KB + kb2) * KE, n_base, full);
           } else {
           const uint32_t full = bar0 + 8 * s;
           mbar_arrive_expect_tx(full, bytes);
@@ -437,7 +449,7 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
       int64_t m[MB];
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        const TileCoord t = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank : 0));
+        const TileCoord t = decode_block(g, sm * MBT + mb + (CG == 2 ? (int)rank * MB : 0));
         m[mb] = -1;
         if (!t.valid) continue;
         if (g.mode == 0) {
