@@ -83,7 +83,16 @@ static bool plan(int H, int Cin, int Cout, SlabPlan* out) {
   return true;
 }
 
-template <int BN, bool RES, int MBC = 0>
+// AVVAD_SLAB_CG2=0: layer1 stays on single CTAs (default: CTA pairs, see conv_slab.cuh)
+static int slab_pair() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_SLAB_CG2");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v;
+}
+
+template <int BN, bool RES, int MBC = 0, int CG = 1>
 static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep, size_t smem, double flops,
                     cudaStream_t st) {
   static std::mutex mu;
@@ -94,7 +103,7 @@ static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep
     AVVAD_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "device index out of range");
     std::lock_guard<std::mutex> lk(mu);
     if (smem > attr_set[dev]) {
-      AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES, MBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      AVVAD_CUDA(cudaFuncSetAttribute(tc_slab_kernel<BN, RES, MBC, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set[dev] = smem;
     }
   }
@@ -103,10 +112,32 @@ static int launch_k(const SlabMaps& maps, const SlabGeom& g, const EpiParams& ep
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n > 0 ? n : 148;
   }();
-  const unsigned grid = (unsigned)(g.total_tiles < num_sms ? g.total_tiles : num_sms);
   void* tok = nullptr;
+  if (CG == 2) {
+    const int64_t pairs = num_sms / 2, want = (g.total_tiles + 1) / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)(want < pairs ? want : pairs));
+    cfg.blockDim = dim3(kSlabThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la;
+    cfg.numAttrs = 1;
+    prof_begin(st, &tok);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_slab_kernel<BN, RES, MBC, CG>, maps, g, ep);
+    if (le != cudaSuccess) {
+      set_error(std::string("slab pair launch failed: ") + cudaGetErrorString(le));
+      return AVVAD_ERR_CUDA;
+    }
+    AVVAD_LAUNCHED();
+    prof_end(st, tok, 0, flops);
+    return AVVAD_OK;
+  }
+  const unsigned grid = (unsigned)(g.total_tiles < num_sms ? g.total_tiles : num_sms);
   prof_begin(st, &tok);
-  tc_slab_kernel<BN, RES, MBC><<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
+  tc_slab_kernel<BN, RES, MBC, CG><<<grid, kSlabThreads, smem, st>>>(maps, g, ep);
   AVVAD_LAUNCHED();
   prof_end(st, tok, 0, flops);
   return AVVAD_OK;
@@ -197,9 +228,12 @@ int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiP
   const uint32_t estr[4] = {1, 1, 1, 1};
   int rc = encode_act_map(&maps.a, in, Cin, H, H, n, box, estr);
   if (rc) return rc;
-  rc = encode_weight_map(&maps.b, w, (uint64_t)9 * Cin, (uint64_t)Cout, (uint32_t)p.bn);
+  const bool pair = p.resident && slab_pair() && g.n_tiles == 1;
+  rc = encode_weight_map(&maps.b, w, (uint64_t)9 * Cin, (uint64_t)Cout, (uint32_t)(pair ? p.bn / 2 : p.bn));
   if (rc) return rc;
   const double flops = 2.0 * (double)n * H * H * Cout * 9.0 * Cin;
+  if (pair && p.mb == 3) return launch_k<64, true, 3, 2>(maps, g, ep, p.smem, flops, st);
+  if (pair) return launch_k<64, true, 0, 2>(maps, g, ep, p.smem, flops, st);
   if (p.resident && p.mb == 3) return launch_k<64, true, 3>(maps, g, ep, p.smem, flops, st);
   if (p.resident) return launch_k<64, true>(maps, g, ep, p.smem, flops, st);
   return launch_k<64, false>(maps, g, ep, p.smem, flops, st);

@@ -44,15 +44,26 @@ __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t saddr, int use_b
 // 9 x MBC x 4 MMAs of a channel block are straight-line code with immediate descriptor offsets -- the issuing thread
 // was spending ~45 % of its slots on short-scoreboard stalls (constant-bank reloads, loop arithmetic) between
 // 48-cycle MMAs.  MBC = 0 keeps the generic loops.
-template <int BN, bool RESIDENT_B, int MBC = 0>
+// CG = 2 (resident weights only): a CTA PAIR works on two consecutive tiles at once as M = 256 MMAs (tcgen05
+// cta_group::2).  Each CTA stages the slab of ITS tile and keeps HALF of the weights (BN/2 output channels of every
+// tap); both tensor cores read both halves, so a K16 step reads 5 KB of operands per SM instead of 6 KB: 40 cycles
+// instead of 48 for 32 cycles of math at N = 64.
+template <int BN, bool RESIDENT_B, int MBC = 0, int CG = 1>
 __global__ void __launch_bounds__(kSlabThreads)
 tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const EpiParams ep) {
+  static_assert(CG == 1 || RESIDENT_B, "pair mode needs resident weights");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t slab_bytes = ((uint32_t)g.slab_rows * 128u + 1023u) & ~1023u;
-  const uint32_t b_tile = BN * 128u;
+  const uint32_t b_tile = (BN / CG) * 128u;  // per CTA
+  const uint32_t rank = (CG == 2) ? pair_rank() : 0u;
+  // pair mode: cluster c works on tiles 2c + rank, 2c + rank + 2 * clusters, ...; a tile index past the end is harmless
+  // (TMA zero-fills frames >= n_frames, the epilogue stores nothing for them)
+  const int64_t tile0 = (CG == 2) ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
+  const int64_t tile_step = (CG == 2) ? (int64_t)gridDim.x : (int64_t)gridDim.x;
+  const int64_t tile_end = (CG == 2) ? ((g.total_tiles + 1) / 2) * 2 : g.total_tiles;
   const int KB = 9 * g.cpb;
   const int nB = RESIDENT_B ? KB : g.b_stages;
   const uint32_t w_base = base + 2 * slab_bytes;
@@ -73,7 +84,7 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
       mbar_init(BAR(0 + i), 1);              // slab full (expect_tx)
       mbar_init(BAR(2 + i), 1);              // slab empty (tcgen05.commit)
       mbar_init(BAR(4 + i), 1);              // tmem full
-      mbar_init(BAR(6 + i), kSlabEpiWarps);  // tmem empty
+      mbar_init(BAR(6 + i), CG * kSlabEpiWarps);  // tmem empty (pair mode: both CTAs' warps, on the leader)
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(BAR(kBarBFull + i), 1);
@@ -84,21 +95,42 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
     tma_prefetch_desc(&maps.b);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(const_cast<uint32_t*>(tmem_slot))),
+                   "r"(tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), tmem_cols);
+      tmem_relinquish();
+    }
   }
   {  // folded-BN bias -> shared memory (zero when absent); the region sits behind the barriers
     float* bs = reinterpret_cast<float*>(smem + (bar0 - base) + 8 * 24 + 16);
     for (int i = threadIdx.x; i < g.N; i += kSlabThreads) bs[i] = ep.bias ? ep.bias[i] : 0.f;
   }
+  if (CG == 2 && warp == 0) {
+    // pair mode: this CTA's half of the weights is loaded (and waited for) before the pair synchronises, so the leader's
+    // MMAs may read both halves
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(BAR(kBarBFull), (uint32_t)KB * b_tile);
+      for (int kb = 0; kb < KB; ++kb)
+        tma_load_2d(w_base + kb * b_tile, &maps.b, kb * BK, (int)rank * (BN / CG), BAR(kBarBFull));
+    }
+    __syncwarp();
+    mbar_wait(BAR(kBarBFull), 0);
+  }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) pair_sync();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t bar0_leader = (CG == 2) ? pair_mapa(bar0, 0) : bar0;
 
   if (warp == 0) {
     // ================= TMA producer (warp-converged; one elected lane issues) =================
-    if (RESIDENT_B) {
+    if (RESIDENT_B && CG == 1) {
       // all weight K blocks, once (n_tiles == 1 in this mode)
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(BAR(kBarBFull), (uint32_t)KB * b_tile);
@@ -107,7 +139,7 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
       __syncwarp();
     }
     uint32_t si = 0, bi = 0;  // slab / weight-ring counters
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile0; tile < tile_end; tile += tile_step) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
       const int64_t mt = tile / g.n_tiles;
       const int band = (int)(mt % g.nb);
@@ -117,8 +149,13 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
         const int sb = si & 1;
         mbar_wait(BAR(2 + sb), ((si >> 1) & 1u) ^ 1u);
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(BAR(0 + sb), g.slab_tx);
-          tma_load_4d(base + sb * slab_bytes, &maps.a, cb * BK, -1, hstart - 1, n0, BAR(0 + sb));
+          if (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(BAR(0 + sb), 2 * g.slab_tx);  // both CTAs' slabs
+            tma_load_4d_2sm(base + sb * slab_bytes, &maps.a, cb * BK, -1, hstart - 1, n0, bar0_leader + 8u * (uint32_t)sb);
+          } else {
+            mbar_arrive_expect_tx(BAR(0 + sb), g.slab_tx);
+            tma_load_4d(base + sb * slab_bytes, &maps.a, cb * BK, -1, hstart - 1, n0, BAR(0 + sb));
+          }
         }
         __syncwarp();
         if (!RESIDENT_B) {
@@ -136,13 +173,14 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
     }
   } else if (warp == 1) {
     // ================= MMA issuer (warp-converged; one elected lane issues MMAs and commits) =================
-    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc = (CG == 2) ? make_idesc_m256(BN) : make_idesc(BN);
     uint32_t si = 0, bi = 0, tl = 0;
-    if (RESIDENT_B) {
+    if (RESIDENT_B && CG == 1) {
       mbar_wait(BAR(kBarBFull), 0);
       tc_fence_after();
     }
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+    if (CG == 1 || rank == 0)  // pair mode: the leader issues for both CTAs
+    for (int64_t tile = tile0; tile < tile_end; tile += tile_step, ++tl) {
       const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
       mbar_wait(BAR(6 + acc), aph ^ 1u);
       tc_fence_after();
@@ -166,10 +204,17 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
                 const uint32_t first = (cb | tap) != 0;
 #pragma unroll
                 for (int m = 0; m < MBC; ++m) {
-                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u, w_lo, idesc, first);
-                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 2, w_lo + 2, idesc, 1);
-                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 4, w_lo + 4, idesc, 1);
-                  umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 6, w_lo + 6, idesc, 1);
+                  if (CG == 2) {
+                    umma2_f16_lo2(d0 + m * BN, a0 + m * 1024u, w_lo, idesc, first, kDescHi);
+                    umma2_f16_lo2(d0 + m * BN, a0 + m * 1024u + 2, w_lo + 2, idesc, 1, kDescHi);
+                    umma2_f16_lo2(d0 + m * BN, a0 + m * 1024u + 4, w_lo + 4, idesc, 1, kDescHi);
+                    umma2_f16_lo2(d0 + m * BN, a0 + m * 1024u + 6, w_lo + 6, idesc, 1, kDescHi);
+                  } else {
+                    umma_f16_lo(d0 + m * BN, a0 + m * 1024u, w_lo, idesc, first);
+                    umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 2, w_lo + 2, idesc, 1);
+                    umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 4, w_lo + 4, idesc, 1);
+                    umma_f16_lo(d0 + m * BN, a0 + m * 1024u + 6, w_lo + 6, idesc, 1);
+                  }
                 }
               }
             } else {
@@ -182,15 +227,27 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
                 uint32_t d_tmem = d0;
                 const uint32_t first = (cb | tap) != 0;
                 for (int m = 0; m < mb; ++m, a_lo += 1024u, d_tmem += BN) {
-                  umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
-                  umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
-                  umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
-                  umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+                  if (CG == 2) {
+                    umma2_f16_lo2(d_tmem, a_lo, w_lo, idesc, first, kDescHi);
+                    umma2_f16_lo2(d_tmem, a_lo + 2, w_lo + 2, idesc, 1, kDescHi);
+                    umma2_f16_lo2(d_tmem, a_lo + 4, w_lo + 4, idesc, 1, kDescHi);
+                    umma2_f16_lo2(d_tmem, a_lo + 6, w_lo + 6, idesc, 1, kDescHi);
+                  } else {
+                    umma_f16_lo(d_tmem, a_lo, w_lo, idesc, first);
+                    umma_f16_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1);
+                    umma_f16_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1);
+                    umma_f16_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1);
+                  }
                 }
               }
             }
-            umma_commit(BAR(2 + sb));
-            if (cb == g.cpb - 1) umma_commit(BAR(4 + acc));
+            if (CG == 2) {
+              umma2_commit_mc2(BAR(2 + sb));
+              if (cb == g.cpb - 1) umma2_commit_mc2(BAR(4 + acc));
+            } else {
+              umma_commit(BAR(2 + sb));
+              if (cb == g.cpb - 1) umma_commit(BAR(4 + acc));
+            }
           }
           __syncwarp();
         } else {
@@ -260,7 +317,7 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
     const __nv_bfloat16* resp = ep.residual;
     __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(ep.C);
     const bool relu = ep.relu != 0;
-    for (int64_t tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++tl) {
+    for (int64_t tile = tile0; tile < tile_end; tile += tile_step, ++tl) {
       const int n_base = (int)(tile % g.n_tiles) * BN;
       const int64_t mt = tile / g.n_tiles;
       const int band = (int)(mt % g.nb);
@@ -331,15 +388,20 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(6 + acc));
+      if (lane == 0) {
+        if (CG == 2) pair_arrive(bar0_leader + 8u * (uint32_t)(6 + acc));
+        else mbar_arrive(BAR(6 + acc));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) pair_sync();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc(tmem_acc, tmem_cols);
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(tmem_cols) : "memory");
+    else tmem_dealloc(tmem_acc, tmem_cols);
   }
 }
 

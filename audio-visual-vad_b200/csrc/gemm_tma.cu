@@ -168,7 +168,8 @@ static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int ep
   epd.debug = epi_debug;
   void* tok = nullptr;
   if (CG == 2) {
-    const int64_t pairs = num_sms / 2;
+    int64_t pairs = num_sms / 2;
+    if (g.grid_cap > 0 && g.grid_cap / 2 < pairs) pairs = g.grid_cap / 2 > 0 ? g.grid_cap / 2 : 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2u * (unsigned)(g.total_tiles < pairs ? g.total_tiles : pairs));
     cfg.blockDim = dim3(kTmaThreads);
@@ -189,7 +190,8 @@ static int launch_bn(const TmaMaps& maps, TmaGeom g, const EpiParams& ep, int ep
     prof_end(st, tok, cat, flops);
     return AVVAD_OK;
   }
-  const int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
+  int64_t resident = (int64_t)num_sms * C::kCtasPerSm;
+  if (g.grid_cap > 0 && g.grid_cap < resident) resident = g.grid_cap;
   const unsigned grid = (unsigned)(g.total_tiles < resident ? g.total_tiles : resident);
   prof_begin(st, &tok);
   tc_tma_kernel<BN, KE, MB, CG><<<grid, kTmaThreads, C::kSmemBytes, st>>>(maps, g, epd, epi_mode);
@@ -367,7 +369,7 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
 }
 
 int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
-                       int N, int K, const float* bias, float* xT, cudaStream_t st) {
+                       int64_t T_stride, int N, int K, const float* bias, float* xT, cudaStream_t st, int grid_cap) {
   AVVAD_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 32 == 0, "TMA gemm (xT): K % 64, lda % 8, N % 32");
   const int64_t Bp = (B + 127) / 128 * 128;
   AVVAD_CHECK_ARG(T * Bp < (1ll << 31), "TMA gemm (xT): T * B too large");
@@ -382,6 +384,7 @@ int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16*
   g.N = N;
   g.tm_bp = (int)Bp;
   g.tm_b = (int)B;
+  g.grid_cap = grid_cap;
   const int bn = pick_bn(N, 0);
   g.n_tiles = (N + bn - 1) / bn;
   g.m_tiles = T * Bp / BM;
@@ -391,7 +394,8 @@ int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16*
   TmaMaps maps;
   // (k, b, t): a box is 128 batch items of one time step; rows past B are zero-filled by the hardware
   const uint64_t dims[4] = {(uint64_t)K, (uint64_t)B, (uint64_t)T, 1};
-  const uint64_t strides[3] = {(uint64_t)lda * 2 * (uint64_t)T, (uint64_t)lda * 2, (uint64_t)lda * 2 * (uint64_t)T * (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)lda * 2 * (uint64_t)T_stride, (uint64_t)lda * 2,
+                               (uint64_t)lda * 2 * (uint64_t)T_stride * (uint64_t)B};
   const uint32_t box[4] = {64, 128, 1, 1};
   const uint32_t estr[4] = {1, 1, 1, 1};
   int rc = encode4(&maps.a[0], X, dims, strides, box, estr);

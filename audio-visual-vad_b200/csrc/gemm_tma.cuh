@@ -58,6 +58,7 @@ struct TmaGeom {
   // time-major GEMM over a [B][T][K] operand (launch_tma_gemm_xt): row index m = t * tm_bp + b, tm_bp = B rounded up to
   // 128, so that a 128-row tile is 128 consecutive batch items of ONE time step (0 = plain row order)
   int tm_bp, tm_b;
+  int grid_cap;  // host only: at most this many CTAs (0 = all SMs) -- for launches that share the GPU with a recurrence
   uint32_t bytesA[2];   // TMA box bytes per phase
   uint32_t bytesB;
 };
@@ -680,8 +681,9 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
                     int64_t split_stride = 0);
 // xT[t][u][b][4] (fp32, b < Bp = B rounded up to 128) = X[b][t][:] * Wt[4u+g][:]^T + bias[4u+g] for an operand X laid out
 // [B][T][lda]: the LSTM input projection in the layout the persistent recurrences read (N = 4H, N % 32 == 0)
+// X points at time step 0 of the chunk, T = steps in the chunk, T_stride = steps between consecutive batch items of X
 int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
-                       int N, int K, const float* bias, float* xT, cudaStream_t st);
+                       int64_t T_stride, int N, int K, const float* bias, float* xT, cudaStream_t st, int grid_cap = 0);
 
 }  // namespace tc
 }  // namespace avvad

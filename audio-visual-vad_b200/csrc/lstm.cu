@@ -118,6 +118,11 @@ struct avvad_lstm {
   bool set[8];
   bool head_set;
   BpttGraphCache* bptt;      // cached CUDA graphs of the backward recurrence (lstm_train.cu)
+  // layer overlap (lstm_forward_impl): layer 1 follows layer 0 one chunk of time steps behind on a side stream
+  cudaStream_t side = nullptr;
+  int side_device = -1;
+  cudaEvent_t ev_chunk[32] = {};
+  cudaEvent_t ev_done = nullptr;
 };
 
 extern "C" int avvad_lstm_create(avvad_lstm** out, int layers, int input_size, int hidden, int y_dim) {
@@ -162,6 +167,10 @@ extern "C" void avvad_lstm_destroy(avvad_lstm* h) {
   cudaFree(h->head_w16);
   cudaFree(h->head_b);
   bptt_cache_destroy(h->bptt);
+  for (auto e : h->ev_chunk)
+    if (e) cudaEventDestroy(e);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->side) cudaStreamDestroy(h->side);
   delete h;
 }
 
@@ -224,6 +233,8 @@ namespace {
 constexpr size_t kCounterBytes = 16384;
 struct LstmWs {
   float* xproj;
+  float* xproj1;  // second input-projection buffer: layer 1's chunks are written while layer 0 still reads its own
+  float* c1;
   __nv_bfloat16* hseq[2];
   __nv_bfloat16* hbuf[2];
   float* c;
@@ -241,13 +252,15 @@ LstmWs carve(const avvad_lstm* h, int64_t B, int64_t T, void* base) {
   };
   const int64_t H = h->H;
   w.xproj = (float*)take((size_t)((B + 127) / 128 * 128) * T * 4 * H * sizeof(float));  // xT layout pads B to 128
+  w.xproj1 = (h->layers >= 2) ? (float*)take((size_t)((B + 127) / 128 * 128) * T * 4 * H * sizeof(float)) : nullptr;
+  w.c1 = (float*)take((size_t)B * H * sizeof(float));
   w.hseq[0] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
   w.hseq[1] = (__nv_bfloat16*)take((size_t)B * T * H * 2);
   w.hbuf[0] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.hbuf[1] = (__nv_bfloat16*)take((size_t)B * H * 2);
   w.c = (float*)take((size_t)B * H * sizeof(float));
   w.hlast = (__nv_bfloat16*)take((size_t)B * H * 2);
-  w.counters = (unsigned int*)take(kCounterBytes);  // per-CTA step flags of the persistent recurrences
+  w.counters = (unsigned int*)take(2 * kCounterBytes);  // per-CTA step flags of the persistent recurrences (two layers in flight)
   w.total = off;
   return w;
 }
@@ -333,9 +346,10 @@ static int run_pair_cfg(tc::LstmMaps maps, tc::PairGeom g, const __nv_bfloat16* 
 
 static int run_pair(const tc::LstmMaps& maps, const __nv_bfloat16* w_hh, const float4* xT, int64_t Bp,
                     __nv_bfloat16* hseq, const int32_t* lengths, int64_t Bc, int64_t T, int H, unsigned int* counters,
-                    cudaStream_t st, __nv_bfloat16* gates_out, float* c_out) {
+                    cudaStream_t st, __nv_bfloat16* gates_out, float* c_out, int t0, int t1, float* c_state) {
   tc::PairGeom g{};
   g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64;
+  g.t0 = t0; g.t1 = t1; g.c_state = c_state;
   g.xT = xT;
   g.Bp = (int)Bp;
   g.hseq = hseq;
@@ -358,7 +372,7 @@ static int run_pair(const tc::LstmMaps& maps, const __nv_bfloat16* w_hh, const f
     const char* e = getenv("AVVAD_LSTM_EPI_WARPS");
     return e ? atoi(e) : 8;
   }();
-  const double flops = 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1);
+  const double flops = 2.0 * (double)Bc * 4.0 * H * H * (double)(t1 - (t0 > 1 ? t0 : 1));
   if (np == 64 && 4 * H / 64 <= 64) {
     if (epi_warps == 4) return run_pair_cfg<4, 64>(maps, g, w_hh, counters, st, flops);
     return run_pair_cfg<8, 64>(maps, g, w_hh, counters, st, flops);
@@ -388,10 +402,11 @@ static bool persistent_ok(const avvad_lstm* h, int64_t T) {
 }
 
 // xproj: the input projection in the xT layout (tc::launch_tma_gemm_xt) over the whole batch, Bp = B rounded up to 128
+// Steps [t0, t1) of layer l; c_state f32 [B][H] carries the cell state between chunks.
 static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, __nv_bfloat16* hseq,
                                      const int32_t* lengths, int64_t B, int64_t T, unsigned int* counters,
-                                     cudaStream_t st, bool* done, __nv_bfloat16* gates_out = nullptr,
-                                     float* c_out = nullptr) {
+                                     cudaStream_t st, bool* done, __nv_bfloat16* gates_out, float* c_out, int t0, int t1,
+                                     float* c_state) {
   *done = false;
   const int H = h->H;
   if (!persistent_ok(h, T)) return AVVAD_OK;
@@ -423,7 +438,8 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     if (rc) return rc;
     if (pair_mode() && max_ms <= 2 && Bc > 128 && n_slices % 2 == 0 && n_slices / 2 <= 32) {
       rc = run_pair(maps, h->w_hh[l], reinterpret_cast<const float4*>(xproj) + g0, Bp, hs, lengths + g0, Bc, T, H, counters, st,
-                    gates_out ? gates_out + g0 * T * 4 * H : nullptr, c_out ? c_out + g0 * T * H : nullptr);
+                    gates_out ? gates_out + g0 * T * 4 * H : nullptr, c_out ? c_out + g0 * T * H : nullptr, t0, t1,
+                    c_state + g0 * H);
       if (rc == AVVAD_OK) continue;
       if (rc != AVVAD_ERR_STATE) return rc;  // AVVAD_ERR_STATE: the pairs do not fit this device -> one CTA per block
     }
@@ -431,6 +447,7 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     g.B = (int)Bc; g.T = (int)T; g.H = H; g.KB = H / 64; g.n_slices = n_slices;
     g.xT = reinterpret_cast<const float4*>(xproj) + g0;
     g.Bp = (int)Bp;
+    g.t0 = t0; g.t1 = t1; g.c_state = c_state + g0 * H;
     g.hseq = hs;
     g.lengths = lengths + g0;
     g.counters = counters;
@@ -494,7 +511,7 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
                                              dim3(tc::kLstmThreads), args, smem, st));
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    tc::prof_end(st, tok, 2, 2.0 * (double)Bc * 4.0 * H * H * (double)(T - 1));
+    tc::prof_end(st, tok, 2, 2.0 * (double)Bc * 4.0 * H * H * (double)(t1 - (t0 > 1 ? t0 : 1)));
   }
   *done = true;
   return AVVAD_OK;
@@ -547,6 +564,70 @@ static int lstm_forward_impl(avvad_lstm* h, const void* x_bf16, const int32_t* l
   const __nv_bfloat16* layer_in = (const __nv_bfloat16*)x_bf16;
   int64_t ld_in = h->ld0;
   __nv_bfloat16* layer_out = nullptr;
+  const bool persistent = persistent_ok(h, T);
+
+  // ---- two layers, chunked: layer 1 follows layer 0 one chunk of time steps behind on a side stream.  Both recurrences
+  // are latency chains on 64 SMs each, so they overlap almost perfectly; layer 1's input projection of a chunk (a GEMM
+  // over the chunk's h0 rows) runs on the SMs layer 0 leaves free.  AVVAD_LSTM_CHUNKS = 1 runs the layers back to back.
+  static int n_chunks_pref = [] {
+    const char* e = getenv("AVVAD_LSTM_CHUNKS");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 32 ? 32 : v);
+  }();
+  int n_chunks = n_chunks_pref;
+  while (n_chunks > 1 && T / n_chunks < 16) --n_chunks;
+  if (persistent && h->layers == 2 && n_chunks > 1) {
+    int dev = 0;
+    AVVAD_CUDA(cudaGetDevice(&dev));
+    if (!h->side || h->side_device != dev) {
+      if (h->side) cudaStreamDestroy(h->side);
+      for (auto& e : h->ev_chunk) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+      }
+      if (h->ev_done) cudaEventDestroy(h->ev_done);
+      h->ev_done = nullptr;
+      AVVAD_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+      for (auto& e : h->ev_chunk) AVVAD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      AVVAD_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+      h->side_device = dev;
+    }
+    __nv_bfloat16* out0 = ws.hseq[0];
+    __nv_bfloat16* out1 = ws.hseq[1];
+    TapeView tv0{}, tv1{};
+    if (tape) {
+      tv0 = tape_layer(tape, 0, H, B, T);
+      tv1 = tape_layer(tape, 1, H, B, T);
+      out0 = tv0.hseq;
+      out1 = tv1.hseq;
+    }
+    const int64_t Bp = (B + 127) / 128 * 128;
+    int rc = tc::launch_tma_gemm_xt(layer_in, ld_in, h->w_ih[0], ld_in, B, T, T, H4, (int)ld_in, h->bias[0], ws.xproj, st);
+    if (rc) return rc;
+    const int free_sms = lstm_num_sms() - 2 * (4 * H / 128);  // SMs a layer-0 pair launch leaves to the projection GEMM
+    for (int c = 0; c < n_chunks; ++c) {
+      const int t0 = (int)(T * c / n_chunks), t1 = (int)(T * (c + 1) / n_chunks);
+      bool done = false;
+      rc = run_recurrence_persistent(h, 0, ws.xproj, out0, lengths, B, T, ws.counters, st, &done, tv0.gates, tv0.c, t0, t1,
+                                     ws.c);
+      if (rc) return rc;
+      if (!done) {
+        set_error("lstm: persistent recurrence unavailable");
+        return AVVAD_ERR_STATE;
+      }
+      AVVAD_CUDA(cudaEventRecord(h->ev_chunk[c], st));
+      AVVAD_CUDA(cudaStreamWaitEvent(h->side, h->ev_chunk[c], 0));
+      rc = tc::launch_tma_gemm_xt(out0 + (int64_t)t0 * H, H, h->w_ih[1], H, B, t1 - t0, T, H4, H, h->bias[1],
+                                  ws.xproj1 + (int64_t)t0 * H4 * Bp, h->side, free_sms > 16 ? free_sms : 0);
+      if (rc) return rc;
+      rc = run_recurrence_persistent(h, 1, ws.xproj1, out1, lengths, B, T, ws.counters + kCounterBytes / 4, h->side, &done,
+                                     tv1.gates, tv1.c, t0, t1, ws.c1);
+      if (rc) return rc;
+    }
+    AVVAD_CUDA(cudaEventRecord(h->ev_done, h->side));
+    AVVAD_CUDA(cudaStreamWaitEvent(st, h->ev_done, 0));
+    layer_out = out1;
+  } else {
   for (int l = 0; l < h->layers; ++l) {
     layer_out = ws.hseq[l & 1];
     TapeView tv{};
@@ -556,15 +637,15 @@ static int lstm_forward_impl(avvad_lstm* h, const void* x_bf16, const int32_t* l
     }
     // (1) input projection for every (b,t): xproj = X * W_ih'^T + (b_ih + b_hh)'.  The persistent recurrences read it
     // time-major and unit-major (xT[t][u][b][4]: lane = batch row -> coalesced), the per-step fallback row-major.
-    const bool persistent = persistent_ok(h, T);
-    int rc = persistent ? tc::launch_tma_gemm_xt(layer_in, ld_in, h->w_ih[l], ld_in, B, T, H4, (int)ld_in, h->bias[l],
+    int rc = persistent ? tc::launch_tma_gemm_xt(layer_in, ld_in, h->w_ih[l], ld_in, B, T, T, H4, (int)ld_in, h->bias[l],
                                                  ws.xproj, st)
                         : avvad_gemm_bf16(layer_in, ld_in, h->w_ih[l], ld_in, h->bias[l], ws.xproj, H4, 0, 0, rows, H4,
                                           ld_in, st);
     if (rc) return rc;
     // (2) recurrence: one persistent cooperative kernel per layer, or (fallback) one GEMM launch per time step
     bool done = false;
-    rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done, tv.gates, tv.c);
+    rc = run_recurrence_persistent(h, l, ws.xproj, layer_out, lengths, B, T, ws.counters, st, &done, tv.gates, tv.c, 0,
+                                   (int)T, ws.c);
     if (rc) return rc;
     if (persistent && !done) {
       set_error("lstm: persistent recurrence unavailable after the xT input projection");
@@ -596,6 +677,7 @@ static int lstm_forward_impl(avvad_lstm* h, const void* x_bf16, const int32_t* l
     }
     layer_in = layer_out;
     ld_in = H;
+  }
   }
   if (logits || post || dec) {
     float* lg = logits;

@@ -45,6 +45,10 @@ struct PairGeom {
   unsigned int* counters;  // flags [2][kLstmMaxSlices], zeroed before the launch
   __nv_bfloat16* gates_out;  // training tape (may be null)
   float* c_out;
+  // This launch runs steps [t0, t1) of the sequence (the driver splits a layer into chunks so that layer l+1 can follow
+  // layer l one chunk behind on the idle SMs): h_{t0-1} is already in hseq, the cell state crosses launches in c_state
+  int t0, t1;
+  float* c_state;  // f32 [B][H]: read when t0 > 0, written at the end
   unsigned long long* trace;  // kTrace only: [CTA][T][kPairTraceSlots] globaltimer stamps
   // diagnostics (AVVAD_LSTM_VARIANT): 2 = acquire fence behind the poll, 4 = generic->async proxy fence behind the poll
   // (neither is needed: the producers release h_t at gpu scope before their flag and TMA reads L2; measured +0.6 us
@@ -171,8 +175,9 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     // lane l watches kPerKb / 2 ... flags such that K block kb is covered by ballot bits 2kb, 2kb+1:
     //   NP = 128: one flag per lane (pairs 2kb, 2kb+1);  NP = 64: two flags per lane in one 8-byte load (pairs 4kb..4kb+3)
     uint32_t it = 0;
-    for (int t = 1; t < g.T; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
-      const unsigned int target = (unsigned int)t;
+    for (int t = (g.t0 > 1 ? g.t0 : 1); t < g.t1; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
+      // flags count the steps published in THIS launch; h_{t0-1} comes from the previous launch (target 0)
+      const unsigned int target = (unsigned int)(t - g.t0);
       bool ok = false;
       int kb = 0;
       uint32_t spins = 0;
@@ -223,9 +228,10 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_pair(NP);
       uint32_t it = 0;
-      for (int t = 1; t < g.T; ++t) {
-        const uint32_t a = (uint32_t)t & 1u;
-        if (t >= 3) mbar_wait(BAR(kBarTE + a), (uint32_t)((t - 3) >> 1) & 1u);  // step t-2 has left this accumulator
+      const int tb = g.t0 > 1 ? g.t0 : 1;  // first step with an MMA
+      for (int t = tb; t < g.t1; ++t) {
+        const uint32_t k = (uint32_t)(t - tb), a = k & 1u;
+        if (k >= 2) mbar_wait(BAR(kBarTE + a), ((k >> 1) - 1u) & 1u);  // step t-2 has left this accumulator
         tc_fence_after();
         const uint32_t d = tmem_acc + a * (uint32_t)NP;
         for (int kb = 0; kb < g.KB; ++kb, ++it) {
@@ -263,15 +269,24 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
     const int len = row_ok ? g.lengths[b] : 0;
     const int H4 = 4 * g.H;
     const bool tr = kTrace && warp == 2 && lane == 0;
+    const int unit0 = pair * kUnitsPair + chunk * kU;  // first hidden unit of this thread
     float c[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) c[u] = 0.f;
-    const int unit0 = pair * kUnitsPair + chunk * kU;  // first hidden unit of this thread
+    if (g.t0 > 0 && row_ok) {
+      const float4* cs = reinterpret_cast<const float4*>(g.c_state + (int64_t)b * g.H + unit0);
+#pragma unroll
+      for (int u = 0; u < kU / 4; ++u) {
+        const float4 v4 = cs[u];
+        c[4 * u] = v4.x; c[4 * u + 1] = v4.y; c[4 * u + 2] = v4.z; c[4 * u + 3] = v4.w;
+      }
+    }
+    const int tb = g.t0 > 1 ? g.t0 : 1;
     // lane = batch row: a warp's load of one unit's gates is one contiguous 512-byte run
     const float4* xcol = g.xT + (int64_t)unit0 * g.Bp + (row_ok ? b : 0);
     __nv_bfloat16* hrow = g.hseq + ((int64_t)(row_ok ? b : 0) * g.T) * g.H + unit0;
     const uint32_t t_row = tmem_acc + (uint32_t)(chunk * kCols) + ((uint32_t)(q * 32) << 16);
-    for (int t = 0; t < g.T; ++t) {
+    for (int t = g.t0; t < g.t1; ++t) {
       // input projection of this step: independent of h, requested before the wait on the accumulator
       float4 x[kU];
       if (g.variant & 256) {  // diagnostic: no input-projection loads (wrong results; what do these loads cost?)
@@ -282,9 +297,9 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
 #pragma unroll
         for (int u = 0; u < kU; ++u, xp += g.Bp) x[u] = __ldg(xp);
       }
-      const uint32_t a = (uint32_t)t & 1u;
+      const uint32_t k = (uint32_t)(t - tb), a = k & 1u;
       if (t > 0) {
-        mbar_wait(BAR(kBarTF + a), (uint32_t)((t - 1) >> 1) & 1u);
+        mbar_wait(BAR(kBarTF + a), (k >> 1) & 1u);
         tc_fence_after();
         if (tr) trace[t * kPairTraceSlots + 5] = globaltimer_ns();
       }
@@ -355,9 +370,15 @@ lstm_pair_kernel(const __grid_constant__ LstmMaps maps, const PairGeom g) {
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
       if (warp == 2 && lane == 0) {
         if (kTrace) trace[t * kPairTraceSlots + 9] = globaltimer_ns();
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + pair), "r"((unsigned int)(t + 1)) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + pair), "r"((unsigned int)(t + 1 - g.t0))
+                     : "memory");
         if (kTrace) trace[t * kPairTraceSlots + 10] = globaltimer_ns();
       }
+    }
+    if (row_ok && g.c_state) {  // hand the cell state to the next chunk
+      float4* cs = reinterpret_cast<float4*>(g.c_state + (int64_t)b * g.H + unit0);
+#pragma unroll
+      for (int u = 0; u < kU / 4; ++u) cs[u] = make_float4(c[4 * u], c[4 * u + 1], c[4 * u + 2], c[4 * u + 3]);
     }
   }
 

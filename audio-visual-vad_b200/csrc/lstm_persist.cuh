@@ -41,6 +41,9 @@ struct LstmGeom {
   // training only (may be null): post-activation gates (i,f,g,o per unit, bf16 [B][T][4H]) and cell states (f32 [B][T][H])
   __nv_bfloat16* gates_out;
   float* c_out;
+  // This launch runs steps [t0, t1) (see lstm_pair.cuh: chunked layers); the cell state crosses launches in c_state
+  int t0, t1;
+  float* c_state;  // f32 [B][H]: read when t0 > 0, written at the end
   int cluster;  // CTAs per cluster sharing h through TMA multicast (1 = none)
   int variant;  // tuning knobs (AVVAD_LSTM_VARIANT): 1 = every thread fences before the barrier, 2 = back-off between
                 // polls, 32 / 64 = acquire / proxy fence behind the poll
@@ -157,8 +160,8 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     if (CL > 1) {
       // cluster mode: slots are armed in K order by every member; the member that owns kb waits for its four producer
       // flags (lanes 0,1 read the two flag pairs), fences once and multicasts the box to all members
-      for (int t = 1; t < g.T; ++t) {
-        const unsigned int target = (unsigned int)t;
+      for (int t = (g.t0 > 1 ? g.t0 : 1); t < g.t1; ++t) {
+        const unsigned int target = (unsigned int)(t - g.t0);
         for (int kb = 0; kb < g.KB; ++kb, ++it) {
           const int s = it % kLstmStages;
           mbar_wait(BAR(kLstmStages + s), ((it / kLstmStages) & 1u) ^ 1u);
@@ -187,8 +190,9 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     // lane l watches the flags of slices 2l and 2l+1; K block kb is produced by slices 4kb .. 4kb+3 = lanes 2kb, 2kb+1
     const int f0 = 2 * lane, f1 = 2 * lane + 1;
     const unsigned long long* fpair = reinterpret_cast<const unsigned long long*>(flags + f0);  // both flags in one load
-    for (int t = 1; t < g.T; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
-      const unsigned int target = (unsigned int)t;
+    for (int t = (g.t0 > 1 ? g.t0 : 1); t < g.t1; ++t) {  // step 0 has h_{-1} = 0: no operand to fetch
+      // flags count the steps published in THIS launch; h_{t0-1} comes from the previous launch (target 0)
+      const unsigned int target = (unsigned int)(t - g.t0);
       bool ok = false;
       int kb = 0;
       uint32_t spins = 0;
@@ -233,9 +237,10 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     mbar_wait(BAR(kBarW), 0);
     tc_fence_after();
     uint32_t it = 0;
-    for (int t = 1; t < g.T; ++t) {
-      const uint32_t acc = (uint32_t)t & 1u;
-      if (t >= 3) mbar_wait(BAR(kBarTE + acc), (uint32_t)((t - 3) >> 1) & 1u);  // step t-2 has left this accumulator
+    const int tb = g.t0 > 1 ? g.t0 : 1;  // first step with an MMA
+    for (int t = tb; t < g.t1; ++t) {
+      const uint32_t k = (uint32_t)(t - tb), acc = k & 1u;
+      if (k >= 2) mbar_wait(BAR(kBarTE + acc), ((k >> 1) - 1u) & 1u);  // step t-2 has left this accumulator
       tc_fence_after();
       const uint32_t d = tmem_acc + acc * 64u;
       for (int kb = 0; kb < g.KB; ++kb, ++it) {
@@ -270,10 +275,16 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
     float c[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) c[u] = 0.f;
+    if (g.t0 > 0 && row_ok) {
+      const float4* cs = reinterpret_cast<const float4*>(g.c_state + (int64_t)b * g.H + ns * 16 + half * 8);
+      const float4 c0 = cs[0], c1 = cs[1];
+      c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    }
+    const int tb = g.t0 > 1 ? g.t0 : 1;
     // lane = batch row: a warp's load of one unit's gates is one contiguous 512-byte run
     const float4* xcol = g.xT + (int64_t)(ns * 16 + half * 8) * g.Bp + (row_ok ? b : 0);
     __nv_bfloat16* hrow = g.hseq + ((int64_t)(row_ok ? b : 0) * g.T) * g.H + ns * 16 + half * 8;
-    for (int t = 0; t < g.T; ++t) {
+    for (int t = g.t0; t < g.t1; ++t) {
       // input projection of this step: independent of h, requested before the wait on the accumulator
       float4 x[8];
       if (row_ok) {
@@ -283,8 +294,8 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
       }
       uint32_t v[32];
       if (t > 0) {
-        const uint32_t acc = (uint32_t)t & 1u;
-        mbar_wait(BAR(kBarT + acc), (uint32_t)((t - 1) >> 1) & 1u);
+        const uint32_t k = (uint32_t)(t - tb), acc = k & 1u;
+        mbar_wait(BAR(kBarT + acc), (k >> 1) & 1u);
         tc_fence_after();
         tmem_ld32(tmem_acc + acc * 64u + (uint32_t)(half * 32) + ((uint32_t)(q * 32) << 16), v);
         tmem_ld_wait();
@@ -344,16 +355,21 @@ lstm_persist_kernel(const __grid_constant__ LstmMaps maps, const LstmGeom g) {
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2 && lane == 0)
-          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + ns), "r"((unsigned int)(t + 1)) : "memory");
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + ns), "r"((unsigned int)(t + 1 - g.t0)) : "memory");
       } else {
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2 && lane == 0) {
-          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + ns), "r"((unsigned int)(t + 1)) : "memory");
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + ns), "r"((unsigned int)(t + 1 - g.t0)) : "memory");
         }
         // (variant bit 4: hold the other warps until the flag is out, so that MEMBAR.GPU does not wait behind the next
         // step's input-projection reads.  Measured without instrumentation: 7.6 ms with, 7.4-7.5 ms without -> off.)
         if (g.variant & 16) asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+    }
+    if (row_ok && g.c_state) {  // hand the cell state to the next chunk
+      float4* cs = reinterpret_cast<float4*>(g.c_state + (int64_t)b * g.H + ns * 16 + half * 8);
+      cs[0] = make_float4(c[0], c[1], c[2], c[3]);
+      cs[1] = make_float4(c[4], c[5], c[6], c[7]);
     }
   }
 

@@ -534,13 +534,112 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     AVVAD_LAUNCHED();
   }
 
-  const float* dY = dY_head;  // null (y_dim == 1): the top layer takes dl * w_head on the fly
-  float* dX_out = dY_head ? dYb : dYa;
-  for (int l = layers - 1; l >= 0; --l) {
+  // ---- parameter gradients of layer l from its complete gate gradients dGl [BT][4H]; optionally dX = dGl * W_ih'
+  auto weight_grads = [&](int l, const __nv_bfloat16* dGl, float* dx_dst) -> int {
     TapeView tv = tape_layer(tape, l, H, B, T);
     const int64_t ld_in = (l == 0) ? ld0 : H;
     const int I = (l == 0) ? input_size : H;
     const __nv_bfloat16* Xin = (l == 0) ? (const __nv_bfloat16*)x_bf16 : tape_layer(tape, l - 1, H, B, T).hseq;
+    // db (= db_ih = db_hh)
+    bias_grad_partial_kernel<<<dim3(H4 / 256, kBiasChunks), 256, 0, st>>>(dGl, BT, H4, dWp);  // dWp is free here
+    AVVAD_LAUNCHED();
+    bias_grad_final_kernel<<<(unsigned)ceil_div(H4, 256), 256, 0, st>>>(dWp, H, db[l]);
+    AVVAD_LAUNCHED();
+    // dG^T [4H][BTp]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H4, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(dGl, BT, H4, H4, BTp, 0, (int)T, dGT);
+      AVVAD_LAUNCHED();
+    }
+    // dW_ih' = dG^T * X  -> [4H][ld_in]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(ld_in, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(Xin, BT, (int)ld_in, ld_in, BTp, 0, (int)T, XT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dWp;
+      ep.ldc = ld_in;
+      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, (int)ld_in, (int)BTp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * I, 256), 256, 0, st>>>(dWp, H, I, (int)ld_in, dW_ih[l]);
+      AVVAD_LAUNCHED();
+    }
+    // dW_hh' = dG^T * H_prev -> [4H][H]
+    {
+      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H, 32));
+      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(tv.hseq, BT, H, H, BTp, 1, (int)T, XT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dWp;
+      ep.ldc = H;
+      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, H, (int)BTp, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(dWp, H, H, H, dW_hh[l]);
+      AVVAD_LAUNCHED();
+    }
+    if (dx_dst) {
+      transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * ld_in, 256), 256, 0, st>>>(w_ih[l], H4, (int)ld_in,
+                                                                                       (int)ld_in, WT);
+      AVVAD_LAUNCHED();
+      tc::EpiParams ep{};
+      ep.C = dx_dst;
+      ep.ldc = (l == 0) ? I : ld_in;
+      // l == 0: only the first I (un-padded) columns are written (N guard in the epilogue)
+      int rc = tc::gemm_dispatch(dGl, H4, WT, H4, BT, (l == 0) ? I : (int)ld_in, H4, ep, tc::EPI_F32, 0, st);
+      if (rc) return rc;
+    }
+    return AVVAD_OK;
+  };
+
+  if (bptt_wavefront(layers, B)) {
+    // ---- both layers as one wavefront: T + 1 (cell, GEMM) pairs instead of 2T (see lstm_bwd_cell_wf_kernel)
+    __nv_bfloat16* dG0 = (__nv_bfloat16*)take((size_t)BT * H4 * 2);
+    __nv_bfloat16* Abuf = (__nv_bfloat16*)take((size_t)128 * 8 * H * 2);
+    __nv_bfloat16* Wcat = (__nv_bfloat16*)take((size_t)2 * H * 8 * H * 2);
+    float* Cpart = (float*)take((size_t)kBpttSplit * 128 * 2 * H * 4);
+    float* dc2 = (float*)take((size_t)2 * B * H * 4);
+    TapeView t1 = tape_layer(tape, 1, H, B, T), t0 = tape_layer(tape, 0, H, B, T);
+    lstm_wf_pack_w_kernel<<<(unsigned)ceil_div((int64_t)2 * H * 8 * H, 256), 256, 0, st>>>(w_hh[1], w_ih[1], w_hh[0], H,
+                                                                                          Wcat);
+    AVVAD_LAUNCHED();
+    AVVAD_CUDA(cudaMemsetAsync(dc2, 0, (size_t)2 * B * H * 4, st));
+    AVVAD_CUDA(cudaMemsetAsync(Abuf, 0, (size_t)128 * 8 * H * 2, st));  // rows 2B..127 of the MMA block stay zero
+    const int64_t cstride = 2 * B * 2 * H;
+    auto wf_gemm = [&](cudaStream_t s2) -> int {
+      tc::EpiParams ep{};
+      ep.C = Cpart;
+      ep.ldc = 2 * H;
+      return tc::launch_tma_gemm(Abuf, 8 * H, Wcat, 8 * H, 2 * B, 2 * H, 8 * H, ep, tc::EPI_F32, 64, s2, kBpttSplit,
+                                 cstride);
+    };
+    auto run_wf = [&](cudaStream_t s2) -> int {
+      for (int s = 0; s <= (int)T; ++s) {
+        lstm_bwd_cell_wf_kernel<<<dim3((unsigned)ceil_div(B * H, 256), 2), 256, 0, s2>>>(
+            t1.gates, t1.c, t0.gates, t0.c, dY_head, dl_step, head_w32, Cpart, kBpttSplit, dc2, len_st, (int)B, (int)T, H,
+            s, dG, dG0, Abuf);
+        AVVAD_LAUNCHED();
+        if (s < (int)T) {
+          int rc = wf_gemm(s2);
+          if (rc) return rc;
+        }
+      }
+      return AVVAD_OK;
+    };
+    const std::vector<uintptr_t> key = {(uintptr_t)t1.gates, (uintptr_t)t1.c, (uintptr_t)t0.gates, (uintptr_t)t0.c,
+                                        (uintptr_t)dY_head, (uintptr_t)dl_step, (uintptr_t)head_w32, (uintptr_t)Cpart,
+                                        (uintptr_t)dc2, (uintptr_t)len_st, (uintptr_t)dG, (uintptr_t)dG0,
+                                        (uintptr_t)Abuf, (uintptr_t)Wcat, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H};
+    int rc = run_captured(use_graph ? cache : nullptr, 2, key, [&]() -> int { return wf_gemm(st); }, run_wf, st);
+    if (rc) return rc;
+    rc = weight_grads(1, dG, nullptr);
+    if (rc) return rc;
+    return weight_grads(0, dG0, dx);
+  }
+
+  const float* dY = dY_head;  // null (y_dim == 1): the top layer takes dl * w_head on the fly
+  float* dX_out = dY_head ? dYb : dYa;
+  for (int l = layers - 1; l >= 0; --l) {
+    TapeView tv = tape_layer(tape, l, H, B, T);
 
     // W_hh'^T [H][4H] for the recurrent gradient GEMM
     transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_hh[l], H4, H, H, WT);
@@ -578,55 +677,10 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
       int rc = run_captured(use_graph ? cache : nullptr, l, key, warm, run_steps, st);
       if (rc) return rc;
     }
-    // db (= db_ih = db_hh)
-    bias_grad_partial_kernel<<<dim3(H4 / 256, kBiasChunks), 256, 0, st>>>(dG, BT, H4, dWp);  // dWp is free here
-    AVVAD_LAUNCHED();
-    bias_grad_final_kernel<<<(unsigned)ceil_div(H4, 256), 256, 0, st>>>(dWp, H, db[l]);
-    AVVAD_LAUNCHED();
-    // dG^T [4H][BTp]
-    {
-      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H4, 32));
-      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(dG, BT, H4, H4, BTp, 0, (int)T, dGT);
-      AVVAD_LAUNCHED();
-    }
-    // dW_ih' = dG^T * X  -> [4H][ld_in]
-    {
-      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(ld_in, 32));
-      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(Xin, BT, (int)ld_in, ld_in, BTp, 0, (int)T, XT);
-      AVVAD_LAUNCHED();
-      tc::EpiParams ep{};
-      ep.C = dWp;
-      ep.ldc = ld_in;
-      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, (int)ld_in, (int)BTp, ep, tc::EPI_F32, 0, st);
-      if (rc) return rc;
-      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * I, 256), 256, 0, st>>>(dWp, H, I, (int)ld_in, dW_ih[l]);
-      AVVAD_LAUNCHED();
-    }
-    // dW_hh' = dG^T * H_prev -> [4H][H]
-    {
-      dim3 grid((unsigned)ceil_div(BTp, 32), (unsigned)ceil_div(H, 32));
-      transpose_bf16_kernel<<<grid, dim3(32, 8), 0, st>>>(tv.hseq, BT, H, H, BTp, 1, (int)T, XT);
-      AVVAD_LAUNCHED();
-      tc::EpiParams ep{};
-      ep.C = dWp;
-      ep.ldc = H;
-      int rc = tc::gemm_dispatch(dGT, BTp, XT, BTp, H4, H, (int)BTp, ep, tc::EPI_F32, 0, st);
-      if (rc) return rc;
-      deinterleave_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(dWp, H, H, H, dW_hh[l]);
-      AVVAD_LAUNCHED();
-    }
-    // dX = dG * W_ih'  (needed below the top layer, or when the caller wants input gradients)
+    float* dst = (l == 0) ? dx : dX_out;
+    int rc = weight_grads(l, dG, (l > 0 || dx) ? dst : nullptr);
+    if (rc) return rc;
     if (l > 0 || dx) {
-      transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * ld_in, 256), 256, 0, st>>>(w_ih[l], H4, (int)ld_in,
-                                                                                       (int)ld_in, WT);
-      AVVAD_LAUNCHED();
-      float* dst = (l == 0) ? dx : dX_out;
-      tc::EpiParams ep{};
-      ep.C = dst;
-      ep.ldc = (l == 0) ? I : ld_in;
-      // l == 0: only the first I (un-padded) columns are written (N guard in the epilogue)
-      int rc = tc::gemm_dispatch(dG, H4, WT, H4, BT, (l == 0) ? I : (int)ld_in, H4, ep, tc::EPI_F32, 0, st);
-      if (rc) return rc;
       dY = dst;
       dX_out = (dX_out == dYa) ? dYb : dYa;
     }
