@@ -83,11 +83,13 @@ static bool plan(int H, int Cin, int Cout, SlabPlan* out) {
   return true;
 }
 
-// AVVAD_SLAB_CG2=0: layer1 stays on single CTAs (default: CTA pairs, see conv_slab.cuh)
+// AVVAD_SLAB_CG2=1: layer1 on CTA pairs (conv_slab.cuh).  Off by default: measured 29.12 ms of convolutions per step with
+// pairs against 29.04 ms without on the same box -- layer1 is bound by its 30 GB of activation traffic per step (64 %
+// of the HBM peak at the same time as 58 % tensor-pipe activity), not by the operand reads of its N = 64 MMAs.
 static int slab_pair() {
   static int v = [] {
     const char* e = getenv("AVVAD_SLAB_CG2");
-    return (e && atoi(e) == 0) ? 0 : 1;
+    return (e && atoi(e) == 1) ? 1 : 0;
   }();
   return v;
 }

@@ -131,9 +131,11 @@ static int pair128_mode() {
   }();
   return v;
 }
-static bool use_pair(int bn, int ksplit, int epi_mode) {
+// kb = K blocks of the launch: short K loops (layer2's first convolution, K = 576) measured slower on pairs of
+// two-block CTAs (307 us against 266 us per 20,288-frame pass), so N = 128 pairs need at least 16 K blocks
+static bool use_pair(int bn, int ksplit, int epi_mode, int kb) {
   if (!pair_enabled() || ksplit > 1 || epi_mode == EPI_LSTM) return false;
-  return bn == 256 || (bn == 128 && pair128_mode() != 0);
+  return bn == 256 || (bn == 128 && pair128_mode() != 0 && kb >= 16);
 }
 
 template <int BN, int KE = 64, int MB = 1, int CG = 1>
@@ -210,7 +212,7 @@ static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiPara
         const char* e = getenv("AVVAD_MB");
         return (e && atoi(e) == 1) ? 0 : 1;
       }();
-      if (use_pair(128, g.ksplit, epi_mode)) {
+      if (g.pair) {
         if (pair128_mode() == 1) return launch_bn<128, 64, 1, 2>(maps, g, ep, epi_mode, cat, flops, st);
         return launch_bn<128, 64, 2, 2>(maps, g, ep, epi_mode, cat, flops, st);
       }
@@ -218,7 +220,7 @@ static int dispatch(int bn, const TmaMaps& maps, const TmaGeom& g, const EpiPara
       return launch_bn<128>(maps, g, ep, epi_mode, cat, flops, st);
     }
     case 256:
-      if (use_pair(256, g.ksplit, epi_mode)) return launch_bn<256, 64, 1, 2>(maps, g, ep, epi_mode, cat, flops, st);
+      if (g.pair) return launch_bn<256, 64, 1, 2>(maps, g, ep, epi_mode, cat, flops, st);
       return launch_bn<256>(maps, g, ep, epi_mode, cat, flops, st);
   }
   set_error("bad BN");
@@ -316,7 +318,8 @@ int launch_tma_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiPa
     }
   }
   const int K = R * S * Cin + (dual ? second->Cin2 : 0);
-  const bool pair = KE == 64 && use_pair(bn, 1, EPI_BF16);
+  const bool pair = KE == 64 && use_pair(bn, 1, EPI_BF16, g.KB + g.KB2);
+  g.pair = pair ? 1 : 0;
   int rc = encode2(&maps.b, w, (uint64_t)K, (uint64_t)Cout, (uint64_t)K * 2, (uint32_t)KE, (uint32_t)(pair ? bn / 2 : bn),
                    KE == 16);
   if (rc) return rc;
@@ -360,8 +363,8 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
   maps.a[1] = maps.a[0];
   maps.a2[0] = maps.a2[1] = maps.a[0];
   g.bytesA[0] = g.bytesA[1] = 128u * 128u;
-  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64,
-               (uint32_t)(use_pair(bn, ksplit, epi_mode) ? bn / 2 : bn));
+  g.pair = use_pair(bn, ksplit, epi_mode, g.KB) ? 1 : 0;
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)(g.pair ? bn / 2 : bn));
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * 128u;
   const double flops = 2.0 * (double)M * N * K;
@@ -403,8 +406,8 @@ int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16*
   maps.a[1] = maps.a[0];
   maps.a2[0] = maps.a2[1] = maps.a[0];
   g.bytesA[0] = g.bytesA[1] = 128u * 128u;
-  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64,
-               (uint32_t)(use_pair(bn, 1, EPI_XT) ? bn / 2 : bn));
+  g.pair = use_pair(bn, 1, EPI_XT, g.KB) ? 1 : 0;
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)(g.pair ? bn / 2 : bn));
   if (rc) return rc;
   g.bytesB = (uint32_t)bn * 128u;
   EpiParams ep{};

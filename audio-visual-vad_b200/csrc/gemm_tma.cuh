@@ -58,6 +58,7 @@ struct TmaGeom {
   // time-major GEMM over a [B][T][K] operand (launch_tma_gemm_xt): row index m = t * tm_bp + b, tm_bp = B rounded up to
   // 128, so that a 128-row tile is 128 consecutive batch items of ONE time step (0 = plain row order)
   int tm_bp, tm_b;
+  int pair;      // host only: launch on CTA pairs (decided where the weight map is encoded: its box is BN/2 rows then)
   int grid_cap;  // host only: at most this many CTAs (0 = all SMs) -- for launches that share the GPU with a recurrence
   uint32_t bytesA[2];   // TMA box bytes per phase
   uint32_t bytesB;

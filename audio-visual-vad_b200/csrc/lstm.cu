@@ -333,7 +333,14 @@ static int run_pair_cfg(tc::LstmMaps maps, tc::PairGeom g, const __nv_bfloat16* 
     cudaGetLastError();
     return AVVAD_ERR_STATE;
   }
-  cfg.numAttrs = 2;
+  // The cooperative attribute guarantees that all CTAs are co-resident (they wait for each other).  ncu cannot launch
+  // cooperative cluster kernels ("LaunchFailed"): AVVAD_LSTM_COOP=0 drops the attribute for profiling runs, where the
+  // serialised kernel has the GPU to itself anyway.
+  static int coop_attr = [] {
+    const char* e = getenv("AVVAD_LSTM_COOP");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  cfg.numAttrs = coop_attr ? 2 : 1;
   AVVAD_CUDA(cudaMemsetAsync(counters, 0, kCounterBytes, st));
   void* args[2] = {(void*)&maps, (void*)&g};
   void* tok = nullptr;

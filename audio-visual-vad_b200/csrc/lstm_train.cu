@@ -75,10 +75,11 @@ __global__ void lstm_bwd_cell_wf_kernel(const __nv_bfloat16* __restrict__ gates1
   if (idx >= B * H) return;
   const int b = idx / H, u = idx - b * H;
   const int t = (layer == 1) ? (T - 1 - s) : (T - s);
-  const int64_t K2 = 8ll * H;              // row length of Abuf
-  uint2* aout = reinterpret_cast<uint2*>(Abuf + (int64_t)(layer == 1 ? b : B + b) * K2 + (layer == 1 ? 0 : 4 * H) + 4 * u);
+  const int64_t K2 = 8ll * H;              // row length of Abuf (null: the GEMMs read dG1 / dG0 directly)
+  uint2* aout = Abuf ? reinterpret_cast<uint2*>(Abuf + (int64_t)(layer == 1 ? b : B + b) * K2 + (layer == 1 ? 0 : 4 * H) + 4 * u)
+                     : nullptr;
   if (t < 0 || t > T - 1) {                // this layer is idle in iteration s: contribute nothing to the GEMM
-    *aout = make_uint2(0u, 0u);
+    if (aout) *aout = make_uint2(0u, 0u);
     return;
   }
   const int64_t row = (int64_t)b * T + t;
@@ -87,7 +88,7 @@ __global__ void lstm_bwd_cell_wf_kernel(const __nv_bfloat16* __restrict__ gates1
   float* dc = dc2 + (int64_t)layer * B * H;
   if (t >= lengths[b]) {
     *gout = make_uint2(0u, 0u);
-    *aout = make_uint2(0u, 0u);
+    if (aout) *aout = make_uint2(0u, 0u);
     dc[idx] = 0.f;
     return;
   }
@@ -121,7 +122,7 @@ __global__ void lstm_bwd_cell_wf_kernel(const __nv_bfloat16* __restrict__ gates1
   o.x = pack_bf16x2(d_i, d_f);
   o.y = pack_bf16x2(d_g, d_o);
   *gout = o;
-  *aout = o;
+  if (aout) *aout = o;
 }
 // Wcat [2H][8H] from the gate-interleaved packed weights W' [4H][ld] (see the layout above)
 __global__ void lstm_wf_pack_w_kernel(const __nv_bfloat16* __restrict__ whh1, const __nv_bfloat16* __restrict__ wih1,
@@ -313,11 +314,16 @@ struct BpttGraphCache {
   // Capture happens on a private stream: PyTorch's default current stream is the legacy NULL stream, which cannot be
   // captured; the instantiated graph is then launched into the caller's stream (any stream, the NULL stream included).
   cudaStream_t cap_stream = nullptr;
+  cudaStream_t cap_stream2 = nullptr;  // forked branch of the two-GEMM wavefront
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int cap_device = -1;
   ~BpttGraphCache() {
     for (auto e : exec)
       if (e) cudaGraphExecDestroy(e);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (cap_stream2) cudaStreamDestroy(cap_stream2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
   }
 };
 BpttGraphCache* bptt_cache_create() { return new BpttGraphCache(); }
@@ -332,13 +338,21 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        float* dx, cudaStream_t st, BpttGraphCache* cache);
 constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
 
-// The wavefront needs both layers' gate gradients at once and fits one 128-row MMA block: 2 layers, 2B <= 128.
-static bool bptt_wavefront(int layers, int64_t B) {
+// Two layers run as a wavefront (layer 0 one step behind layer 1): T + 1 dependent iterations instead of 2T.
+//   mode 1 (2B <= 128): one block-structured GEMM per iteration (both layers in one 128-row MMA block)
+//   mode 2 (larger batches): two GEMMs per iteration on forked streams of the captured graph
+// AVVAD_BPTT_WAVEFRONT=0 disables both, =1 (default) allows only mode 1, =2 both.  Measured (B200, T = 317, backward of
+// 2 x LSTM-1024): mode 1 7.9 -> 6.1 ms at B = 32 and 8.8 -> 7.3 ms at B = 64; mode 2 with the GEMMs in order 9.9 -> 9.5 ms
+// at B = 96, 11.9 -> 11.8 at B = 128 and 15.5 -> 19.0 ms at B = 256 (the merged cell kernel and the extra N = H columns
+// cost more than the shorter chain saves once a step fills the GPU), forked onto two captured streams 43.7 ms.
+static int bptt_wavefront(int layers, int64_t B) {
   static int v = [] {
     const char* e = getenv("AVVAD_BPTT_WAVEFRONT");
-    return (e && atoi(e) == 0) ? 0 : 1;
+    return e ? atoi(e) : 1;
   }();
-  return v != 0 && layers == 2 && 2 * B <= 128;
+  if (v == 0 || layers != 2) return 0;
+  if (2 * B <= 128) return 1;
+  return v >= 2 ? 2 : 0;
 }
 
 static bool bptt_graph_enabled() {
@@ -384,10 +398,11 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
   s += align_up((size_t)B * 4, 256) + align_up((size_t)BT * 4, 256);  // stable copies of lengths / dlogits (y_dim == 1)
   if (bptt_wavefront(layers, B)) {
+    const int64_t rows = 2 * B > 128 ? 2 * B : 128;
     s += align_up((size_t)BT * 4 * H * 2, 256);                        // second dG (both layers are live at once)
-    s += align_up((size_t)128 * 8 * H * 2, 256);                       // A [2B <= 128][8H]
+    s += align_up((size_t)128 * 8 * H * 2, 256);                       // A [2B <= 128][8H] (mode 1)
     s += align_up((size_t)2 * H * 8 * H * 2, 256);                     // Wcat [2H][8H]
-    s += align_up((size_t)kBpttSplit * 128 * 2 * H * 4, 256);          // C partials [split][2B][2H]
+    s += align_up((size_t)kBpttSplit * rows * 2 * H * 4, 256);         // C partials [split][2B][2H]
     s += align_up((size_t)2 * B * H * 4, 256);                         // dc of both layers
   }
   if (y_dim > 1) {
@@ -411,8 +426,15 @@ static int run_captured(BpttGraphCache* cache, int slot, std::vector<uintptr_t> 
   key.push_back((uintptr_t)dev);
   if (!cache->cap_stream || cache->cap_device != dev) {
     if (cache->cap_stream) cudaStreamDestroy(cache->cap_stream);
-    cache->cap_stream = nullptr;
+    if (cache->cap_stream2) cudaStreamDestroy(cache->cap_stream2);
+    if (cache->ev_fork) cudaEventDestroy(cache->ev_fork);
+    if (cache->ev_join) cudaEventDestroy(cache->ev_join);
+    cache->cap_stream = cache->cap_stream2 = nullptr;
+    cache->ev_fork = cache->ev_join = nullptr;
     AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream, cudaStreamNonBlocking));
+    AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream2, cudaStreamNonBlocking));
+    AVVAD_CUDA(cudaEventCreateWithFlags(&cache->ev_fork, cudaEventDisableTiming));
+    AVVAD_CUDA(cudaEventCreateWithFlags(&cache->ev_join, cudaEventDisableTiming));
     cache->cap_device = dev;
   }
   if (!cache->exec[slot] || cache->key[slot] != key) {
@@ -591,20 +613,23 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     return AVVAD_OK;
   };
 
-  if (bptt_wavefront(layers, B)) {
-    // ---- both layers as one wavefront: T + 1 (cell, GEMM) pairs instead of 2T (see lstm_bwd_cell_wf_kernel)
+  const int wf_mode = bptt_wavefront(layers, B);
+  if (wf_mode) {
+    // ---- both layers as one wavefront: T + 1 dependent iterations instead of 2T (see lstm_bwd_cell_wf_kernel)
+    const int64_t rows = 2 * B > 128 ? 2 * B : 128;
     __nv_bfloat16* dG0 = (__nv_bfloat16*)take((size_t)BT * H4 * 2);
     __nv_bfloat16* Abuf = (__nv_bfloat16*)take((size_t)128 * 8 * H * 2);
     __nv_bfloat16* Wcat = (__nv_bfloat16*)take((size_t)2 * H * 8 * H * 2);
-    float* Cpart = (float*)take((size_t)kBpttSplit * 128 * 2 * H * 4);
+    float* Cpart = (float*)take((size_t)kBpttSplit * rows * 2 * H * 4);
     float* dc2 = (float*)take((size_t)2 * B * H * 4);
     TapeView t1 = tape_layer(tape, 1, H, B, T), t0 = tape_layer(tape, 0, H, B, T);
     lstm_wf_pack_w_kernel<<<(unsigned)ceil_div((int64_t)2 * H * 8 * H, 256), 256, 0, st>>>(w_hh[1], w_ih[1], w_hh[0], H,
                                                                                           Wcat);
     AVVAD_LAUNCHED();
     AVVAD_CUDA(cudaMemsetAsync(dc2, 0, (size_t)2 * B * H * 4, st));
-    AVVAD_CUDA(cudaMemsetAsync(Abuf, 0, (size_t)128 * 8 * H * 2, st));  // rows 2B..127 of the MMA block stay zero
+    if (wf_mode == 1) AVVAD_CUDA(cudaMemsetAsync(Abuf, 0, (size_t)128 * 8 * H * 2, st));  // rows 2B..127 stay zero
     const int64_t cstride = 2 * B * 2 * H;
+    // mode 1: C [2B][2H] = A [2B][8H] * Wcat^T
     auto wf_gemm = [&](cudaStream_t s2) -> int {
       tc::EpiParams ep{};
       ep.C = Cpart;
@@ -612,15 +637,58 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
       return tc::launch_tma_gemm(Abuf, 8 * H, Wcat, 8 * H, 2 * B, 2 * H, 8 * H, ep, tc::EPI_F32, 64, s2, kBpttSplit,
                                  cstride);
     };
-    auto run_wf = [&](cudaStream_t s2) -> int {
+    // mode 2: rows 0..B-1 = dG1_t [B][4H] * [W_hh1^T | W_ih1^T] (N = 2H); rows B..2B-1 = dG0_t * W_hh0^T (N = H); both
+    // read the first / second 4H columns of Wcat's rows
+    auto gemm_l1 = [&](int t, cudaStream_t s2) -> int {
+      tc::EpiParams ep{};
+      ep.C = Cpart;
+      ep.ldc = 2 * H;
+      return tc::launch_tma_gemm(dG + (int64_t)t * H4, (int64_t)T * H4, Wcat, 8 * H, B, 2 * H, H4, ep, tc::EPI_F32, 64, s2,
+                                 kBpttSplit, cstride);
+    };
+    auto gemm_l0 = [&](int t, cudaStream_t s2) -> int {
+      tc::EpiParams ep{};
+      ep.C = Cpart + B * 2 * H;
+      ep.ldc = 2 * H;
+      return tc::launch_tma_gemm(dG0 + (int64_t)t * H4, (int64_t)T * H4, Wcat + H4, 8 * H, B, H, H4, ep, tc::EPI_F32, 64, s2,
+                                 kBpttSplit, cstride);
+    };
+    auto run_wf = [&](cudaStream_t s1) -> int {
+      // Forking the layer-0 GEMM onto a second captured stream was measured 3-4x SLOWER than issuing both GEMMs in order
+      // (B = 256: 43.7 ms against 15.5 ms for the layer-by-layer loop): AVVAD_BPTT_FORK=1 keeps the experiment reachable.
+      static int fork_pref = [] {
+        const char* e = getenv("AVVAD_BPTT_FORK");
+        return e ? atoi(e) : 0;
+      }();
+      cudaStream_t s2 = (use_graph && wf_mode == 2 && fork_pref) ? cache->cap_stream2 : nullptr;
       for (int s = 0; s <= (int)T; ++s) {
-        lstm_bwd_cell_wf_kernel<<<dim3((unsigned)ceil_div(B * H, 256), 2), 256, 0, s2>>>(
+        lstm_bwd_cell_wf_kernel<<<dim3((unsigned)ceil_div(B * H, 256), 2), 256, 0, s1>>>(
             t1.gates, t1.c, t0.gates, t0.c, dY_head, dl_step, head_w32, Cpart, kBpttSplit, dc2, len_st, (int)B, (int)T, H,
-            s, dG, dG0, Abuf);
+            s, dG, dG0, wf_mode == 1 ? Abuf : nullptr);
         AVVAD_LAUNCHED();
-        if (s < (int)T) {
-          int rc = wf_gemm(s2);
+        if (s >= (int)T) break;
+        if (wf_mode == 1) {
+          int rc = wf_gemm(s1);
           if (rc) return rc;
+          continue;
+        }
+        const int tl1 = (int)T - 1 - s, tl0 = (int)T - s;   // the steps the layers just finished
+        const bool need0 = s >= 1 && tl0 > 0;               // layer 0's recurrent term for step tl0 - 1
+        if (need0 && s2) {
+          AVVAD_CUDA(cudaEventRecord(cache->ev_fork, s1));
+          AVVAD_CUDA(cudaStreamWaitEvent(s2, cache->ev_fork, 0));
+          int rc = gemm_l0(tl0, s2);
+          if (rc) return rc;
+          AVVAD_CUDA(cudaEventRecord(cache->ev_join, s2));
+        }
+        int rc = gemm_l1(tl1, s1);
+        if (rc) return rc;
+        if (need0) {
+          if (s2) AVVAD_CUDA(cudaStreamWaitEvent(s1, cache->ev_join, 0));
+          else {
+            rc = gemm_l0(tl0, s1);
+            if (rc) return rc;
+          }
         }
       }
       return AVVAD_OK;
@@ -628,8 +696,14 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     const std::vector<uintptr_t> key = {(uintptr_t)t1.gates, (uintptr_t)t1.c, (uintptr_t)t0.gates, (uintptr_t)t0.c,
                                         (uintptr_t)dY_head, (uintptr_t)dl_step, (uintptr_t)head_w32, (uintptr_t)Cpart,
                                         (uintptr_t)dc2, (uintptr_t)len_st, (uintptr_t)dG, (uintptr_t)dG0,
-                                        (uintptr_t)Abuf, (uintptr_t)Wcat, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H};
-    int rc = run_captured(use_graph ? cache : nullptr, 2, key, [&]() -> int { return wf_gemm(st); }, run_wf, st);
+                                        (uintptr_t)Abuf, (uintptr_t)Wcat, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H,
+                                        (uintptr_t)wf_mode};
+    auto warm = [&]() -> int {
+      if (wf_mode == 1) return wf_gemm(st);
+      int rc = gemm_l1(0, st);
+      return rc ? rc : gemm_l0(0, st);
+    };
+    int rc = run_captured(use_graph ? cache : nullptr, 2, key, warm, run_wf, st);
     if (rc) return rc;
     rc = weight_grads(1, dG, nullptr);
     if (rc) return rc;

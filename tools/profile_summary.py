@@ -37,9 +37,14 @@ def launch_table():
     return "\n".join(lines), agg, tot
 
 
-def ncu_table():
-    raw = subprocess.run(["ncu", "-i", f"{OUT}/prof_full.ncu-rep", "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
+def ncu_table(name="prof_full"):
+    # tools/gpu/profile.sh exports the raw page on the GPU box (the .ncu-rep itself may exceed gpurun's 64 MiB limit)
+    import os
+    if os.path.exists(f"{OUT}/{name}_raw.csv") and os.path.getsize(f"{OUT}/{name}_raw.csv") > 0:
+        raw = open(f"{OUT}/{name}_raw.csv").read()
+    else:
+        raw = subprocess.run(["ncu", "-i", f"{OUT}/{name}.ncu-rep", "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
     r = list(csv.reader(io.StringIO(raw)))
     h = r[0]
     idx = {n: i for i, n in enumerate(h)}
@@ -86,6 +91,13 @@ def main():
     print(lt)
     print("\n## `ncu --set full --clock-control none --import-source on`, one pass of 20,288 frames (`--batch 64`)\n")
     print(nt)
+    try:
+        pt = ncu_table("prof_lstm_pair")[0]
+        print("\n## `ncu --set full` of the CTA-pair LSTM recurrence at the benchmark batch (B = 256, T = 317, one launch per layer: "
+              "`AVVAD_LSTM_CHUNKS=1 AVVAD_LSTM_COOP=0`)\n")
+        print(pt)
+    except Exception as e:  # capture absent
+        print(f"\n(no LSTM pair capture: {e})")
     # machine-readable copy for bench.py's roofline.traffic (profiles/*traffic*.json, newest file wins)
     if len(sys.argv) > 1:
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
