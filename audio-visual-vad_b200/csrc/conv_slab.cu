@@ -6,6 +6,7 @@
 
 #include "conv_slab.cuh"
 #include "conv_slab2.cuh"
+#include "conv_block.cuh"
 
 namespace avvad {
 namespace tc {
@@ -239,6 +240,67 @@ int launch_slab_conv(const __nv_bfloat16* in, const __nv_bfloat16* w, const EpiP
   if (p.resident && p.mb == 3) return launch_k<64, true, 3>(maps, g, ep, p.smem, flops, st);
   if (p.resident) return launch_k<64, true>(maps, g, ep, p.smem, flops, st);
   return launch_k<64, false>(maps, g, ep, p.smem, flops, st);
+}
+
+// ---- fused BasicBlock of layer1 (conv_block.cuh); AVVAD_BLOCK17=0 keeps the two slab convolutions
+bool block17_enabled() {
+  static int v = [] {
+    const char* e = getenv("AVVAD_BLOCK17");
+    return (e && atoi(e) == 0) ? 0 : 1;
+  }();
+  return v != 0 && tma_available();
+}
+
+int launch_block17(const __nv_bfloat16* x, const __nv_bfloat16* wa, const float* bias_a, const __nv_bfloat16* wb,
+                   const float* bias_b, __nv_bfloat16* z, int64_t n, cudaStream_t st) {
+  AVVAD_CHECK_ARG(x && wa && wb && z && n > 0, "block17: bad argument");
+  AVVAD_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 31) == 0, "block17: 32-byte aligned activations");
+  static PerDeviceOnce once;
+  AVVAD_CUDA(once.run([] {
+    return cudaFuncSetAttribute(tc_block17_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem);
+  }));
+  static int num_sms = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  BlockMaps maps;
+  const uint32_t box[4] = {64, (uint32_t)kBlkWp, (uint32_t)kBlkWp, 1};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  int rc = encode_act_map(&maps.x, x, 64, kBlkW, kBlkW, n, box, estr);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps.wa, wa, 576, 64, 32);
+  if (rc) return rc;
+  rc = encode_weight_map(&maps.wb, wb, 576, 64, 32);
+  if (rc) return rc;
+  BlockGeom g{};
+  g.n_frames = n;
+  const int64_t want = (n + 1) / 2, pairs = num_sms / 2;
+  g.n_pairs = (int)(want < pairs ? want : pairs);
+  g.bias_a = bias_a;
+  g.bias_b = bias_b;
+  g.x = x;
+  g.z = z;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2u * (unsigned)g.n_pairs);
+  cfg.blockDim = dim3(kBlkThreads);
+  cfg.dynamicSmemBytes = kBlkSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  cfg.attrs = la;
+  cfg.numAttrs = 1;
+  void* tok = nullptr;
+  prof_begin(st, &tok);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, tc_block17_kernel, maps, g);
+  if (le != cudaSuccess) {
+    set_error(std::string("block17 launch failed: ") + cudaGetErrorString(le));
+    return AVVAD_ERR_CUDA;
+  }
+  AVVAD_LAUNCHED();
+  prof_end(st, tok, 0, 2.0 * 2.0 * (double)n * kBlkW * kBlkW * 64.0 * 576.0);
+  return AVVAD_OK;
 }
 
 }  // namespace tc

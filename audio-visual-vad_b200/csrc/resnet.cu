@@ -20,6 +20,15 @@
 #include "stem_s2d.cuh"
 
 namespace avvad {
+namespace tc {
+// conv_block.cuh (compiled in conv_slab.cu): fused BasicBlock of layer1
+int launch_block17(const __nv_bfloat16* x, const __nv_bfloat16* wa, const float* bias_a, const __nv_bfloat16* wb,
+                   const float* bias_b, __nv_bfloat16* z, int64_t n, cudaStream_t st);
+bool block17_enabled();
+}  // namespace tc
+}  // namespace avvad
+
+namespace avvad {
 
 struct ConvSpec {
   int cin, cout, k, stride, pad, hin, hout;
@@ -535,6 +544,16 @@ static int run_trunk_chunk(avvad_resnet18* h, const StemInput& in, int64_t n, __
         __nv_bfloat16* y0 = buf[o[0]] + f0 * kStageOut[stage];
         __nv_bfloat16* y1 = buf[o[1]] + f0 * kStageOut[stage];
         __nv_bfloat16* y2 = buf[o[2]] + f0 * kStageOut[stage];
+        if (stage == 0 && !whole && tc::block17_enabled() &&
+            ((reinterpret_cast<uintptr_t>(xin) | reinterpret_cast<uintptr_t>(y2)) & 31) == 0) {
+          // layer1: the whole BasicBlock in one kernel, conv_a's output stays in shared memory (conv_block.cuh)
+          int rcb = tc::launch_block17(xin, h->w[la], h->bias[la], h->w[lb], h->bias[lb], y2, nn, st);
+          if (rcb) return rcb;
+          cur = o[2];
+          *last = cur;
+          layer += 2;
+          continue;
+        }
         int rc = run_conv(h, la, xin, nullptr, y0, nn, 1, st);
         if (rc) return rc;
         if (upto == la) { *last = o[0]; return AVVAD_OK; }
