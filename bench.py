@@ -514,6 +514,8 @@ def run_ours(args, rank, world, local_rank):
     peak_tf, peak_hbm, peak_src = measured_peaks()
     achieved = conv_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else None
     traffic = traffic_from_profiles()
+    # layer1's two BasicBlocks are one launch each unless AVVAD_BLOCK17=0 (then two slab convolutions per block)
+    conv_launches_per_pass = 14 if os.environ.get("AVVAD_BLOCK17", "1") != "0" else 16
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -532,9 +534,11 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor",
-                     "kernel": "tcgen05 implicit-GEMM convolutions of the ResNet-18 trunk (19 layers in 16 launches per pass: "
-                               "tc_slab_kernel<64> for layer1, tc_tma_kernel<BN=128/256> TMA-box im2col for layer2-4 "
-                               "with the downsample 1x1 branches K-concatenated into conv_b)",
+                     "kernel": "tcgen05 implicit-GEMM convolutions of the ResNet-18 trunk on CTA pairs (cta_group::2, "
+                               f"M = 256): 19 layers in {conv_launches_per_pass} launches per pass -- "
+                               "tc_block17_kernel (fused BasicBlock, conv_a's output stays in shared memory) for layer1, "
+                               "tc_tma_kernel<BN=128/256, CG=2> TMA-box im2col for layer2-4 with the downsample 1x1 "
+                               "branches K-concatenated into conv_b",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
                      # dram__bytes_read.sum + dram__bytes_write.sum per conv launch from the newest committed ncu
@@ -547,11 +551,11 @@ def run_ours(args, rank, world, local_rank):
                      "algorithmic_flops_per_frame": 2 * CONV_MAC_PER_FRAME,
                      "peak_source": peak_src,
                      # one CUDA-event record brackets the four convolution launches of a ResNet stage and trunk pass
-                     "launches": int(conv_n) * 4, "event_records": int(conv_n),
+                     "launches": int(conv_n) * conv_launches_per_pass // 4, "event_records": int(conv_n),
                      "kernel_ms_per_step": conv_ms / args.steps,
                      "share_of_step": conv_ms / ms if ms > 0 else None,
-                     "flops_per_launch_avg": conv_flops / (conv_n * 4) if conv_n else None,
-                     "ms_per_launch_avg": conv_ms / (conv_n * 4) if conv_n else None},
+                     "flops_per_launch_avg": conv_flops / (conv_n * conv_launches_per_pass / 4) if conv_n else None,
+                     "ms_per_launch_avg": conv_ms / (conv_n * conv_launches_per_pass / 4) if conv_n else None},
         "variants": {"dedup_video": {
             "value": frames_per_step * args.steps / (dedup_ms / 1e3), "unit": "frames/s",
             "ms_per_step": dedup_ms / args.steps,

@@ -8,7 +8,7 @@ AVVAD_LSTM_COOP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-contr
     --log-file gpurun_out/launches.csv python bench.py --ncu --warmup 0 > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit=$?"
 AVVAD_LSTM_COOP=0 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"tc_slab_kernel|tc_tma_kernel|stem_s2d|lstm_persist|lstm_pair|mcb_row|frontend_kernel" -c 30 \
+    -k regex:"tc_slab_kernel|tc_block17|tc_tma_kernel|stem_s2d|lstm_persist|lstm_pair|mcb_row|frontend_kernel" -c 30 \
     -o gpurun_out/prof_full -f python bench.py --ncu --warmup 0 --batch 64 > gpurun_out/ncu_full.log 2>&1
 echo "full capture exit=$?"
 # the CTA-pair LSTM recurrence at the benchmark batch (one launch per layer: AVVAD_LSTM_CHUNKS=1)

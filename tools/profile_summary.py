@@ -69,7 +69,7 @@ def ncu_table(name="prof_full"):
         t_us = t * 1000 if units["gpu__time_duration.sum"] == "ms" else (t / 1000 if units["gpu__time_duration.sum"] == "ns" else t)
         rd = mb(g("dram__bytes_read.sum"), units["dram__bytes_read.sum"])
         wr = mb(g("dram__bytes_write.sum"), units["dram__bytes_write.sum"])
-        if "tc_slab" in name or ("tc_tma" in name and rd > 100):  # the xproj GEMMs read only 50 MB
+        if "tc_slab" in name or "tc_block17" in name or ("tc_tma" in name and rd > 100):  # the xproj GEMMs read only 50 MB
             conv_rd += rd
             conv_wr += wr
             n_conv += 1
@@ -103,11 +103,12 @@ def main():
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
         frames = 64 * 317
         # algorithmic operand bytes of the same launches: bf16 activations in + out per conv layer (NHWC), weights once
-        layers = [(17, 64, 64, 17)] * 4 + [(17, 64, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9),
+        # layer1: two fused BasicBlocks (x in, z out; conv_a's output never leaves the SM, the residual is x itself)
+        layers = [(17, 64, 64, 17)] * 2 + [(17, 64, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9), (9, 128, 128, 9),
                   (9, 128, 256, 5), (5, 256, 256, 5), (5, 256, 256, 5), (5, 256, 256, 5),
                   (5, 256, 512, 3), (3, 512, 512, 3), (3, 512, 512, 3), (3, 512, 512, 3)]
         alg = sum(frames * 2 * (hi * hi * ci + ho * ho * co) for hi, ci, co, ho in layers)
-        alg += frames * 2 * (17 * 17 * 64 * 2 + 9 * 9 * 128 * 2 + 5 * 5 * 256 * 2 + 3 * 3 * 512 * 2)  # residual reads + ds inputs
+        alg += frames * 2 * (9 * 9 * 128 * 2 + 5 * 5 * 256 * 2 + 3 * 3 * 512 * 2)  # residual reads + ds inputs of layer2-4
         json.dump({"commit": commit, "source": "ncu --set full --clock-control none, bench.py --ncu --warmup 0 --batch 64 "
                                                "(one 20,288-frame trunk pass), dram__bytes_read.sum + dram__bytes_write.sum",
                    "conv_launches": n, "conv_dram_bytes_per_launch": (rd + wr) * 1e6 / max(n, 1),
