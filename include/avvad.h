@@ -333,7 +333,10 @@ size_t avvad_lstm_workspace_bytes(const avvad_lstm* h, int64_t B, int64_t T);
  * lengths : i32 [B] device
  * logits  : f32 [B][T][y_dim]; rows t >= len_b receive the head bias (zeros through the Linear)
  * post, dec : optional f32 / i32 [B][T][y_dim]: sigmoid(logit) and (sigmoid > 0.5)
- * last_logits: optional f32 [B][y_dim]: head applied to the last valid step (return_last=True) */
+ * last_logits: optional f32 [B][y_dim]: head applied to the last valid step (return_last=True)
+ * Streams: with two layers the call forks onto a handle-owned side stream (layer 1 follows layer 0 one chunk of time
+ * steps behind) and joins `stream` again before it returns; every output is ordered on `stream` as usual.  One call at a
+ * time per handle (the handle owns the side stream, its events and the flag area inside `workspace`). */
 int avvad_lstm_forward(avvad_lstm* h, const void* x_bf16, const int32_t* lengths, int64_t B, int64_t T,
                        void* workspace, size_t workspace_bytes, float* logits, float* post,
                        int32_t* dec, float* last_logits, void* stream);
