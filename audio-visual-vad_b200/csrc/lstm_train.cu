@@ -336,7 +336,19 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
                        int64_t B, int64_t T, void* tape, const float* dlogits, void* workspace, size_t workspace_bytes,
                        float* const* dW_ih, float* const* dW_hh, float* const* db, float* dW_head, float* db_head,
                        float* dx, cudaStream_t st, BpttGraphCache* cache);
-constexpr int kBpttSplit = 4;  // split-K factor of the per-step recurrent-gradient GEMM
+// split-K factor of the per-step recurrent-gradient GEMMs (AVVAD_BPTT_SPLIT = 1..8, buffers are sized for 8)
+constexpr int kBpttSplitMax = 8;
+// Default: 8 for per-rank batches up to 64 rows (one m-tile: 256 CTAs instead of 128, backward 6.0 -> 5.4 ms at B = 32),
+// 4 above (B = 256: 16.7 ms with 4, 17.0 with 8, 19.7 with 2).
+static int bptt_split(int64_t B) {
+  static int v = [] {
+    const char* e = getenv("AVVAD_BPTT_SPLIT");
+    int x = e ? atoi(e) : 0;
+    return x < 0 ? 0 : (x > kBpttSplitMax ? kBpttSplitMax : x);
+  }();
+  return v ? v : (B <= 64 ? 8 : 4);
+}
+#define kBpttSplit (bptt_split(B))
 
 // Two layers run as a wavefront (layer 0 one step behind layer 1): T + 1 dependent iterations instead of 2T.
 //   mode 1 (2B <= 128): one block-structured GEMM per iteration (both layers in one 128-row MMA block)
@@ -392,7 +404,7 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
   s += align_up((size_t)4 * H * BTp * 2, 256);         // dG^T
   s += align_up((size_t)maxI * BTp * 2, 256);          // X^T / H_prev^T
   s += 2 * align_up((size_t)BT * maxI * 4, 256);       // dY ping-pong (f32)
-  s += (kBpttSplit + 1) * align_up((size_t)B * H * 4, 256);  // dh_rec split-K partials, dc
+  s += (kBpttSplitMax + 1) * align_up((size_t)B * H * 4, 256);  // dh_rec split-K partials, dc
   s += align_up((size_t)4 * H * maxI * 4, 256);        // dW' (interleaved)
   s += align_up((size_t)maxI * 4 * H * 2, 256);        // W^T (bf16)
   s += align_up((size_t)1024 * (H + 1) * 4, 256);      // head partials
@@ -402,7 +414,7 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
     s += align_up((size_t)BT * 4 * H * 2, 256);                        // second dG (both layers are live at once)
     s += align_up((size_t)128 * 8 * H * 2, 256);                       // A [2B <= 128][8H] (mode 1)
     s += align_up((size_t)2 * H * 8 * H * 2, 256);                     // Wcat [2H][8H]
-    s += align_up((size_t)kBpttSplit * rows * 2 * H * 4, 256);         // C partials [split][2B][2H]
+    s += align_up((size_t)kBpttSplitMax * rows * 2 * H * 4, 256);         // C partials [split][2B][2H]
     s += align_up((size_t)2 * B * H * 4, 256);                         // dc of both layers
   }
   if (y_dim > 1) {
@@ -492,7 +504,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   __nv_bfloat16* XT = (__nv_bfloat16*)take((size_t)maxI * BTp * 2);
   float* dYa = (float*)take((size_t)BT * maxI * 4);
   float* dYb = (float*)take((size_t)BT * maxI * 4);
-  float* dh_rec = (float*)take((size_t)kBpttSplit * align_up((size_t)B * H * 4, 256));
+  float* dh_rec = (float*)take((size_t)kBpttSplitMax * align_up((size_t)B * H * 4, 256));
   float* dc = (float*)take((size_t)B * H * 4);
   float* dWp = (float*)take((size_t)H4 * maxI * 4);
   __nv_bfloat16* WT = (__nv_bfloat16*)take((size_t)maxI * H4 * 2);
@@ -620,7 +632,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     __nv_bfloat16* dG0 = (__nv_bfloat16*)take((size_t)BT * H4 * 2);
     __nv_bfloat16* Abuf = (__nv_bfloat16*)take((size_t)128 * 8 * H * 2);
     __nv_bfloat16* Wcat = (__nv_bfloat16*)take((size_t)2 * H * 8 * H * 2);
-    float* Cpart = (float*)take((size_t)kBpttSplit * rows * 2 * H * 4);
+    float* Cpart = (float*)take((size_t)kBpttSplitMax * rows * 2 * H * 4);
     float* dc2 = (float*)take((size_t)2 * B * H * 4);
     TapeView t1 = tape_layer(tape, 1, H, B, T), t0 = tape_layer(tape, 0, H, B, T);
     lstm_wf_pack_w_kernel<<<(unsigned)ceil_div((int64_t)2 * H * 8 * H, 256), 256, 0, st>>>(w_hh[1], w_ih[1], w_hh[0], H,
