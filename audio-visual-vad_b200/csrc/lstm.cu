@@ -443,7 +443,13 @@ static int run_recurrence_persistent(avvad_lstm* h, int l, const float* xproj, _
     const uint32_t wbox[2] = {64, 64};
     rc = tc::encode_tiled_bf16(&maps.w, h->w_hh[l], 2, wd, wstr, wbox);
     if (rc) return rc;
-    if (pair_mode() && max_ms <= 2 && Bc > 128 && n_slices % 2 == 0 && n_slices / 2 <= 32) {
+    // AVVAD_LSTM_PAIR_MIN: smallest batch (of a group) the pair kernel takes.  With <= 128 rows the second CTA of every
+    // pair works on zero-filled rows, but the kernel is still the faster one (full-sector h stores, half the CTAs polling)
+    static int pair_min = [] {
+      const char* e = getenv("AVVAD_LSTM_PAIR_MIN");
+      return e ? atoi(e) : 1;
+    }();
+    if (pair_mode() && max_ms <= 2 && Bc >= pair_min && n_slices % 2 == 0 && n_slices / 2 <= 32) {
       rc = run_pair(maps, h->w_hh[l], reinterpret_cast<const float4*>(xproj) + g0, Bp, hs, lengths + g0, Bc, T, H, counters, st,
                     gates_out ? gates_out + g0 * T * 4 * H : nullptr, c_out ? c_out + g0 * T * H : nullptr, t0, t1,
                     c_state + g0 * H);

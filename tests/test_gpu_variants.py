@@ -42,7 +42,7 @@ def test_trunk_pairs_and_fused_block_bit_identical(tmp_path, n_frames, full):
 @pytest.mark.parametrize("B,T,full", [(256, 80, True), (200, 48, False), (300, 40, False), (64, 80, False)])
 def test_lstm_pair_and_chunked_layers_bit_identical(tmp_path, B, T, full):
     """2 x LSTM-1024 + head, ragged lengths: one CTA per block and the layers back to back vs CTA pairs (B > 128) and the
-    chunk-interleaved layers; B = 300 spans two batch groups, B = 64 keeps the single-CTA kernel but chunks it."""
+    chunk-interleaved layers; B = 300 spans two batch groups, B = 64 leaves the second CTA of every pair without rows."""
     plain = _run("lstm_ab.py", [B, T], {"AVVAD_LSTM_PAIR": "0", "AVVAD_LSTM_CHUNKS": "1"}, str(tmp_path / "plain.pt"))
     fast = _run("lstm_ab.py", [B, T], {}, str(tmp_path / "fast.pt"))
     assert torch.isfinite(plain).all() and plain.std() > 1e-3
