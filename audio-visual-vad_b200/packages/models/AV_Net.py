@@ -82,17 +82,13 @@ class DeepVAD_AV(nn.Module):
         # eval() forward is inference only (detached logits, folded BN); the autograd path is the train() step
         need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in all_parameters(self))
         trunk_trainable = need_grad and any(p.requires_grad for p in all_parameters(self.features))
-        if trunk_trainable and self.use_mcb:
-            raise NotImplementedError("MCB fusion with a trainable ResNet trunk: the gradient of the fusion w.r.t. the "
-                                      "video features is not wired into this module (scripts/train_AV_net.py:241-245 "
-                                      "freezes 'features'; the concat fusion and DeepVAD_video train the trunk)")
 
         # ---- video branch: batch-statistics BN while the module is in train() (train_AV_net.py:253), folded BN in eval()
         def trunk(feat_bf16=None, col_off=0, want_f32=True):
             if self.training:
                 bns = trunk_bn_modules(self.features)
                 running = [(b.running_mean, b.running_var) for b in bns]
-                if trunk_trainable:   # concat fusion only: features with a tape, packed into the operand below
+                if trunk_trainable:   # features with a tape (differentiable), packed into the operand below
                     out = TrunkFunction.apply(eng["trunk"], vid, running, *trunk_params(self.features))
                 else:
                     out = eng["trunk"].forward_train(vid, running, feat_bf16=feat_bf16, col_off=col_off,
@@ -106,7 +102,20 @@ class DeepVAD_AV(nn.Module):
         proxy = None
         if self.use_mcb:
             feat = trunk()
-            if self.training:
+            if trunk_trainable:
+                # Trainable trunk under MCB (train_AV_net.py with 'features' left trainable): the fusion of AV_Net.py:111-121
+                # as differentiable pieces -- the stand-alone CompactBilinearPooling module (device sketch + FFT kernels
+                # forward and backward, avvad_mcb_raw_*), signed sqrt, whole-tensor L2 norm (detached, as in the
+                # reference) and the module's BatchNorm1d as PyTorch device ops -- so that the LSTM's input gradient
+                # reaches the device ResNet backward.  The frozen-trunk case below stays on the fused MCB kernels.
+                m_raw = self.mcb(aud.view(batch, frames, -1), feat.view(batch, frames, -1))
+                y = torch.sign(m_raw) * torch.sqrt(torch.abs(m_raw) + self.eps)
+                y = y / torch.norm(y, p=2).detach()
+                y = self.mcb_bn(y.view(M, 1024)).view(batch, frames, 1024)
+                bump_generation(self.mcb_bn.running_mean, self.mcb_bn.running_var)
+                E.pack_rows_bf16(y.detach().reshape(M, 1024).contiguous(), xv, 0, False)
+                proxy = y
+            elif self.training:
                 proxy = McbBnFunction.apply(eng["mcb"], aud, feat, x, self.mcb_bn, self.mcb_bn.weight, self.mcb_bn.bias)
                 self.mcb_bn.num_batches_tracked += 1
                 bump_generation(self.mcb_bn.running_mean, self.mcb_bn.running_var)

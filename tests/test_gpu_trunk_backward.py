@@ -173,10 +173,49 @@ def test_av_concat_trainable_trunk_gradients_match_oracle_autograd():
     bad = {k: e for k, e in rep.items() if not k.startswith("features.") and e > 4e-2}
     assert not bad, bad
     assert max(e for k, e in rep.items() if k.startswith("features.")) < 0.5   # see the video-net test above
-    # MCB fusion + trainable trunk is the one combination without a backward path: it must say so
-    m2 = DeepVAD_AV(2, 1024, 1, use_mcb=True).cuda().train()
-    with pytest.raises(NotImplementedError):
-        m2(a.cuda(), v.cuda(), lens)
+
+
+def test_av_mcb_trainable_trunk_gradients_match_oracle_autograd():
+    """train_AV_net.py with `features` left trainable under MCB fusion: the LSTM's input gradient goes back through
+    BatchNorm1d (batch statistics), the detached whole-tensor L2 norm, the signed sqrt and the compact-bilinear pooling
+    (device FFT kernels) into the device ResNet backward."""
+    from packages.models.AV_Net import DeepVAD_AV
+    B, T = 3, 8
+    lens = [8, 5, 8]
+    g = torch.Generator().manual_seed(24)
+    a = torch.randn(B, T, 513, generator=g)
+    v = torch.randn(B, T, 67, 67, generator=g)
+    y = (torch.rand(B, T, 1, generator=g) > 0.5).float()
+    sd = synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 64, "strong")
+    _, ref_loss, p = _oracle_step(
+        lambda q: om.deepvad_av_forward(a, v, lens, q, use_mcb=True, training=True, quant=om.bf16_ste), sd, lens, y,
+        trainable=lambda k: not k.startswith("bn.") and not k.startswith("mcb."))
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    logits = m(a.cuda(), v.cuda(), torch.tensor(lens).cuda())
+    loss, _, dl = E.batch_bce(logits, y.cuda(), lens, 1e-8, want_grad=True)
+    assert abs(loss.item() - ref_loss) < 2e-2 * max(1.0, abs(ref_loss))
+    logits.backward(dl)
+    named = [(k, q) for k, q in m.named_parameters() if not k.startswith("bn.")]
+    rep = _report(named, p)
+    print("AV MCB, trainable trunk:", {k: round(e, 4) for k, e in rep.items() if "conv" in k or "lstm" in k or "mcb" in k})
+    assert any(k.startswith("features.") for k in rep) and "mcb_bn.weight" in rep
+    bad = {k: e for k, e in rep.items() if not k.startswith("features.") and e > 6e-2}
+    assert not bad, bad
+    # trunk: direction and size (the end-to-end trunk gradient is chaotic w.r.t. bf16 rounding, see the video-net test)
+    cos = {}
+    for k, q in named:
+        if k.startswith("features.") and k.endswith("weight") and ("conv" in k or k == "features.0.weight"):
+            r = p[k].grad
+            cos[k] = float((q.grad.cpu().flatten() @ r.flatten()) / (q.grad.cpu().norm() * r.norm() + 1e-30))
+    print("trunk gradient cosines:", {k: round(c, 3) for k, c in cos.items()})
+    # Direction only.  The fusion's signed square root has the derivative 0.5 / sqrt(|m| + 1e-8): pooled values near zero
+    # dominate the gradient w.r.t. the video features and differ between two FFT implementations by more than their
+    # own size, so even the last trunk layer agrees with the oracle's autograd to a cosine of ~0.7 only (measured
+    # 0.69-0.71 over all convolutions); the pooling backward itself is pinned against the reference's hand-written
+    # backward in tests/test_gpu_strong.py, BatchNorm1d / sqrt / norm are PyTorch ops.
+    assert min(cos.values()) > 0.5, cos
 
 
 def test_video_net_optimiser_steps_with_torch_adam_reduce_the_loss():
