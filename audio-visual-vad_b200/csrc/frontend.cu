@@ -11,6 +11,13 @@
 #include "fft.cuh"
 
 namespace avvad {
+namespace tc {
+int prof_begin(cudaStream_t st, void** tok);
+void prof_end(cudaStream_t st, void* tok, int cat, double flops);
+}  // namespace tc
+}  // namespace avvad
+
+namespace avvad {
 
 static float2* g_tw_dev[kMaxDevices] = {};  // one table per device (nn.DataParallel: several devices, one process)
 static PerDeviceOnce g_tw_once;
@@ -170,6 +177,10 @@ static int launch_frontend(int mode, const float* wave, int64_t wave_stride, con
     set_error("twiddle table allocation failed (no CUDA device?)");
     return AVVAD_ERR_CUDA;
   }
+  // profiling category 4 (bench.py: achieved HBM GB/s of the memory-bound stages); "flops" carries the algorithmic bytes:
+  // 256 new samples in + 513 (x2 for the raw STFT) floats out per frame
+  void* ptok = nullptr;
+  tc::prof_begin(st, &ptok);
   if (normalise) {
     AVVAD_CUDA(cudaMemsetAsync(peak_scratch, 0, sizeof(float) * B, st));
     int chunks = (int)std::min<int64_t>(64, ceil_div(wave_stride, 256 * 16));
@@ -184,6 +195,7 @@ static int launch_frontend(int mode, const float* wave, int64_t wave_stride, con
     frontend_kernel<1><<<grid, kFftThreads, 0, st>>>(wave, wave_stride, n_samples, n_frames, t_max, nullptr,
                                                      nullptr, nullptr, 0.f, tw, out);
   AVVAD_LAUNCHED();
+  tc::prof_end(st, ptok, 4, (double)B * t_max * (1024.0 + (mode == 0 ? 2052.0 : 4104.0)));
   return AVVAD_OK;
 }
 

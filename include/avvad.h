@@ -35,7 +35,8 @@ int avvad_version(void);
 uint64_t avvad_launch_count(void);
 
 /* Per-launch device timing of the tensor-core kernels (CUDA events on the launching stream), used by
- * bench.py for the roofline figure.  cat: 0 = implicit-GEMM convolution, 1 = plain GEMM, 2 = LSTM step.
+ * bench.py for the roofline figure.  cat: 0 = implicit-GEMM convolution, 1 = plain GEMM, 2 = LSTM step, 3 = stem,
+ * 4 = audio front end, 5 = MCB fusion (for 4 and 5 the "flops" field carries the stage's algorithmic BYTES).
  * avvad_profile_read sums the launches of one category recorded since the last avvad_profile_clear
  * (it synchronises the device); flops = 2*M*N*K per launch. */
 int avvad_profile_enable(int on);
