@@ -62,7 +62,7 @@ tc_slab_kernel(const __grid_constant__ SlabMaps maps, const SlabGeom g, const Ep
   // pair mode: cluster c works on tiles 2c + rank, 2c + rank + 2 * clusters, ...; a tile index past the end is harmless
   // (TMA zero-fills frames >= n_frames, the epilogue stores nothing for them)
   const int64_t tile0 = (CG == 2) ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
-  const int64_t tile_step = (CG == 2) ? (int64_t)gridDim.x : (int64_t)gridDim.x;
+  const int64_t tile_step = (int64_t)gridDim.x;  // pair mode: 2 tiles per cluster and round
   const int64_t tile_end = (CG == 2) ? ((g.total_tiles + 1) / 2) * 2 : g.total_tiles;
   const int KB = 9 * g.cpb;
   const int nB = RESIDENT_B ? KB : g.b_stages;

@@ -348,7 +348,6 @@ static int bptt_split(int64_t B) {
   }();
   return v ? v : (B <= 64 ? 8 : 4);
 }
-#define kBpttSplit (bptt_split(B))
 
 // Two layers run as a wavefront (layer 0 one step behind layer 1): T + 1 dependent iterations instead of 2T.
 //   mode 1 (2B <= 128): one block-structured GEMM per iteration (both layers in one 128-row MMA block)
@@ -516,6 +515,7 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
   if (y_dim == 1) AVVAD_CUDA(cudaMemcpyAsync(dl_st, dlogits, (size_t)BT * 4, cudaMemcpyDeviceToDevice, st));
   const float* dl_step = (y_dim == 1) ? dl_st : dlogits;
   const bool use_graph = cache && bptt_graph_enabled() && !tc::profiling_on() && !sync_debug();
+  const int kBpttSplit = bptt_split(B);  // split-K factor of the per-step GEMMs of this call
 
   const float* dY_head = nullptr;  // y_dim > 1: gradient of the top layer's output through the head (GEMM)
   if (y_dim == 1) {
