@@ -417,5 +417,52 @@ int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16*
   return dispatch(bn, maps, g, ep, EPI_XT, 1, 2.0 * (double)B * T * N * K, st);
 }
 
+int launch_tma_gemm_tm(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
+                       int64_t T_stride, int N, int K, float* C, int64_t ldc, cudaStream_t st, int grid_cap) {
+  AVVAD_CHECK_ARG(K % 64 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 32 == 0, "TMA gemm (tm): K % 64, lda % 8, N % 32");
+  const int64_t Bp = (B + 127) / 128 * 128;
+  AVVAD_CHECK_ARG(T * Bp < (1ll << 31), "TMA gemm (xT): T * B too large");
+  TmaGeom g{};
+  g.ksplit = 1;
+  g.kb_split = K / 64;
+  g.mode = 0;
+  g.KB = K / 64;
+  g.cpb = g.KB;
+  g.S = 1;
+  g.n_frames = T * Bp;
+  g.N = N;
+  g.tm_bp = (int)Bp;
+  g.tm_b = (int)B;
+  g.tm_tstride = T_stride;
+  g.grid_cap = grid_cap;
+  const int bn = pick_bn(N, 0);
+  g.n_tiles = (N + bn - 1) / bn;
+  g.m_tiles = T * Bp / BM;
+  g.total_tiles = g.m_tiles * g.n_tiles;
+  g.tiles0 = g.m_tiles;
+  g.hb[0] = g.hb[1] = 1; g.nb[0] = g.nb[1] = 1; g.F[0] = g.F[1] = 1; g.OW = 128; g.OH = 1;
+  TmaMaps maps;
+  // (k, b, t): a box is 128 batch items of one time step; rows past B are zero-filled by the hardware
+  const uint64_t dims[4] = {(uint64_t)K, (uint64_t)B, (uint64_t)T, 1};
+  const uint64_t strides[3] = {(uint64_t)lda * 2 * (uint64_t)T_stride, (uint64_t)lda * 2,
+                               (uint64_t)lda * 2 * (uint64_t)T_stride * (uint64_t)B};
+  const uint32_t box[4] = {64, 128, 1, 1};
+  const uint32_t estr[4] = {1, 1, 1, 1};
+  int rc = encode4(&maps.a[0], X, dims, strides, box, estr);
+  if (rc) return rc;
+  maps.a[1] = maps.a[0];
+  maps.a2[0] = maps.a2[1] = maps.a[0];
+  g.bytesA[0] = g.bytesA[1] = 128u * 128u;
+  g.pair = use_pair(bn, 1, EPI_F32, g.KB) ? 1 : 0;
+  rc = encode2(&maps.b, Wt, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, (uint32_t)(g.pair ? bn / 2 : bn));
+  if (rc) return rc;
+  g.bytesB = (uint32_t)bn * 128u;
+  EpiParams ep{};
+  ep.C = C;
+  ep.ldc = ldc;
+  return dispatch(bn, maps, g, ep, EPI_F32, 1, 2.0 * (double)B * T * N * K, st);
+}
+
+
 }  // namespace tc
 }  // namespace avvad

@@ -58,6 +58,7 @@ struct TmaGeom {
   // time-major GEMM over a [B][T][K] operand (launch_tma_gemm_xt): row index m = t * tm_bp + b, tm_bp = B rounded up to
   // 128, so that a 128-row tile is 128 consecutive batch items of ONE time step (0 = plain row order)
   int tm_bp, tm_b;
+  int64_t tm_tstride;   // time-major GEMM with a row-major output (launch_tma_gemm_tm): output row = b * tm_tstride + t
   int pair;      // host only: launch on CTA pairs (decided where the weight map is encoded: its box is BN/2 rows then)
   int grid_cap;  // host only: at most this many CTAs (0 = all SMs) -- for launches that share the GPU with a recurrence
   uint32_t bytesA[2];   // TMA box bytes per phase
@@ -456,6 +457,10 @@ tc_tma_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ TmaG
         if (!t.valid) continue;
         if (g.mode == 0) {
           if (t.n0 + r < g.n_frames) m[mb] = t.n0 + r;
+          if (g.tm_bp && epi_mode != EPI_XT && m[mb] >= 0) {  // time-major tile order, row-major [b][t] output
+            const int64_t tt = m[mb] / g.tm_bp, bb = m[mb] - tt * g.tm_bp;
+            m[mb] = (bb < g.tm_b) ? bb * g.tm_tstride + tt : -1;
+          }
         } else {
           const int hb = g.hb[t.phase];
           const int per_frame = hb * g.OW;
@@ -685,6 +690,10 @@ int launch_tma_gemm(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* Wt
 // X points at time step 0 of the chunk, T = steps in the chunk, T_stride = steps between consecutive batch items of X
 int launch_tma_gemm_xt(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
                        int64_t T_stride, int N, int K, const float* bias, float* xT, cudaStream_t st, int grid_cap = 0);
+// Same time-major traversal of a [B][T][lda] operand chunk, fp32 output in the operand's own row order:
+// C[(b * T_stride + t) * ldc + n] = sum_k X[b][t][k] * Wt[n][k]   (the input gradient of an LSTM layer for a chunk of steps)
+int launch_tma_gemm_tm(const __nv_bfloat16* X, int64_t lda, const __nv_bfloat16* Wt, int64_t ldw, int64_t B, int64_t T,
+                       int64_t T_stride, int N, int K, float* C, int64_t ldc, cudaStream_t st, int grid_cap = 0);
 
 }  // namespace tc
 }  // namespace avvad

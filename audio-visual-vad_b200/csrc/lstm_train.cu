@@ -307,10 +307,16 @@ namespace avvad {
 // captured once into a CUDA graph and replayed while every pointer baked into its kernel parameters is unchanged (the
 // key below); the per-call inputs that PyTorch re-allocates (lengths, dlogits) are first copied into the caller's
 // workspace so that a steady-state training loop always hits the cache.  AVVAD_BPTT_GRAPH=0 disables it.
+constexpr int kBpttSlots = 40;      // graphs: per layer (0, 1), wavefront (2), per (layer, chunk) of the overlapped chains
+constexpr int kBpttMaxChunks = 16;
 struct BpttGraphCache {
-  cudaGraphExec_t exec[8] = {};
-  std::vector<uintptr_t> key[8];
-  size_t nodes[8] = {};
+  cudaGraphExec_t exec[kBpttSlots] = {};
+  std::vector<uintptr_t> key[kBpttSlots];
+  size_t nodes[kBpttSlots] = {};
+  // overlapped two-layer backward: layer 0's chain runs on `side`, one chunk of time steps behind layer 1
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_chunk[kBpttMaxChunks] = {};
+  cudaEvent_t ev_side_done = nullptr;
   // Capture happens on a private stream: PyTorch's default current stream is the legacy NULL stream, which cannot be
   // captured; the instantiated graph is then launched into the caller's stream (any stream, the NULL stream included).
   cudaStream_t cap_stream = nullptr;
@@ -324,6 +330,10 @@ struct BpttGraphCache {
     if (cap_stream2) cudaStreamDestroy(cap_stream2);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+    for (auto e : ev_chunk)
+      if (e) cudaEventDestroy(e);
+    if (ev_side_done) cudaEventDestroy(ev_side_done);
   }
 };
 BpttGraphCache* bptt_cache_create() { return new BpttGraphCache(); }
@@ -416,6 +426,11 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
     s += align_up((size_t)kBpttSplitMax * rows * 2 * H * 4, 256);         // C partials [split][2B][2H]
     s += align_up((size_t)2 * B * H * 4, 256);                         // dc of both layers
   }
+  if (layers == 2 && !bptt_wavefront(layers, B)) {     // overlapped chains (see lstm_backward_impl)
+    s += align_up((size_t)BT * 4 * H * 2, 256);                        // second dG
+    s += (kBpttSplitMax + 1) * align_up((size_t)B * H * 4, 256);       // layer 0's dh_rec partials, dc
+    s += 2 * align_up((size_t)H * 4 * H * 2, 256);                     // W_hh0'^T, W_ih1'^T
+  }
   if (y_dim > 1) {
     const int64_t yp = head_pad(y_dim);
     s += align_up((size_t)BT * yp * 2, 256);           // dlogits bf16, padded columns
@@ -428,13 +443,9 @@ size_t lstm_backward_workspace(int layers, int input_size, int64_t ld0, int H, i
 // Runs `steps(stream)` -- a long chain of tiny dependent launches -- either directly (cache == nullptr) or as a CUDA graph
 // captured once on the cache's private stream and replayed while `key` (every pointer / size baked into the kernel
 // parameters) is unchanged.
-template <class Warm, class Steps>
-static int run_captured(BpttGraphCache* cache, int slot, std::vector<uintptr_t> key, Warm&& warm, Steps&& steps,
-                        cudaStream_t st) {
-  if (!cache) return steps(st);
+static int bptt_cache_streams(BpttGraphCache* cache) {
   int dev = 0;
   AVVAD_CUDA(cudaGetDevice(&dev));
-  key.push_back((uintptr_t)dev);
   if (!cache->cap_stream || cache->cap_device != dev) {
     if (cache->cap_stream) cudaStreamDestroy(cache->cap_stream);
     if (cache->cap_stream2) cudaStreamDestroy(cache->cap_stream2);
@@ -446,8 +457,32 @@ static int run_captured(BpttGraphCache* cache, int slot, std::vector<uintptr_t> 
     AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->cap_stream2, cudaStreamNonBlocking));
     AVVAD_CUDA(cudaEventCreateWithFlags(&cache->ev_fork, cudaEventDisableTiming));
     AVVAD_CUDA(cudaEventCreateWithFlags(&cache->ev_join, cudaEventDisableTiming));
+    if (cache->side) cudaStreamDestroy(cache->side);
+    cache->side = nullptr;
+    AVVAD_CUDA(cudaStreamCreateWithFlags(&cache->side, cudaStreamNonBlocking));
+    for (auto& e : cache->ev_chunk) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+      AVVAD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    if (cache->ev_side_done) cudaEventDestroy(cache->ev_side_done);
+    AVVAD_CUDA(cudaEventCreateWithFlags(&cache->ev_side_done, cudaEventDisableTiming));
     cache->cap_device = dev;
+    for (auto& e : cache->exec) {  // graphs belong to the previous device
+      if (e) cudaGraphExecDestroy(e);
+      e = nullptr;
+    }
   }
+  return AVVAD_OK;
+}
+
+template <class Warm, class Steps>
+static int run_captured(BpttGraphCache* cache, int slot, std::vector<uintptr_t> key, Warm&& warm, Steps&& steps,
+                        cudaStream_t st) {
+  if (!cache) return steps(st);
+  int rcs = bptt_cache_streams(cache);
+  if (rcs) return rcs;
+  key.push_back((uintptr_t)cache->cap_device);
   if (!cache->exec[slot] || cache->key[slot] != key) {
     if (cache->exec[slot]) {
       cudaGraphExecDestroy(cache->exec[slot]);
@@ -718,6 +753,102 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
     int rc = run_captured(use_graph ? cache : nullptr, 2, key, warm, run_wf, st);
     if (rc) return rc;
     rc = weight_grads(1, dG, nullptr);
+    if (rc) return rc;
+    return weight_grads(0, dG0, dx);
+  }
+
+  // ---- two layers, larger batches: the recurrences of both layers as chunked chains on two streams.  Layer 1 runs its
+  // steps in chunks (t descending); after each chunk the input gradient of that chunk (dY0 = dG1 * W_ih1, one time-major
+  // GEMM) and then layer 0's steps of the same chunk run on a side stream while layer 1 continues: every step is a
+  // latency-bound (cell kernel, split-K GEMM) pair, so the two chains overlap.  AVVAD_BPTT_CHUNKS=1 disables it.
+  static int chunks_pref = [] {
+    const char* e = getenv("AVVAD_BPTT_CHUNKS");
+    int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > kBpttMaxChunks ? kBpttMaxChunks : v);
+  }();
+  int n_chunks = chunks_pref;
+  while (n_chunks > 1 && T / n_chunks < 16) --n_chunks;
+  if (layers == 2 && n_chunks > 1 && cache && !tc::profiling_on() && !sync_debug()) {
+    int rcs = bptt_cache_streams(cache);
+    if (rcs) return rcs;
+    __nv_bfloat16* dG0 = (__nv_bfloat16*)take((size_t)BT * H4 * 2);
+    float* dh_rec0 = (float*)take((size_t)kBpttSplitMax * align_up((size_t)B * H * 4, 256));
+    float* dc0 = (float*)take((size_t)B * H * 4);
+    __nv_bfloat16* WT0 = (__nv_bfloat16*)take((size_t)H * H4 * 2);
+    __nv_bfloat16* WTi = (__nv_bfloat16*)take((size_t)H * H4 * 2);
+    float* dY0 = dY_head ? dYb : dYa;  // [BT][H] fp32: gradient w.r.t. layer 0's output, written chunk by chunk
+    TapeView tv1 = tape_layer(tape, 1, H, B, T), tv0 = tape_layer(tape, 0, H, B, T);
+    transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_hh[1], H4, H, H, WT);
+    AVVAD_LAUNCHED();
+    transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_hh[0], H4, H, H, WT0);
+    AVVAD_LAUNCHED();
+    transpose_w_kernel<<<(unsigned)ceil_div((int64_t)H4 * H, 256), 256, 0, st>>>(w_ih[1], H4, H, H, WTi);
+    AVVAD_LAUNCHED();
+    AVVAD_CUDA(cudaMemsetAsync(dc, 0, (size_t)B * H * 4, st));
+    AVVAD_CUDA(cudaMemsetAsync(dc0, 0, (size_t)B * H * 4, st));
+    // steps te-1 .. tb of one layer: (cell, recurrent split-K GEMM) pairs
+    auto steps_of = [&](const TapeView& tv, const float* dYl, float* dh, float* dcl, __nv_bfloat16* dGl,
+                        const __nv_bfloat16* WTl, int tb, int te, cudaStream_t s2) -> int {
+      for (int t = te - 1; t >= tb; --t) {
+        const int has_rec = (t < (int)T - 1) ? kBpttSplit : 0;
+        lstm_bwd_cell_kernel<<<(unsigned)ceil_div(B * H, 256), 256, 0, s2>>>(tv.gates, tv.c, dYl, dl_step, head_w32, dh, dcl,
+                                                                            len_st, (int)B, (int)T, H, t, has_rec, dGl);
+        AVVAD_LAUNCHED();
+        if (t > 0) {
+          tc::EpiParams ep{};
+          ep.C = dh;
+          ep.ldc = H;
+          int rc = tc::launch_tma_gemm(dGl + (int64_t)t * H4, (int64_t)T * H4, WTl, H4, B, H, H4, ep, tc::EPI_F32, 64, s2,
+                                       kBpttSplit, (int64_t)B * H);
+          if (rc) return rc;
+        }
+      }
+      return AVVAD_OK;
+    };
+    auto warm_of = [&](float* dh, const __nv_bfloat16* dGl, const __nv_bfloat16* WTl, cudaStream_t s2) -> int {
+      tc::EpiParams ep{};
+      ep.C = dh;
+      ep.ldc = H;
+      return tc::launch_tma_gemm(dGl, (int64_t)T * H4, WTl, H4, B, H, H4, ep, tc::EPI_F32, 64, s2, kBpttSplit,
+                                 (int64_t)B * H);
+    };
+    cudaStream_t side = cache->side;
+    // one real launch of the step GEMM before any capture (kernel attributes are set on first use, which cannot be
+    // captured); it must not run between chunks: dh_rec carries the recurrent term from one chunk to the next
+    {
+      int rcw = warm_of(dh_rec, dG, WT, st);
+      if (rcw) return rcw;
+    }
+    auto no_warm = []() -> int { return 0; };
+    for (int c = n_chunks - 1; c >= 0; --c) {
+      const int tb = (int)(T * c / n_chunks), te = (int)(T * (c + 1) / n_chunks);
+      {  // layer 1, chunk c, on the caller's stream
+        const std::vector<uintptr_t> key = {(uintptr_t)tv1.gates, (uintptr_t)tv1.c, (uintptr_t)dY_head, (uintptr_t)dl_step,
+                                            (uintptr_t)head_w32, (uintptr_t)dh_rec, (uintptr_t)dc, (uintptr_t)len_st,
+                                            (uintptr_t)dG, (uintptr_t)WT, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H,
+                                            (uintptr_t)tb, (uintptr_t)te, (uintptr_t)kBpttSplit};
+        int rc = run_captured(use_graph ? cache : nullptr, 3 + c, key, no_warm,
+                              [&](cudaStream_t s2) { return steps_of(tv1, dY_head, dh_rec, dc, dG, WT, tb, te, s2); }, st);
+        if (rc) return rc;
+      }
+      AVVAD_CUDA(cudaEventRecord(cache->ev_chunk[c], st));
+      AVVAD_CUDA(cudaStreamWaitEvent(side, cache->ev_chunk[c], 0));
+      // dY0 of the chunk: rows (b, t in [tb, te)) of dG1 times W_ih1
+      int rc = tc::launch_tma_gemm_tm(dG + (int64_t)tb * H4, H4, WTi, H4, B, te - tb, T, H, H4, dY0 + (int64_t)tb * H, H, side);
+      if (rc) return rc;
+      {  // layer 0, chunk c, on the side stream
+        const std::vector<uintptr_t> key = {(uintptr_t)tv0.gates, (uintptr_t)tv0.c, (uintptr_t)dY0, (uintptr_t)dl_step,
+                                            (uintptr_t)head_w32, (uintptr_t)dh_rec0, (uintptr_t)dc0, (uintptr_t)len_st,
+                                            (uintptr_t)dG0, (uintptr_t)WT0, (uintptr_t)B, (uintptr_t)T, (uintptr_t)H,
+                                            (uintptr_t)tb, (uintptr_t)te, (uintptr_t)kBpttSplit};
+        rc = run_captured(use_graph ? cache : nullptr, 3 + kBpttMaxChunks + c, key, no_warm,
+                          [&](cudaStream_t s2) { return steps_of(tv0, dY0, dh_rec0, dc0, dG0, WT0, tb, te, s2); }, side);
+        if (rc) return rc;
+      }
+    }
+    AVVAD_CUDA(cudaEventRecord(cache->ev_side_done, side));
+    AVVAD_CUDA(cudaStreamWaitEvent(st, cache->ev_side_done, 0));
+    int rc = weight_grads(1, dG, nullptr);
     if (rc) return rc;
     return weight_grads(0, dG0, dx);
   }

@@ -72,3 +72,13 @@ def test_bptt_wavefront_matches_layer_by_layer(tmp_path, B):
     for k in plain:
         rel = ((wave[k] - plain[k]).norm() / (plain[k].norm() + 1e-30)).item()
         assert rel < 5e-3, (k, rel)
+
+
+def test_bptt_overlapped_chains_bit_identical(tmp_path):
+    """Larger batches: the two layers' backward recurrences as chunked chains on two streams (layer 0 one chunk behind,
+    its upstream gradient from one time-major GEMM per chunk) against the layer-by-layer loop: same kernels, same order."""
+    plain = _run("bptt_ab.py", [96, 70], {"AVVAD_BPTT_CHUNKS": "1"}, str(tmp_path / "plain.pt"))
+    fast = _run("bptt_ab.py", [96, 70], {}, str(tmp_path / "fast.pt"))
+    assert set(plain) == set(fast)
+    for k in plain:
+        assert torch.isfinite(plain[k]).all() and torch.equal(fast[k], plain[k]), k
