@@ -847,9 +847,10 @@ int lstm_backward_impl(int layers, int input_size, int64_t ld0, int H, int y_dim
       }
     }
     AVVAD_CUDA(cudaEventRecord(cache->ev_side_done, side));
-    AVVAD_CUDA(cudaStreamWaitEvent(st, cache->ev_side_done, 0));
+    // layer 1's parameter gradients (large GEMMs over K = B*T) while layer 0's last chunks still run on the side stream
     int rc = weight_grads(1, dG, nullptr);
     if (rc) return rc;
+    AVVAD_CUDA(cudaStreamWaitEvent(st, cache->ev_side_done, 0));
     return weight_grads(0, dG0, dx);
   }
 
