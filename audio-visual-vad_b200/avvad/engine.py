@@ -484,6 +484,27 @@ class Mcb:
         L.check(L.lib().avvad_mcb_forward(self.h, L.ptr(audio), L.ptr(video), rows, L.ptr(ws), ws.numel(),
                                           L.ptr(out_bf16), ld, L.ptr(out_f32), L.stream_ptr()))
 
+    def forward_grouped(self, audio: torch.Tensor, video: torch.Tensor, lengths, t_max: int,
+                        out_bf16: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None):
+        """audio (B,t_max,513), video (B,t_max,512): every utterance normalised by its own L2 norm over its
+        ``lengths[b]`` valid rows -- B stand-alone forward calls of the reference module in one launch
+        (scripts/evaluate_AV_net.py:186-236 calls the model once per utterance)."""
+        L.require_cuda(audio, video)
+        audio = audio.reshape(-1, 513).contiguous()
+        video = video.reshape(-1, 512).contiguous()
+        t_max = int(t_max)
+        if t_max <= 0 or audio.shape[0] % t_max or video.shape[0] != audio.shape[0]:
+            raise ValueError("forward_grouped: rows must be n_groups * t_max for both inputs")
+        B = audio.shape[0] // t_max
+        lens = _i32(lengths, audio.device)
+        if lens.numel() != B:
+            raise ValueError("forward_grouped: one length per utterance required")
+        nbytes = L.lib().avvad_mcb_grouped_workspace_bytes(B, t_max)
+        ws = self.ws.get(nbytes, audio.device)
+        ld = out_bf16.stride(-2) if out_bf16 is not None else 0
+        L.check(L.lib().avvad_mcb_forward_grouped(self.h, L.ptr(audio), L.ptr(video), B, t_max, L.ptr(lens), L.ptr(ws),
+                                                  ws.numel(), L.ptr(out_bf16), ld, L.ptr(out_f32), L.stream_ptr()))
+
 
 def mcb_forward_train(mcb: "Mcb", audio, video, gamma, beta, running_mean, running_var, out_bf16, momentum=0.1):
     """Training-mode MCB fusion; returns the workspace (kept alive for mcb_backward_bn)."""

@@ -44,16 +44,23 @@ class AVVADPipeline:
         # bit-identical with 2.09x less convolution work.  Off by default: the headline benchmark keeps the
         # reference's order (every 62.5 fps frame through the ResNet).
         self.dedup_video = False
+        # MCB L2 norm per utterance instead of per call: a batched call == one reference call per utterance
+        # (scripts/evaluate_AV_net.py); see infer_device
+        self.per_utterance = False
         self._feat_pad = None
         self._copy_stream = None
         self._events = []
 
     def _buf(self, name, shape, dtype):
+        """Grow-only device scratch: a call with a smaller shape (another t_max / batch) gets a view of the same storage."""
+        n = 1
+        for d in shape:
+            n *= int(d)
         t = self._bufs.get(name)
-        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._bufs[name] = t
-        return t
+        return t[:n].view(shape)
 
     @staticmethod
     def frame_counts(n_samples: Sequence[int], n_src: Sequence[int]):
@@ -61,9 +68,15 @@ class AVVADPipeline:
         return [min(E.stft_num_frames(n), E.upsampled_length(f)) for n, f in zip(n_samples, n_src)]
 
     def infer_device(self, wave: torch.Tensor, n_samples, video_u8: torch.Tensor, n_src, lengths=None,
-                     t_max: Optional[int] = None, _video_ready=None, _wave_ready=None):
+                     t_max: Optional[int] = None, _video_ready=None, _wave_ready=None,
+                     per_utterance: Optional[bool] = None):
         """wave (B,N) f32 and video (B,F,67,67) u8/f32 already on the device.
         Returns (logits, posteriors, decisions), each (B,t_max,y_dim) on the device.
+
+        ``per_utterance`` (default: ``self.per_utterance``): normalise every utterance's MCB output by its own L2 norm
+        over its valid frames, so the batched call returns what B separate forward calls of the reference return --
+        the semantics of scripts/evaluate_AV_net.py:186-236, which calls the model once per utterance.  Off: one norm
+        over the whole padded (B,T,1024) tensor of the call (AV_Net.py:117 for a batched call, the training scripts).
 
         The video branch runs in pieces of ``self.piece`` utterances (frames of an utterance are independent for
         the trunk); ``_video_ready[k]`` / ``_wave_ready`` are optional CUDA events the current stream waits on
@@ -129,12 +142,15 @@ class AVVADPipeline:
             if k == 0 and _wave_ready is not None:
                 front_end()  # the waveforms arrive behind the first video piece
         if self.use_mcb:
-            self.mcb.forward(audio.view(M, 513), feat, out_bf16=xv)
+            if self.per_utterance if per_utterance is None else per_utterance:
+                self.mcb.forward_grouped(audio.view(M, 513), feat, lens, t_max, out_bf16=xv)
+            else:
+                self.mcb.forward(audio.view(M, 513), feat, out_bf16=xv)
         logits, post, dec, _ = self.lstm.forward(x, lens, want_post=True, want_dec=True)
         return logits, post, dec
 
     def infer_host(self, wave_pinned: torch.Tensor, n_samples, video_pinned: torch.Tensor, n_src, lengths=None,
-                   t_max: Optional[int] = None):
+                   t_max: Optional[int] = None, per_utterance: Optional[bool] = None):
         """Host (pinned) buffers in, host posteriors/decisions out.  The uploads run on a copy stream -- first video
         piece, waveforms, remaining video pieces -- while the current stream computes piece by piece, so only the
         first piece's upload is exposed; the D2H read-back is inside the call (this is what bench.py's `e2e` times)."""
@@ -161,13 +177,14 @@ class AVVADPipeline:
                     w.copy_(wave_pinned, non_blocking=True)
                     ew.record(cs)
         _, post, dec = self.infer_device(w, n_samples, v, n_src, lengths=lengths, t_max=t_max, _video_ready=ev,
-                                         _wave_ready=ew)
+                                         _wave_ready=ew, per_utterance=per_utterance)
+        n_out = post.numel()
         hp = self._bufs.get("post_host")
-        if hp is None or hp.shape != post.shape:
-            hp = torch.empty(post.shape, dtype=post.dtype, pin_memory=True)
-            hd = torch.empty(dec.shape, dtype=dec.dtype, pin_memory=True)
-            self._bufs["post_host"], self._bufs["dec_host"] = hp, hd
-        hd = self._bufs["dec_host"]
+        if hp is None or hp.numel() < n_out:  # pinned read-back buffers, grow-only
+            self._bufs["post_host"] = torch.empty(n_out, dtype=post.dtype, pin_memory=True)
+            self._bufs["dec_host"] = torch.empty(n_out, dtype=dec.dtype, pin_memory=True)
+        hp = self._bufs["post_host"][:n_out].view(post.shape)
+        hd = self._bufs["dec_host"][:n_out].view(dec.shape)
         hp.copy_(post, non_blocking=True)
         hd.copy_(dec, non_blocking=True)
         cur.synchronize()

@@ -34,7 +34,8 @@ struct McbTables {
 
 __global__ void __launch_bounds__(kFftThreads)
 mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video, McbTables tb,
-               const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq) {
+               const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq,
+               const int32_t* __restrict__ lengths = nullptr, int t_max = 0) {
   __shared__ float2 sa[kFftN];
   __shared__ float2 sb[kFftN];
   __shared__ float2 stw[kFftTwStage];
@@ -44,6 +45,8 @@ mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video,
 
   const int tid = threadIdx.x;
   const int64_t row = blockIdx.x;
+  // grouped calls (avvad_mcb_forward_grouped): rows behind an utterance's length belong to no call of the reference
+  if (lengths && (int)(row % t_max) >= lengths[row / t_max]) return;
 #pragma unroll
   for (int q = 0; q < kFftTwStage / kFftThreads; ++q)
     stw[tid + q * kFftThreads] = tw_g[kFftTwHann + tid + q * kFftThreads];
@@ -136,6 +139,46 @@ __global__ void mcb_apply_kernel(const float* __restrict__ y, const float* __res
   const int j = (int)(idx - r * kMcbOut);
   const float v = y[idx] / norm[0];
   const float o = (v - bn_mean[j]) * bn_invstd[j] * bn_gamma[j] + bn_beta[j];
+  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
+  if (out_f32) out_f32[idx] = o;
+}
+
+// ---- grouped calls: one L2 norm per utterance (= per forward call of the reference's evaluation loop) ----
+// norms[b] = sqrt(sum_{t < len_b} rowsq[b*t_max + t]); one block per utterance, fixed-order fp64 tree
+__global__ void __launch_bounds__(256) mcb_norm_grouped_kernel(const float* __restrict__ rowsq,
+                                                               const int32_t* __restrict__ lengths, int t_max,
+                                                               float* __restrict__ norms) {
+  __shared__ double sm[256];
+  const int64_t b = blockIdx.x;
+  int n = lengths[b];
+  n = n < 0 ? 0 : (n > t_max ? t_max : n);
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < n; t += 256) acc += (double)rowsq[b * t_max + t];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norms[b] = (float)sqrt(sm[0]);
+}
+
+__global__ void mcb_apply_grouped_kernel(const float* __restrict__ y, const float* __restrict__ norms,
+                                         const int32_t* __restrict__ lengths, int t_max,
+                                         const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                                         const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta,
+                                         int64_t rows, __nv_bfloat16* __restrict__ out_bf16, int64_t ld_out,
+                                         float* __restrict__ out_f32) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * kMcbOut) return;
+  const int64_t r = idx / kMcbOut;
+  const int j = (int)(idx - r * kMcbOut);
+  const int64_t b = r / t_max;
+  float o = 0.f;  // rows behind the utterance's length: zeros (the recurrence never reads them)
+  if ((int)(r - b * t_max) < lengths[b]) {
+    const float v = y[idx] / norms[b];
+    o = (v - bn_mean[j]) * bn_invstd[j] * bn_gamma[j] + bn_beta[j];
+  }
   if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
   if (out_f32) out_f32[idx] = o;
 }
@@ -463,6 +506,59 @@ extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* 
   mcb_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, h->bn_mean, h->bn_invstd, h->bn_gamma,
                                                                    h->bn_beta, rows, (__nv_bfloat16*)out_bf16, ld_out,
                                                                    out_f32);
+  AVVAD_LAUNCHED();
+  tc::prof_end(st, ptok, 5, (double)rows * (4100.0 + (out_f32 ? 4096.0 : 2048.0)));
+  return AVVAD_OK;
+}
+
+
+// Grouped forward: the rows are n_groups utterances of t_max rows each ([b][t] layout, lengths[b] valid rows) and every
+// utterance is normalised by its OWN L2 norm over its valid rows -- what the reference computes when its evaluation
+// loop calls the model once per utterance (scripts/evaluate_AV_net.py:186-236: x[None], v[None], lengths = [T]), so a
+// batched call reproduces n_groups stand-alone forward calls.  Rows behind an utterance's length are skipped (no
+// sketch / FFT work) and written as zeros.
+extern "C" size_t avvad_mcb_grouped_workspace_bytes(int64_t n_groups, int64_t t_max) {
+  if (n_groups <= 0 || t_max <= 0) return 0;
+  return avvad_mcb_workspace_bytes(n_groups * t_max) + align_up((size_t)n_groups * sizeof(float), 256);
+}
+
+extern "C" int avvad_mcb_forward_grouped(avvad_mcb* h, const float* audio, const float* video, int64_t n_groups,
+                                         int64_t t_max, const int32_t* lengths, void* workspace,
+                                         size_t workspace_bytes, void* out_bf16, int64_t ld_out, float* out_f32,
+                                         void* stream) {
+  AVVAD_CHECK_ARG(h && audio && video && workspace && lengths && n_groups > 0 && t_max > 0, "bad argument");
+  AVVAD_CHECK_ARG(out_bf16 || out_f32, "at least one output required");
+  AVVAD_CHECK_ARG(!out_bf16 || ld_out >= kMcbOut, "ld_out must be >= 1024");
+  AVVAD_CHECK_ARG(t_max < (1ll << 31) && n_groups < (1ll << 31) && n_groups * t_max < (1ll << 31), "too many rows");
+  if (!h->loaded) {
+    set_error("mcb: not loaded");
+    return AVVAD_ERR_STATE;
+  }
+  if (workspace_bytes < avvad_mcb_grouped_workspace_bytes(n_groups, t_max)) {
+    set_error("mcb: workspace too small");
+    return AVVAD_ERR_WORKSPACE;
+  }
+  const float2* tw = fft_twiddles_device();
+  if (!tw) {
+    set_error("twiddle table allocation failed");
+    return AVVAD_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = n_groups * t_max;
+  float* y = reinterpret_cast<float*>(workspace);
+  float* rowsq = reinterpret_cast<float*>((uint8_t*)workspace + align_up((size_t)rows * kMcbOut * sizeof(float), 256));
+  float* norms = reinterpret_cast<float*>((uint8_t*)workspace + avvad_mcb_workspace_bytes(rows));
+  McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
+  void* ptok = nullptr;
+  tc::prof_begin(st, &ptok);
+  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq, lengths, (int)t_max);
+  AVVAD_LAUNCHED();
+  mcb_norm_grouped_kernel<<<(unsigned)n_groups, 256, 0, st>>>(rowsq, lengths, (int)t_max, norms);
+  AVVAD_LAUNCHED();
+  const int64_t total = rows * kMcbOut;
+  mcb_apply_grouped_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+      y, norms, lengths, (int)t_max, h->bn_mean, h->bn_invstd, h->bn_gamma, h->bn_beta, rows,
+      (__nv_bfloat16*)out_bf16, ld_out, out_f32);
   AVVAD_LAUNCHED();
   tc::prof_end(st, ptok, 5, (double)rows * (4100.0 + (out_f32 ? 4096.0 : 2048.0)));
   return AVVAD_OK;

@@ -19,6 +19,9 @@ one pass of the whole hot path over one batch: peak-normalise -> STFT/log-power/
   train    : BASELINE config 5, the AV+MCB training step (frozen ResNet in train() mode, device BPTT, ONE NCCL all-reduce
           of the 16.8 M trainable gradients, fused Adam), GLOBAL batch 256 split over the ranks (strong scaling)
   variants.ragged : config 4's variable-length utterances (N ~ U{64,000..102,400}) through the same call
+  config4  : BASELINE config 4 as written -- 10,000 variable-length utterances sharded over the ranks (contiguous
+          blocks, length-sorted calls of 256, per-utterance MCB norm = the reference's one-utterance-per-call evaluation),
+          whole-job valid frames/s, no collective
 
 `--impl reference` times that CPU port alone (the reference's own CPU implementation of the path:
 the reference cannot be pip-installed -- it has no setup.py -- and its MCB branch does not run on
@@ -295,6 +298,80 @@ def ragged_lengths(B: int, seed: int):
     return ns.tolist(), nf.tolist()
 
 
+CONFIG4_UTTERANCES = 10000
+
+
+def config4_block(pipe, rank, world, dev, barrier):
+    """BASELINE config 4 (scripts/evaluate_AV_net.py sharded over the GPUs): 10,000 utterances with N ~ U{64,000..102,400}
+    samples split into contiguous rank blocks (np.array_split, avvad/sharding.py), every block evaluated in length-sorted
+    calls of 256 utterances with the per-utterance MCB norm (avvad/evaluate.py: a batched call == one reference call per
+    utterance, so grouping and order do not change a posterior; tests/test_gpu_evaluate.py).  Inputs resident in HBM: a
+    pool of 256 full-length synthetic utterances per rank, utterance i = the first n_i samples / f_i frames of pool row
+    i mod 256; the per-call gather of the pool rows is inside the timed region.  No collective."""
+    from avvad import engine as E
+    from avvad import synth
+    from avvad.evaluate import padding_overhead, plan_calls
+    from avvad.pipeline import AVVADPipeline
+    from avvad.sharding import shard_bounds
+
+    ns_all, nf_all = ragged_lengths(CONFIG4_UTTERANCES, 777)      # one global list, the same on every rank
+    a, b = shard_bounds(CONFIG4_UTTERANCES, world, rank)
+    ns, nf = ns_all[a:b], nf_all[a:b]
+    T = AVVADPipeline.frame_counts(ns, nf)
+    calls = plan_calls(T, 256)
+    pool = 256
+    wave_h, vid_h, _, _ = synth.batch_inputs(pool, 555 + rank, max(ns_all), max(nf_all))
+    wave_d, vid_d = wave_h.to(dev), vid_h.to(dev)
+    del wave_h, vid_h
+    plan = []
+    for c in calls:
+        ids = torch.tensor([(a + i) % pool for i in c], dtype=torch.int64, device=dev)
+        plan.append((ids, torch.tensor([ns[i] for i in c], dtype=torch.int32, device=dev),
+                     torch.tensor([nf[i] for i in c], dtype=torch.int32, device=dev),
+                     torch.tensor([T[i] for i in c], dtype=torch.int32, device=dev), max(T[i] for i in c)))
+
+    def run(p):
+        ids, n_d, f_d, t_d, t_max = p
+        return pipe.infer_device(wave_d.index_select(0, ids), n_d, vid_d.index_select(0, ids), f_d, lengths=t_d,
+                                 t_max=t_max, per_utterance=True)
+
+    for p in plan[:2] + plan[-1:]:   # warm-up: the longest call sizes every buffer, the last one is the short batch
+        run(p)
+    barrier()
+    l0 = E.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for p in plan:
+        run(p)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    valid = float(sum(T))
+    padded = float(sum(len(c) * max(T[i] for i in c) for c in calls))
+    stats = torch.tensor([ms, valid, padded, float(len(calls)), float(E.launch_count() - l0)], dtype=torch.float64,
+                         device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        ms = float(mx[0])
+    valid, padded, n_calls, launches = float(stats[1]), float(stats[2]), int(stats[3]), int(stats[4])
+    del wave_d, vid_d
+    return {"value": valid / (ms / 1e3), "unit": "valid frames/s", "utterances": CONFIG4_UTTERANCES,
+            "utterances_per_gpu": [shard_bounds(CONFIG4_UTTERANCES, world, r)[1] -
+                                   shard_bounds(CONFIG4_UTTERANCES, world, r)[0] for r in range(world)],
+            "valid_frames": valid, "padded_frames": padded, "padding_overhead": padded / valid - 1.0,
+            "padding_overhead_unsorted": padding_overhead(T, plan_calls(T, 256, sort_by_length=False)),
+            "ms_total": ms, "utterances_per_s": CONFIG4_UTTERANCES / (ms / 1e3), "calls": n_calls,
+            "gpu_launches": launches, "scaling": "strong", "collective": "none",
+            "note": "BASELINE config 4: 10,000 utterances, N ~ U{64,000..102,400} samples (T 247..397), contiguous rank "
+                    "blocks, length-sorted calls of 256 utterances, MCB L2 norm per utterance = the reference's "
+                    "one-utterance-per-call evaluation (scripts/evaluate_AV_net.py:186-236); whole job, max over ranks, "
+                    "inputs resident in HBM (pool of 256 utterances per rank, gathered per call inside the timed region)"}
+
+
 def traffic_from_profiles():
     """dram bytes per launch of the dominant kernel from the newest committed ncu summary (profiles/*traffic*.json)."""
     import glob
@@ -488,6 +565,13 @@ def run_ours(args, rank, world, local_rank):
     pipe._bufs.clear()
     torch.cuda.empty_cache()
 
+    # ---- variant: BASELINE config 4 as written -- 10,000 variable-length utterances sharded over the ranks ----
+    cfg4 = None
+    if not args.no_config4:
+        cfg4 = config4_block(pipe, rank, world, dev, barrier)
+        pipe._bufs.clear()
+        torch.cuda.empty_cache()
+
     # ---- BASELINE config 5: the training step (the only path with a collective) ----
     train = None
     if not args.no_train:
@@ -573,6 +657,7 @@ def run_ours(args, rank, world, local_rank):
                         "(T 247..397), zero-padded to the longest of the batch as the reference's collate does; the padded "
                         "frames run through the ResNet and MCB exactly as in the reference (SURVEY 8g), so the gap to the "
                         "headline is the padding + imbalance cost"}},
+        "config4": cfg4,
         "train": train,
         # achieved HBM GB/s of the memory-bound stages = algorithmic bytes (per-frame figures of SURVEY 8d x
         # frames) / CUDA-event time inside the timed region, against the measured HBM peak.  Both are bound by the
@@ -624,6 +709,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="utterances per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block (config 5)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 10,000-utterance sharded evaluation (config 4)")
     ap.add_argument("--train-batch", type=int, default=256, help="GLOBAL utterances per training step")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: warm-up + one pass, prints nothing")
     args = ap.parse_args()

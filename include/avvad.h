@@ -274,6 +274,16 @@ int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* video, int6
                       void* workspace, size_t workspace_bytes, void* out_bf16, int64_t ld_out,
                       float* out_f32, void* stream);
 
+/* Grouped forward: rows = n_groups utterances x t_max rows ([b][t] layout), lengths i32 [n_groups] (device) valid rows
+ * each.  Every utterance is divided by its OWN L2 norm over its valid rows, i.e. a batched call reproduces n_groups
+ * stand-alone forward calls of the reference module -- what scripts/evaluate_AV_net.py:186-236 does (x[None], v[None],
+ * lengths = [T]: one utterance per call, so AV_Net.py:117's whole-tensor norm is a per-utterance norm there).  Rows
+ * behind an utterance's length are skipped and written as zeros. */
+size_t avvad_mcb_grouped_workspace_bytes(int64_t n_groups, int64_t t_max);
+int avvad_mcb_forward_grouped(avvad_mcb* h, const float* audio, const float* video, int64_t n_groups, int64_t t_max,
+                              const int32_t* lengths, void* workspace, size_t workspace_bytes, void* out_bf16,
+                              int64_t ld_out, float* out_f32, void* stream);
+
 /* Training mode (module in train()): BatchNorm1d uses this call's batch statistics and the CURRENT gamma/beta, updates
  * running_mean/var in place (NULL = leave); the workspace then carries what avvad_mcb_backward_bn needs to turn the
  * gradient w.r.t. the BN output (dx, f32 [rows][ld_dx]) into dgamma / dbeta [1024]. */

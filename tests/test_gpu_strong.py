@@ -179,8 +179,8 @@ def test_benchmark_shape_pipeline_matches_oracle():
     wave_d, vid_d = wave.cuda(), vid.cuda()
     pipe = AVVADPipeline(sd, mean, std, synth.VIDEO_MEAN, synth.VIDEO_STD, use_mcb=True)
     logits0 = pipe.infer_device(wave_d, ns, vid_d, nf)[0].cpu().numpy()
-    audio_dev = pipe._bufs["audio"].view(B, T, 513)
-    feat_dev = pipe._bufs["feat"].view(B, T, 512)
+    audio_dev = pipe._bufs["audio"][: B * T * 513].view(B, T, 513)
+    feat_dev = pipe._bufs["feat"][: B * T * 512].view(B, T, 512)
 
     sample = [0, 37, 63, 64, 127, 128, 200, 255]
     a_s, v_s, lens_s = cpu_av_inputs([wave[i].numpy() for i in sample], [vid[i].numpy() for i in sample], mean, std,
