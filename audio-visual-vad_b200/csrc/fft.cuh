@@ -22,6 +22,9 @@ constexpr int kFftThreads = 256;
 #endif
 constexpr int kFftTwHann = 512;
 constexpr int kFftTwStage = 1024;
+//   [1536, 1792)  stage-B table of the register FFT (fft_reg.cuh): exp(-2*pi*i*r*k/256) at [r*16 + k], r, k in [0,16)
+constexpr int kFftTwB = 256;
+constexpr int kFftTwTotal = kFftTwHann + kFftTwStage + kFftTwB;
 __host__ __device__ __forceinline__ constexpr int fft_tw_off(int s) { return s == 1 ? 0 : s == 2 ? 12 : s == 3 ? 60 : 252; }
 const float2* fft_twiddles_device();  // returns device pointer, initialising on first use (nullptr on error)
 

@@ -26,9 +26,14 @@ const float2* fft_twiddles_device() {
   int cur = 0;
   if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= kMaxDevices) return nullptr;
   const cudaError_t e = g_tw_once.run([cur] {
-    static float2 host[kFftTwHann + kFftTwStage];
+    static float2 host[kFftTwTotal];
     const double two_pi = 6.283185307179586476925286766559;
-    for (int k = 0; k < kFftTwHann + kFftTwStage; ++k) host[k] = make_float2(1.f, 0.f);
+    for (int k = 0; k < kFftTwTotal; ++k) host[k] = make_float2(1.f, 0.f);
+    for (int r = 0; r < 16; ++r)
+      for (int k = 0; k < 16; ++k) {
+        double a = -two_pi * (double)(r * k) / 256.0;
+        host[kFftTwHann + kFftTwStage + r * 16 + k] = make_float2((float)cos(a), (float)sin(a));
+      }
     for (int k = 0; k < 512; ++k) {
       double a = -two_pi * (double)k / 1024.0;
       host[k] = make_float2((float)cos(a), (float)sin(a));

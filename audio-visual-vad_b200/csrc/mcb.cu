@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fft.cuh"
+#include "fft_reg.cuh"
 
 namespace avvad {
 namespace tc {
@@ -112,6 +113,153 @@ mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video,
     for (int w = 0; w < 8; ++w) t += red[w];
     rowsq[row] = t;
   }
+}
+
+// ---- the same row function on the register FFT (fft_reg.cuh) ----------------------------------------------------
+// Persistent CTAs of four 64-thread groups; a group owns one row at a time and never synchronises with the other
+// groups (named barriers).  Staged ONCE per CTA: the two twiddle tables and the CSR count-sketch tables (offsets as
+// u16, (input index, sign) pairs), which mcb_row_kernel re-read from L2 for every row (~20 KB per row of 4 KB input).
+// A thread computes its 16 sketch outputs j = t + 64 m straight into the registers the first transform starts from
+// (same summation order as mcb_row_kernel: ascending input index inside a bucket), the spectrum product needs one
+// exchange through the group's buffer (partner of k is N - k: thread 64 - t), and the second transform leaves the
+// thread with the 16 outputs it writes.  Shared-memory traffic per row: ~107 KB instead of ~225 KB.
+constexpr int kRowGroups = 4;
+constexpr int kRowXin = 1040;  // 513 + 512 inputs of a row, padded
+struct RowSmem {
+  float2 buf[kRowGroups][kRfBufEntries];
+  float xin[kRowGroups][kRowXin];
+  float2 twB[kFftTwB];
+  float2 twC[kFftTwC];
+  int2 ent1[kNA + 1];  // (input index, sign as float bits) in bucket order
+  int2 ent2[kNV];
+  uint16_t off1[kMcbOut + 2];
+  uint16_t off2[kMcbOut + 2];
+  float red[kRowGroups];
+};
+
+__global__ void __launch_bounds__(kRowGroups * kRfThreads, 3)
+mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ video, McbTables tb,
+                   const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq,
+                   int64_t rows, const int32_t* __restrict__ lengths, int t_max) {
+  extern __shared__ __align__(16) uint8_t row_smem_raw[];
+  RowSmem& sm = *reinterpret_cast<RowSmem*>(row_smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6, t = tid & 63;
+  const int bar_id = 1 + g;
+
+  for (int i = tid; i < kFftTwB; i += blockDim.x) sm.twB[i] = tw_g[kFftTwHann + kFftTwStage + i];
+  for (int i = tid; i < kFftTwC; i += blockDim.x) sm.twC[i] = tw_g[kFftTwHann + fft_tw_off(4) + i];
+  for (int i = tid; i <= kMcbOut; i += blockDim.x) {
+    sm.off1[i] = (uint16_t)tb.off1[i];
+    sm.off2[i] = (uint16_t)tb.off2[i];
+  }
+  for (int e = tid; e < kNA; e += blockDim.x) {
+    const int i = tb.idx1[e];
+    sm.ent1[e] = make_int2(i, __float_as_int(tb.s1[i]));
+  }
+  for (int e = tid; e < kNV; e += blockDim.x) {
+    const int i = tb.idx2[e];
+    sm.ent2[e] = make_int2(i, __float_as_int(tb.s2[i]));
+  }
+  __syncthreads();
+
+  float2* buf = sm.buf[g];
+  float* xa = sm.xin[g];
+  float* xv = xa + 528;  // 16-byte aligned behind the 513 audio values
+  for (int64_t row = (int64_t)blockIdx.x * kRowGroups + g; row < rows; row += (int64_t)gridDim.x * kRowGroups) {
+    if (lengths && (int)(row % t_max) >= lengths[row / t_max]) continue;  // group-uniform
+    for (int i = t; i < kNA; i += kRfThreads) xa[i] = audio[row * kNA + i];
+    for (int i = t; i < kNV; i += kRfThreads) xv[i] = video[row * kNV + i];
+    rf_group_bar(bar_id);
+
+    // count sketches of the thread's 16 outputs j = t + 64 m, parked in the exchange buffer (rolled loop: the fully
+    // unrolled form made the kernel 126 KB of SASS and the instruction cache its bound -- ncu: stall_no_instruction 3.1)
+    float2* mine = buf + (t >> 4) * kRfPitch + (t & 15);  // logical index t + 64 m lives at mine[4 m * kRfPitch]
+#pragma unroll 1
+    for (int m = 0; m < 16; ++m) {
+      const int j = t + 64 * m;
+      float px = 0.f, py = 0.f;
+      for (int e = sm.off1[j], e1 = sm.off1[j + 1]; e < e1; ++e) {
+        const int2 en = sm.ent1[e];
+        px += xa[en.x] * __int_as_float(en.y);
+      }
+      for (int e = sm.off2[j], e1 = sm.off2[j + 1]; e < e1; ++e) {
+        const int2 en = sm.ent2[e];
+        py += xv[en.x] * __int_as_float(en.y);
+      }
+      mine[4 * m * kRfPitch] = make_float2(px, py);
+    }
+    float2 v[16];
+    // pass 0: Z = FFT(px + i py).  pass 1: FFT(conj(X Y)) = N * ifft(X Y) with X[k] = (Z[k] + conj(Z[N-k])) / 2,
+    // Y[k] = (Z[k] - conj(Z[N-k])) / (2i); the partner of k = t + 64 m is held by thread 64 - t, hence the exchange.
+    // One rolled loop so that the transform's code exists once.
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 0) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = mine[4 * m * kRfPitch];  // the thread's own stores: no barrier needed
+      } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) mine[4 * m * kRfPitch] = v[m];
+        rf_group_bar(bar_id);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const int kn = (kFftN - (t + 64 * m)) & (kFftN - 1);
+          const float2 zn = buf[(kn >> 4) * kRfPitch + (kn & 15)];
+          const float2 zk = v[m];
+          const float2 X = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+          const float2 Y = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+          const float2 P = cmul(X, Y);
+          v[m] = make_float2(P.x, -P.y);
+        }
+      }
+      rf_group_bar(bar_id);  // the buffer is free (pass 0: nobody else read it; pass 1: all partners fetched)
+      fft1024_reg(v, buf, sm.twB, sm.twC, t, bar_id);
+    }
+
+    float ss = 0.f;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const float p = v[m].x * (1.0f / kFftN);
+      const float r = sqrtf(fabsf(p) + eps);  // torch.sign(p) * sqrt(|p| + eps)   (sign(0) = 0)
+      const float y = (p > 0.f) ? r : ((p < 0.f) ? -r : 0.f);
+      y_out[row * kMcbOut + t + 64 * m] = y;
+      ss += y * y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (t == 32) sm.red[g] = ss;
+    rf_group_bar(bar_id);
+    if (t == 0) rowsq[row] = ss + sm.red[g];
+  }
+}
+
+// MCB row pass: the register-FFT kernel (default) or the radix-4 shared-memory kernel (AVVAD_MCB_REG=0)
+static int launch_mcb_rows(const float* audio, const float* video, const McbTables& tb, const float2* tw, float eps,
+                           float* y, float* rowsq, int64_t rows, const int32_t* lengths, int t_max, cudaStream_t st) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AVVAD_MCB_REG");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (mode == 0) {
+    mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, eps, y, rowsq, lengths, t_max);
+    AVVAD_LAUNCHED();
+    return AVVAD_OK;
+  }
+  static PerDeviceOnce attr_once;
+  int sms = 0, dev = 0;
+  AVVAD_CUDA(cudaGetDevice(&dev));
+  AVVAD_CUDA(attr_once.run([] {
+    return cudaFuncSetAttribute(mcb_row_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowSmem));
+  }));
+  AVVAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t want = ceil_div(rows, (int64_t)kRowGroups);
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 3);
+  mcb_row_reg_kernel<<<grid, kRowGroups * kRfThreads, sizeof(RowSmem), st>>>(audio, video, tb, tw, eps, y, rowsq, rows,
+                                                                            lengths, t_max);
+  AVVAD_LAUNCHED();
+  return AVVAD_OK;
 }
 
 // whole-tensor L2 norm: deterministic two-level reduction in double
@@ -498,8 +646,7 @@ extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* 
   // profiling category 5: "flops" carries the algorithmic bytes (513 + 512 floats in, 1024 bf16 or fp32 out per row)
   void* ptok = nullptr;
   tc::prof_begin(st, &ptok);
-  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq);
-  AVVAD_LAUNCHED();
+  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
   mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
   AVVAD_LAUNCHED();
   const int64_t total = rows * kMcbOut;
@@ -551,8 +698,7 @@ extern "C" int avvad_mcb_forward_grouped(avvad_mcb* h, const float* audio, const
   McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
   void* ptok = nullptr;
   tc::prof_begin(st, &ptok);
-  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq, lengths, (int)t_max);
-  AVVAD_LAUNCHED();
+  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, lengths, (int)t_max, st)) return rc;
   mcb_norm_grouped_kernel<<<(unsigned)n_groups, 256, 0, st>>>(rowsq, lengths, (int)t_max, norms);
   AVVAD_LAUNCHED();
   const int64_t total = rows * kMcbOut;
@@ -585,8 +731,7 @@ extern "C" int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const f
   float* norm = reinterpret_cast<float*>((uint8_t*)rowsq + align_up((size_t)rows * sizeof(float), 256));
   float* mean_invstd = norm + 64;
   McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
-  mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, h->eps, y, rowsq);
-  AVVAD_LAUNCHED();
+  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
   mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
   AVVAD_LAUNCHED();
   mcb_bn_stats_kernel<<<kMcbOut, 256, 0, st>>>(y, norm, rows, h->eps, momentum, mean_invstd, running_mean, running_var);

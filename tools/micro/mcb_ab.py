@@ -1,0 +1,64 @@
+"""A/B of the two MCB row kernels (radix-4 shared-memory FFT vs register FFT, AVVAD_MCB_REG=0/1) at the bench shape
+B = 256 x T = 317 rows: device time of the whole avvad_mcb_forward call and agreement of the fp32 outputs.  The kernel
+choice is read once per process, so each mode runs in a child process."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "audio-visual-vad_b200"))
+
+
+def child(mode: str, out_path: str):
+    import torch
+
+    from avvad import engine as E
+
+    torch.manual_seed(0)
+    dev = "cuda"
+    rows = 256 * 317
+    sd = {"mcb.sketch1.h": torch.randint(0, 1024, (513,)), "mcb.sketch2.h": torch.randint(0, 1024, (512,)),
+          "mcb.sketch1.s": torch.randint(0, 2, (513,)).float() * 2 - 1,
+          "mcb.sketch2.s": torch.randint(0, 2, (512,)).float() * 2 - 1,
+          "mcb_bn.weight": torch.ones(1024), "mcb_bn.bias": torch.zeros(1024), "mcb_bn.running_mean": torch.zeros(1024),
+          "mcb_bn.running_var": torch.full((1024,), 1.0 / (rows * 1024.0))}
+    mcb = E.Mcb()
+    mcb.load(sd, dev)
+    a = torch.randn(rows, 513, device=dev)
+    v = torch.randn(rows, 512, device=dev).abs()
+    ob = torch.empty(rows, 1024, dtype=torch.bfloat16, device=dev)
+    o32 = torch.empty(rows, 1024, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    mcb.forward(a, v, out_bf16=ob, out_f32=o32)
+    torch.cuda.synchronize()
+    torch.save(o32[::97].cpu(), out_path)
+    ts = []
+    for i in range(23):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mcb.forward(a, v, out_bf16=ob)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"AVVAD_MCB_REG={mode}: mcb forward (row + norm + apply) {ts[len(ts) // 2]:.4f} ms median, {ts[0]:.4f} min")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        child(sys.argv[1], sys.argv[2])
+        sys.exit(0)
+    import torch
+
+    outs = []
+    for mode in ("0", "1"):
+        path = f"/tmp/mcb_ab_{mode}.pt"
+        env = dict(os.environ, AVVAD_MCB_REG=mode)
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), mode, path], env=env)
+        outs.append(torch.load(path))
+    d = (outs[0] - outs[1]).abs().max().item()
+    rel = ((outs[0] - outs[1]).norm() / outs[0].norm()).item()
+    print(f"register FFT vs shared-memory FFT: max |diff| {d:.3e}, rel fro {rel:.3e} (output std {outs[0].std().item():.3f})")
+    assert rel < 1e-5, rel
