@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "fft.cuh"
+#include "fft_reg.cuh"
 
 namespace avvad {
 namespace tc {
@@ -149,6 +150,79 @@ frontend_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32
   }
 }
 
+// ---- log-power front end on the register FFT (fft_reg.cuh) -------------------------------------------------------
+// Same arithmetic per sample and per bin as frontend_kernel<0> (window from the same twiddle table, __fdiv_rn peak
+// normalisation, logf, standardisation), one frame per transform as before (a frame's features never depend on which
+// other frames share the launch), but a frame is a 64-thread group with the radix-16 butterflies in registers, CTAs are
+// persistent and stage the twiddle tables, the window and the per-bin statistics once instead of 8 KB per frame.
+constexpr int kFeGroups = 4;
+struct FeSmem {
+  float2 buf[kFeGroups][kRfBufEntries];
+  float2 twB[kFftTwB];
+  float2 twC[kFftTwC];
+  float win[kFftN];
+  float mean[520];
+  float stdv[520];
+};
+
+__global__ void __launch_bounds__(kFeGroups * kRfThreads, 3)
+frontend_reg_kernel(const float* __restrict__ wave, int64_t wave_stride, const int32_t* __restrict__ n_samples,
+                    const int32_t* __restrict__ n_frames, int B, int t_max, const float* __restrict__ peak,
+                    const float* __restrict__ mean, const float* __restrict__ stdv, float eps,
+                    const float2* __restrict__ tw_g, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t fe_smem_raw[];
+  FeSmem& sm = *reinterpret_cast<FeSmem*>(fe_smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6, t = tid & 63;
+  const int bar_id = 1 + g;
+  for (int i = tid; i < kFftTwB; i += blockDim.x) sm.twB[i] = tw_g[kFftTwHann + kFftTwStage + i];
+  for (int i = tid; i < kFftTwC; i += blockDim.x) sm.twC[i] = tw_g[kFftTwHann + fft_tw_off(4) + i];
+  for (int i = tid; i < kFftN; i += blockDim.x) {
+    // periodic Hann: 0.5 - 0.5*cos(2*pi*i/1024); cos from the twiddle table
+    const float c = (i < 512) ? tw_g[i].x : -tw_g[i - 512].x;
+    sm.win[i] = 0.5f - 0.5f * c;
+  }
+  for (int i = tid; i < 513; i += blockDim.x) {
+    sm.mean[i] = mean ? mean[i] : 0.f;
+    sm.stdv[i] = mean ? stdv[i] : 0.f;
+  }
+  __syncthreads();
+  const bool has_stats = mean != nullptr;
+  const bool norm = peak != nullptr;
+  float2* buf = sm.buf[g];
+  const int64_t frames = (int64_t)B * t_max;
+  for (int64_t f = (int64_t)blockIdx.x * kFeGroups + g; f < frames; f += (int64_t)gridDim.x * kFeGroups) {
+    const int b = (int)(f / t_max), fr = (int)(f - (int64_t)b * t_max);
+    float* o = out + f * 513;
+    if (fr >= min(n_frames[b], t_max)) {
+      // collate padding: zeros are padded BEFORE standardisation -> (0 - mean) / (std + eps)
+      for (int k = t; k < 513; k += kRfThreads) o[k] = has_stats ? (0.f - sm.mean[k]) / (sm.stdv[k] + eps) : 0.f;
+      continue;
+    }
+    const int n = n_samples[b];
+    const float* x = wave + (int64_t)b * wave_stride;
+    const float pk = norm ? peak[b] : 1.0f;
+    float2 v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int i = t + 64 * m;
+      const int i0 = fr * 256 + i;
+      float v0 = (i0 < n) ? x[i0] : 0.f;  // samples past the end are the pad-at-end zeros
+      if (norm) v0 = __fdiv_rn(v0, pk);
+      v[m] = make_float2(v0 * sm.win[i], 0.f);
+    }
+    fft1024_reg(v, buf, sm.twB, sm.twC, t, bar_id);
+#pragma unroll
+    for (int m = 0; m <= 8; ++m) {
+      const int k = t + 64 * m;
+      if (k <= 512) {
+        const float la = logf(v[m].x * v[m].x + v[m].y * v[m].y + eps);
+        o[k] = has_stats ? (la - sm.mean[k]) / (sm.stdv[k] + eps) : la;
+      }
+    }
+  }
+}
+
 }  // namespace avvad
 
 using namespace avvad;
@@ -193,7 +267,24 @@ static int launch_frontend(int mode, const float* wave, int64_t wave_stride, con
     AVVAD_LAUNCHED();
   }
   dim3 grid(t_max, B);
-  if (mode == 0)
+  static int reg_mode = -1;  // AVVAD_FE_REG=0: log-power frames through the radix-4 shared-memory kernel as well
+  if (reg_mode < 0) {
+    const char* e = getenv("AVVAD_FE_REG");
+    reg_mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (mode == 0 && reg_mode) {
+    static PerDeviceOnce attr_once;
+    int sms = 0, dev = 0;
+    AVVAD_CUDA(cudaGetDevice(&dev));
+    AVVAD_CUDA(attr_once.run([] {
+      return cudaFuncSetAttribute(frontend_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FeSmem));
+    }));
+    AVVAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t want = ceil_div((int64_t)B * t_max, (int64_t)kFeGroups);
+    const unsigned ctas = (unsigned)std::min<int64_t>(want, (int64_t)sms * 3);
+    frontend_reg_kernel<<<ctas, kFeGroups * kRfThreads, sizeof(FeSmem), st>>>(
+        wave, wave_stride, n_samples, n_frames, B, t_max, normalise ? peak_scratch : nullptr, mean, stdv, eps, tw, out);
+  } else if (mode == 0)
     frontend_kernel<0><<<grid, kFftThreads, 0, st>>>(wave, wave_stride, n_samples, n_frames, t_max,
                                                      normalise ? peak_scratch : nullptr, mean, stdv, eps, tw, out);
   else

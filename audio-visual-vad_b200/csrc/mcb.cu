@@ -125,20 +125,34 @@ mcb_row_kernel(const float* __restrict__ audio, const float* __restrict__ video,
 // thread with the 16 outputs it writes.  Shared-memory traffic per row: ~107 KB instead of ~225 KB.
 constexpr int kRowGroups = 4;
 constexpr int kRowXin = 1040;  // 513 + 512 inputs of a row, padded
+constexpr int kMaxRounds = 32;
+// Count sketch as conflict-free scatter ROUNDS: round r holds the inputs that are the r-th member (ascending input
+// index) of their bucket, so inside a round no two inputs share a bucket and out[h] += s*x needs no atomics; a group
+// barrier separates the rounds.  Every bucket therefore accumulates its members in ascending input order starting from
+// zero -- exactly the sums of mcb_row_kernel's CSR gather, bit for bit -- but the work is one straight pass over the
+// 513 + 512 inputs (8 per thread) instead of 2 x 1024 data-dependent gather loops (ncu: the gather form was 43 % of
+// the kernel's shared-memory wavefronts and put branch_resolving among the top stalls).
+struct McbRounds {
+  const int32_t* ent1;   // [513] input index | bucket << 16, sorted by (round, input index)
+  const int32_t* ent2;   // [512]
+  const int32_t* roff1;  // [kMaxRounds + 1] first entry of every round
+  const int32_t* roff2;
+  int n_rounds;          // max over both sketches
+};
 struct RowSmem {
   float2 buf[kRowGroups][kRfBufEntries];
   float xin[kRowGroups][kRowXin];
   float2 twB[kFftTwB];
   float2 twC[kFftTwC];
-  int2 ent1[kNA + 1];  // (input index, sign as float bits) in bucket order
+  int2 ent1[kNA + 1];  // (input index | physical float offset of the bucket << 16, sign as float bits), round order
   int2 ent2[kNV];
-  uint16_t off1[kMcbOut + 2];
-  uint16_t off2[kMcbOut + 2];
+  int roff1[kMaxRounds + 1];
+  int roff2[kMaxRounds + 1];
   float red[kRowGroups];
 };
 
 __global__ void __launch_bounds__(kRowGroups * kRfThreads, 3)
-mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ video, McbTables tb,
+mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ video, McbTables tb, McbRounds rd,
                    const float2* __restrict__ tw_g, float eps, float* __restrict__ y_out, float* __restrict__ rowsq,
                    int64_t rows, const int32_t* __restrict__ lengths, int t_max) {
   extern __shared__ __align__(16) uint8_t row_smem_raw[];
@@ -149,19 +163,21 @@ mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ vi
 
   for (int i = tid; i < kFftTwB; i += blockDim.x) sm.twB[i] = tw_g[kFftTwHann + kFftTwStage + i];
   for (int i = tid; i < kFftTwC; i += blockDim.x) sm.twC[i] = tw_g[kFftTwHann + fft_tw_off(4) + i];
-  for (int i = tid; i <= kMcbOut; i += blockDim.x) {
-    sm.off1[i] = (uint16_t)tb.off1[i];
-    sm.off2[i] = (uint16_t)tb.off2[i];
+  for (int i = tid; i <= kMaxRounds; i += blockDim.x) {
+    sm.roff1[i] = rd.roff1[i];
+    sm.roff2[i] = rd.roff2[i];
   }
+  // bucket j of the sketch pair lives at float offset 2 * phys(j) (+1 for the video sketch) of the exchange buffer
   for (int e = tid; e < kNA; e += blockDim.x) {
-    const int i = tb.idx1[e];
-    sm.ent1[e] = make_int2(i, __float_as_int(tb.s1[i]));
+    const int p = rd.ent1[e], i = p & 0xFFFF, j = p >> 16;
+    sm.ent1[e] = make_int2(i | ((2 * ((j >> 4) * kRfPitch + (j & 15))) << 16), __float_as_int(tb.s1[i]));
   }
   for (int e = tid; e < kNV; e += blockDim.x) {
-    const int i = tb.idx2[e];
-    sm.ent2[e] = make_int2(i, __float_as_int(tb.s2[i]));
+    const int p = rd.ent2[e], i = p & 0xFFFF, j = p >> 16;
+    sm.ent2[e] = make_int2(i | ((2 * ((j >> 4) * kRfPitch + (j & 15)) + 1) << 16), __float_as_int(tb.s2[i]));
   }
   __syncthreads();
+  const int n_rounds = rd.n_rounds;
 
   float2* buf = sm.buf[g];
   float* xa = sm.xin[g];
@@ -170,24 +186,25 @@ mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ vi
     if (lengths && (int)(row % t_max) >= lengths[row / t_max]) continue;  // group-uniform
     for (int i = t; i < kNA; i += kRfThreads) xa[i] = audio[row * kNA + i];
     for (int i = t; i < kNV; i += kRfThreads) xv[i] = video[row * kNV + i];
-    rf_group_bar(bar_id);
-
-    // count sketches of the thread's 16 outputs j = t + 64 m, parked in the exchange buffer (rolled loop: the fully
-    // unrolled form made the kernel 126 KB of SASS and the instruction cache its bound -- ncu: stall_no_instruction 3.1)
+    // count sketches into the exchange buffer (.x audio, .y video), round by round (McbRounds)
     float2* mine = buf + (t >> 4) * kRfPitch + (t & 15);  // logical index t + 64 m lives at mine[4 m * kRfPitch]
+#pragma unroll
+    for (int m = 0; m < 16; ++m) mine[4 * m * kRfPitch] = make_float2(0.f, 0.f);
+    rf_group_bar(bar_id);  // zeros and inputs visible to the group
+    {
+      float* sk = reinterpret_cast<float*>(buf);
 #pragma unroll 1
-    for (int m = 0; m < 16; ++m) {
-      const int j = t + 64 * m;
-      float px = 0.f, py = 0.f;
-      for (int e = sm.off1[j], e1 = sm.off1[j + 1]; e < e1; ++e) {
-        const int2 en = sm.ent1[e];
-        px += xa[en.x] * __int_as_float(en.y);
+      for (int r = 0; r < n_rounds; ++r) {
+        for (int e = sm.roff1[r] + t, e1 = sm.roff1[r + 1]; e < e1; e += kRfThreads) {
+          const int2 en = sm.ent1[e];
+          sk[en.x >> 16] += xa[en.x & 0xFFFF] * __int_as_float(en.y);
+        }
+        for (int e = sm.roff2[r] + t, e1 = sm.roff2[r + 1]; e < e1; e += kRfThreads) {
+          const int2 en = sm.ent2[e];
+          sk[en.x >> 16] += xv[en.x & 0xFFFF] * __int_as_float(en.y);
+        }
+        rf_group_bar(bar_id);
       }
-      for (int e = sm.off2[j], e1 = sm.off2[j + 1]; e < e1; ++e) {
-        const int2 en = sm.ent2[e];
-        py += xv[en.x] * __int_as_float(en.y);
-      }
-      mine[4 * m * kRfPitch] = make_float2(px, py);
     }
     float2 v[16];
     // pass 0: Z = FFT(px + i py).  pass 1: FFT(conj(X Y)) = N * ifft(X Y) with X[k] = (Z[k] + conj(Z[N-k])) / 2,
@@ -197,7 +214,7 @@ mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ vi
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 0) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = mine[4 * m * kRfPitch];  // the thread's own stores: no barrier needed
+        for (int m = 0; m < 16; ++m) v[m] = mine[4 * m * kRfPitch];  // behind the last round's barrier
       } else {
 #pragma unroll
         for (int m = 0; m < 16; ++m) mine[4 * m * kRfPitch] = v[m];
@@ -213,7 +230,7 @@ mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ vi
           v[m] = make_float2(P.x, -P.y);
         }
       }
-      rf_group_bar(bar_id);  // the buffer is free (pass 0: nobody else read it; pass 1: all partners fetched)
+      rf_group_bar(bar_id);  // the buffer is free (pass 0: sketches fetched; pass 1: all partners fetched)
       fft1024_reg(v, buf, sm.twB, sm.twC, t, bar_id);
     }
 
@@ -235,14 +252,15 @@ mcb_row_reg_kernel(const float* __restrict__ audio, const float* __restrict__ vi
 }
 
 // MCB row pass: the register-FFT kernel (default) or the radix-4 shared-memory kernel (AVVAD_MCB_REG=0)
-static int launch_mcb_rows(const float* audio, const float* video, const McbTables& tb, const float2* tw, float eps,
-                           float* y, float* rowsq, int64_t rows, const int32_t* lengths, int t_max, cudaStream_t st) {
+static int launch_mcb_rows(const float* audio, const float* video, const McbTables& tb, const McbRounds& rd,
+                           const float2* tw, float eps, float* y, float* rowsq, int64_t rows, const int32_t* lengths,
+                           int t_max, cudaStream_t st) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("AVVAD_MCB_REG");
     mode = (e && e[0] == '0') ? 0 : 1;
   }
-  if (mode == 0) {
+  if (mode == 0 || rd.n_rounds > kMaxRounds) {  // > 32 inputs in one bucket: not a hash any more, gather kernel
     mcb_row_kernel<<<(unsigned)rows, kFftThreads, 0, st>>>(audio, video, tb, tw, eps, y, rowsq, lengths, t_max);
     AVVAD_LAUNCHED();
     return AVVAD_OK;
@@ -256,8 +274,8 @@ static int launch_mcb_rows(const float* audio, const float* video, const McbTabl
   AVVAD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t want = ceil_div(rows, (int64_t)kRowGroups);
   const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 3);
-  mcb_row_reg_kernel<<<grid, kRowGroups * kRfThreads, sizeof(RowSmem), st>>>(audio, video, tb, tw, eps, y, rowsq, rows,
-                                                                            lengths, t_max);
+  mcb_row_reg_kernel<<<grid, kRowGroups * kRfThreads, sizeof(RowSmem), st>>>(audio, video, tb, rd, tw, eps, y, rowsq,
+                                                                            rows, lengths, t_max);
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }
@@ -277,18 +295,60 @@ __global__ void __launch_bounds__(1024) mcb_norm_kernel(const float* __restrict_
   if (threadIdx.x == 0) norm_out[0] = (float)sqrt(sm[0]);
 }
 
-__global__ void mcb_apply_kernel(const float* __restrict__ y, const float* __restrict__ norm,
-                                 const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
-                                 const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta, int64_t rows,
-                                 __nv_bfloat16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * kMcbOut) return;
-  const int64_t r = idx / kMcbOut;
-  const int j = (int)(idx - r * kMcbOut);
-  const float v = y[idx] / norm[0];
-  const float o = (v - bn_mean[j]) * bn_invstd[j] * bn_gamma[j] + bn_beta[j];
-  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
-  if (out_f32) out_f32[idx] = o;
+// y / norm -> BatchNorm1d (eval) -> bf16 (and / or fp32).  Eight consecutive channels per thread: two 128-bit loads of y,
+// one 128-bit bf16 store (the scalar form ran at 1.8 TB/s: one 2-byte store and five loads per element).  `norms` holds
+// one value (whole-call norm) or, with `lengths`, one per utterance of t_max rows (rows behind the length: zeros).
+__global__ void __launch_bounds__(256)
+mcb_apply_kernel(const float* __restrict__ y, const float* __restrict__ norms, const int32_t* __restrict__ lengths,
+                 int t_max, const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
+                 const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta, int64_t rows,
+                 __nv_bfloat16* __restrict__ out_bf16, int64_t ld_out, float* __restrict__ out_f32) {
+  const int64_t idx8 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 channels
+  if (idx8 >= rows * (kMcbOut / 8)) return;
+  const int64_t r = idx8 / (kMcbOut / 8);
+  const int j = (int)(idx8 - r * (kMcbOut / 8)) * 8;
+  float o[8];
+  bool live = true;
+  float nrm;
+  if (lengths) {
+    const int64_t b = r / t_max;
+    live = (int)(r - b * t_max) < lengths[b];
+    nrm = norms[b];
+  } else {
+    nrm = norms[0];
+  }
+  if (live) {
+    const float4 y0 = *reinterpret_cast<const float4*>(y + r * kMcbOut + j);
+    const float4 y1 = *reinterpret_cast<const float4*>(y + r * kMcbOut + j + 4);
+    const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = yy[e] / nrm;
+      o[e] = (v - __ldg(bn_mean + j + e)) * __ldg(bn_invstd + j + e) * __ldg(bn_gamma + j + e) + __ldg(bn_beta + j + e);
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  }
+  if (out_bf16) {
+    __nv_bfloat16* op = out_bf16 + r * ld_out + j;
+    if ((reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+      uint4 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      pk.z = pack_bf16x2(o[4], o[5]);
+      pk.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(op) = pk;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) op[e] = __float2bfloat16_rn(o[e]);
+    }
+  }
+  if (out_f32) {
+    float4* of = reinterpret_cast<float4*>(out_f32 + r * kMcbOut + j);
+    of[0] = make_float4(o[0], o[1], o[2], o[3]);
+    of[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
 }
 
 // ---- grouped calls: one L2 norm per utterance (= per forward call of the reference's evaluation loop) ----
@@ -309,26 +369,6 @@ __global__ void __launch_bounds__(256) mcb_norm_grouped_kernel(const float* __re
     __syncthreads();
   }
   if (threadIdx.x == 0) norms[b] = (float)sqrt(sm[0]);
-}
-
-__global__ void mcb_apply_grouped_kernel(const float* __restrict__ y, const float* __restrict__ norms,
-                                         const int32_t* __restrict__ lengths, int t_max,
-                                         const float* __restrict__ bn_mean, const float* __restrict__ bn_invstd,
-                                         const float* __restrict__ bn_gamma, const float* __restrict__ bn_beta,
-                                         int64_t rows, __nv_bfloat16* __restrict__ out_bf16, int64_t ld_out,
-                                         float* __restrict__ out_f32) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * kMcbOut) return;
-  const int64_t r = idx / kMcbOut;
-  const int j = (int)(idx - r * kMcbOut);
-  const int64_t b = r / t_max;
-  float o = 0.f;  // rows behind the utterance's length: zeros (the recurrence never reads them)
-  if ((int)(r - b * t_max) < lengths[b]) {
-    const float v = y[idx] / norms[b];
-    o = (v - bn_mean[j]) * bn_invstd[j] * bn_gamma[j] + bn_beta[j];
-  }
-  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
-  if (out_f32) out_f32[idx] = o;
 }
 
 // ---- training mode: BatchNorm1d with batch statistics over all rows, and the gradients of its affine parameters ----
@@ -369,19 +409,6 @@ __global__ void __launch_bounds__(256) mcb_bn_stats_kernel(const float* __restri
       running_var[j] = (1.f - momentum) * running_var[j] + momentum * (float)unbiased;
     }
   }
-}
-__global__ void mcb_apply_train_kernel(const float* __restrict__ y, const float* __restrict__ norm,
-                                       const float* __restrict__ mean_invstd, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, int64_t rows, __nv_bfloat16* __restrict__ out_bf16,
-                                       int64_t ld_out, float* __restrict__ out_f32) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * kMcbOut) return;
-  const int64_t r = idx / kMcbOut;
-  const int j = (int)(idx - r * kMcbOut);
-  const float v = y[idx] / norm[0];
-  const float o = (v - mean_invstd[j]) * mean_invstd[kMcbOut + j] * gamma[j] + beta[j];
-  if (out_bf16) out_bf16[r * ld_out + j] = __float2bfloat16_rn(o);
-  if (out_f32) out_f32[idx] = o;
 }
 // dgamma[j] = sum_r dx[r][j] * xhat[r][j], dbeta[j] = sum_r dx[r][j]
 __global__ void __launch_bounds__(256) mcb_bn_grad_kernel(const float* __restrict__ y, const float* __restrict__ norm,
@@ -537,11 +564,17 @@ using namespace avvad;
 
 struct avvad_mcb {
   int32_t *off1, *idx1, *off2, *idx2;
+  int32_t *rnd;  // scatter rounds (McbRounds): ent1 [513] | ent2 [512] | roff1 [33] | roff2 [33]
+  int n_rounds;
   float *s1, *s2;
   float *bn_gamma, *bn_beta, *bn_mean, *bn_invstd;
   float eps;
   bool loaded;
 };
+
+static McbRounds rounds_of(const avvad_mcb* h) {
+  return McbRounds{h->rnd, h->rnd + kNA, h->rnd + kNA + kNV, h->rnd + kNA + kNV + kMaxRounds + 1, h->n_rounds};
+}
 
 extern "C" int avvad_mcb_create(avvad_mcb** out) {
   AVVAD_CHECK_ARG(out, "null out");
@@ -551,6 +584,8 @@ extern "C" int avvad_mcb_create(avvad_mcb** out) {
   AVVAD_CUDA(cudaMalloc(&h->off2, sizeof(int32_t) * 1025));
   AVVAD_CUDA(cudaMalloc(&h->idx1, sizeof(int32_t) * kNA));
   AVVAD_CUDA(cudaMalloc(&h->idx2, sizeof(int32_t) * kNV));
+  AVVAD_CUDA(cudaMalloc(&h->rnd, sizeof(int32_t) * (kNA + kNV + 2 * (kMaxRounds + 1))));
+  h->n_rounds = 0;
   AVVAD_CUDA(cudaMalloc(&h->s1, sizeof(float) * kNA));
   AVVAD_CUDA(cudaMalloc(&h->s2, sizeof(float) * kNV));
   AVVAD_CUDA(cudaMalloc(&h->bn_gamma, sizeof(float) * kMcbOut));
@@ -563,13 +598,14 @@ extern "C" int avvad_mcb_create(avvad_mcb** out) {
 
 extern "C" void avvad_mcb_destroy(avvad_mcb* h) {
   if (!h) return;
-  cudaFree(h->off1); cudaFree(h->off2); cudaFree(h->idx1); cudaFree(h->idx2);
+  cudaFree(h->off1); cudaFree(h->off2); cudaFree(h->idx1); cudaFree(h->idx2); cudaFree(h->rnd);
   cudaFree(h->s1); cudaFree(h->s2);
   cudaFree(h->bn_gamma); cudaFree(h->bn_beta); cudaFree(h->bn_mean); cudaFree(h->bn_invstd);
   delete h;
 }
 
-static int build_csr(const int64_t* h_dev, int n, int32_t* off_dev, int32_t* idx_dev, cudaStream_t st) {
+static int build_csr(const int64_t* h_dev, int n, int32_t* off_dev, int32_t* idx_dev, cudaStream_t st,
+                     int32_t* ent_dev = nullptr, int32_t* roff_dev = nullptr, int* n_rounds = nullptr) {
   std::vector<int64_t> hh(n);
   AVVAD_CUDA(cudaMemcpyAsync(hh.data(), h_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, st));
   AVVAD_CUDA(cudaStreamSynchronize(st));
@@ -586,6 +622,27 @@ static int build_csr(const int64_t* h_dev, int n, int32_t* off_dev, int32_t* idx
   for (int i = 0; i < n; ++i) idx[cur[hh[i]]++] = i;  // ascending i inside each bucket
   AVVAD_CUDA(cudaMemcpyAsync(off_dev, off.data(), sizeof(int32_t) * (kMcbOut + 1), cudaMemcpyHostToDevice, st));
   AVVAD_CUDA(cudaMemcpyAsync(idx_dev, idx.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  std::vector<int32_t> ent, roff(kMaxRounds + 1, n);
+  if (ent_dev) {
+    // scatter rounds: round r = the r-th member (ascending input index) of every bucket, each round in ascending
+    // input order (coalesced input reads)
+    std::vector<int32_t> rank(n);
+    int rounds = 0;
+    for (int j = 0; j < kMcbOut; ++j)
+      for (int e = off[j]; e < off[j + 1]; ++e) {
+        rank[idx[e]] = e - off[j];
+        rounds = std::max(rounds, e - off[j] + 1);
+      }
+    ent.reserve(n);
+    for (int r = 0; r < rounds; ++r) {
+      if (r <= kMaxRounds) roff[r] = (int32_t)ent.size();
+      for (int i = 0; i < n; ++i)
+        if (rank[i] == r) ent.push_back(i | ((int32_t)hh[i] << 16));
+    }
+    *n_rounds = rounds;
+    AVVAD_CUDA(cudaMemcpyAsync(ent_dev, ent.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    AVVAD_CUDA(cudaMemcpyAsync(roff_dev, roff.data(), sizeof(int32_t) * (kMaxRounds + 1), cudaMemcpyHostToDevice, st));
+  }
   AVVAD_CUDA(cudaStreamSynchronize(st));
   return AVVAD_OK;
 }
@@ -595,10 +652,12 @@ extern "C" int avvad_mcb_load(avvad_mcb* h, const int64_t* h1, const float* s1, 
                               float eps, void* stream) {
   AVVAD_CHECK_ARG(h && h1 && s1 && h2 && s2 && bn_gamma && bn_beta && bn_mean && bn_var, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = build_csr(h1, kNA, h->off1, h->idx1, st);
+  int r1 = 0, r2 = 0;
+  int rc = build_csr(h1, kNA, h->off1, h->idx1, st, h->rnd, h->rnd + kNA + kNV, &r1);
   if (rc) return rc;
-  rc = build_csr(h2, kNV, h->off2, h->idx2, st);
+  rc = build_csr(h2, kNV, h->off2, h->idx2, st, h->rnd + kNA, h->rnd + kNA + kNV + kMaxRounds + 1, &r2);
   if (rc) return rc;
+  h->n_rounds = std::max(r1, r2);
   AVVAD_CUDA(cudaMemcpyAsync(h->s1, s1, sizeof(float) * kNA, cudaMemcpyDeviceToDevice, st));
   AVVAD_CUDA(cudaMemcpyAsync(h->s2, s2, sizeof(float) * kNV, cudaMemcpyDeviceToDevice, st));
   AVVAD_CUDA(cudaMemcpyAsync(h->bn_gamma, bn_gamma, sizeof(float) * kMcbOut, cudaMemcpyDeviceToDevice, st));
@@ -646,13 +705,13 @@ extern "C" int avvad_mcb_forward(avvad_mcb* h, const float* audio, const float* 
   // profiling category 5: "flops" carries the algorithmic bytes (513 + 512 floats in, 1024 bf16 or fp32 out per row)
   void* ptok = nullptr;
   tc::prof_begin(st, &ptok);
-  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
+  if (int rc = launch_mcb_rows(audio, video, tb, rounds_of(h), tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
   mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
   AVVAD_LAUNCHED();
   const int64_t total = rows * kMcbOut;
-  mcb_apply_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, h->bn_mean, h->bn_invstd, h->bn_gamma,
-                                                                   h->bn_beta, rows, (__nv_bfloat16*)out_bf16, ld_out,
-                                                                   out_f32);
+  mcb_apply_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, st>>>(y, norm, nullptr, 0, h->bn_mean, h->bn_invstd,
+                                                                       h->bn_gamma, h->bn_beta, rows,
+                                                                       (__nv_bfloat16*)out_bf16, ld_out, out_f32);
   AVVAD_LAUNCHED();
   tc::prof_end(st, ptok, 5, (double)rows * (4100.0 + (out_f32 ? 4096.0 : 2048.0)));
   return AVVAD_OK;
@@ -698,11 +757,11 @@ extern "C" int avvad_mcb_forward_grouped(avvad_mcb* h, const float* audio, const
   McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
   void* ptok = nullptr;
   tc::prof_begin(st, &ptok);
-  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, lengths, (int)t_max, st)) return rc;
+  if (int rc = launch_mcb_rows(audio, video, tb, rounds_of(h), tw, h->eps, y, rowsq, rows, lengths, (int)t_max, st)) return rc;
   mcb_norm_grouped_kernel<<<(unsigned)n_groups, 256, 0, st>>>(rowsq, lengths, (int)t_max, norms);
   AVVAD_LAUNCHED();
   const int64_t total = rows * kMcbOut;
-  mcb_apply_grouped_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+  mcb_apply_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, st>>>(
       y, norms, lengths, (int)t_max, h->bn_mean, h->bn_invstd, h->bn_gamma, h->bn_beta, rows,
       (__nv_bfloat16*)out_bf16, ld_out, out_f32);
   AVVAD_LAUNCHED();
@@ -731,14 +790,15 @@ extern "C" int avvad_mcb_forward_train(avvad_mcb* h, const float* audio, const f
   float* norm = reinterpret_cast<float*>((uint8_t*)rowsq + align_up((size_t)rows * sizeof(float), 256));
   float* mean_invstd = norm + 64;
   McbTables tb{h->off1, h->idx1, h->s1, h->off2, h->idx2, h->s2};
-  if (int rc = launch_mcb_rows(audio, video, tb, tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
+  if (int rc = launch_mcb_rows(audio, video, tb, rounds_of(h), tw, h->eps, y, rowsq, rows, nullptr, 0, st)) return rc;
   mcb_norm_kernel<<<1, 1024, 0, st>>>(rowsq, rows, norm);
   AVVAD_LAUNCHED();
   mcb_bn_stats_kernel<<<kMcbOut, 256, 0, st>>>(y, norm, rows, h->eps, momentum, mean_invstd, running_mean, running_var);
   AVVAD_LAUNCHED();
   const int64_t total = rows * kMcbOut;
-  mcb_apply_train_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, norm, mean_invstd, gamma, beta, rows,
-                                                                         (__nv_bfloat16*)out_bf16, ld_out, out_f32);
+  mcb_apply_kernel<<<(unsigned)ceil_div(total / 8, 256), 256, 0, st>>>(y, norm, nullptr, 0, mean_invstd,
+                                                                       mean_invstd + kMcbOut, gamma, beta, rows,
+                                                                       (__nv_bfloat16*)out_bf16, ld_out, out_f32);
   AVVAD_LAUNCHED();
   return AVVAD_OK;
 }

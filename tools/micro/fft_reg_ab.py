@@ -1,6 +1,7 @@
-"""A/B of the two MCB row kernels (radix-4 shared-memory FFT vs register FFT, AVVAD_MCB_REG=0/1) at the bench shape
-B = 256 x T = 317 rows: device time of the whole avvad_mcb_forward call and agreement of the fp32 outputs.  The kernel
-choice is read once per process, so each mode runs in a child process."""
+"""A/B of the FFT-based kernels -- MCB row pass and log-power front end -- on the radix-4 shared-memory FFT vs the
+register FFT (AVVAD_MCB_REG / AVVAD_FE_REG = 0/1) at the bench shape B = 256 x T = 317: device time of the whole
+avvad_mcb_forward / avvad_frontend_logpower call and agreement of the fp32 outputs.  The kernel choice is read once per
+process, so each mode runs in a child process."""
 import os
 import subprocess
 import sys
@@ -31,7 +32,17 @@ def child(mode: str, out_path: str):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     mcb.forward(a, v, out_bf16=ob, out_f32=o32)
     torch.cuda.synchronize()
-    torch.save(o32[::97].cpu(), out_path)
+    B, T = 256, 317
+    N = (T - 1) * 256 + 1024
+    wave = torch.randn(B, N, device=dev) * 0.1
+    mean = torch.randn(513, device=dev)
+    std = torch.rand(513, device=dev) + 1.0
+    fe = torch.empty(B, T, 513, device=dev)
+    nsamp = [N - 37 * i for i in range(B)]
+    nfr = [T - (i % 5) for i in range(B)]
+    E.frontend_logpower(wave, nsamp, nfr, T, mean, std, out=fe)
+    torch.cuda.synchronize()
+    torch.save((o32[::97].cpu(), fe[::3].cpu()), out_path)
     ts = []
     for i in range(23):
         flush.zero_()
@@ -44,6 +55,18 @@ def child(mode: str, out_path: str):
             ts.append(e0.elapsed_time(e1))
     ts.sort()
     print(f"AVVAD_MCB_REG={mode}: mcb forward (row + norm + apply) {ts[len(ts) // 2]:.4f} ms median, {ts[0]:.4f} min")
+    ts = []
+    for i in range(23):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        E.frontend_logpower(wave, nsamp, nfr, T, mean, std, out=fe)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    print(f"AVVAD_FE_REG={mode}: front end (peak + log-power frames) {ts[len(ts) // 2]:.4f} ms median, {ts[0]:.4f} min")
 
 
 if __name__ == "__main__":
@@ -55,10 +78,11 @@ if __name__ == "__main__":
     outs = []
     for mode in ("0", "1"):
         path = f"/tmp/mcb_ab_{mode}.pt"
-        env = dict(os.environ, AVVAD_MCB_REG=mode)
+        env = dict(os.environ, AVVAD_MCB_REG=mode, AVVAD_FE_REG=mode)
         subprocess.check_call([sys.executable, os.path.abspath(__file__), mode, path], env=env)
         outs.append(torch.load(path))
-    d = (outs[0] - outs[1]).abs().max().item()
-    rel = ((outs[0] - outs[1]).norm() / outs[0].norm()).item()
-    print(f"register FFT vs shared-memory FFT: max |diff| {d:.3e}, rel fro {rel:.3e} (output std {outs[0].std().item():.3f})")
-    assert rel < 1e-5, rel
+    for name, a, b in (("mcb", outs[0][0], outs[1][0]), ("front end", outs[0][1], outs[1][1])):
+        d = (a - b).abs().max().item()
+        rel = ((a - b).norm() / a.norm()).item()
+        print(f"{name}: register FFT vs shared-memory FFT: max |diff| {d:.3e}, rel fro {rel:.3e} (output std {a.std().item():.3f})")
+        assert rel < 1e-5, (name, rel)
