@@ -321,10 +321,31 @@ mcb_apply_kernel(const float* __restrict__ y, const float* __restrict__ norms, c
     const float4 y0 = *reinterpret_cast<const float4*>(y + r * kMcbOut + j);
     const float4 y1 = *reinterpret_cast<const float4*>(y + r * kMcbOut + j + 4);
     const float yy[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    // 128-bit loads of the per-channel constants (32 scalar loads per thread throttled the load queue: ncu lg_throttle 40)
+    float pm[8], pi[8], pg[8], pb[8];
+    const bool vec = ((reinterpret_cast<uintptr_t>(bn_mean) | reinterpret_cast<uintptr_t>(bn_invstd) |
+                       reinterpret_cast<uintptr_t>(bn_gamma) | reinterpret_cast<uintptr_t>(bn_beta)) & 15) == 0;
+    if (!vec) {  // caller-owned gamma / beta (training) at an unaligned address
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        pm[e] = bn_mean[j + e]; pi[e] = bn_invstd[j + e]; pg[e] = bn_gamma[j + e]; pb[e] = bn_beta[j + e];
+      }
+    } else
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bn_mean + j) + hlf);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bn_invstd + j) + hlf);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(bn_gamma + j) + hlf);
+      const float4 d = __ldg(reinterpret_cast<const float4*>(bn_beta + j) + hlf);
+      pm[4 * hlf] = a.x; pm[4 * hlf + 1] = a.y; pm[4 * hlf + 2] = a.z; pm[4 * hlf + 3] = a.w;
+      pi[4 * hlf] = b.x; pi[4 * hlf + 1] = b.y; pi[4 * hlf + 2] = b.z; pi[4 * hlf + 3] = b.w;
+      pg[4 * hlf] = c.x; pg[4 * hlf + 1] = c.y; pg[4 * hlf + 2] = c.z; pg[4 * hlf + 3] = c.w;
+      pb[4 * hlf] = d.x; pb[4 * hlf + 1] = d.y; pb[4 * hlf + 2] = d.z; pb[4 * hlf + 3] = d.w;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float v = yy[e] / nrm;
-      o[e] = (v - __ldg(bn_mean + j + e)) * __ldg(bn_invstd + j + e) * __ldg(bn_gamma + j + e) + __ldg(bn_beta + j + e);
+      o[e] = (v - pm[e]) * pi[e] * pg[e] + pb[e];
     }
   } else {
 #pragma unroll
@@ -634,6 +655,8 @@ static int build_csr(const int64_t* h_dev, int n, int32_t* off_dev, int32_t* idx
         rounds = std::max(rounds, e - off[j] + 1);
       }
     ent.reserve(n);
+    // (ordering a round's entries so that every 32 consecutive ones hit 32 distinct banks for both the input gather and
+    // the bucket update was measured: no change, 0.7159 vs 0.7158 ms -- left in ascending input order)
     for (int r = 0; r < rounds; ++r) {
       if (r <= kMaxRounds) roff[r] = (int32_t)ent.size();
       for (int i = 0; i < n; ++i)
