@@ -436,6 +436,7 @@ struct StemInput {
   const int32_t* n_src = nullptr;
   const int32_t* n_out = nullptr;
   int f_max = 0, t_max = 0, num = 0, den = 0, standardise = 0;
+  int64_t src_bytes = 0;  // size of `src`
   float mean = 0.f, denom = 1.f;
   StemInput advance(int64_t f0) const {  // the same source seen from frame f0 on (chunking)
     StemInput r = *this;
@@ -476,7 +477,7 @@ static int launch_stem_s2d(avvad_resnet18* h, const StemInput& in, int64_t n, __
   if (in.src) {
     // frame n of this launch is global frame in.first + n = (b, k); shift the per-utterance arrays so that the kernel's
     // n / t_max arithmetic stays local: only whole-utterance offsets are representable, so pass `first` through
-    p.src = in.src; p.n_src = in.n_src; p.n_out = in.n_out;
+    p.src = in.src; p.n_src = in.n_src; p.n_out = in.n_out; p.src_bytes = in.src_bytes;
     p.f_max = in.f_max; p.t_max = in.t_max; p.num = in.num; p.den = in.den;
     p.mean = in.mean; p.denom = in.denom; p.standardise = in.standardise;
     p.first = in.first;
@@ -658,6 +659,7 @@ extern "C" int avvad_resnet18_forward_u8(avvad_resnet18* h, const uint8_t* src, 
   in.src = src; in.n_src = n_src; in.n_out = n_out;
   in.f_max = f_max; in.t_max = t_max; in.num = num; in.den = den;
   in.mean = mean; in.denom = stdv + eps; in.standardise = standardise;
+  in.src_bytes = (int64_t)B * f_max * kFrameHW;
   return forward_common(h, in, (int64_t)B * t_max, chunk_frames, workspace, workspace_bytes, feat, feat_bf16, ld_bf16,
                         col_off, (cudaStream_t)stream);
 }

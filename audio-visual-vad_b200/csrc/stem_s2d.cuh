@@ -63,7 +63,12 @@ constexpr uint32_t kS2OffEdgeHp = kS2OffRing + kS2RingBytes;
 constexpr uint32_t kS2OffLut = kS2OffEdgeHp + kS2EdgeHpBytes;
 constexpr uint32_t kS2OffBias = kS2OffLut + 512;
 constexpr uint32_t kS2OffBar = kS2OffBias + 256;
-constexpr uint32_t kS2Smem = 1024 + kS2OffBar + 128;
+// MODE 1: raw bytes of a u8 source frame as 16-byte chunks from the 16-byte boundary below its first byte (4,489 bytes
+// + up to 15 of misalignment = 282 chunks), double buffered
+constexpr uint32_t kS2StageBytes = 288 * 16;
+constexpr uint32_t kS2OffStage = kS2OffBar + 128;
+constexpr uint32_t kS2Smem = 1024 + kS2OffStage + 2 * kS2StageBytes;
+static_assert(kS2Smem <= 227 * 1024, "stem kernel: shared memory");
 
 struct StemS2Params {
   // input mode 0: fp32 frames [n_frames][67*67] (already standardised)
@@ -79,6 +84,7 @@ struct StemS2Params {
   int64_t n_frames;
   int64_t first;             // mode 1: global index of local frame 0 (chunked calls)
   const __nv_bfloat16* w1b;  // folded conv1 weights [64][64], k = fr*7 + fs
+  int64_t src_bytes;         // mode 1: size of the whole `src` buffer (the 16-byte chunk loads never leave it)
   const float* bias;         // folded BN bias [64] (NULL = zero)
   __nv_bfloat16* out;        // [n_frames][17][17][64]
   double* stats;             // STATS kernels: per-channel sum [64] and sum of squares [64] of the conv1 outputs
@@ -199,8 +205,25 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
     // item j of a thread = (source row r, pixel pair q): padded pixels 2q, 2q+1 <-> source columns 2q-3, 2q-2.
     // The pixels of a frame are fetched into registers one frame ahead, so the global latency overlaps the wait for
     // a free batch buffer and the stores of the previous frame.
-    uint32_t px[kS2Items];  // MODE 0: packed bf16 pair; MODE 1: packed lut indices (lo | hi << 8), bit 16/17 = column valid
+    // MODE 0: px = packed bf16 pairs, fetched one frame ahead.
+    // MODE 1: the raw bytes of the next frame are fetched as two aligned 16-byte chunks per thread (ck0, ck1) and NOT
+    // touched until that frame's turn, so the loads really are in flight across the stores of the current frame (the
+    // first version combined 20 byte loads per thread into px[] inside fetch(): ncu had 17 % of the kernel's samples
+    // on that line, waiting for L2).  At its turn the chunks go to a staging buffer, a builder-only barrier makes the
+    // frame visible, and the items take their bytes from shared memory.
+    uint32_t px[MODE == 0 ? kS2Items : 1];
+    uint4 ck0 = make_uint4(0u, 0u, 0u, 0u), ck1 = ck0;
+    bool live_next = false;
+    uint32_t mis_next = 0;
+    auto load_chunk = [&](const uint8_t* ptr) -> uint4 {
+      if (ptr >= p.src && ptr + 16 <= p.src + p.src_bytes) return __ldg(reinterpret_cast<const uint4*>(ptr));
+      uint32_t w[4] = {0u, 0u, 0u, 0u};  // first / last chunk of the whole buffer: byte by byte
+      for (int i = 0; i < 16; ++i)
+        if (ptr + i >= p.src && ptr + i < p.src + p.src_bytes) w[i >> 2] |= (uint32_t)__ldg(ptr + i) << (8 * (i & 3));
+      return make_uint4(w[0], w[1], w[2], w[3]);
+    };
     auto fetch = [&](int64_t n) {
+      if (MODE == 1) live_next = false;
       if (n >= p.n_frames) return;
       if (MODE == 0) {
         const float* f32 = p.frames + n * (67 * 67);
@@ -218,22 +241,32 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         const int64_t ng = p.first + n;
         const int b = (int)(ng / p.t_max), k = (int)(ng - (int64_t)b * p.t_max);
         const int F = p.n_src[b], T = p.n_out[b];
-        const bool live = (k < T && F > 0);
-        const uint8_t* u8 = live ? p.src + ((int64_t)b * p.f_max + s2_src_index(k, F, p.num, p.den)) * (67 * 67) : p.src;
-#pragma unroll
-        for (int j = 0; j < kS2Items; ++j) {
-          const int item = tid + j * kS2Builders;
-          const int r = item / 37, q = item - r * 37;
-          const int c0 = 2 * q - 3, c1 = c0 + 1;
-          const bool ok0 = (unsigned)c0 < 67u && r < 67, ok1 = (unsigned)c1 < 67u && r < 67;
-          uint32_t lo = 0u, hi = 0u;  // collate zero frame: source value 0
-          if (live && ok0) lo = __ldg(u8 + r * 67 + c0);
-          if (live && ok1) hi = __ldg(u8 + r * 67 + c1);
-          px[j] = lo | (hi << 8) | (ok0 ? 0x10000u : 0u) | (ok1 ? 0x20000u : 0u);
-        }
+        if (!(k < T && F > 0)) return;  // collate zero frame: source value 0 everywhere
+        const uint8_t* u8 = p.src + ((int64_t)b * p.f_max + s2_src_index(k, F, p.num, p.den)) * (67 * 67);
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(u8) & 15u);
+        const uint8_t* a0 = u8 - mis;
+        live_next = true;
+        mis_next = mis;
+        ck0 = load_chunk(a0 + 16 * tid);
+        if (16u * (uint32_t)(kS2Builders + tid) < 67u * 67u + mis) ck1 = load_chunk(a0 + 16 * (kS2Builders + tid));
       }
     };
-    auto store = [&](uint8_t* bufp, int fi) {
+    uint32_t stage_sel = 0;
+    const uint8_t* sb = nullptr;  // MODE 1: first byte of the current frame in its staging buffer
+    bool live = false;            // MODE 1: the current frame has source pixels (else: collate zero frame)
+    auto store = [&]() {          // MODE 1: the chunks fetched for this frame -> staging buffer
+      if (MODE == 1) {
+        uint8_t* stage = smem + kS2OffStage + stage_sel * kS2StageBytes;
+        stage_sel ^= 1u;
+        live = live_next;
+        if (live) {
+          reinterpret_cast<uint4*>(stage)[tid] = ck0;
+          if (kS2Builders + tid < (int)(kS2StageBytes / 16)) reinterpret_cast<uint4*>(stage)[kS2Builders + tid] = ck1;
+        }
+        sb = stage + mis_next;
+      }
+    };
+    auto build = [&](uint8_t* bufp, int fi) {
 #pragma unroll
       for (int j = 0; j < kS2Items; ++j) {
         const int item = tid + j * kS2Builders;
@@ -243,8 +276,9 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
         if (MODE == 0) {
           w = px[j];
         } else {
-          const uint32_t lo = (px[j] & 0x10000u) ? (uint32_t)lut[px[j] & 0xFFu] : 0u;
-          const uint32_t hi = (px[j] & 0x20000u) ? (uint32_t)lut[(px[j] >> 8) & 0xFFu] : 0u;
+          const int c0 = 2 * q - 3, c1 = c0 + 1;
+          const uint32_t lo = ((unsigned)c0 < 67u) ? (uint32_t)lut[live ? sb[r * 67 + c0] : 0] : 0u;
+          const uint32_t hi = ((unsigned)c1 < 67u) ? (uint32_t)lut[live ? sb[r * 67 + c1] : 0] : 0u;
           w = lo | (hi << 16);
         }
         const int pr = r + 3;  // padded row
@@ -266,10 +300,17 @@ __global__ void __launch_bounds__(kS2Threads, 1) stem_s2d_kernel(const StemS2Par
 #pragma unroll
       for (int fi = 0; fi < kS2FramesPerBatch; ++fi) {
         const int64_t n = bi * kS2FramesPerBatch + fi;
-        if (n < p.n_frames) store(bufp, fi);
+        const bool have = n < p.n_frames;  // CTA-uniform
+        if (have) store();
+        if (MODE == 0 && have) build(bufp, fi);  // px holds THIS frame until the fetch below overwrites it
         // next frame of this CTA: the second of this batch, or the first of the next one
         const int64_t nn = (fi + 1 < kS2FramesPerBatch) ? n + 1 : (bi + gridDim.x) * kS2FramesPerBatch;
         if (fi + 1 < kS2FramesPerBatch || bi + gridDim.x < n_batches) fetch(nn);
+        if (MODE == 1 && have) {
+          // staging buffer complete; it is rewritten two frames from now, behind the next frame's barrier
+          named_bar_sync(2, kS2Builders);
+          build(bufp, fi);
+        }
       }
       fence_proxy_async();
       mbar_arrive(BAR(0 + buf));
