@@ -20,6 +20,11 @@ class DeepVAD_AV(nn.Module):
         self.dropout = nn.Dropout(p=0.05)
         self.use_mcb = use_mcb
         self.eps = eps
+        # Extension (default off = the reference's semantics): in eval(), normalise every utterance's MCB output by its
+        # OWN L2 norm over its `lengths[b]` valid frames, so ONE batched forward returns what the reference returns
+        # when it is called once per utterance, as scripts/evaluate_AV_net.py:186-236 does (x[None], v[None],
+        # lengths = [T]); rows behind an utterance's length are ignored (they do not exist in those calls).
+        self.norm_per_utterance = False
 
         # parameter containers only: the child named 'features' must exist (train_AV_net.py:242-245)
         resnet = models.resnet18(weights=None)
@@ -119,6 +124,8 @@ class DeepVAD_AV(nn.Module):
                 proxy = McbBnFunction.apply(eng["mcb"], aud, feat, x, self.mcb_bn, self.mcb_bn.weight, self.mcb_bn.bias)
                 self.mcb_bn.num_batches_tracked += 1
                 bump_generation(self.mcb_bn.running_mean, self.mcb_bn.running_var)
+            elif self.norm_per_utterance:
+                eng["mcb"].forward_grouped(aud, feat, lengths, frames, out_bf16=xv)
             else:
                 eng["mcb"].forward(aud, feat, out_bf16=xv)
         else:

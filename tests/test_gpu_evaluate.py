@@ -9,7 +9,7 @@ from avvad import synth
 from avvad.evaluate import evaluate_shard, evaluate_sharded, plan_calls
 from avvad.pipeline import AVVADPipeline
 from oracle.reference_port import RefDeepVADAV, cpu_av_step
-from util import check_logits
+from util import check_logits, eval_single_inputs, golden
 
 pytestmark = pytest.mark.gpu
 
@@ -108,3 +108,31 @@ def test_posteriors_do_not_depend_on_the_call_grouping():
     f = [int(np.asarray(v).shape[0]) for _, v in utts]
     T = AVVADPipeline.frame_counts(n, f)
     assert plan_calls(T, 7)[0][0] == int(np.argmax(T))
+
+
+def test_batched_module_call_matches_reference_called_once_per_utterance():
+    """Pinned against the reference itself: tests/golden/ref_eval_single.npz holds the logits of the UNMODIFIED
+    DeepVAD_AV(use_mcb=True) called once per utterance (scripts/evaluate_AV_net.py:186-236).  ONE batched forward of the
+    drop-in module with norm_per_utterance = True must reproduce them; with the flag off it reproduces the reference's
+    batched call instead (whole-call norm over the padded tensor), which differs by up to 1.1 in the logits."""
+    from packages.models.AV_Net import DeepVAD_AV
+    g = golden("ref_eval_single.npz")
+    a, v, lens = eval_single_inputs()
+    sd = synth.calibrate_mcb_bn_(synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 43, "strong"), 20)
+    sd["vad_merged.bias"] = torch.tensor(g["bias"])
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    m.norm_per_utterance = True
+    out = m(torch.tensor(a).cuda(), torch.tensor(v).cuda(), lens).cpu().numpy()
+    check_logits(out, g["logits"], lens, "module, per-utterance norm vs reference single calls")
+    m.norm_per_utterance = False
+    out = m(torch.tensor(a).cuda(), torch.tensor(v).cuda(), lens).cpu().numpy()
+    # (the head bias was placed for the single-call logits, so only the two error gates here, not the decision gate)
+    mask = np.zeros(out.shape[:2], dtype=bool)
+    for b, n in enumerate(lens):
+        mask[b, :n] = True
+    ref = g["batched_call_logits"][mask].astype(np.float64)
+    got = out[mask].astype(np.float64)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 2e-2
+    assert np.abs(1 / (1 + np.exp(-got)) - 1 / (1 + np.exp(-ref))).max() <= 1e-2

@@ -134,3 +134,26 @@ def test_training_step_video_trainable_trunk_matches_reference(gs, gref):
     assert err_stats(logits.detach().numpy(), gs["train_video_logits"])["rel_fro"] < 1e-4
     assert abs(loss.item() - float(gs["train_video_loss"])) < 1e-4 * abs(float(gs["train_video_loss"]))
     _check_digest(gs, "train_video", [(k, t.grad) for k, t in p.items() if t.requires_grad], 5e-3)
+
+
+def test_one_call_per_utterance_matches_reference_evaluation_pattern():
+    """scripts/evaluate_AV_net.py:186-236 calls the model once per utterance (x[None], v[None], lengths = [T]); the golden
+    holds the UNMODIFIED reference module's logits for that call pattern.  The oracle called the same way must agree --
+    and ONE batched call of the same utterances must NOT (AV_Net.py:117 normalises over the whole padded tensor), which
+    is why the batched device path has a per-utterance norm (avvad_mcb_forward_grouped)."""
+    from util import eval_single_inputs
+    g = golden("ref_eval_single.npz")
+    a, v, lens = eval_single_inputs()
+    assert lens == g["lens"].tolist()
+    sd = synth.calibrate_mcb_bn_(_sd("av", 43, "strong", use_mcb=True), 20)
+    sd["vad_merged.bias"] = torch.tensor(g["bias"])
+    worst_batched = 0.0
+    for b, n in enumerate(lens):
+        out = om.deepvad_av_forward(torch.tensor(a[b:b + 1, :n]), torch.tensor(v[b:b + 1, :n]), [n], sd, use_mcb=True,
+                                    eps=1e-8).numpy()[0]
+        assert err_stats(out, g["logits"][b, :n])["rel_fro"] < 2e-5, b
+        worst_batched = max(worst_batched, float(np.abs(g["batched_call_logits"][b, :n] - g["logits"][b, :n]).max()))
+    assert worst_batched > 0.5   # the reference itself: a batched call is a different function
+    batched = om.deepvad_av_forward(torch.tensor(a), torch.tensor(v), lens, sd, use_mcb=True, eps=1e-8).numpy()
+    for b, n in enumerate(lens):
+        assert err_stats(batched[b, :n], g["batched_call_logits"][b, :n])["rel_fro"] < 2e-5, b

@@ -59,3 +59,14 @@ def check_logits(got, ref, lens=None, what=""):
     assert post <= POST_TOL, (what, post)
     assert agree >= AGREE, (what, agree)
     return rel, post, agree
+
+
+EVAL_SINGLE_LENS = [23, 9, 16, 31]
+
+
+def eval_single_inputs():
+    """Inputs of tests/golden/ref_eval_single.npz (tools/make_golden.py::eval_single_inputs, same PCG64 streams)."""
+    B, T = len(EVAL_SINGLE_LENS), max(EVAL_SINGLE_LENS)
+    a = np.random.default_rng(91).standard_normal((B, T, 513)).astype(np.float32)
+    v = np.random.default_rng(92).standard_normal((B, T, 67, 67)).astype(np.float32)
+    return a, v, list(EVAL_SINGLE_LENS)

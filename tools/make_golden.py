@@ -337,6 +337,53 @@ def ref_strong():
            for k in d if k.endswith("_strong") or k.startswith("av_mcb_out")})
 
 
+EVAL_SINGLE_LENS = [23, 9, 16, 31]
+
+
+def eval_single_inputs():
+    """Inputs of ref_eval_single(), regenerated by the tests from the same PCG64 streams instead of being stored."""
+    B, T = len(EVAL_SINGLE_LENS), max(EVAL_SINGLE_LENS)
+    a = np.random.default_rng(91).standard_normal((B, T, 513)).astype(np.float32)
+    v = np.random.default_rng(92).standard_normal((B, T, 67, 67)).astype(np.float32)
+    return a, v, list(EVAL_SINGLE_LENS)
+
+
+def ref_eval_single():
+    """The reference's evaluation call pattern (scripts/evaluate_AV_net.py:186-236): the UNMODIFIED DeepVAD_AV
+    (use_mcb=True, eval()) called ONCE PER UTTERANCE with x[None], v[None], lengths = [T], so AV_Net.py:117's
+    whole-tensor L2 norm is a per-utterance norm.  Strong weight family, head bias placed by synth.decision_bias over all
+    utterances.  -> tests/golden/ref_eval_single.npz (logits padded to (B, Tmax, 1), bias)."""
+    sys.path.insert(0, REF)
+    install_legacy_fft_shim()
+    from packages.models.AV_Net import DeepVAD_AV
+
+    a, v, lens = eval_single_inputs()
+    m = DeepVAD_AV(2, 1024, 1, use_mcb=True, eps=1e-8)
+    m.load_state_dict(synth.calibrate_mcb_bn_(synth.seeded_state_dict(synth.model_spec("av", use_mcb=True), 43, "strong"), 20))
+    m.eval()
+
+    def run():
+        out = np.zeros((len(lens), max(lens), 1), dtype=np.float32)
+        with torch.no_grad():
+            for b, n in enumerate(lens):
+                out[b, :n] = m(torch.tensor(a[b:b + 1, :n]), torch.tensor(v[b:b + 1, :n]), [n]).numpy()[0]
+        return out
+
+    out0 = run()
+    with torch.no_grad():
+        nb = synth.decision_bias(out0, lens, m.vad_merged.bias.detach().numpy())
+        m.vad_merged.bias.copy_(nb)
+    out = run()
+    with torch.no_grad():  # for contrast: ONE batched call of the same utterances (whole-call norm over the padded tensor)
+        batched = m(torch.tensor(a), torch.tensor(v), lens).numpy()
+    np.savez_compressed(os.path.join(OUT, "ref_eval_single.npz"), logits=out, bias=nb.numpy(), lens=np.asarray(lens),
+                        batched_call_logits=batched)
+    valid = np.concatenate([out[b, :n, 0] for b, n in enumerate(lens)])
+    print("ref_eval_single.npz: logits range [%.2f, %.2f] std %.2f; batched-call logits differ by up to %.2f" %
+          (valid.min(), valid.max(), valid.std(),
+           max(np.abs(out[b, :n] - batched[b, :n]).max() for b, n in enumerate(lens))))
+
+
 def golden_h5():
     """Two small files of the reference copied verbatim (data, 4 KB + 9 KB) and the first LZF chunks of a video file:
     they pin the HDF5 writer (message bytes, chunk shapes) and the LZF encoder (stored bytes) of avvad/h5min.py."""
@@ -439,6 +486,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[2] == "strong":
         ref_strong()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == "eval_single":
+        ref_eval_single()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "helpers":
         ref_helpers()
         ref_target_masks()
@@ -447,6 +497,7 @@ if __name__ == "__main__":
     golden_upsample()
     ref_models()
     ref_strong()
+    ref_eval_single()
     golden_h5()
     ref_helpers()
     ref_target_masks()
