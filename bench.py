@@ -568,7 +568,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- variant: BASELINE config 4 as written -- 10,000 variable-length utterances sharded over the ranks ----
     cfg4 = None
     if not args.no_config4:
-        cfg4 = config4_block(pipe, rank, world, dev, barrier)
+        try:
+            cfg4 = config4_block(pipe, rank, world, dev, barrier)
+        except Exception as ex:  # reported, never hidden; must not erase the headline numbers measured above
+            cfg4 = {"failed": f"{type(ex).__name__}: {ex}"}
+            if world > 1:
+                raise
         pipe._bufs.clear()
         torch.cuda.empty_cache()
 
