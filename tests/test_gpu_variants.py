@@ -82,3 +82,14 @@ def test_bptt_overlapped_chains_bit_identical(tmp_path):
     assert set(plain) == set(fast)
     for k in plain:
         assert torch.isfinite(plain[k]).all() and torch.equal(fast[k], plain[k]), k
+
+
+def test_register_fft_kernels_match_the_shared_memory_fft_kernels():
+    """MCB row pass (whole-call and per-utterance norm) and log-power front end: register FFT (default) vs the radix-4
+    shared-memory FFT kernels they replaced (AVVAD_MCB_REG=0 / AVVAD_FE_REG=0, also the fallback for degenerate hash
+    tables), at the bench shape.  Different butterfly order -> different fp32 rounding: agreement to 1e-5 relative is
+    asserted inside the tool (measured 5e-7 / 1e-7), which runs each mode in its own child process."""
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tools", "micro", "fft_reg_ab.py")], capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mcb grouped: register FFT vs shared-memory FFT" in r.stdout
