@@ -661,7 +661,8 @@ def run_ours(args, rank, world, local_rank):
                 "note": "BASELINE config 4 input statistics: utterance lengths N ~ U{64,000..102,400} samples "
                         "(T 247..397), zero-padded to the longest of the batch as the reference's collate does; the padded "
                         "frames run through the ResNet and MCB exactly as in the reference (SURVEY 8g), so the gap to the "
-                        "headline is the padding + imbalance cost"}},
+                        "headline is the padding + imbalance cost; `config4` runs the same length distribution the way "
+                        "scripts/evaluate_AV_net.py evaluates it (one norm per utterance, length-sorted calls)"}},
         "config4": cfg4,
         "train": train,
         # achieved HBM GB/s of the memory-bound stages = algorithmic bytes (per-frame figures of SURVEY 8d x
